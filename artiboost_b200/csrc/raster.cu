@@ -1,0 +1,467 @@
+// Batched hand+object view rasteriser (sm_100a).
+//
+// Replaces Renderer.__call__ (anakin/utils/renderer.py:101-123) over pyrender's OffscreenRenderer
+// (anakin/utils/frender_utils.py:179-205): B views per call instead of one GL draw + two glReadPixels per call.
+// The rule set (fixed-point snapping, top-left fill rule, 1/z depth, z-test key, shading) is the one stated at the
+// top of oracle/raster.c; every fp32 operation below is individually rounded in the same order (this file is
+// compiled with -fmad=false and uses explicit __fmaf_rn where the rules say "fma").
+//
+// Views are processed in chunks; per chunk three kernels run back to back on the caller's stream:
+//   1. raster_vertex_kernel    one thread per (view, vertex): object model matrix, pinhole projection, snapping
+//                              to 24.8 fixed point.  16 B per projected vertex, coalesced, into an L2-resident scratch.
+//   2. raster_triangle_kernel  one thread per (view, triangle): integer set-up, cull, pixel bbox, coverage with
+//                              exact integer edge functions (32-bit when the bbox is < 128 px, else 64-bit),
+//                              z-test by RED.MIN.U64 on key = depth_bits << 32 | prim_id into the chunk's key
+//                              buffer (8 B / pixel, L2-resident).  At 256^2 most triangles cover 0-2 pixel centres,
+//                              so the pass is set-up bound, not fill bound.
+//   3. raster_resolve_kernel   one thread per 4 consecutive pixels: winner triangle re-set-up, exact depth,
+//                              shading, background compositing; 16-byte RGBA / depth stores, 4-byte seg stores;
+//                              restores the key buffer to "empty" where it was hit.
+// HBM traffic per view is the output (9 B / pixel) plus the 9.4 KB of per-view inputs; scratch never needs to
+// leave L2 when `chunk` is sized so (chunk * (8*W*H + 16*verts)) stays well under the 126 MB L2.
+#include "common.cuh"
+
+namespace ab {
+
+constexpr int kMaxObjects = 64;
+constexpr unsigned long long kEmptyKey = ~0ull;
+
+struct RasterParams {
+    // scene
+    const float* obj_verts;
+    const int4* obj_faces;
+    const uchar4* obj_colors;
+    const int4* hand_faces;
+    const uchar4* hand_colors;
+    const uint8_t* bgs;
+    int n_obj, n_hv, n_hf, n_tex, n_bg, bg_h, bg_w;
+    int max_ov, max_of;  // launch sizing
+    // camera
+    int W, H;
+    float fx, fy, cx, cy, znear, ambient, diffuse;
+    int cull;
+    int bg_r, bg_g, bg_b;
+    // per-view inputs (already offset to the chunk's first view)
+    const float* hand_verts;
+    const int32_t* hand_tex;
+    const int32_t* obj_id;
+    const float* obj_pose;
+    const float* light;
+    const int32_t* bg_sel;
+    // outputs (offset to the chunk)
+    uint8_t* rgba;
+    float* depth;
+    uint8_t* seg;
+    // scratch
+    unsigned long long* keys;  // [chunk][H][W]
+    int4* pv;                  // [chunk][pv_stride]  {x, y, iz bits, ok}
+    int pv_stride;
+    int n_views;
+    int vert_off[kMaxObjects + 1];
+    int face_off[kMaxObjects + 1];
+};
+
+// ---- rule: vertex ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int snap(float u) {
+    float s = __fmul_rn(u, 256.0f);
+    if (!(s >= -4194304.0f)) s = -4194304.0f;  // also catches NaN
+    if (s > 4194304.0f) s = 4194304.0f;
+    return __float2int_rn(s);
+}
+
+__device__ __forceinline__ int4 project(const RasterParams& P, float X, float Y, float Z) {
+    int4 r;
+    r.w = (Z >= P.znear) ? 1 : 0;
+    float iz = __fdiv_rn(1.0f, Z);
+    r.z = __float_as_int(iz);
+    r.x = snap(__fmaf_rn(P.fx, __fmul_rn(X, iz), P.cx));
+    r.y = snap(__fmaf_rn(P.fy, __fmul_rn(Y, iz), P.cy));
+    return r;
+}
+
+__device__ __forceinline__ void xform(const float* __restrict__ M, float x, float y, float z, float* o) {
+    o[0] = __fmaf_rn(M[2], z, __fmaf_rn(M[1], y, __fmaf_rn(M[0], x, M[3])));
+    o[1] = __fmaf_rn(M[6], z, __fmaf_rn(M[5], y, __fmaf_rn(M[4], x, M[7])));
+    o[2] = __fmaf_rn(M[10], z, __fmaf_rn(M[9], y, __fmaf_rn(M[8], x, M[11])));
+}
+
+__global__ void __launch_bounds__(256)
+raster_vertex_kernel(const __grid_constant__ RasterParams P) {
+    const int view = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oid = P.obj_id[view];
+    const int n_ov = oid >= 0 ? P.vert_off[oid + 1] - P.vert_off[oid] : 0;
+    if (t >= n_ov + P.n_hv) return;
+    float c[3];
+    if (t < n_ov) {
+        const float* v = P.obj_verts + 3 * (size_t)(P.vert_off[oid] + t);
+        xform(P.obj_pose + 16 * (size_t)view, v[0], v[1], v[2], c);
+    } else {
+        const float* v = P.hand_verts + 3 * ((size_t)view * P.n_hv + (t - n_ov));
+        c[0] = v[0]; c[1] = v[1]; c[2] = v[2];
+    }
+    P.pv[(size_t)view * P.pv_stride + t] = project(P, c[0], c[1], c[2]);
+}
+
+// ---- rule: triangle ----------------------------------------------------------------------------------------
+struct Tri {
+    int x[3], y[3];
+    float iz[3];
+    int s;                 // +1 when area2 > 0 (back-facing in the y-down image), -1 otherwise
+    long long sarea;       // |area2|
+    int bias[3];           // 0 on top/left edges, -1 elsewhere: inside <=> E_i + bias_i >= 0
+};
+
+// returns false if discarded
+__device__ __forceinline__ bool tri_setup(int cull, const int4& a, const int4& b, const int4& d, Tri& t) {
+    if (!(a.w & b.w & d.w)) return false;
+    const long long area2 = (long long)(b.x - a.x) * (long long)(d.y - a.y) - (long long)(d.x - a.x) * (long long)(b.y - a.y);
+    if (area2 == 0) return false;
+    if (area2 > 0 && cull) return false;
+    t.s = area2 > 0 ? 1 : -1;
+    t.sarea = area2 > 0 ? area2 : -area2;
+    t.x[0] = a.x; t.x[1] = b.x; t.x[2] = d.x;
+    t.y[0] = a.y; t.y[1] = b.y; t.y[2] = d.y;
+    t.iz[0] = __int_as_float(a.z); t.iz[1] = __int_as_float(b.z); t.iz[2] = __int_as_float(d.z);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // edge i runs v[i+1] -> v[i+2], opposite vertex i
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+        const long long dx = (long long)t.s * (t.x[i2] - t.x[i1]);
+        const long long dy = (long long)t.s * (t.y[i2] - t.y[i1]);
+        t.bias[i] = ((dy < 0) || (dy == 0 && dx > 0)) ? 0 : -1;
+    }
+    return true;
+}
+
+__device__ __forceinline__ long long edge64(const Tri& t, int i, long long px, long long py) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    const long long dx = t.x[i2] - t.x[i1], dy = t.y[i2] - t.y[i1];
+    return (long long)t.s * (dx * (py - t.y[i1]) - dy * (px - t.x[i1]));
+}
+
+// depth and the three partial products of the rule "depth"; e_i are the (non-negative) edge values
+__device__ __forceinline__ float depth_at(const Tri& t, float f0, float f1, float f2, float* num_out, float* a) {
+    a[0] = __fmul_rn(f0, t.iz[0]);
+    a[1] = __fmul_rn(f1, t.iz[1]);
+    a[2] = __fmul_rn(f2, t.iz[2]);
+    const float num = __fmaf_rn(f2, t.iz[2], __fmaf_rn(f1, t.iz[1], a[0]));
+    *num_out = num;
+    return __fdiv_rn(__ll2float_rn(t.sarea), num);
+}
+
+__device__ __forceinline__ int floordiv256(int v) { return v >> 8; }
+
+__device__ __forceinline__ void emit(unsigned long long* __restrict__ keys, int idx, float z, int f) {
+    const unsigned long long k = ((unsigned long long)__float_as_uint(z) << 32) | (unsigned)f;
+    atomicMin(keys + idx, k);  // result unused -> RED.E.MIN.64
+}
+
+__global__ void __launch_bounds__(256)
+raster_triangle_kernel(const __grid_constant__ RasterParams P) {
+    const int view = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oid = P.obj_id[view];
+    int n_of = 0, n_ov = 0;
+    if (oid >= 0) {
+        n_of = P.face_off[oid + 1] - P.face_off[oid];
+        n_ov = P.vert_off[oid + 1] - P.vert_off[oid];
+    }
+    if (f >= n_of + P.n_hf) return;
+    int4 idx;
+    int off;
+    if (f < n_of) { idx = __ldg(P.obj_faces + P.face_off[oid] + f); off = 0; }
+    else { idx = __ldg(P.hand_faces + (f - n_of)); off = n_ov; }
+    const int4* pv = P.pv + (size_t)view * P.pv_stride + off;
+    const int4 a = pv[idx.x], b = pv[idx.y], d = pv[idx.z];
+    Tri t;
+    if (!tri_setup(P.cull, a, b, d, t)) return;
+    const int minx = min(t.x[0], min(t.x[1], t.x[2])), maxx = max(t.x[0], max(t.x[1], t.x[2]));
+    const int miny = min(t.y[0], min(t.y[1], t.y[2])), maxy = max(t.y[0], max(t.y[1], t.y[2]));
+    const int x0 = max(floordiv256(minx - 128 + 255), 0), x1 = min(floordiv256(maxx - 128), P.W - 1);
+    const int y0 = max(floordiv256(miny - 128 + 255), 0), y1 = min(floordiv256(maxy - 128), P.H - 1);
+    if (x0 > x1 || y0 > y1) return;
+    unsigned long long* keys = P.keys + (size_t)view * P.W * P.H;
+    if (maxx - minx < 16384 && maxy - miny < 16384) {
+        // every factor below is < 2^14 + 2^8 in magnitude: the products and their difference are exact in int32
+        int ex[3], ey[3], row[3];
+        const int cx0 = 256 * x0 + 128, cy0 = 256 * y0 + 128;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+            const int dx = t.s * (t.x[i2] - t.x[i1]), dy = t.s * (t.y[i2] - t.y[i1]);
+            row[i] = dx * (cy0 - t.y[i1]) - dy * (cx0 - t.x[i1]);
+            ex[i] = -256 * dy;  // step of E_i per pixel in x: |256*dy| < 2^23
+            ey[i] = 256 * dx;
+        }
+        for (int py = y0; py <= y1; ++py) {
+            int e0 = row[0], e1 = row[1], e2 = row[2];
+            for (int px = x0; px <= x1; ++px) {
+                if (((e0 + t.bias[0]) | (e1 + t.bias[1]) | (e2 + t.bias[2])) >= 0) {
+                    float num, aa[3];
+                    const float z = depth_at(t, __int2float_rn(e0), __int2float_rn(e1), __int2float_rn(e2), &num, aa);
+                    emit(keys, py * P.W + px, z, f);
+                }
+                e0 += ex[0]; e1 += ex[1]; e2 += ex[2];
+            }
+            row[0] += ey[0]; row[1] += ey[1]; row[2] += ey[2];
+        }
+    } else {
+        for (int py = y0; py <= y1; ++py)
+            for (int px = x0; px <= x1; ++px) {
+                const long long cx = 256ll * px + 128, cy = 256ll * py + 128;
+                const long long e0 = edge64(t, 0, cx, cy), e1 = edge64(t, 1, cx, cy), e2 = edge64(t, 2, cx, cy);
+                if (((e0 + t.bias[0]) | (e1 + t.bias[1]) | (e2 + t.bias[2])) >= 0) {
+                    float num, aa[3];
+                    const float z = depth_at(t, __ll2float_rn(e0), __ll2float_rn(e1), __ll2float_rn(e2), &num, aa);
+                    emit(keys, py * P.W + px, z, f);
+                }
+            }
+    }
+}
+
+// ---- rule: shading + resolve -------------------------------------------------------------------------------
+struct PixelOut { uchar4 rgba; float depth; uint8_t seg; };
+
+__device__ __forceinline__ PixelOut shade_pixel(const RasterParams& P, int view, int oid, int n_ov, int n_of, int px,
+                                                int py, unsigned f) {
+    int4 idx;
+    int off;
+    const bool is_obj = (int)f < n_of;
+    if (is_obj) { idx = __ldg(P.obj_faces + P.face_off[oid] + f); off = 0; }
+    else { idx = __ldg(P.hand_faces + (f - n_of)); off = n_ov; }
+    const int4* pv = P.pv + (size_t)view * P.pv_stride + off;
+    const int vi[3] = {idx.x, idx.y, idx.z};
+    Tri t;
+    tri_setup(0, pv[vi[0]], pv[vi[1]], pv[vi[2]], t);
+    const long long cx = 256ll * px + 128, cy = 256ll * py + 128;
+    const long long e0 = edge64(t, 0, cx, cy), e1 = edge64(t, 1, cx, cy), e2 = edge64(t, 2, cx, cy);
+    float num, a[3];
+    const float z = depth_at(t, __ll2float_rn(e0), __ll2float_rn(e1), __ll2float_rn(e2), &num, a);
+    float p[3][3];
+    uchar4 col[3];
+    if (is_obj) {
+        const float* M = P.obj_pose + 16 * (size_t)view;
+        const int vo = P.vert_off[oid];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float* v = P.obj_verts + 3 * (size_t)(vo + vi[j]);
+            xform(M, v[0], v[1], v[2], p[j]);
+            col[j] = __ldg(P.obj_colors + vo + vi[j]);
+        }
+    } else {
+        const float* hv = P.hand_verts + 3 * (size_t)view * P.n_hv;
+        const uchar4* hc = P.hand_colors + (size_t)P.hand_tex[view] * P.n_hv;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            p[j][0] = hv[3 * vi[j]]; p[j][1] = hv[3 * vi[j] + 1]; p[j][2] = hv[3 * vi[j] + 2];
+            col[j] = __ldg(hc + vi[j]);
+        }
+    }
+    const float inv = __fdiv_rn(1.0f, num);
+    const float w0 = __fmul_rn(a[0], inv), w1 = __fmul_rn(a[1], inv), w2 = __fmul_rn(a[2], inv);
+    const float e1x = __fsub_rn(p[1][0], p[0][0]), e1y = __fsub_rn(p[1][1], p[0][1]), e1z = __fsub_rn(p[1][2], p[0][2]);
+    const float e2x = __fsub_rn(p[2][0], p[0][0]), e2y = __fsub_rn(p[2][1], p[0][1]), e2z = __fsub_rn(p[2][2], p[0][2]);
+    const float nx = __fmaf_rn(e1y, e2z, -__fmul_rn(e1z, e2y));
+    const float ny = __fmaf_rn(e1z, e2x, -__fmul_rn(e1x, e2z));
+    const float nz = __fmaf_rn(e1x, e2y, -__fmul_rn(e1y, e2x));
+    const float rx = __fdiv_rn(__fsub_rn(__fadd_rn((float)px, 0.5f), P.cx), P.fx);
+    const float ry = __fdiv_rn(__fsub_rn(__fadd_rn((float)py, 0.5f), P.cy), P.fy);
+    const float Px = __fmul_rn(rx, z), Py = __fmul_rn(ry, z), Pz = z;
+    const float d2 = __fmaf_rn(Px, Px, __fmaf_rn(Py, Py, __fmul_rn(Pz, Pz)));
+    const float n2 = __fmaf_rn(nx, nx, __fmaf_rn(ny, ny, __fmul_rn(nz, nz)));
+    const float ndp = fabsf(__fmaf_rn(nx, Px, __fmaf_rn(ny, Py, __fmul_rn(nz, Pz))));
+    const float den = __fsqrt_rn(__fmul_rn(n2, d2));
+    const float cosv = den > 0.0f ? __fdiv_rn(ndp, den) : 0.0f;
+    const float sh = __fmaf_rn(__fmul_rn(P.diffuse, P.light[view]), __fdiv_rn(cosv, d2), P.ambient);
+    const float c0[3] = {(float)col[0].x, (float)col[0].y, (float)col[0].z};
+    const float c1[3] = {(float)col[1].x, (float)col[1].y, (float)col[1].z};
+    const float c2[3] = {(float)col[2].x, (float)col[2].y, (float)col[2].z};
+    uint8_t o[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float cc = __fmaf_rn(w2, c2[ch], __fmaf_rn(w1, c1[ch], __fmul_rn(w0, c0[ch])));
+        float v = __fmul_rn(cc, sh);
+        if (!(v >= 0.0f)) v = 0.0f;
+        if (v > 255.0f) v = 255.0f;
+        o[ch] = (uint8_t)__float2int_rn(v);
+    }
+    PixelOut r;
+    r.rgba = make_uchar4(o[0], o[1], o[2], 255);
+    r.depth = z;
+    r.seg = is_obj ? 2 : 1;
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+raster_resolve_kernel(const __grid_constant__ RasterParams P) {
+    const int view = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 consecutive pixels
+    const int npx = P.W * P.H;
+    if (4 * q >= npx) return;
+    const int oid = P.obj_id[view];
+    int n_of = 0, n_ov = 0;
+    if (oid >= 0) {
+        n_of = P.face_off[oid + 1] - P.face_off[oid];
+        n_ov = P.vert_off[oid + 1] - P.vert_off[oid];
+    }
+    unsigned long long* kp = P.keys + (size_t)view * npx + 4 * (size_t)q;
+    const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(kp);
+    const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(kp + 2);
+    const unsigned long long k[4] = {k01.x, k01.y, k23.x, k23.y};
+    const int py = (4 * q) / P.W, px0 = (4 * q) % P.W;
+    const int32_t* sel = P.bg_sel ? P.bg_sel + 5 * (size_t)view : nullptr;
+    const bool has_bg = sel && P.bgs && sel[0] >= 0;
+    uchar4 c[4];
+    float z[4];
+    uint8_t s[4];
+    bool hit = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (k[j] == kEmptyKey) {
+            uchar4 bg = make_uchar4((uint8_t)P.bg_r, (uint8_t)P.bg_g, (uint8_t)P.bg_b, 0);
+            if (has_bg) {
+                const int px = px0 + j;
+                const int sx = sel[1] + (int)(((long long)(2 * px + 1) * sel[3]) / (2 * P.W));
+                const int sy = sel[2] + (int)(((long long)(2 * py + 1) * sel[4]) / (2 * P.H));
+                const uint8_t* src = P.bgs + 3 * (((size_t)sel[0] * P.bg_h + sy) * P.bg_w + sx);
+                bg = make_uchar4(src[0], src[1], src[2], 0);
+            }
+            c[j] = bg; z[j] = 0.0f; s[j] = 0;
+        } else {
+            hit = true;
+            const PixelOut r = shade_pixel(P, view, oid, n_ov, n_of, px0 + j, py, (unsigned)(k[j] & 0xffffffffull));
+            c[j] = r.rgba; z[j] = r.depth; s[j] = r.seg;
+        }
+    }
+    if (hit) {
+        const ulonglong2 e = make_ulonglong2(kEmptyKey, kEmptyKey);
+        *reinterpret_cast<ulonglong2*>(kp) = e;
+        *reinterpret_cast<ulonglong2*>(kp + 2) = e;
+    }
+    const size_t o = (size_t)view * npx + 4 * (size_t)q;
+    if (P.rgba) {
+        uint4 v;
+        v.x = *reinterpret_cast<unsigned*>(&c[0]); v.y = *reinterpret_cast<unsigned*>(&c[1]);
+        v.z = *reinterpret_cast<unsigned*>(&c[2]); v.w = *reinterpret_cast<unsigned*>(&c[3]);
+        __stcs(reinterpret_cast<uint4*>(P.rgba + 4 * o), v);
+    }
+    if (P.depth) __stcs(reinterpret_cast<float4*>(P.depth + o), make_float4(z[0], z[1], z[2], z[3]));
+    if (P.seg) __stcs(reinterpret_cast<unsigned*>(P.seg + o), (unsigned)s[0] | ((unsigned)s[1] << 8) | ((unsigned)s[2] << 16) | ((unsigned)s[3] << 24));
+}
+
+static int max_hand_obj_verts(const ab_scene* s) {
+    int m = 0;
+    for (int i = 0; i < s->n_obj; ++i) m = max(m, s->obj_vert_off_host[i + 1] - s->obj_vert_off_host[i]);
+    return m;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace ab
+
+extern "C" uint64_t ab_render_workspace_bytes(const ab_scene* scene, const ab_camera* cam, int chunk) {
+    if (!scene || !cam || chunk <= 0 || cam->width <= 0 || cam->height <= 0) return 0;
+    if (scene->n_obj > 0 && !scene->obj_vert_off_host) return 0;
+    const size_t keys = ab::align_up((size_t)chunk * cam->width * cam->height * 8, 256);
+    const size_t pv = (size_t)chunk * ab::align_up((size_t)ab::max_hand_obj_verts(scene) + scene->n_hand_verts, 8) * 16;
+    return keys + pv;
+}
+
+extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int batch, int chunk,
+                               const float* hand_verts, const int32_t* hand_tex, const int32_t* obj_id,
+                               const int32_t* obj_id_host, const float* obj_pose, const float* light,
+                               const int32_t* bg_sel, uint8_t* rgba, float* depth, uint8_t* seg, void* ws,
+                               void* stream) {
+    using namespace ab;
+    AB_REQUIRE(scene && cam, "null scene / camera");
+    AB_REQUIRE(batch >= 0 && chunk > 0, "bad batch / chunk");
+    AB_REQUIRE(cam->width > 0 && cam->height > 0 && cam->width <= 4096 && cam->height <= 4096, "bad image size");
+    if ((cam->width & 3) != 0) {
+        set_error("ab_render_batch: width must be a multiple of 4");
+        return AB_ERR_UNSUPPORTED;
+    }
+    AB_REQUIRE(scene->n_obj >= 0 && scene->n_obj <= kMaxObjects, "n_obj out of range (max 64)");
+    AB_REQUIRE(scene->n_obj == 0 || (scene->obj_verts && scene->obj_faces && scene->obj_colors &&
+                                     scene->obj_vert_off_host && scene->obj_face_off_host), "null object arrays");
+    AB_REQUIRE(scene->n_hand_verts > 0 && scene->n_hand_faces > 0 && scene->n_hand_tex > 0 && scene->hand_faces &&
+                   scene->hand_colors, "bad hand mesh");
+    if (batch == 0) return AB_OK;
+    AB_REQUIRE(hand_verts && hand_tex && obj_id && obj_pose && light && ws, "null per-view input / workspace");
+    AB_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+    AB_REQUIRE(!rgba || ((uintptr_t)rgba & 15) == 0, "rgba must be 16-byte aligned");
+    AB_REQUIRE(!depth || ((uintptr_t)depth & 15) == 0, "depth must be 16-byte aligned");
+    AB_REQUIRE(!seg || ((uintptr_t)seg & 3) == 0, "seg must be 4-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    RasterParams P;
+    P.obj_verts = scene->obj_verts;
+    P.obj_faces = reinterpret_cast<const int4*>(scene->obj_faces);
+    P.obj_colors = reinterpret_cast<const uchar4*>(scene->obj_colors);
+    P.hand_faces = reinterpret_cast<const int4*>(scene->hand_faces);
+    P.hand_colors = reinterpret_cast<const uchar4*>(scene->hand_colors);
+    P.bgs = scene->bgs;
+    P.n_obj = scene->n_obj; P.n_hv = scene->n_hand_verts; P.n_hf = scene->n_hand_faces; P.n_tex = scene->n_hand_tex;
+    P.n_bg = scene->n_bg; P.bg_h = scene->bg_h; P.bg_w = scene->bg_w;
+    P.W = cam->width; P.H = cam->height;
+    P.fx = cam->fx; P.fy = cam->fy; P.cx = cam->cx; P.cy = cam->cy; P.znear = cam->znear;
+    P.ambient = cam->ambient; P.diffuse = cam->diffuse; P.cull = cam->cull_backface;
+    P.bg_r = cam->bg_r; P.bg_g = cam->bg_g; P.bg_b = cam->bg_b;
+    int scene_max_ov = 0, scene_max_of = 0;
+    for (int i = 0; i <= scene->n_obj; ++i) {
+        P.vert_off[i] = scene->n_obj ? scene->obj_vert_off_host[i] : 0;
+        P.face_off[i] = scene->n_obj ? scene->obj_face_off_host[i] : 0;
+        if (i > 0) {
+            AB_REQUIRE(P.vert_off[i] >= P.vert_off[i - 1] && P.face_off[i] >= P.face_off[i - 1], "offsets not sorted");
+            scene_max_ov = max(scene_max_ov, P.vert_off[i] - P.vert_off[i - 1]);
+            scene_max_of = max(scene_max_of, P.face_off[i] - P.face_off[i - 1]);
+        }
+    }
+    const int npx = P.W * P.H;
+    P.pv_stride = (int)align_up((size_t)scene_max_ov + P.n_hv, 8);
+    P.keys = (unsigned long long*)ws;
+    P.pv = (int4*)((char*)ws + align_up((size_t)chunk * npx * 8, 256));
+    AB_CUDA(cudaMemsetAsync(P.keys, 0xFF, (size_t)min(chunk, batch) * npx * 8, st));
+
+    for (int v0 = 0; v0 < batch; v0 += chunk) {
+        const int n = min(chunk, batch - v0);
+        int max_ov = scene_max_ov, max_of = scene_max_of;
+        if (obj_id_host) {
+            max_ov = max_of = 0;
+            for (int i = 0; i < n; ++i) {
+                const int o = obj_id_host[v0 + i];
+                AB_REQUIRE(o < scene->n_obj, "obj_id out of range");
+                if (o >= 0) {
+                    max_ov = max(max_ov, P.vert_off[o + 1] - P.vert_off[o]);
+                    max_of = max(max_of, P.face_off[o + 1] - P.face_off[o]);
+                }
+            }
+        }
+        P.max_ov = max_ov; P.max_of = max_of;
+        P.n_views = n;
+        P.hand_verts = hand_verts + (size_t)v0 * P.n_hv * 3;
+        P.hand_tex = hand_tex + v0;
+        P.obj_id = obj_id + v0;
+        P.obj_pose = obj_pose + (size_t)v0 * 16;
+        P.light = light + v0;
+        P.bg_sel = bg_sel ? bg_sel + (size_t)v0 * 5 : nullptr;
+        P.rgba = rgba ? rgba + (size_t)v0 * npx * 4 : nullptr;
+        P.depth = depth ? depth + (size_t)v0 * npx : nullptr;
+        P.seg = seg ? seg + (size_t)v0 * npx : nullptr;
+        {
+            StageTimer tm(AB_STAGE_RASTER_VERTEX, st);
+            raster_vertex_kernel<<<dim3(cdiv(max_ov + P.n_hv, 256), n), 256, 0, st>>>(P);
+        }
+        {
+            StageTimer tm(AB_STAGE_RASTER_TRIANGLE, st);
+            raster_triangle_kernel<<<dim3(cdiv(max_of + P.n_hf, 256), n), 256, 0, st>>>(P);
+        }
+        {
+            StageTimer tm(AB_STAGE_RASTER_RESOLVE, st);
+            raster_resolve_kernel<<<dim3(cdiv(npx / 4, 256), n), 256, 0, st>>>(P);
+        }
+        count_launch(3);
+        int rc = check_launch("ab_render_batch");
+        if (rc) return rc;
+    }
+    return AB_OK;
+}

@@ -1,0 +1,119 @@
+"""ctypes binding of the C-ABI library (include/artiboost_b200.h).  There is no CPU fallback: if the sm_100a
+library is missing or a call fails, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libartiboost_b200.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_i32_p = C.POINTER(C.c_int32)
+c_u8_p = C.POINTER(C.c_uint8)
+
+
+class ManoModelStruct(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("v_template", "shapedirs_t", "posedirs_t", "j_template", "j_shapedirs",
+                                          "weights")]
+
+
+class SceneStruct(C.Structure):
+    _fields_ = [("n_obj", C.c_int32), ("obj_verts", C.c_void_p), ("obj_faces", C.c_void_p), ("obj_colors", C.c_void_p),
+                ("obj_vert_off_host", c_i32_p), ("obj_face_off_host", c_i32_p),
+                ("n_hand_verts", C.c_int32), ("n_hand_faces", C.c_int32), ("n_hand_tex", C.c_int32),
+                ("hand_faces", C.c_void_p), ("hand_colors", C.c_void_p), ("bgs", C.c_void_p),
+                ("n_bg", C.c_int32), ("bg_h", C.c_int32), ("bg_w", C.c_int32)]
+
+
+class CameraStruct(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
+                ("cy", C.c_float), ("znear", C.c_float), ("cull_backface", C.c_int32), ("ambient", C.c_float),
+                ("diffuse", C.c_float), ("bg_r", C.c_int32), ("bg_g", C.c_int32), ("bg_b", C.c_int32)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "ab_version": (C.c_int, []),
+    "ab_last_error": (C.c_char_p, []),
+    "ab_launch_count": (C.c_uint64, []),
+    "ab_profile_enable": (C.c_int, [C.c_int]),
+    "ab_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
+    "ab_mano_forward": (C.c_int, [C.POINTER(ManoModelStruct), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_ccv_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_view_from_id": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_pose_generate_workspace_bytes": (C.c_uint64, [C.c_int]),
+    "ab_pose_generate": (C.c_int, [C.POINTER(ManoModelStruct), C.c_int] + [C.c_void_p] * 13),
+    "ab_render_workspace_bytes": (C.c_uint64, [C.POINTER(SceneStruct), C.POINTER(CameraStruct), C.c_int]),
+    "ab_render_batch": (C.c_int, [C.POINTER(SceneStruct), C.POINTER(CameraStruct), C.c_int, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, c_i32_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+class AbError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the library (once).  Raises if it was not built: run `python -m artiboost_b200.build`."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AbError(f"{LIB_PATH} is missing: build it with `python -m artiboost_b200.build` "
+                          "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise AbError(f"{what} failed (rc={rc}): {load().ab_last_error().decode()}")
+
+
+def ptr(t):
+    """Device (or host, for *_host arguments) address of a contiguous tensor; None -> NULL."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "C-ABI arguments must be contiguous"
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise AbError(f"{name} must live on a CUDA device: artiboost_b200 has no CPU path")
+
+
+def launch_count() -> int:
+    return int(load().ab_launch_count())
+
+
+STAGES = {0: "raster_vertex_kernel", 1: "raster_triangle_kernel", 2: "raster_resolve_kernel", 3: "mano_lbs_kernel",
+          4: "posegen_prelude_kernel", 5: "ccv_cdf+draw_kernels", 6: "view_kernel"}
+
+
+def profile_enable(on: bool) -> None:
+    check(load().ab_profile_enable(int(on)), "ab_profile_enable")
+
+
+def profile_collect() -> dict:
+    """-> {stage name: (total ms, launches)} for everything launched since profiling was enabled / last collected."""
+    n = 16
+    ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+    check(load().ab_profile_collect(ms, cnt, n), "ab_profile_collect")
+    return {STAGES.get(i, f"stage{i}"): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}

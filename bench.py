@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Benchmark of the ArtiBoost synthesis hot path: synthesised views/s (BASELINE.json metric), rasteriser workload.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA kernels through the C-ABI)
+  python bench.py --impl reference --gpus N ...            reference arm: the CPU restatement on the host cores
+
+Workload (BASELINE.json configs[1]): batch-512 hand+object rasteriser, RGBA8 + depth f32 + seg u8 at 256x256, HO3D CCV
+space (4 objects x 288 views x 50 grasps), synthetic MANO-shaped hand (778 verts / 1538 faces) and synthetic YCB-shaped
+objects (8192 verts / 16380 faces).  A step = one pass of ab_render_batch over one batch of 512 views whose per-view
+inputs (posed hand vertices, object poses, ids, light, background crop) are already resident in HBM.  One process per
+GPU, views sharded across ranks with no data-path collective (weak scaling).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 512
+SIZE = 256
+BYTES_PER_VIEW_OUT = SIZE * SIZE * 9                # RGBA8 + depth f32 + seg u8
+BYTES_PER_VIEW_IN = 778 * 12 + 64 + 4 + 4 + 4 + 20  # hand verts, pose, obj id, texture id, light, bg_sel
+ALGO_BYTES_PER_VIEW = BYTES_PER_VIEW_OUT + BYTES_PER_VIEW_IN
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {getattr(nv, n): n[len("nvmlClocksThrottleReason"):] for n in dir(nv)
+                     if n.startswith("nvmlClocksThrottleReason") and isinstance(getattr(nv, n), int)}
+            while not self._stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if bit and (mask & bit) == bit and name not in ("None", "All"):
+                        self.reasons.add(name)
+                time.sleep(self.period)
+        except Exception as e:  # NVML missing: report it instead of failing the bench
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        rename = {"GpuIdle": "gpu_idle", "SwPowerCap": "sw_power_cap", "HwSlowdown": "hw_slowdown",
+                  "HwThermalSlowdown": "hw_thermal_slowdown", "SwThermalSlowdown": "sw_thermal_slowdown",
+                  "HwPowerBrakeSlowdown": "hw_power_brake_slowdown", "ApplicationsClocksSetting": "applications_clocks_setting",
+                  "SyncBoost": "sync_boost", "DisplayClockSetting": "display_clock_setting"}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "samples": len(s),
+                "reasons": sorted(rename.get(r, r) for r in self.reasons if r != "GpuIdle")}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference(steps, warmup, sample_views, threads=None):
+    """The CPU restatement of the same workload (oracle/: numpy pose generator -> C rasteriser, OpenMP over views)."""
+    from artiboost_b200 import assets
+    from oracle.synth_cpu import CpuSynth
+    threads = threads or os.cpu_count() or 1
+    synth = CpuSynth(assets, seed=0)
+    inp = synth.sample(sample_views)
+    out = None
+    for _ in range(warmup):
+        out = synth.render(inp, n_threads=threads, out=out)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = synth.render(inp, n_threads=threads, out=out)
+    dt = time.perf_counter() - t0
+    return sample_views * steps / dt, dt / steps * 1e3, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 256
+    vps, ms, threads = cpu_reference(args.steps, args.warmup, sample)
+    line = {
+        "impl": "reference", "metric": "synthesised views/sec (rasteriser, RGBA+depth+seg 256x256)", "value": vps,
+        "unit": "views/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, sample_views_per_step=sample),
+        "cpu_baseline": {"value": vps, "unit": "views/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} views/step x {args.steps} steps of the batch-512 workload, oracle/raster.c "
+                                   f"with OpenMP over views on {threads} host threads (pyrender/EGL cannot run here)"},
+        "e2e": {"value": vps, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, **extra):
+    cfg = {"workload": "BASELINE.json configs[1]: batch-512 hand+object rasteriser only (RGBA8+depth f32+seg u8, 256x256)",
+           "views_per_step_per_gpu": BATCH, "image": [SIZE, SIZE], "ccv_space": [4, 288, 50],
+           "hand_mesh": [778, 1538], "object_mesh": [8192, 16380], "parallelism": f"views sharded over {n_gpus} rank(s), no collective",
+           "l2": "each step writes 302 MB of views (> 126 MB L2); meshes (1.2 MB) are shared by the batch and L2-resident by design"}
+    cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from artiboost_b200 import build, lib
+    from artiboost_b200.synth import SynthPipeline
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if not os.path.exists(lib.LIB_PATH):
+        build.build()
+    lib.load()
+
+    pipe = SynthPipeline(device=dev, seed=1 + rank, chunk=args.chunk)
+    poses = pipe.sample_poses(BATCH)            # CCV draw -> view -> grasp -> pose generator (device)
+    rand = pipe.draw_render_randoms(BATCH)
+    out = {"rgba": torch.empty((BATCH, SIZE, SIZE, 4), dtype=torch.uint8, device=dev),
+           "depth": torch.empty((BATCH, SIZE, SIZE), dtype=torch.float32, device=dev),
+           "seg": torch.empty((BATCH, SIZE, SIZE), dtype=torch.uint8, device=dev)}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        pipe.render(poses, rand, out=out)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    ids = [v for v in vis.split(",") if v.strip().isdigit()]
+    sampler = ClockSampler(int(ids[local]) if len(ids) > local else local)
+    sampler.start()
+    lib.profile_enable(True)
+    l0 = lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.launch_count() - l0
+    lib.profile_enable(False)
+    stages = lib.profile_collect()
+    clocks = sampler.stop()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * BATCH * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the host-buffer API: pinned inputs H2D, views D2H, every step
+    pin = lambda x: x.detach().cpu().pin_memory()  # noqa: E731
+    h_in = [pin(poses["obj_id"]), pin(poses["final_obj_pose"]), pin(poses["final_hand_verts"]), pin(rand["hand_tex"]),
+            pin(rand["light"]), pin(rand["bg_sel"])]
+    h_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step():
+        pipe.renderer.render_batch_host(*h_in, out=h_out, sub_batch=args.chunk)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * BATCH * e2e_steps / (float(t.item()) * 1e-3)
+    h2d = sum(x.numel() * x.element_size() for x in h_in)
+    d2h = sum(x.numel() * x.element_size() for x in h_out.values())
+    same = all(torch.equal(h_out[k], out[k].cpu()) for k in out)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (largest share of the timed region)
+    peak, peak_src = load_peaks()
+    dom = max(stages.items(), key=lambda kv: kv[1][0])
+    dom_ms, dom_n = dom[1]
+    views_per_launch = BATCH * args.steps / dom_n
+    achieved = ALGO_BYTES_PER_VIEW * views_per_launch / (dom_ms / dom_n * 1e-3) / 1e9
+    step_gbs = ALGO_BYTES_PER_VIEW * BATCH * args.steps / (sum(v[0] for v in stages.values()) * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_view": ALGO_BYTES_PER_VIEW, "views_per_launch": views_per_launch,
+                "kernel_share_of_step": dom_ms / sum(v[0] for v in stages.values()),
+                "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak},
+                "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
+                "note": "set-up bound, not HBM bound: ~17.9k mostly sub-pixel triangles per view (SURVEY.md 8d)"}
+    traffic_file = os.path.join(ROOT, "profiles", "raster_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(dom[0])
+        except Exception:
+            pass
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        vps, _, threads = cpu_reference(steps=40, warmup=2, sample_views=256)
+        cpu = {"value": vps, "unit": "views/s", "cores": threads, "kind": "port",
+               "sample": f"256 views x 40 passes of the same workload, oracle/raster.c, OpenMP over views on {threads} host threads"}
+
+    line = {
+        "metric": "synthesised views/sec (rasteriser, RGBA+depth+seg 256x256)", "value": value, "unit": "views/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world, chunk=args.chunk),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "matches_device_path": bool(same),
+                "api": "Renderer.render_batch_host: pinned host inputs -> ab_render_batch -> pinned host RGBA+depth+seg"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunk", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: `python bench.py --gpus N` re-launches itself as one rank per GPU like the driver does
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+/* artiboost_b200 -- C ABI of the B200-native ArtiBoost synthesis + clasbased-network hot path.
+ *
+ * The reference (lixiny/ArtiBoost) has no FFI: its boundaries are Python classes.  Each
+ * entry point below names the reference interface whose arithmetic it replaces; the Python drop-ins in
+ * artiboost_b200/ (ManoLayer, PreProcessorPoseGenerator, Renderer / RendererProvider, IntegralDeconvHead ...)
+ * call these through ctypes.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / CUDA types in signatures.  `stream` is a cudaStream_t passed as void*
+ *    (NULL = legacy default stream).  All data pointers are DEVICE pointers unless the name ends in `_host`.
+ *  - nothing allocates: the caller owns every buffer, workspaces are sized by the *_workspace_bytes() queries.
+ *  - all calls are asynchronous on `stream` and re-entrant across streams.
+ *  - return 0 on success, <0 for an argument error, >0 for a CUDA error code; ab_last_error() gives the text
+ *    (thread-local).
+ *  - row-major everywhere; matrices are [rows][cols]; 4x4 poses are row-major with translation in column 3.
+ */
+#ifndef ARTIBOOST_B200_H
+#define ARTIBOOST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AB_API __attribute__((visibility("default")))
+#else
+#define AB_API
+#endif
+
+#define AB_OK 0
+#define AB_ERR_ARG (-1)
+#define AB_ERR_UNSUPPORTED (-2)
+
+#define AB_MANO_VERTS 778
+#define AB_MANO_JOINTS 16
+#define AB_MANO_KEYPOINTS 21
+#define AB_MANO_POSE_FEAT 135
+
+AB_API int ab_version(void);
+AB_API const char* ab_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches counter) */
+AB_API uint64_t ab_launch_count(void);
+
+/* Per-stage device timing for bench.py's roofline line: when enabled, every kernel launch of this library is
+ * bracketed by CUDA events on the launching stream; ab_profile_collect waits for them and returns the summed
+ * milliseconds and launch counts per stage id (AB_STAGE_*).  Off by default.                                  */
+#define AB_STAGE_RASTER_VERTEX 0
+#define AB_STAGE_RASTER_TRIANGLE 1
+#define AB_STAGE_RASTER_RESOLVE 2
+#define AB_STAGE_MANO_LBS 3
+#define AB_STAGE_POSEGEN_PRELUDE 4
+#define AB_STAGE_CCV 5
+#define AB_STAGE_VIEW 6
+#define AB_STAGE_COUNT 16
+AB_API int ab_profile_enable(int on);
+AB_API int ab_profile_collect(double* ms_per_stage, int64_t* launches_per_stage, int n_stages);
+
+/* ------------------------------------------------------------------------------------------------ MANO LBS
+ * Replaces manotorch.ManoLayer.forward as called at anakin/artiboost/preprocessor.py:25,62,
+ * anakin/artiboost/refiner.py:138 and anakin/artiboost/grasp_engine.py:90-95,149-155
+ * (algorithm: anakin/postprocess/iknet/manolayer.py:182-276).
+ * Model constants are device arrays prepared once by the host (artiboost_b200/manolayer.py):              */
+typedef struct {
+    const float* v_template;    /* [778*3]                                   */
+    const float* shapedirs_t;   /* [10][778*3]   k-major                     */
+    const float* posedirs_t;    /* [135][778*3]  k-major                     */
+    const float* j_template;    /* [16*3]     = J_regressor . v_template     */
+    const float* j_shapedirs;   /* [16*3][10] = J_regressor . shapedirs      */
+    const float* weights;       /* [778][16]                                 */
+} ab_mano_model;
+
+/* pose [B,48] axis-angle (root first), betas [B,10] or NULL (zeros, the NullRefine case refiner.py:138),
+ * post_rt [B,12] or NULL: optional rigid map applied to verts and joints, x' = R x + t, R = post_rt[0:9] row-major.
+ * center_idx <0 => none.  Outputs: verts [B,778,3], joints [B,21,3] (MANO 21-keypoint order),
+ * transforms_abs [B,16,4,4] or NULL.                                                                       */
+AB_API int ab_mano_forward(const ab_mano_model* model, int batch, const float* pose, const float* betas, const float* post_rt,
+                    int center_idx, float* verts, float* joints, float* transforms_abs, void* stream);
+
+/* ------------------------------------------------------------------------------------------ CCV-space sampler
+ * Replaces OVGSet.update's Categorical draw + row_col_calc (anakin/artiboost/ovg_set.py:104-132,161-170):
+ * inverse-CDF draw of n flat cells from weight_map[n_cells] with caller-supplied uniforms u[n] in [0,1);
+ * cdf_ws is a float64[n_cells] workspace.  Outputs int32 obj/persp/grasp ids and (optional, may be NULL)
+ * occurrence counts int32[n_cells] (ovg_set.py:172-178), which the caller zeroes.                           */
+AB_API int ab_ccv_sample(const float* weight_map, int n_obj, int n_persp, int n_grasp, const float* uniforms, int n,
+                  double* cdf_ws, int32_t* obj_id, int32_t* persp_id, int32_t* grasp_id, int32_t* occurrence,
+                  void* stream);
+
+/* Replaces ViewEngine.get_view (anakin/artiboost/view_engine.py:17-86).  rand4 [n,4] = U[0,1) draws for
+ * (u jitter, theta jitter, in-plane roll, z).  Outputs persp_rotmat [n,9], camera_free_transf [n,16], z_offset [n,3]. */
+AB_API int ab_view_from_id(const int32_t* persp_id, int n, int u_bins, int theta_bins, float z_min, float z_max,
+                    const float* rand4, float* persp_rotmat, float* camera_free_transf, float* z_offset, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- pose generator
+ * Replaces PreProcessorPoseGenerator.forward (anakin/artiboost/preprocessor.py:20-99) with the `random`
+ * scrambler (scrambler.py:65-81; noise_tsl [B,3] and noise_angle [B,16] are pre-scaled N(0,sigma) draws, NULL = no
+ * scrambling) and NullRefine (refiner.py:131-147).
+ * Inputs as in the synth_extend dict: hand_pose [B,48], hand_shape [B,10], hand_tsl [B,3], persp_rotmat [B,9],
+ * camera_free_transf [B,16], z_offset [B,3].  Outputs final_obj_pose [B,16], final_hand_verts [B,778,3],
+ * final_joints [B,21,3].  ws: float workspace of ab_pose_generate_workspace_bytes(B) bytes.                   */
+AB_API uint64_t ab_pose_generate_workspace_bytes(int batch);
+AB_API int ab_pose_generate(const ab_mano_model* model, int batch, const float* hand_pose, const float* hand_shape,
+                     const float* hand_tsl, const float* persp_rotmat, const float* camera_free_transf,
+                     const float* z_offset, const float* noise_tsl, const float* noise_angle, float* final_obj_pose,
+                     float* final_hand_verts, float* final_joints, void* ws, void* stream);
+
+/* --------------------------------------------------------------------------------------------------- rasteriser
+ * Replaces Renderer.__call__ (anakin/utils/renderer.py:101-123) over pyrender's OffscreenRenderer
+ * (anakin/utils/frender_utils.py:179-205), batched: one call renders `batch` hand+object views.
+ * Rule set (pixel-exact on seg/coverage/depth-bits against oracle/raster.c): see DESIGN.md "Raster rules".   */
+typedef struct {
+    int32_t n_obj;              /* number of object meshes                                              */
+    const float* obj_verts;     /* [sum V,3] canonical (bbox-centred) vertices, all objects concatenated  */
+    const int32_t* obj_faces;   /* [sum F,4] per-object-local vertex ids, 4th component unused (16-byte rows) */
+    const uint8_t* obj_colors;  /* [sum V,4] RGBA vertex colours                                        */
+    const int32_t* obj_vert_off_host; /* HOST [n_obj+1] prefix offsets into obj_verts / obj_colors       */
+    const int32_t* obj_face_off_host; /* HOST [n_obj+1] prefix offsets into obj_faces                    */
+    int32_t n_hand_verts, n_hand_faces, n_hand_tex;
+    const int32_t* hand_faces;  /* [n_hand_faces,4]                                                     */
+    const uint8_t* hand_colors; /* [n_hand_tex, n_hand_verts, 4]                                        */
+    const uint8_t* bgs;         /* [n_bg, bg_h, bg_w, 3] or NULL                                        */
+    int32_t n_bg, bg_h, bg_w;
+} ab_scene;
+
+typedef struct {
+    int32_t width, height;
+    float fx, fy, cx, cy;       /* renderer.py:76 IntrinsicsCamera(K[0,0], K[1,1], K[0,2], K[1,2])       */
+    float znear;                /* 0.05 (pyrender default)                                               */
+    int32_t cull_backface;
+    float ambient, diffuse;     /* ambient 0.8 (renderer.py:77)                                          */
+    int32_t bg_r, bg_g, bg_b;   /* flat background when no bg image is selected (bg_color 0.5 -> 128)    */
+} ab_camera;
+
+/* Per-view inputs: hand_verts [B,778,3] camera space, hand_tex [B] texture id (renderer.py:102), obj_id [B]
+ * (<0 = CONST.DUMMY: hand only), obj_pose [B,16], light [B] point-light intensity (renderer.py:103-104),
+ * bg_sel [B,5] = {bg id (<0 none), x0, y0, crop_w, crop_h} or NULL.
+ * obj_id_host: HOST copy of obj_id or NULL.  When given, launches are sized to the largest selected object;
+ * when NULL they are sized to the largest object in the scene (no host sync either way).
+ * Outputs: rgba u8[B,H,W,4], depth f32[B,H,W] (0 = background), seg u8[B,H,W] (0 bg, 1 hand, 2 object); any may
+ * be NULL.  ws: workspace of ab_render_workspace_bytes() bytes; views are processed in chunks of `chunk`
+ * views so the scratch stays L2-resident.                                                                 */
+AB_API uint64_t ab_render_workspace_bytes(const ab_scene* scene, const ab_camera* cam, int chunk);
+AB_API int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int batch, int chunk, const float* hand_verts,
+                    const int32_t* hand_tex, const int32_t* obj_id, const int32_t* obj_id_host, const float* obj_pose,
+                    const float* light, const int32_t* bg_sel, uint8_t* rgba, float* depth, uint8_t* seg, void* ws,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
