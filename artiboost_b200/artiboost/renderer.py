@@ -81,9 +81,11 @@ class Renderer:
             voff.append(voff[-1] + v.shape[0])
             foff.append(foff[-1] + f.shape[0])
         cat = lambda xs, shape, dt: (np.concatenate(xs) if xs else np.zeros(shape, dt))  # noqa: E731
-        self.obj_verts = torch.from_numpy(cat(verts, (0, 3), np.float32)).to(dev)
-        self.obj_faces = torch.from_numpy(cat(faces, (0, 4), np.int32)).to(dev)
-        self.obj_colors = torch.from_numpy(cat(cols, (0, 4), np.uint8)).to(dev)
+        # the C-ABI takes raw pointers: every upload is forced to C order first
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev).contiguous()  # noqa: E731
+        self.obj_verts = up(cat(verts, (0, 3), np.float32))
+        self.obj_faces = up(cat(faces, (0, 4), np.int32))
+        self.obj_colors = up(cat(cols, (0, 4), np.uint8))
         self._voff = (C.c_int32 * len(voff))(*voff)
         self._foff = (C.c_int32 * len(foff))(*foff)
         if len(hand_meshes) == 0:
@@ -91,8 +93,8 @@ class Renderer:
         hf = np.asarray(hand_meshes[0].faces, np.int32)
         n_hv = int(np.asarray(hand_meshes[0].vertices).shape[0])
         self.n_hand_verts, self.n_hand_tex = n_hv, len(hand_meshes)
-        self.hand_faces = torch.from_numpy(np.concatenate([hf, np.zeros((hf.shape[0], 1), np.int32)], axis=1)).to(dev)
-        self.hand_colors = torch.from_numpy(np.stack([_vertex_colors(m, n_hv) for m in hand_meshes])).to(dev)
+        self.hand_faces = up(np.concatenate([hf, np.zeros((hf.shape[0], 1), np.int32)], axis=1))
+        self.hand_colors = up(np.stack([_vertex_colors(m, n_hv) for m in hand_meshes]))
         # backgrounds: resized to 1.5x the render size like the reference (renderer.py:98-99), nearest neighbour
         self.backgrounds = None
         if backgrounds:
@@ -103,7 +105,7 @@ class Renderer:
                 ys = (np.arange(bh) * a.shape[0]) // bh
                 xs = (np.arange(bw) * a.shape[1]) // bw
                 bgs.append(a[ys][:, xs])
-            self.backgrounds = torch.from_numpy(np.stack(bgs)).to(dev)
+            self.backgrounds = up(np.stack(bgs))
         self.scene = lib.SceneStruct(
             len(self.obj_names), self.obj_verts.data_ptr(), self.obj_faces.data_ptr(), self.obj_colors.data_ptr(),
             C.cast(self._voff, lib.c_i32_p), C.cast(self._foff, lib.c_i32_p), n_hv, hf.shape[0], self.n_hand_tex,

@@ -112,7 +112,8 @@ __global__ void view_kernel(const int32_t* __restrict__ persp_id, int n, int u_b
     f[12] = 0; f[13] = 0;  f[14] = 0; f[15] = 1;
     z_offset[(size_t)i * 3] = 0.0f;
     z_offset[(size_t)i * 3 + 1] = 0.0f;
-    z_offset[(size_t)i * 3 + 2] = z_min + r.w * (z_max - z_min);  // torch Uniform.sample: low + rand * (high - low), fp32
+    // torch Uniform.sample: low + rand * (high - low), three separately rounded fp32 operations
+    z_offset[(size_t)i * 3 + 2] = __fadd_rn(z_min, __fmul_rn(r.w, __fsub_rn(z_max, z_min)));
 }
 
 }  // namespace ab

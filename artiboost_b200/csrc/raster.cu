@@ -104,49 +104,33 @@ raster_vertex_kernel(const __grid_constant__ RasterParams P) {
 }
 
 // ---- rule: triangle ----------------------------------------------------------------------------------------
-struct Tri {
-    int x[3], y[3];
+// Triangles whose snapped bbox is under 64 px in both axes (all of them in valid ArtiBoost views) take the "small"
+// path: every factor of the edge functions is below 2^14 + 2^8 in magnitude, so products and their differences are
+// exact in int32.  Larger ones take the int64 path.  Both produce the same integers, hence the same floats.
+constexpr int kSmallExtent = 16384;  // 64 px in 24.8 fixed point
+constexpr int kTriThreads = 256;
+
+struct TriRec {            // one per surviving triangle of a CTA (shared memory); 27 words: odd stride, no bank pattern
+    int x0, y0, w;         // pixel bbox origin, width
+    int f;                 // primitive id
+    int e[3];              // small path: edge values at the centre of pixel (x0, y0)
+    int ex[3], ey[3];      // small path: edge steps per pixel in x / y
     float iz[3];
-    int s;                 // +1 when area2 > 0 (back-facing in the y-down image), -1 otherwise
-    long long sarea;       // |area2|
-    int bias[3];           // 0 on top/left edges, -1 elsewhere: inside <=> E_i + bias_i >= 0
+    float sarea;           // (float)|area2|
+    int nbias;             // bit i set <=> edge i is not a top/left edge (E_i == 0 is outside)
+    int big;               // 1 -> int64 path from vx, vy, s
+    int vx[3], vy[3], s;
+    int pad;
 };
 
-// returns false if discarded
-__device__ __forceinline__ bool tri_setup(int cull, const int4& a, const int4& b, const int4& d, Tri& t) {
-    if (!(a.w & b.w & d.w)) return false;
-    const long long area2 = (long long)(b.x - a.x) * (long long)(d.y - a.y) - (long long)(d.x - a.x) * (long long)(b.y - a.y);
-    if (area2 == 0) return false;
-    if (area2 > 0 && cull) return false;
-    t.s = area2 > 0 ? 1 : -1;
-    t.sarea = area2 > 0 ? area2 : -area2;
-    t.x[0] = a.x; t.x[1] = b.x; t.x[2] = d.x;
-    t.y[0] = a.y; t.y[1] = b.y; t.y[2] = d.y;
-    t.iz[0] = __int_as_float(a.z); t.iz[1] = __int_as_float(b.z); t.iz[2] = __int_as_float(d.z);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {  // edge i runs v[i+1] -> v[i+2], opposite vertex i
-        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-        const long long dx = (long long)t.s * (t.x[i2] - t.x[i1]);
-        const long long dy = (long long)t.s * (t.y[i2] - t.y[i1]);
-        t.bias[i] = ((dy < 0) || (dy == 0 && dx > 0)) ? 0 : -1;
-    }
-    return true;
-}
-
-__device__ __forceinline__ long long edge64(const Tri& t, int i, long long px, long long py) {
-    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-    const long long dx = t.x[i2] - t.x[i1], dy = t.y[i2] - t.y[i1];
-    return (long long)t.s * (dx * (py - t.y[i1]) - dy * (px - t.x[i1]));
-}
-
-// depth and the three partial products of the rule "depth"; e_i are the (non-negative) edge values
-__device__ __forceinline__ float depth_at(const Tri& t, float f0, float f1, float f2, float* num_out, float* a) {
-    a[0] = __fmul_rn(f0, t.iz[0]);
-    a[1] = __fmul_rn(f1, t.iz[1]);
-    a[2] = __fmul_rn(f2, t.iz[2]);
-    const float num = __fmaf_rn(f2, t.iz[2], __fmaf_rn(f1, t.iz[1], a[0]));
+__device__ __forceinline__ float depth_from(const float* iz, float sarea, float f0, float f1, float f2, float* num_out,
+                                            float* a) {
+    a[0] = __fmul_rn(f0, iz[0]);
+    a[1] = __fmul_rn(f1, iz[1]);
+    a[2] = __fmul_rn(f2, iz[2]);
+    const float num = __fmaf_rn(f2, iz[2], __fmaf_rn(f1, iz[1], a[0]));
     *num_out = num;
-    return __fdiv_rn(__ll2float_rn(t.sarea), num);
+    return __fdiv_rn(sarea, num);
 }
 
 __device__ __forceinline__ int floordiv256(int v) { return v >> 8; }
@@ -156,66 +140,140 @@ __device__ __forceinline__ void emit(unsigned long long* __restrict__ keys, int 
     atomicMin(keys + idx, k);  // result unused -> RED.E.MIN.64
 }
 
-__global__ void __launch_bounds__(256)
+// signed 2*area with the sign convention of the rule set; `small` selects the exact-in-int32 evaluation
+__device__ __forceinline__ long long area2_of(const int4& a, const int4& b, const int4& d, bool small) {
+    if (small) return (long long)((b.x - a.x) * (d.y - a.y) - (d.x - a.x) * (b.y - a.y));
+    return (long long)(b.x - a.x) * (long long)(d.y - a.y) - (long long)(d.x - a.x) * (long long)(b.y - a.y);
+}
+
+__device__ __forceinline__ long long edge64(const int* x, const int* y, int s, int i, long long px, long long py) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    const long long dx = x[i2] - x[i1], dy = y[i2] - y[i1];
+    return (long long)s * (dx * (py - y[i1]) - dy * (px - x[i1]));
+}
+
+// Phase A: one thread per triangle -- gather, pixel bbox (most sub-pixel triangles stop here), area / cull, edge
+// set-up into shared memory.  Phase B: the CTA's surviving bbox ROWS are dealt out evenly to all 256 threads (block
+// scan + binary search), so lanes stay busy although triangles differ in size by two orders of magnitude.
+__global__ void __launch_bounds__(kTriThreads)
 raster_triangle_kernel(const __grid_constant__ RasterParams P) {
+    __shared__ TriRec recs[kTriThreads];
+    __shared__ int prefix[kTriThreads + 1];
+    __shared__ int warp_tot[kTriThreads / 32];
     const int view = blockIdx.y;
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = threadIdx.x;
+    const int f = blockIdx.x * kTriThreads + t;
     const int oid = P.obj_id[view];
     int n_of = 0, n_ov = 0;
     if (oid >= 0) {
         n_of = P.face_off[oid + 1] - P.face_off[oid];
         n_ov = P.vert_off[oid + 1] - P.vert_off[oid];
     }
-    if (f >= n_of + P.n_hf) return;
-    int4 idx;
-    int off;
-    if (f < n_of) { idx = __ldg(P.obj_faces + P.face_off[oid] + f); off = 0; }
-    else { idx = __ldg(P.hand_faces + (f - n_of)); off = n_ov; }
-    const int4* pv = P.pv + (size_t)view * P.pv_stride + off;
-    const int4 a = pv[idx.x], b = pv[idx.y], d = pv[idx.z];
-    Tri t;
-    if (!tri_setup(P.cull, a, b, d, t)) return;
-    const int minx = min(t.x[0], min(t.x[1], t.x[2])), maxx = max(t.x[0], max(t.x[1], t.x[2]));
-    const int miny = min(t.y[0], min(t.y[1], t.y[2])), maxy = max(t.y[0], max(t.y[1], t.y[2]));
-    const int x0 = max(floordiv256(minx - 128 + 255), 0), x1 = min(floordiv256(maxx - 128), P.W - 1);
-    const int y0 = max(floordiv256(miny - 128 + 255), 0), y1 = min(floordiv256(maxy - 128), P.H - 1);
-    if (x0 > x1 || y0 > y1) return;
-    unsigned long long* keys = P.keys + (size_t)view * P.W * P.H;
-    if (maxx - minx < 16384 && maxy - miny < 16384) {
-        // every factor below is < 2^14 + 2^8 in magnitude: the products and their difference are exact in int32
-        int ex[3], ey[3], row[3];
-        const int cx0 = 256 * x0 + 128, cy0 = 256 * y0 + 128;
+    if (blockIdx.x * kTriThreads >= n_of + P.n_hf) return;  // whole CTA past the end (launch sized for the largest object)
+    int rows = 0;
+    if (f < n_of + P.n_hf) {
+        int4 idx;
+        int off;
+        if (f < n_of) { idx = __ldg(P.obj_faces + P.face_off[oid] + f); off = 0; }
+        else { idx = __ldg(P.hand_faces + (f - n_of)); off = n_ov; }
+        const int4* pv = P.pv + (size_t)view * P.pv_stride + off;
+        const int4 a = pv[idx.x], b = pv[idx.y], d = pv[idx.z];
+        if (a.w & b.w & d.w) {
+            const int minx = min(a.x, min(b.x, d.x)), maxx = max(a.x, max(b.x, d.x));
+            const int miny = min(a.y, min(b.y, d.y)), maxy = max(a.y, max(b.y, d.y));
+            const int x0 = max(floordiv256(minx - 128 + 255), 0), x1 = min(floordiv256(maxx - 128), P.W - 1);
+            const int y0 = max(floordiv256(miny - 128 + 255), 0), y1 = min(floordiv256(maxy - 128), P.H - 1);
+            if (x0 <= x1 && y0 <= y1) {
+                const bool small = (maxx - minx < kSmallExtent) && (maxy - miny < kSmallExtent);
+                const long long area2 = area2_of(a, b, d, small);
+                if (area2 != 0 && !(area2 > 0 && P.cull)) {
+                    TriRec& r = recs[t];
+                    const int s = area2 > 0 ? 1 : -1;
+                    const int vx[3] = {a.x, b.x, d.x}, vy[3] = {a.y, b.y, d.y};
+                    r.x0 = x0; r.y0 = y0; r.w = x1 - x0 + 1; r.f = f;
+                    r.iz[0] = __int_as_float(a.z); r.iz[1] = __int_as_float(b.z); r.iz[2] = __int_as_float(d.z);
+                    r.sarea = __ll2float_rn(area2 > 0 ? area2 : -area2);
+                    r.big = small ? 0 : 1;
+                    r.s = s;
+                    int nbias = 0;
+                    const int cx0 = 256 * x0 + 128, cy0 = 256 * y0 + 128;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-            const int dx = t.s * (t.x[i2] - t.x[i1]), dy = t.s * (t.y[i2] - t.y[i1]);
-            row[i] = dx * (cy0 - t.y[i1]) - dy * (cx0 - t.x[i1]);
-            ex[i] = -256 * dy;  // step of E_i per pixel in x: |256*dy| < 2^23
-            ey[i] = 256 * dx;
-        }
-        for (int py = y0; py <= y1; ++py) {
-            int e0 = row[0], e1 = row[1], e2 = row[2];
-            for (int px = x0; px <= x1; ++px) {
-                if (((e0 + t.bias[0]) | (e1 + t.bias[1]) | (e2 + t.bias[2])) >= 0) {
-                    float num, aa[3];
-                    const float z = depth_at(t, __int2float_rn(e0), __int2float_rn(e1), __int2float_rn(e2), &num, aa);
-                    emit(keys, py * P.W + px, z, f);
-                }
-                e0 += ex[0]; e1 += ex[1]; e2 += ex[2];
-            }
-            row[0] += ey[0]; row[1] += ey[1]; row[2] += ey[2];
-        }
-    } else {
-        for (int py = y0; py <= y1; ++py)
-            for (int px = x0; px <= x1; ++px) {
-                const long long cx = 256ll * px + 128, cy = 256ll * py + 128;
-                const long long e0 = edge64(t, 0, cx, cy), e1 = edge64(t, 1, cx, cy), e2 = edge64(t, 2, cx, cy);
-                if (((e0 + t.bias[0]) | (e1 + t.bias[1]) | (e2 + t.bias[2])) >= 0) {
-                    float num, aa[3];
-                    const float z = depth_at(t, __ll2float_rn(e0), __ll2float_rn(e1), __ll2float_rn(e2), &num, aa);
-                    emit(keys, py * P.W + px, z, f);
+                    for (int i = 0; i < 3; ++i) {  // edge i runs v[i+1] -> v[i+2], opposite vertex i
+                        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+                        const int dx = s * (vx[i2] - vx[i1]), dy = s * (vy[i2] - vy[i1]);  // |.| <= 2^23: no overflow
+                        if (!((dy < 0) || (dy == 0 && dx > 0))) nbias |= 1 << i;
+                        r.vx[i] = vx[i]; r.vy[i] = vy[i];
+                        if (small) {
+                            r.e[i] = dx * (cy0 - vy[i1]) - dy * (cx0 - vx[i1]);
+                            r.ex[i] = -256 * dy;
+                            r.ey[i] = 256 * dx;
+                        }
+                    }
+                    r.nbias = nbias;
+                    rows = y1 - y0 + 1;
                 }
             }
+        }
+    }
+    // ---- exclusive block scan of the row counts
+    const int lane = t & 31, wid = t >> 5;
+    int incl = rows;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < kTriThreads / 32; ++w) base += (w < wid) ? warp_tot[w] : 0;
+    prefix[t] = base + incl - rows;
+    if (t == kTriThreads - 1) prefix[kTriThreads] = base + incl;
+    __syncthreads();
+    const int total = prefix[kTriThreads];
+    unsigned long long* keys = P.keys + (size_t)view * P.W * P.H;
+    // ---- phase B: one bbox row per thread per iteration
+    for (int c = t; c < total; c += kTriThreads) {
+        int lo = 1, hi = kTriThreads;  // first index with prefix[idx] > c; prefix[0] = 0 <= c, 256 candidates -> 8 halvings
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int mid = (lo + hi) >> 1;
+            if (prefix[mid] > c) hi = mid; else lo = mid + 1;
+        }
+        const TriRec& r = recs[lo - 1];
+        const int row = c - prefix[lo - 1];
+        const int py = r.y0 + row;
+        const int b0 = -(r.nbias & 1), b1 = -((r.nbias >> 1) & 1), b2 = -((r.nbias >> 2) & 1);
+        const float iz[3] = {r.iz[0], r.iz[1], r.iz[2]};
+        const float sarea = r.sarea;
+        const int fid = r.f, w = r.w, kbase = py * P.W + r.x0;
+        if (!r.big) {
+            int e0 = r.e[0] + row * r.ey[0], e1 = r.e[1] + row * r.ey[1], e2 = r.e[2] + row * r.ey[2];
+            const int ex0 = r.ex[0], ex1 = r.ex[1], ex2 = r.ex[2];
+            for (int i = 0; i < w; ++i) {
+                if (((e0 + b0) | (e1 + b1) | (e2 + b2)) >= 0) {
+                    float num, aa[3];
+                    const float z = depth_from(iz, sarea, __int2float_rn(e0), __int2float_rn(e1), __int2float_rn(e2), &num, aa);
+                    emit(keys, kbase + i, z, fid);
+                }
+                e0 += ex0; e1 += ex1; e2 += ex2;
+            }
+        } else {
+            const int vx[3] = {r.vx[0], r.vx[1], r.vx[2]}, vy[3] = {r.vy[0], r.vy[1], r.vy[2]};
+            const int s = r.s;
+            const long long cy = 256ll * py + 128;
+            for (int i = 0; i < w; ++i) {
+                const long long cx = 256ll * (r.x0 + i) + 128;
+                const long long e0 = edge64(vx, vy, s, 0, cx, cy), e1 = edge64(vx, vy, s, 1, cx, cy),
+                                e2 = edge64(vx, vy, s, 2, cx, cy);
+                if (((e0 + b0) | (e1 + b1) | (e2 + b2)) >= 0) {
+                    float num, aa[3];
+                    const float z = depth_from(iz, sarea, __ll2float_rn(e0), __ll2float_rn(e1), __ll2float_rn(e2), &num, aa);
+                    emit(keys, kbase + i, z, fid);
+                }
+            }
+        }
     }
 }
 
@@ -231,12 +289,31 @@ __device__ __forceinline__ PixelOut shade_pixel(const RasterParams& P, int view,
     else { idx = __ldg(P.hand_faces + (f - n_of)); off = n_ov; }
     const int4* pv = P.pv + (size_t)view * P.pv_stride + off;
     const int vi[3] = {idx.x, idx.y, idx.z};
-    Tri t;
-    tri_setup(0, pv[vi[0]], pv[vi[1]], pv[vi[2]], t);
-    const long long cx = 256ll * px + 128, cy = 256ll * py + 128;
-    const long long e0 = edge64(t, 0, cx, cy), e1 = edge64(t, 1, cx, cy), e2 = edge64(t, 2, cx, cy);
+    const int4 a4 = pv[vi[0]], b4 = pv[vi[1]], d4 = pv[vi[2]];
+    // the winner passed set-up in the triangle pass: recompute its edge values at this pixel the same way
+    const int vx[3] = {a4.x, b4.x, d4.x}, vy[3] = {a4.y, b4.y, d4.y};
+    const float iz[3] = {__int_as_float(a4.z), __int_as_float(b4.z), __int_as_float(d4.z)};
+    const int minx = min(vx[0], min(vx[1], vx[2])), maxx = max(vx[0], max(vx[1], vx[2]));
+    const int miny = min(vy[0], min(vy[1], vy[2])), maxy = max(vy[0], max(vy[1], vy[2]));
+    const bool small = (maxx - minx < kSmallExtent) && (maxy - miny < kSmallExtent);
+    const long long area2 = area2_of(a4, b4, d4, small);
+    const int s = area2 > 0 ? 1 : -1;
+    float fe[3];
+    if (small) {
+        const int cx = 256 * px + 128, cy = 256 * py + 128;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+            const int dx = s * (vx[i2] - vx[i1]), dy = s * (vy[i2] - vy[i1]);
+            fe[i] = __int2float_rn(dx * (cy - vy[i1]) - dy * (cx - vx[i1]));
+        }
+    } else {
+        const long long cx = 256ll * px + 128, cy = 256ll * py + 128;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) fe[i] = __ll2float_rn(edge64(vx, vy, s, i, cx, cy));
+    }
     float num, a[3];
-    const float z = depth_at(t, __ll2float_rn(e0), __ll2float_rn(e1), __ll2float_rn(e2), &num, a);
+    const float z = depth_from(iz, __ll2float_rn(area2 > 0 ? area2 : -area2), fe[0], fe[1], fe[2], &num, a);
     float p[3][3];
     uchar4 col[3];
     if (is_obj) {
@@ -292,61 +369,46 @@ __device__ __forceinline__ PixelOut shade_pixel(const RasterParams& P, int view,
     return r;
 }
 
+// One thread per pixel: a warp covers 32 consecutive pixels of a row, so background warps (most of the frame)
+// never enter the shading path, and the RGBA / depth stores are full 128-byte lines per warp.
 __global__ void __launch_bounds__(256)
 raster_resolve_kernel(const __grid_constant__ RasterParams P) {
     const int view = blockIdx.y;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 consecutive pixels
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int npx = P.W * P.H;
-    if (4 * q >= npx) return;
-    const int oid = P.obj_id[view];
-    int n_of = 0, n_ov = 0;
-    if (oid >= 0) {
-        n_of = P.face_off[oid + 1] - P.face_off[oid];
-        n_ov = P.vert_off[oid + 1] - P.vert_off[oid];
-    }
-    unsigned long long* kp = P.keys + (size_t)view * npx + 4 * (size_t)q;
-    const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(kp);
-    const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(kp + 2);
-    const unsigned long long k[4] = {k01.x, k01.y, k23.x, k23.y};
-    const int py = (4 * q) / P.W, px0 = (4 * q) % P.W;
-    const int32_t* sel = P.bg_sel ? P.bg_sel + 5 * (size_t)view : nullptr;
-    const bool has_bg = sel && P.bgs && sel[0] >= 0;
-    uchar4 c[4];
-    float z[4];
-    uint8_t s[4];
-    bool hit = false;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (k[j] == kEmptyKey) {
-            uchar4 bg = make_uchar4((uint8_t)P.bg_r, (uint8_t)P.bg_g, (uint8_t)P.bg_b, 0);
-            if (has_bg) {
-                const int px = px0 + j;
-                const int sx = sel[1] + (int)(((long long)(2 * px + 1) * sel[3]) / (2 * P.W));
-                const int sy = sel[2] + (int)(((long long)(2 * py + 1) * sel[4]) / (2 * P.H));
-                const uint8_t* src = P.bgs + 3 * (((size_t)sel[0] * P.bg_h + sy) * P.bg_w + sx);
-                bg = make_uchar4(src[0], src[1], src[2], 0);
-            }
-            c[j] = bg; z[j] = 0.0f; s[j] = 0;
-        } else {
-            hit = true;
-            const PixelOut r = shade_pixel(P, view, oid, n_ov, n_of, px0 + j, py, (unsigned)(k[j] & 0xffffffffull));
-            c[j] = r.rgba; z[j] = r.depth; s[j] = r.seg;
+    if (p >= npx) return;
+    unsigned long long* kp = P.keys + (size_t)view * npx + p;
+    const unsigned long long k = *kp;
+    const int py = p / P.W, px = p - py * P.W;
+    uchar4 c;
+    float z;
+    uint8_t s;
+    if (k == kEmptyKey) {
+        c = make_uchar4((uint8_t)P.bg_r, (uint8_t)P.bg_g, (uint8_t)P.bg_b, 0);
+        const int32_t* sel = P.bg_sel ? P.bg_sel + 5 * (size_t)view : nullptr;
+        if (sel && P.bgs && sel[0] >= 0) {
+            const int sx = sel[1] + (int)(((long long)(2 * px + 1) * sel[3]) / (2 * P.W));
+            const int sy = sel[2] + (int)(((long long)(2 * py + 1) * sel[4]) / (2 * P.H));
+            const uint8_t* src = P.bgs + 3 * (((size_t)sel[0] * P.bg_h + sy) * P.bg_w + sx);
+            c = make_uchar4(src[0], src[1], src[2], 0);
         }
+        z = 0.0f;
+        s = 0;
+    } else {
+        const int oid = P.obj_id[view];
+        int n_of = 0, n_ov = 0;
+        if (oid >= 0) {
+            n_of = P.face_off[oid + 1] - P.face_off[oid];
+            n_ov = P.vert_off[oid + 1] - P.vert_off[oid];
+        }
+        const PixelOut r = shade_pixel(P, view, oid, n_ov, n_of, px, py, (unsigned)(k & 0xffffffffull));
+        c = r.rgba; z = r.depth; s = r.seg;
+        *kp = kEmptyKey;  // leave the key buffer empty for the next chunk
     }
-    if (hit) {
-        const ulonglong2 e = make_ulonglong2(kEmptyKey, kEmptyKey);
-        *reinterpret_cast<ulonglong2*>(kp) = e;
-        *reinterpret_cast<ulonglong2*>(kp + 2) = e;
-    }
-    const size_t o = (size_t)view * npx + 4 * (size_t)q;
-    if (P.rgba) {
-        uint4 v;
-        v.x = *reinterpret_cast<unsigned*>(&c[0]); v.y = *reinterpret_cast<unsigned*>(&c[1]);
-        v.z = *reinterpret_cast<unsigned*>(&c[2]); v.w = *reinterpret_cast<unsigned*>(&c[3]);
-        __stcs(reinterpret_cast<uint4*>(P.rgba + 4 * o), v);
-    }
-    if (P.depth) __stcs(reinterpret_cast<float4*>(P.depth + o), make_float4(z[0], z[1], z[2], z[3]));
-    if (P.seg) __stcs(reinterpret_cast<unsigned*>(P.seg + o), (unsigned)s[0] | ((unsigned)s[1] << 8) | ((unsigned)s[2] << 16) | ((unsigned)s[3] << 24));
+    const size_t o = (size_t)view * npx + p;
+    if (P.rgba) __stcs(reinterpret_cast<uchar4*>(P.rgba) + o, c);
+    if (P.depth) __stcs(P.depth + o, z);
+    if (P.seg) P.seg[o] = s;
 }
 
 static int max_hand_obj_verts(const ab_scene* s) {
@@ -376,10 +438,6 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
     AB_REQUIRE(scene && cam, "null scene / camera");
     AB_REQUIRE(batch >= 0 && chunk > 0, "bad batch / chunk");
     AB_REQUIRE(cam->width > 0 && cam->height > 0 && cam->width <= 4096 && cam->height <= 4096, "bad image size");
-    if ((cam->width & 3) != 0) {
-        set_error("ab_render_batch: width must be a multiple of 4");
-        return AB_ERR_UNSUPPORTED;
-    }
     AB_REQUIRE(scene->n_obj >= 0 && scene->n_obj <= kMaxObjects, "n_obj out of range (max 64)");
     AB_REQUIRE(scene->n_obj == 0 || (scene->obj_verts && scene->obj_faces && scene->obj_colors &&
                                      scene->obj_vert_off_host && scene->obj_face_off_host), "null object arrays");
@@ -388,9 +446,8 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
     if (batch == 0) return AB_OK;
     AB_REQUIRE(hand_verts && hand_tex && obj_id && obj_pose && light && ws, "null per-view input / workspace");
     AB_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
-    AB_REQUIRE(!rgba || ((uintptr_t)rgba & 15) == 0, "rgba must be 16-byte aligned");
-    AB_REQUIRE(!depth || ((uintptr_t)depth & 15) == 0, "depth must be 16-byte aligned");
-    AB_REQUIRE(!seg || ((uintptr_t)seg & 3) == 0, "seg must be 4-byte aligned");
+    AB_REQUIRE(!rgba || ((uintptr_t)rgba & 3) == 0, "rgba must be 4-byte aligned");
+    AB_REQUIRE(!depth || ((uintptr_t)depth & 3) == 0, "depth must be 4-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
 
     RasterParams P;
@@ -453,11 +510,11 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
         }
         {
             StageTimer tm(AB_STAGE_RASTER_TRIANGLE, st);
-            raster_triangle_kernel<<<dim3(cdiv(max_of + P.n_hf, 256), n), 256, 0, st>>>(P);
+            raster_triangle_kernel<<<dim3(cdiv(max_of + P.n_hf, kTriThreads), n), kTriThreads, 0, st>>>(P);
         }
         {
             StageTimer tm(AB_STAGE_RASTER_RESOLVE, st);
-            raster_resolve_kernel<<<dim3(cdiv(npx / 4, 256), n), 256, 0, st>>>(P);
+            raster_resolve_kernel<<<dim3(cdiv(npx, 256), n), 256, 0, st>>>(P);
         }
         count_launch(3);
         int rc = check_launch("ab_render_batch");
