@@ -1,0 +1,315 @@
+// Data-movement kernels around the tensor-core contraction (gemm_tc.cu) for the clasbased network, NHWC bf16.
+//
+//   ab_image_to_nhwc        image f32 [B,C,H,W] -> bf16 [B,H,W,Cp] (Cp >= C, zero padded)   (resnet.py:200 input)
+//   ab_im2col_nhwc          [B,H,W,C] -> rows [B*Ho*Wo, Kp], K order (ky, kx, c), zero padded to Kp
+//                           (the A operand of conv = GEMM; resnet.py:154, conv3x3 / 1x1 stride-2 downsample)
+//   ab_maxpool3x3s2_nhwc    nn.MaxPool2d(3, 2, 1)                                             (resnet.py:157,203)
+//   ab_avgpool_nhwc         x.mean(3).mean(2)                                                 (resnet.py:219-221)
+//   ab_deconv4x4s2_col2im   gather form of ConvTranspose2d(k4, s2, p1) after the GEMM X . W -> [B*H*W, 16*Cout],
+//                           fused with the BatchNorm affine + ReLU that follow it          (simplebaseline.py:161-172)
+//   ab_head_decode          softmax over D*H*W per class, confidence, re-normalisation, 3-D soft-argmax
+//                           (simplebaseline.py:16-71,182-190) in ONE pass over the logits
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ab {
+
+__global__ void image_to_nhwc_kernel(const float* __restrict__ img, int B, int C, int H, int W, int Cp,
+                                     __nv_bfloat16* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*H*W
+    const long long n = (long long)B * H * W;
+    if (i >= n) return;
+    const int b = (int)(i / ((long long)H * W));
+    const long long hw = i - (long long)b * H * W;
+    __nv_bfloat16* o = out + i * Cp;
+    for (int c = 0; c < Cp; ++c)
+        o[c] = __float2bfloat16(c < C ? img[((long long)b * C + c) * H * W + hw] : 0.0f);
+}
+
+// one thread per (output row, tap, 8-channel group) when C % 8 == 0
+__global__ void im2col_vec8_kernel(const uint4* __restrict__ in, int B, int H, int W, int C8, int kh, int kw, int stride,
+                                   int pad, int Ho, int Wo, int Kp8, uint4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Ho * Wo * Kp8;
+    if (i >= total) return;
+    const int k8 = (int)(i % Kp8);
+    const long long m = i / Kp8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    const int tap = k8 / C8;
+    if (tap < kh * kw) {
+        const int c8 = k8 - tap * C8;
+        const int ky = tap / kw, kx = tap - ky * kw;
+        const int ox = (int)(m % Wo);
+        const long long t = m / Wo;
+        const int oy = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(in + (((long long)b * H + iy) * W + ix) * C8 + c8);
+    }
+    out[i] = v;
+}
+
+// generic element-wise variant (conv1: C = 3 or 4)
+__global__ void im2col_scalar_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int C, int kh, int kw,
+                                     int stride, int pad, int Ho, int Wo, int Kp, __nv_bfloat16* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Ho * Wo * Kp;
+    if (i >= total) return;
+    const int k = (int)(i % Kp);
+    const long long m = i / Kp;
+    __nv_bfloat16 v = __float2bfloat16(0.0f);
+    const int tap = k / C;
+    if (tap < kh * kw) {
+        const int c = k - tap * C;
+        const int ky = tap / kw, kx = tap - ky * kw;
+        const int ox = (int)(m % Wo);
+        const long long t = m / Wo;
+        const int oy = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = in[(((long long)b * H + iy) * W + ix) * C + c];
+    }
+    out[i] = v;
+}
+
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+    uint4 r;
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+    __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pr[j] = __hmax2(pa[j], pb[j]);
+    return r;
+}
+
+__global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int B, int H, int W, int C8, int Ho, int Wo,
+                                    uint4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Ho * Wo * C8;
+    if (i >= total) return;
+    const int c8 = (int)(i % C8);
+    long long t = i / C8;
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    bool any = false;
+    uint4 best = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
+            if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+            const uint4 v = __ldg(in + (((long long)b * H + iy) * W + ix) * C8 + c8);
+            best = any ? bf16x8_max(best, v) : v;
+            any = true;
+        }
+    out[i] = best;
+}
+
+// [B, HW, C] bf16 -> mean over HW: fp32 [B, C] and bf16 [B, C].  One thread per (b, c); consecutive threads read
+// consecutive channels.
+__global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ in, int B, int HW, int C, float* __restrict__ out_f32,
+                               __nv_bfloat16* __restrict__ out_bf16) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    const int b = i / C, c = i - b * C;
+    float s = 0.0f;
+    for (int p = 0; p < HW; ++p) s += __bfloat162float(in[((long long)b * HW + p) * C + c]);
+    s /= (float)HW;
+    if (out_f32) out_f32[i] = s;
+    if (out_bf16) out_bf16[i] = __float2bfloat16(s);
+}
+
+// ConvTranspose2d(k=4, s=2, p=1): oy = 2*iy - 1 + ky.  ycol [B*H*W, 16*Cout] fp32 with column order (ky, kx, co).
+// One thread per (b, oy, ox, 4 output channels): sums its 4 contributing taps, applies scale/bias (+ReLU), writes bf16.
+__global__ void deconv_col2im_kernel(const float4* __restrict__ ycol, int B, int H, int W, int Cout4,
+                                     const float* __restrict__ scale, const float* __restrict__ bias, int relu,
+                                     __nv_bfloat16* __restrict__ out, float* __restrict__ out_raw) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int Ho = 2 * H, Wo = 2 * W;
+    const long long total = (long long)B * Ho * Wo * Cout4;
+    if (i >= total) return;
+    const int c4 = (int)(i % Cout4);
+    long long t = i / Cout4;
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int iy0 = (oy + 1) >> 1, ix0 = (ox + 1) >> 1;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const int iy = iy0 - dy, ky = oy + 1 - 2 * iy;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int ix = ix0 - dx, kx = ox + 1 - 2 * ix;
+            if (ix < 0 || ix >= W) continue;
+            const float4 v = __ldg(ycol + ((((long long)b * H + iy) * W + ix) * 16 + (ky * 4 + kx)) * Cout4 + c4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    if (out_raw) reinterpret_cast<float4*>(out_raw)[i] = acc;
+    if (out) {
+        const int c = 4 * c4;
+        float y[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            y[j] = fmaf(y[j], scale ? scale[c + j] : 1.0f, bias ? bias[c + j] : 0.0f);
+            if (relu) y[j] = fmaxf(y[j], 0.0f);
+        }
+        __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(out + i * 4);
+        o[0] = __floats2bfloat162_rn(y[0], y[1]);
+        o[1] = __floats2bfloat162_rn(y[2], y[3]);
+    }
+}
+
+// logits fp32 [B, H*W, ncls*D] (channel = cls*D + d, i.e. NHWC of the reference's [B, ncls*D, H, W]).
+// One CTA per (b, cls).  p = softmax over (d,h,w); confd = max p; p /= (sum p + 1e-7); u = sum p*w/W, v = sum p*h/H,
+// d = sum p*d/D.  Two sweeps over the class's D*H*W logits (max, then exp-sums); they stay in L1/L2.
+constexpr int kDecodeThreads = 256;
+__global__ void __launch_bounds__(kDecodeThreads)
+head_decode_kernel(const float* __restrict__ logits, int ncls, int D, int H, int W, float* __restrict__ kp3d,
+                   float* __restrict__ confd) {
+    __shared__ float red[4][kDecodeThreads / 32];
+    const int b = blockIdx.x / ncls, cls = blockIdx.x % ncls;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int HW = H * W, n = HW * D, ldc = ncls * D;
+    const float* base = logits + (long long)b * HW * ldc + cls * D;
+    float mx = -INFINITY;
+    for (int i = tid; i < n; i += kDecodeThreads) {
+        const int p = i / D, d = i - p * D;
+        mx = fmaxf(mx, base[(long long)p * ldc + d]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[0][wid] = mx;
+    __syncthreads();
+    mx = red[0][0];
+#pragma unroll
+    for (int w = 1; w < kDecodeThreads / 32; ++w) mx = fmaxf(mx, red[0][w]);
+    __syncthreads();
+    float s = 0.f, su = 0.f, sv = 0.f, sd = 0.f;
+    for (int i = tid; i < n; i += kDecodeThreads) {
+        const int p = i / D, d = i - p * D;
+        const int h = p / W, w = p - h * W;
+        const float e = expf(base[(long long)p * ldc + d] - mx);
+        s += e; su += e * (float)w; sv += e * (float)h; sd += e * (float)d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        su += __shfl_xor_sync(0xffffffffu, su, o);
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        sd += __shfl_xor_sync(0xffffffffu, sd, o);
+    }
+    if (lane == 0) { red[0][wid] = s; red[1][wid] = su; red[2][wid] = sv; red[3][wid] = sd; }
+    __syncthreads();
+    if (tid == 0) {
+        float S = 0.f, SU = 0.f, SV = 0.f, SD = 0.f;
+        for (int w = 0; w < kDecodeThreads / 32; ++w) { S += red[0][w]; SU += red[1][w]; SV += red[2][w]; SD += red[3][w]; }
+        // softmax p_i = e_i / S: sum p = 1 up to rounding; the reference divides by (sum p + 1e-7) once more
+        const float inv = 1.0f / S;
+        const float renorm = 1.0f / (1.0f + 1e-7f);
+        float* o = kp3d + ((long long)b * ncls + cls) * 3;
+        o[0] = SU * inv * renorm / (float)W;
+        o[1] = SV * inv * renorm / (float)H;
+        o[2] = SD * inv * renorm / (float)D;
+        confd[(long long)b * ncls + cls] = inv;  // max p = exp(0) / S
+    }
+}
+
+static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace ab
+
+using namespace ab;
+
+extern "C" int ab_image_to_nhwc(const float* image, int B, int C, int H, int W, int Cp, void* out, void* stream) {
+    AB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && Cp >= C, "bad shape");
+    if (B == 0) return AB_OK;
+    AB_REQUIRE(image && out, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_ELEMENTWISE, st);
+    image_to_nhwc_kernel<<<blocks_for((long long)B * H * W, 256), 256, 0, st>>>(image, B, C, H, W, Cp, (__nv_bfloat16*)out);
+    count_launch();
+    return check_launch("image_to_nhwc_kernel");
+}
+
+extern "C" int ab_im2col_nhwc(const void* in, int B, int H, int W, int C, int kh, int kw, int stride, int pad, int Kp,
+                              void* out, void* stream) {
+    AB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, "bad shape");
+    AB_REQUIRE(Kp >= kh * kw * C && Kp % 8 == 0, "Kp must be a multiple of 8 and >= kh*kw*C");
+    if (B == 0) return AB_OK;
+    AB_REQUIRE(in && out, "null pointer");
+    const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+    AB_REQUIRE(Ho > 0 && Wo > 0, "empty output");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_IM2COL, st);
+    if (C % 8 == 0) {
+        AB_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "16-byte alignment required");
+        const long long total = (long long)B * Ho * Wo * (Kp / 8);
+        im2col_vec8_kernel<<<blocks_for(total, 256), 256, 0, st>>>((const uint4*)in, B, H, W, C / 8, kh, kw, stride, pad, Ho,
+                                                                   Wo, Kp / 8, (uint4*)out);
+    } else {
+        const long long total = (long long)B * Ho * Wo * Kp;
+        im2col_scalar_kernel<<<blocks_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)in, B, H, W, C, kh, kw, stride,
+                                                                     pad, Ho, Wo, Kp, (__nv_bfloat16*)out);
+    }
+    count_launch();
+    return check_launch("im2col_kernel");
+}
+
+extern "C" int ab_maxpool3x3s2_nhwc(const void* in, int B, int H, int W, int C, void* out, void* stream) {
+    AB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad shape (C must be a multiple of 8)");
+    if (B == 0) return AB_OK;
+    AB_REQUIRE(in && out, "null pointer");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_ELEMENTWISE, st);
+    maxpool3x3s2_kernel<<<blocks_for((long long)B * Ho * Wo * (C / 8), 256), 256, 0, st>>>((const uint4*)in, B, H, W, C / 8,
+                                                                                           Ho, Wo, (uint4*)out);
+    count_launch();
+    return check_launch("maxpool3x3s2_kernel");
+}
+
+extern "C" int ab_avgpool_nhwc(const void* in, int B, int HW, int C, float* out_f32, void* out_bf16, void* stream) {
+    AB_REQUIRE(B >= 0 && HW > 0 && C > 0, "bad shape");
+    if (B == 0) return AB_OK;
+    AB_REQUIRE(in && (out_f32 || out_bf16), "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_ELEMENTWISE, st);
+    avgpool_kernel<<<blocks_for((long long)B * C, 128), 128, 0, st>>>((const __nv_bfloat16*)in, B, HW, C, out_f32,
+                                                                      (__nv_bfloat16*)out_bf16);
+    count_launch();
+    return check_launch("avgpool_kernel");
+}
+
+extern "C" int ab_deconv4x4s2_col2im(const float* ycol, int B, int H, int W, int Cout, const float* scale,
+                                     const float* bias, int relu, void* out_bf16, float* out_raw, void* stream) {
+    AB_REQUIRE(B >= 0 && H > 0 && W > 0 && Cout > 0 && Cout % 4 == 0, "bad shape (Cout must be a multiple of 4)");
+    if (B == 0) return AB_OK;
+    AB_REQUIRE(ycol && (out_bf16 || out_raw), "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_ELEMENTWISE, st);
+    const long long total = (long long)B * 4 * H * W * (Cout / 4);
+    deconv_col2im_kernel<<<blocks_for(total, 256), 256, 0, st>>>((const float4*)ycol, B, H, W, Cout / 4, scale, bias, relu,
+                                                                 (__nv_bfloat16*)out_bf16, out_raw);
+    count_launch();
+    return check_launch("deconv_col2im_kernel");
+}
+
+extern "C" int ab_head_decode(const float* logits, int B, int ncls, int D, int H, int W, float* kp3d, float* confd,
+                              void* stream) {
+    AB_REQUIRE(B >= 0 && ncls > 0 && D > 0 && H > 0 && W > 0, "bad shape");
+    if (B == 0) return AB_OK;
+    AB_REQUIRE(logits && kp3d && confd, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_HEAD_DECODE, st);
+    head_decode_kernel<<<B * ncls, kDecodeThreads, 0, st>>>(logits, ncls, D, H, W, kp3d, confd);
+    count_launch();
+    return check_launch("head_decode_kernel");
+}

@@ -1,0 +1,314 @@
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+//   D[M,N] = epilogue( A[M,K] . B[N,K]^T )          A, B bf16 row-major with K contiguous ("TN"), fp32 accumulate
+//   epilogue: y = acc * scale[n] + bias[n] (+ residual[m,n]) -> optional ReLU -> bf16 or fp32 store
+//             (folded BatchNorm / conv bias / residual add / ReLU of anakin/models/resnet.py:72-152 fused into
+//              the producing GEMM), optional per-column sum / sum-of-squares for training-mode BatchNorm.
+//
+// This is the contraction behind every convolution, transposed convolution and linear layer of the clasbased
+// network: conv = im2col rows x filter matrix, see conv.cu.
+//
+// Structure (one 128 x BN output tile per CTA, 2 CTAs co-resident per SM so one tile's epilogue overlaps the
+// other's main loop):
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles of A (128 x 64) and B (BN x 64), 128-byte swizzle, into a
+//            STAGES-deep shared-memory ring; completion by mbarrier transaction bytes.  Out-of-range rows / K tail
+//            are zero-filled by the TMA unit, so M, N, K need no padding (K only a multiple of 8 for the 16-byte pitch).
+//   warp 1   MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) four
+//            times per stage from shared-memory descriptors; tcgen05.commit releases the stage / signals the epilogue.
+//   warp 2   TMEM allocator (BN fp32 columns x 128 lanes).
+//   warps 4-7 epilogue: tcgen05.ld 32x32b (one accumulator row per thread), fused math, 16-byte global stores.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ab {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 256;
+
+struct GemmEpilogue {
+    void* D;                 // bf16 or fp32 [M, ldd]
+    long long ldd;
+    int out_fp32;
+    const float* scale;      // [N] or null (1)
+    const float* bias;       // [N] or null (0)
+    const __nv_bfloat16* residual;  // [M, ldr] or null
+    long long ldr;
+    int relu;
+    float* col_sum;          // [N] or null: += sum over rows of the PRE-epilogue accumulator
+    float* col_sumsq;        // [N] or null
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile in shared memory, rows of 64 bf16 (128 B), 128-byte swizzle, 8-row atoms of 1024 B:
+// start address >> 4 | LBO (ignored for swizzled K-major) = 1 | SBO = 1024 B >> 4 | version 1 (Blackwell) | SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(const void* smem_tile) {
+    return (uint64_t)((smem_u32(smem_tile) >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    __nv_bfloat16 a[STAGES][kBM * kBK];
+    __nv_bfloat16 b[STAGES][BN * kBK];
+    uint64_t full[STAGES], empty[STAGES], tmem_full;
+    uint32_t tmem_base;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                    const GemmEpilogue ep) {
+    extern __shared__ uint8_t smem_raw[];
+    auto& sm = *reinterpret_cast<GemmSmem<BN, STAGES>*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+    const int num_k = (K + kBK - 1) / kBK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+        mbar_init(&sm.tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(&sm.tmem_base, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&sm.empty[s], ph ^ 1);
+                mbar_expect_tx(&sm.full[s], (kBM + BN) * kBK * 2);
+                tma_load_2d(sm.a[s], &tmA, &sm.full[s], kb * kBK, tile_m * kBM);
+                tma_load_2d(sm.b[s], &tmB, &sm.full[s], kb * kBK, tile_n * BN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&sm.full[s], ph);
+                tc_fence_after();
+                const uint64_t ad = umma_desc_k_sw128(sm.a[s]), bd = umma_desc_k_sw128(sm.b[s]);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k)  // +32 bytes (16 bf16) along K inside the swizzled row: +2 in the address field
+                    umma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(&sm.empty[s]);  // frees the stage when these MMAs have read it
+            }
+            umma_commit(&sm.tmem_full);
+        }
+    } else if (warp >= 4) {
+        mbar_wait(&sm.tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const int row = tile_m * kBM + q * 32 + lane;
+        const bool row_ok = row < M;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            const int col = tile_n * BN + c0;
+            if (col >= N) break;  // warp-uniform
+            uint32_t r[16];
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            if (ep.col_sum) {  // training-mode BatchNorm statistics of the raw convolution output
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float s1 = row_ok ? v[j] : 0.0f, s2 = s1 * s1;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                    }
+                    if (lane == 0 && col + j < N) {
+                        atomicAdd(ep.col_sum + col + j, s1);
+                        atomicAdd(ep.col_sumsq + col + j, s2);
+                    }
+                }
+            }
+            if (!row_ok) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // two groups of 8 columns (N is a multiple of 8)
+                const int cc = col + 8 * h;
+                if (cc >= N) break;
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float sc = ep.scale ? __ldg(ep.scale + cc + j) : 1.0f;
+                    const float bi = ep.bias ? __ldg(ep.bias + cc + j) : 0.0f;
+                    y[j] = fmaf(v[8 * h + j], sc, bi);
+                }
+                if (ep.residual) {
+                    const uint4 rr = *reinterpret_cast<const uint4*>(ep.residual + (size_t)row * ep.ldr + cc);
+                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __bfloat1622float2(rp[j]);
+                        y[2 * j] += f.x; y[2 * j + 1] += f.y;
+                    }
+                }
+                if (ep.relu) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.0f);
+                }
+                if (ep.out_fp32) {
+                    float4* o = reinterpret_cast<float4*>((float*)ep.D + (size_t)row * ep.ldd + cc);
+                    o[0] = make_float4(y[0], y[1], y[2], y[3]);
+                    o[1] = make_float4(y[4], y[5], y[6], y[7]);
+                } else {
+                    uint4 pk;
+                    __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) pp[j] = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+                    *reinterpret_cast<uint4*>((__nv_bfloat16*)ep.D + (size_t)row * ep.ldd + cc) = pk;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, BN);
+}
+
+// --------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p) fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor map of a row-major [rows, cols] matrix with pitch ld (elements): box = 64 cols x box_rows, 128B swizzle
+static int make_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return AB_ERR_UNSUPPORTED; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return AB_ERR_ARG; }
+    return AB_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t st) {
+    const size_t smem = sizeof(GemmSmem<BN, STAGES>) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        AB_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(cdiv(M, kBM), cdiv(N, BN));
+    StageTimer tm(AB_STAGE_GEMM, st);
+    gemm_bf16_tn_kernel<BN, STAGES><<<grid, kGemmThreads, smem, st>>>(ta, tb, M, N, K, ep);
+    count_launch();
+    return check_launch("gemm_bf16_tn_kernel");
+}
+
+int gemm_bf16_tn(int M, int N, int K, const void* A, long long lda, const void* B, long long ldb, const GemmEpilogue& ep,
+                 cudaStream_t st) {
+    // tile N: the smallest of {64, 128} that keeps the tile count low; BN = 64 lets 2 CTAs share an SM
+    const int bn = (N <= 64) ? 64 : 128;
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, A, M, K, lda, kBM);
+    if (rc) return rc;
+    rc = make_map(&tb, B, N, K, ldb, bn);
+    if (rc) return rc;
+    return bn == 64 ? launch_gemm<64, 4>(ta, tb, M, N, K, ep, st) : launch_gemm<128, 3>(ta, tb, M, N, K, ep, st);
+}
+
+}  // namespace ab
+
+extern "C" int ab_gemm_bf16(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
+                            int out_fp32, const float* scale, const float* bias, const void* residual, int64_t ldr,
+                            int relu, float* col_sum, float* col_sumsq, void* stream) {
+    AB_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative size");
+    if (M == 0 || N == 0) return AB_OK;
+    AB_REQUIRE(K > 0, "K must be positive");
+    AB_REQUIRE(A && B && D, "null matrix");
+    AB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "K, lda, ldb must be multiples of 8 (16-byte rows for TMA)");
+    AB_REQUIRE(N % 8 == 0 && ldd % 8 == 0 && (!residual || ldr % 8 == 0), "N, ldd, ldr must be multiples of 8");
+    AB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)D & 15) == 0 &&
+                   ((uintptr_t)residual & 15) == 0, "matrices must be 16-byte aligned");
+    AB_REQUIRE((col_sum == nullptr) == (col_sumsq == nullptr), "col_sum and col_sumsq go together");
+    ab::GemmEpilogue ep;
+    ep.D = D; ep.ldd = ldd; ep.out_fp32 = out_fp32; ep.scale = scale; ep.bias = bias;
+    ep.residual = (const __nv_bfloat16*)residual; ep.ldr = ldr; ep.relu = relu; ep.col_sum = col_sum; ep.col_sumsq = col_sumsq;
+    return ab::gemm_bf16_tn(M, N, K, A, lda, B, ldb, ep, (cudaStream_t)stream);
+}

@@ -53,6 +53,16 @@ EXPORTS = {
     "ab_render_batch": (C.c_int, [C.POINTER(SceneStruct), C.POINTER(CameraStruct), C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_void_p, c_i32_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_gemm_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                               C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                               C.c_void_p, C.c_void_p]),
+    "ab_image_to_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    "ab_im2col_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]),
+    "ab_maxpool3x3s2_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
+    "ab_avgpool_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 3 + [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_deconv4x4s2_col2im": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                                      C.c_void_p, C.c_void_p]),
+    "ab_head_decode": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -104,7 +114,8 @@ def launch_count() -> int:
 
 
 STAGES = {0: "raster_vertex_kernel", 1: "raster_triangle_kernel", 2: "raster_resolve_kernel", 3: "mano_lbs_kernel",
-          4: "posegen_prelude_kernel", 5: "ccv_cdf+draw_kernels", 6: "view_kernel"}
+          4: "posegen_prelude_kernel", 5: "ccv_cdf+draw_kernels", 6: "view_kernel", 7: "gemm_bf16_tn_kernel",
+          8: "im2col_kernel", 9: "elementwise_kernels", 10: "head_decode_kernel"}
 
 
 def profile_enable(on: bool) -> None:

@@ -1,0 +1,192 @@
+"""NHWC bf16 activations and the layer primitives of the clasbased network on top of the C-ABI.
+
+Every convolution / transposed convolution / linear layer is `im2col rows x packed filter matrix` on the tcgen05
+GEMM (ab_gemm_bf16) with the BatchNorm affine, bias, residual add and ReLU fused into its epilogue.  Parameters stay
+ordinary fp32 `nn.Parameter`s in the reference's layouts (state_dict compatible); packed bf16 copies are cached and
+rebuilt when a parameter's version counter changes.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import lib, ops
+
+
+@dataclass
+class Act:
+    """bf16 [B*H*W, C] view of an NHWC activation."""
+    data: torch.Tensor
+    B: int
+    H: int
+    W: int
+    C: int
+
+    def nchw(self, dtype=torch.float32) -> torch.Tensor:
+        return self.data.view(self.B, self.H, self.W, self.C).permute(0, 3, 1, 2).to(dtype)
+
+
+_cache = {}
+
+
+def _cached(key, versions, build):
+    hit = _cache.get(key)
+    if hit is not None and hit[0] == versions:
+        return hit[1]
+    val = build()
+    _cache[key] = (versions, val)
+    return val
+
+
+def _ver(*tensors):
+    return tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, kh, kw] fp32 -> bf16 [Cout, Kp], K order (ky, kx, ci), zero padded to a multiple of 8."""
+    cout = w.shape[0]
+    m = w.detach().permute(0, 2, 3, 1).reshape(cout, -1)
+    kp = _pad8(m.shape[1])
+    out = torch.zeros((cout, kp), dtype=torch.bfloat16, device=w.device)
+    out[:, :m.shape[1]] = m.to(torch.bfloat16)
+    return out
+
+
+def bn_affine(bn, training: bool):
+    """Folded (scale, bias) of an eval-mode / frozen BatchNorm (resnet.py:44-69, nn.BatchNorm2d eval)."""
+    if bn is None:
+        return None, None
+    if training and isinstance(bn, nn.BatchNorm2d):
+        raise NotImplementedError("training-mode BatchNorm (batch statistics) is not on the tensor-core path yet; "
+                                  "call .eval() or build the backbone with FREEZE_BATCHNORM: true")
+
+    def build():
+        eps = getattr(bn, "eps", 1e-5)
+        scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + eps)
+        bias = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+        return scale.contiguous(), bias.contiguous()
+
+    return _cached(("bn", id(bn)), _ver(bn.weight, bn.bias, bn.running_mean, bn.running_var), build)
+
+
+def image_to_act(image: torch.Tensor) -> Act:
+    lib.require_cuda(image, "image")
+    B, C, H, W = image.shape
+    img = image.contiguous().float()
+    out = torch.empty((B * H * W, C), dtype=torch.bfloat16, device=image.device)
+    with torch.cuda.device(image.device):
+        rc = lib.load().ab_image_to_nhwc(img.data_ptr(), B, C, H, W, C, out.data_ptr(), lib.stream_ptr(image.device))
+    lib.check(rc, "ab_image_to_nhwc")
+    return Act(out, B, H, W, C)
+
+
+def conv_bn_act(x: Act, conv: nn.Conv2d, bn=None, relu: bool = False, residual: Optional[Act] = None,
+                training: bool = False, out_fp32: bool = False):
+    """Conv2d (+ folded BN / conv bias) (+ residual) (+ ReLU).  -> Act (bf16) or fp32 [B*Ho*Wo, Cout] when out_fp32."""
+    kh, kw = conv.kernel_size
+    stride, pad = conv.stride[0], conv.padding[0]
+    cout = conv.out_channels
+    assert conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1] and conv.groups == 1
+    wp = _cached(("w", id(conv)), _ver(conv.weight), lambda: pack_conv_weight(conv.weight))
+    scale, bias = bn_affine(bn, training)
+    if conv.bias is not None:
+        cb = conv.bias.detach().float()
+        bias = cb if bias is None else bias + cb * scale
+    Ho, Wo = (x.H + 2 * pad - kh) // stride + 1, (x.W + 2 * pad - kw) // stride + 1
+    dev = x.data.device
+    if kh == 1 and kw == 1 and stride == 1 and pad == 0 and x.C % 8 == 0:
+        a = x.data
+    else:
+        kp = wp.shape[1]
+        a = torch.empty((x.B * Ho * Wo, kp), dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.load().ab_im2col_nhwc(x.data.data_ptr(), x.B, x.H, x.W, x.C, kh, kw, stride, pad, kp, a.data_ptr(),
+                                           lib.stream_ptr(dev))
+        lib.check(rc, "ab_im2col_nhwc")
+    out = ops.gemm_bf16(a, wp, scale=scale, bias=bias, residual=None if residual is None else residual.data, relu=relu,
+                        out_fp32=out_fp32)
+    return out if out_fp32 else Act(out, x.B, Ho, Wo, cout)
+
+
+def maxpool3x3s2(x: Act) -> Act:
+    Ho, Wo = (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1
+    out = torch.empty((x.B * Ho * Wo, x.C), dtype=torch.bfloat16, device=x.data.device)
+    with torch.cuda.device(x.data.device):
+        rc = lib.load().ab_maxpool3x3s2_nhwc(x.data.data_ptr(), x.B, x.H, x.W, x.C, out.data_ptr(),
+                                             lib.stream_ptr(x.data.device))
+    lib.check(rc, "ab_maxpool3x3s2_nhwc")
+    return Act(out, x.B, Ho, Wo, x.C)
+
+
+def avgpool(x: Act):
+    """-> (fp32 [B, C], bf16 [B, C])"""
+    dev = x.data.device
+    f = torch.empty((x.B, x.C), dtype=torch.float32, device=dev)
+    h = torch.empty((x.B, x.C), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.load().ab_avgpool_nhwc(x.data.data_ptr(), x.B, x.H * x.W, x.C, f.data_ptr(), h.data_ptr(),
+                                        lib.stream_ptr(dev))
+    lib.check(rc, "ab_avgpool_nhwc")
+    return f, h
+
+
+def deconv4x4s2_bn_relu(x: Act, deconv: nn.ConvTranspose2d, bn, relu: bool = True, training: bool = False) -> Act:
+    """ConvTranspose2d(k=4, s=2, p=1) + BN + ReLU (simplebaseline.py:152-175): X . W -> [B*H*W, 16*Cout], then the
+    gather form of col2im with the BN affine and ReLU fused."""
+    if deconv.kernel_size != (4, 4) or deconv.stride != (2, 2) or deconv.padding != (1, 1) or deconv.output_padding != (0, 0):
+        raise NotImplementedError("only ConvTranspose2d(kernel 4, stride 2, padding 1) (NUM_DECONV_KERNELS: 4)")
+    cout = deconv.out_channels
+
+    def build():  # [Cin, Cout, ky, kx] -> [(ky, kx, co), ci]
+        return deconv.weight.detach().permute(2, 3, 1, 0).reshape(16 * cout, -1).to(torch.bfloat16).contiguous()
+
+    wp = _cached(("dw", id(deconv)), _ver(deconv.weight), build)
+    scale, bias = bn_affine(bn, training)
+    if deconv.bias is not None:
+        db = deconv.bias.detach().float()
+        bias = db if bias is None else bias + db * scale
+    ycol = ops.gemm_bf16(x.data, wp, out_fp32=True)
+    dev = x.data.device
+    out = torch.empty((x.B * 4 * x.H * x.W, cout), dtype=torch.bfloat16, device=dev)
+    p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    with torch.cuda.device(dev):
+        rc = lib.load().ab_deconv4x4s2_col2im(ycol.data_ptr(), x.B, x.H, x.W, cout, p(scale), p(bias), int(relu),
+                                              out.data_ptr(), None, lib.stream_ptr(dev))
+    lib.check(rc, "ab_deconv4x4s2_col2im")
+    return Act(out, x.B, 2 * x.H, 2 * x.W, cout)
+
+
+def linear(x_bf16: torch.Tensor, fc: nn.Linear, relu: bool = False, out_fp32: bool = False) -> torch.Tensor:
+    """nn.Linear on the tensor-core GEMM; out features padded to a multiple of 8 internally."""
+    n = fc.out_features
+    npad = _pad8(n)
+
+    def build():
+        w = torch.zeros((npad, _pad8(fc.in_features)), dtype=torch.bfloat16, device=fc.weight.device)
+        w[:n, :fc.in_features] = fc.weight.detach().to(torch.bfloat16)
+        b = torch.zeros(npad, dtype=torch.float32, device=fc.weight.device)
+        if fc.bias is not None:
+            b[:n] = fc.bias.detach().float()
+        return w, b
+
+    w, b = _cached(("fc", id(fc)), _ver(fc.weight, fc.bias), build)
+    out = ops.gemm_bf16(x_bf16, w, bias=b, relu=relu, out_fp32=out_fp32)
+    return out[:, :n]
+
+
+def head_decode(logits_f32: torch.Tensor, B: int, ncls: int, D: int, H: int, W: int):
+    dev = logits_f32.device
+    kp3d = torch.empty((B, ncls, 3), dtype=torch.float32, device=dev)
+    confd = torch.empty((B, ncls), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.load().ab_head_decode(logits_f32.data_ptr(), B, ncls, D, H, W, kp3d.data_ptr(), confd.data_ptr(),
+                                       lib.stream_ptr(dev))
+    lib.check(rc, "ab_head_decode")
+    return kp3d, confd

@@ -1,0 +1,197 @@
+"""ResNet backbones (anakin/models/resnet.py:44-275): same classes, cfg keys, forward contract and state_dict names;
+forward runs NHWC bf16 on the tensor-core GEMM with BN / ReLU / residual fused into the epilogues."""
+from collections import OrderedDict
+from typing import Dict
+
+import torch
+import torch.nn as nn
+
+from . import nhwc
+from .registry import BACKBONE, enable_lower_param
+
+
+class FrozenBatchNorm2d(nn.Module):
+    """BatchNorm2d with fixed statistics and affine parameters (resnet.py:24-69)."""
+
+    def __init__(self, n):
+        super().__init__()
+        self.register_buffer("weight", torch.ones(n))
+        self.register_buffer("bias", torch.zeros(n))
+        self.register_buffer("running_mean", torch.zeros(n))
+        self.register_buffer("running_var", torch.ones(n))
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        num_batches_tracked_key = prefix + "num_batches_tracked"
+        if num_batches_tracked_key in state_dict:
+            del state_dict[num_batches_tracked_key]
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+
+def conv3x3(in_planes, out_planes, stride=1):
+    return nn.Conv2d(in_planes, out_planes, kernel_size=3, stride=stride, padding=1, bias=False)
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, bn_layer=nn.BatchNorm2d):
+        super().__init__()
+        self.conv1 = conv3x3(inplanes, planes, stride)
+        self.bn1 = bn_layer(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = conv3x3(planes, planes)
+        self.bn2 = bn_layer(planes)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward_act(self, x: nhwc.Act) -> nhwc.Act:
+        tr = self.training
+        residual = x if self.downsample is None else nhwc.conv_bn_act(x, self.downsample[0], self.downsample[1], training=tr)
+        out = nhwc.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=tr)
+        return nhwc.conv_bn_act(out, self.conv2, self.bn2, relu=True, residual=residual, training=tr)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, bn_layer=nn.BatchNorm2d):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=1, bias=False)
+        self.bn1 = bn_layer(planes)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.bn2 = bn_layer(planes)
+        self.conv3 = nn.Conv2d(planes, planes * self.expansion, kernel_size=1, bias=False)
+        self.bn3 = bn_layer(planes * self.expansion)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward_act(self, x: nhwc.Act) -> nhwc.Act:
+        tr = self.training
+        residual = x if self.downsample is None else nhwc.conv_bn_act(x, self.downsample[0], self.downsample[1], training=tr)
+        out = nhwc.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=tr)
+        out = nhwc.conv_bn_act(out, self.conv2, self.bn2, relu=True, training=tr)
+        return nhwc.conv_bn_act(out, self.conv3, self.bn3, relu=True, residual=residual, training=tr)
+
+
+class ResNet(nn.Module):
+
+    def __init__(self, block, layers, num_classes=1000, interm_feat=True, **kwargs):
+        super().__init__()
+        self.bn_layer = FrozenBatchNorm2d if kwargs["FREEZE_BATCHNORM"] else nn.BatchNorm2d
+        self.inplanes = 64
+        self.interm_feat = kwargs["INTERM_FEAT"] if "INTERM_FEAT" in kwargs else interm_feat
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = self.bn_layer(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.layer1 = self._make_layer(block, 64, layers[0])
+        self.layer2 = self._make_layer(block, 128, layers[1], stride=2)
+        self.layer3 = self._make_layer(block, 256, layers[2], stride=2)
+        self.layer4 = self._make_layer(block, 512, layers[3], stride=2)
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc = nn.Linear(512 * block.expansion, num_classes)  # unused ImageNet head, kept for checkpoint names
+        self.features = 512 * block.expansion
+        self.output_channel = self.inplanes
+        self.init_weights()
+
+    def init_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, self.bn_layer):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    def _make_layer(self, block, planes, blocks, stride=1):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            downsample = nn.Sequential(
+                nn.Conv2d(self.inplanes, planes * block.expansion, kernel_size=1, stride=stride, bias=False),
+                self.bn_layer(planes * block.expansion),
+            )
+        layers = [block(self.inplanes, planes, stride, downsample, self.bn_layer)]
+        self.inplanes = planes * block.expansion
+        for _ in range(1, blocks):
+            layers.append(block(self.inplanes, planes))
+        return nn.Sequential(*layers)
+
+    def load_pretrained(self):
+        raise RuntimeError("ImageNet weights cannot be downloaded here (no network): load a state_dict instead")
+
+    @torch.no_grad()
+    def forward_acts(self, image: torch.Tensor) -> Dict[str, object]:
+        """NHWC bf16 feature maps (what the head consumes without a layout round trip)."""
+        x = nhwc.image_to_act(image)
+        x = nhwc.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=self.training)
+        x = nhwc.maxpool3x3s2(x)
+        feats = OrderedDict()
+        for name in ("layer1", "layer2", "layer3", "layer4"):
+            for blk in getattr(self, name):
+                x = blk.forward_act(x)
+            feats["res_" + name] = x
+        feats["res_layer4_mean"], feats["res_layer4_mean_bf16"] = nhwc.avgpool(x)
+        return feats
+
+    def forward(self, **kwargs) -> Dict:
+        """-> OrderedDict{res_layer1..4 fp32 NCHW, res_layer4_mean fp32 [B, C]} (resnet.py:199-224)."""
+        feats = self.forward_acts(kwargs["image"])
+        features = OrderedDict()
+        for k in ("res_layer1", "res_layer2", "res_layer3", "res_layer4"):
+            features[k] = feats[k].nchw()
+        features["res_layer4_mean"] = feats["res_layer4_mean"]
+        if self.interm_feat:
+            return features
+        out = {"res_output": nhwc.linear(feats["res_layer4_mean_bf16"], self.fc, out_fp32=True)}
+        out.update(features)
+        return out
+
+
+@BACKBONE.register_module
+class ResNet18(ResNet):
+
+    @enable_lower_param
+    def __init__(self, **cfg):
+        super().__init__(BasicBlock, [2, 2, 2, 2], **cfg)
+        if cfg["PRETRAINED"]:
+            self.load_pretrained()
+
+
+@BACKBONE.register_module
+class ResNet34(ResNet):
+
+    @enable_lower_param
+    def __init__(self, **cfg):
+        super().__init__(BasicBlock, [3, 4, 6, 3], **cfg)
+        if cfg["PRETRAINED"]:
+            self.load_pretrained()
+
+
+@BACKBONE.register_module
+class ResNet50(ResNet):
+
+    @enable_lower_param
+    def __init__(self, **cfg):
+        super().__init__(Bottleneck, [3, 4, 6, 3], **cfg)
+        if cfg["PRETRAINED"]:
+            self.load_pretrained()
+
+
+@BACKBONE.register_module
+class ResNet101(ResNet):
+
+    @enable_lower_param
+    def __init__(self, **cfg):
+        super().__init__(Bottleneck, [3, 4, 23, 3], **cfg)
+        if cfg["PRETRAINED"]:
+            self.load_pretrained()
+
+
+@BACKBONE.register_module
+class ResNet152(ResNet):
+
+    @enable_lower_param
+    def __init__(self, **cfg):
+        super().__init__(Bottleneck, [3, 8, 36, 3], **cfg)
+        if cfg["PRETRAINED"]:
+            self.load_pretrained()

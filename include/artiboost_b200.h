@@ -53,6 +53,10 @@ AB_API uint64_t ab_launch_count(void);
 #define AB_STAGE_POSEGEN_PRELUDE 4
 #define AB_STAGE_CCV 5
 #define AB_STAGE_VIEW 6
+#define AB_STAGE_GEMM 7
+#define AB_STAGE_IM2COL 8
+#define AB_STAGE_ELEMENTWISE 9
+#define AB_STAGE_HEAD_DECODE 10
 #define AB_STAGE_COUNT 16
 AB_API int ab_profile_enable(int on);
 AB_API int ab_profile_collect(double* ms_per_stage, int64_t* launches_per_stage, int n_stages);
@@ -145,6 +149,40 @@ AB_API int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int batc
                     const int32_t* hand_tex, const int32_t* obj_id, const int32_t* obj_id_host, const float* obj_pose,
                     const float* light, const int32_t* bg_sel, uint8_t* rgba, float* depth, uint8_t* seg, void* ws,
                     void* stream);
+
+/* ------------------------------------------------------------------------------------- tensor-core contraction
+ * The contraction behind every conv / deconv / linear layer of the clasbased network (anakin/models/resnet.py:154-221,
+ * simplebaseline.py:152-190, mlp.py:11-25), which the reference hands to cuDNN / cuBLAS through torch.nn.
+ * D[M,N] = epilogue(A[M,K] . B[N,K]^T): A, B bf16 row-major (K contiguous, pitches lda / ldb in elements), fp32
+ * accumulation in tensor memory (tcgen05).  epilogue: y = acc * scale[n] + bias[n] (+ residual[m,n]) (ReLU) -> bf16
+ * (out_fp32 = 0) or fp32 store with pitch ldd.  scale / bias / residual may be NULL.  col_sum / col_sumsq (both or
+ * neither): fp32 [N] accumulators that receive the per-column sum and sum of squares of the raw accumulator (the
+ * batch statistics of training-mode BatchNorm); the caller zeroes them.
+ * K, N, lda, ldb, ldd, ldr multiples of 8; pointers 16-byte aligned.                                           */
+AB_API int ab_gemm_bf16(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
+                        int out_fp32, const float* scale, const float* bias, const void* residual, int64_t ldr, int relu,
+                        float* col_sum, float* col_sumsq, void* stream);
+
+/* ------------------------------------------------------------------- data movement around the contraction (NHWC bf16)
+ * Activations are bf16 NHWC ([B,H,W,C], C contiguous) between layers; the reference keeps fp32 NCHW and lets cuDNN
+ * pick layouts (anakin/models/resnet.py:199-221).
+ * ab_image_to_nhwc: f32 [B,C,H,W] -> bf16 [B,H,W,Cp], channels C..Cp-1 zero.
+ * ab_im2col_nhwc:   -> rows [B*Ho*Wo, Kp] with K order (ky, kx, c), columns kh*kw*C..Kp-1 zero; Ho = (H+2*pad-kh)/stride+1.
+ * ab_maxpool3x3s2_nhwc: nn.MaxPool2d(3, 2, 1) (resnet.py:157).  ab_avgpool_nhwc: mean over H*W (resnet.py:219).
+ * ab_deconv4x4s2_col2im: ycol f32 [B*H*W, 16*Cout] (column order ky, kx, co) = X . W of a ConvTranspose2d(4, 2, 1)
+ *   (simplebaseline.py:161-170) -> out[b, 2H, 2W, Cout] = sum of the 4 contributing taps, * scale + bias, ReLU, bf16;
+ *   out_raw (optional) receives the un-normalised f32 sums for training-mode batch statistics.
+ * ab_head_decode: logits f32 [B, H*W, ncls*D] (channel = cls*D + d) -> kp3d f32 [B,ncls,3] = (u,v,d) in [0,1),
+ *   confd f32 [B,ncls]: IntegralDeconvHead.forward after the final conv (simplebaseline.py:182-190).            */
+AB_API int ab_image_to_nhwc(const float* image, int B, int C, int H, int W, int Cp, void* out, void* stream);
+AB_API int ab_im2col_nhwc(const void* in, int B, int H, int W, int C, int kh, int kw, int stride, int pad, int Kp,
+                          void* out, void* stream);
+AB_API int ab_maxpool3x3s2_nhwc(const void* in, int B, int H, int W, int C, void* out, void* stream);
+AB_API int ab_avgpool_nhwc(const void* in, int B, int HW, int C, float* out_f32, void* out_bf16, void* stream);
+AB_API int ab_deconv4x4s2_col2im(const float* ycol, int B, int H, int W, int Cout, const float* scale, const float* bias,
+                                 int relu, void* out_bf16, float* out_raw, void* stream);
+AB_API int ab_head_decode(const float* logits, int B, int ncls, int D, int H, int W, float* kp3d, float* confd,
+                          void* stream);
 
 #ifdef __cplusplus
 }
