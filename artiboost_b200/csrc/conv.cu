@@ -73,6 +73,32 @@ __global__ void im2col_scalar_kernel(const __nv_bfloat16* __restrict__ in, int B
     out[i] = v;
 }
 
+// C == 4 (the RGB image padded to 4 channels: 8 bytes per pixel).  One thread per (output row, filter row ky): the kw
+// pixels of a filter row are contiguous in NHWC, copied as kw 8-byte loads / stores; the last filter row's thread also
+// zero-fills the K padding.
+__global__ void im2col_c4_kernel(const uint2* __restrict__ in, int B, int H, int W, int kh, int kw, int stride, int pad,
+                                 int Ho, int Wo, int Kp4, uint2* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Ho * Wo * kh;
+    if (i >= total) return;
+    const int ky = (int)(i % kh);
+    const long long m = i / kh;
+    const int ox = (int)(m % Wo);
+    const long long t = m / Wo;
+    const int oy = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const int iy = oy * stride - pad + ky, ix0 = ox * stride - pad;
+    uint2* o = out + m * Kp4 + ky * kw;
+    const bool row_ok = iy >= 0 && iy < H;
+    const uint2* src = in + ((long long)b * H + (row_ok ? iy : 0)) * W;
+    for (int kx = 0; kx < kw; ++kx) {
+        const int ix = ix0 + kx;
+        o[kx] = (row_ok && ix >= 0 && ix < W) ? __ldg(src + ix) : make_uint2(0, 0);
+    }
+    if (ky == kh - 1)
+        for (int k = kh * kw; k < Kp4; ++k) out[m * Kp4 + k] = make_uint2(0, 0);
+}
+
 __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
     uint4 r;
     const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
@@ -254,6 +280,11 @@ extern "C" int ab_im2col_nhwc(const void* in, int B, int H, int W, int C, int kh
         const long long total = (long long)B * Ho * Wo * (Kp / 8);
         im2col_vec8_kernel<<<blocks_for(total, 256), 256, 0, st>>>((const uint4*)in, B, H, W, C / 8, kh, kw, stride, pad, Ho,
                                                                    Wo, Kp / 8, (uint4*)out);
+    } else if (C == 4 && Kp % 4 == 0) {
+        AB_REQUIRE(((uintptr_t)in & 7) == 0 && ((uintptr_t)out & 7) == 0, "8-byte alignment required");
+        const long long total = (long long)B * Ho * Wo * kh;
+        im2col_c4_kernel<<<blocks_for(total, 256), 256, 0, st>>>((const uint2*)in, B, H, W, kh, kw, stride, pad, Ho, Wo, Kp / 4,
+                                                                 (uint2*)out);
     } else {
         const long long total = (long long)B * Ho * Wo * Kp;
         im2col_scalar_kernel<<<blocks_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)in, B, H, W, C, kh, kw, stride,

@@ -95,6 +95,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+
+// Implicit-GEMM geometry: the A operand is the NHWC activation itself, fetched by TMA in im2col mode -- one
+// (filter tap, 64-channel slice) per k-block, 128 consecutive output pixels per tile, padding zero-filled by the
+// TMA unit.  K index of the packed filter matrix = tap * C + channel (pack_conv_weight order).
+struct ConvGeom {
+    int Ho, Wo, stride, pad, kw, cblocks;  // cblocks = C / 64
+};
+
 // K-major operand tile in shared memory, rows of 64 bf16 (128 B), 128-byte swizzle, 8-row atoms of 1024 B:
 // start address >> 4 | LBO (ignored for swizzled K-major) = 1 | SBO = 1024 B >> 4 | version 1 (Blackwell) | SWIZZLE_128B
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(const void* smem_tile) {
@@ -109,10 +124,10 @@ struct GemmSmem {
     uint32_t tmem_base;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool IM2COL>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                    const GemmEpilogue ep) {
+                    const GemmEpilogue ep, const ConvGeom cg) {
     extern __shared__ uint8_t smem_raw[];
     auto& sm = *reinterpret_cast<GemmSmem<BN, STAGES>*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,12 +151,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {
+            int base_w = 0, base_h = 0, img = 0;
+            if (IM2COL) {  // first output pixel of this tile -> top-left input pixel of its filter window
+                const int m0 = tile_m * kBM, per = cg.Ho * cg.Wo;
+                img = m0 / per;
+                const int r = m0 - img * per, oy = r / cg.Wo, ox = r - oy * cg.Wo;
+                base_w = ox * cg.stride - cg.pad;
+                base_h = oy * cg.stride - cg.pad;
+            }
             for (int kb = 0; kb < num_k; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&sm.empty[s], ph ^ 1);
                 mbar_expect_tx(&sm.full[s], (kBM + BN) * kBK * 2);
-                tma_load_2d(sm.a[s], &tmA, &sm.full[s], kb * kBK, tile_m * kBM);
+                if (IM2COL) {
+                    const int tap = kb / cg.cblocks, cb = kb - tap * cg.cblocks;
+                    const int ky = tap / cg.kw, kx = tap - ky * cg.kw;
+                    tma_load_im2col_4d(sm.a[s], &tmA, &sm.full[s], cb * kBK, base_w, base_h, img, (uint16_t)kx, (uint16_t)ky);
+                } else {
+                    tma_load_2d(sm.a[s], &tmA, &sm.full[s], kb * kBK, tile_m * kBM);
+                }
                 tma_load_2d(sm.b[s], &tmB, &sm.full[s], kb * kBK, tile_n * BN);
             }
         }
@@ -266,17 +295,53 @@ static int make_map(CUtensorMap* m, const void* ptr, long long rows, long long c
     return AB_OK;
 }
 
-template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t st) {
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn get_encode_im2col() {
+    static EncodeIm2colFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess && p) fn = (EncodeIm2colFn)p;
+    }
+    return fn;
+}
+
+// im2col-mode map over an NHWC bf16 activation [B,H,W,C]: 64 channels x 128 output pixels per load.  The pixel box
+// corners bound the TOP-LEFT pixel of the filter window: [-pad, W - 1 + pad - (kw - 1)] (the CUTLASS fprop convention).
+static int make_im2col_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int kh, int kw, int stride, int pad) {
+    EncodeIm2colFn enc = get_encode_im2col();
+    if (!enc) { set_error("cuTensorMapEncodeIm2col unavailable"); return AB_ERR_UNSUPPORTED; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    int lower[2] = {-pad, -pad};
+    int upper[2] = {pad - (kw - 1), pad - (kh - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper, (cuuint32_t)kBK,
+                     (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed (%d)", (int)r); return AB_ERR_ARG; }
+    // driver workaround carried by CUTLASS (copy_traits_sm90_im2col.hpp): small tensors must not set bit 21 of word 1
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    if (drv <= 13010 && (size_t)B * H * W * C * 2 < 131072) reinterpret_cast<uint64_t*>(m)[1] &= ~(1llu << 21);
+    return AB_OK;
+}
+
+template <int BN, int STAGES, bool IM2COL>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpilogue& ep,
+                       const ConvGeom& cg, cudaStream_t st) {
     const size_t smem = sizeof(GemmSmem<BN, STAGES>) + 1024;
     static bool configured = false;
     if (!configured) {
-        AB_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AB_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, STAGES, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid(cdiv(M, kBM), cdiv(N, BN));
-    StageTimer tm(AB_STAGE_GEMM, st);
-    gemm_bf16_tn_kernel<BN, STAGES><<<grid, kGemmThreads, smem, st>>>(ta, tb, M, N, K, ep);
+    StageTimer tm(IM2COL ? AB_STAGE_CONV_IMPLICIT : AB_STAGE_GEMM, st);
+    gemm_bf16_tn_kernel<BN, STAGES, IM2COL><<<grid, kGemmThreads, smem, st>>>(ta, tb, M, N, K, ep, cg);
     count_launch();
     return check_launch("gemm_bf16_tn_kernel");
 }
@@ -290,7 +355,23 @@ int gemm_bf16_tn(int M, int N, int K, const void* A, long long lda, const void* 
     if (rc) return rc;
     rc = make_map(&tb, B, N, K, ldb, bn);
     if (rc) return rc;
-    return bn == 64 ? launch_gemm<64, 4>(ta, tb, M, N, K, ep, st) : launch_gemm<128, 3>(ta, tb, M, N, K, ep, st);
+    const ConvGeom cg{};
+    return bn == 64 ? launch_gemm<64, 4, false>(ta, tb, M, N, K, ep, cg, st) : launch_gemm<128, 3, false>(ta, tb, M, N, K, ep, cg, st);
+}
+
+// Convolution as implicit GEMM: x bf16 NHWC [B,H,W,C] (C % 64 == 0), w packed [Cout, kh*kw*C] (K order ky, kx, c).
+int conv_bf16_implicit(const void* x, int B, int H, int W, int C, const void* w, int Cout, int kh, int kw, int stride, int pad,
+                       const GemmEpilogue& ep, cudaStream_t st) {
+    const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+    const int M = B * Ho * Wo, K = kh * kw * C;
+    const int bn = (Cout <= 64) ? 64 : 128;
+    CUtensorMap ta, tb;
+    int rc = make_im2col_map(&ta, x, B, H, W, C, kh, kw, stride, pad);
+    if (rc) return rc;
+    rc = make_map(&tb, w, Cout, K, K, bn);
+    if (rc) return rc;
+    const ConvGeom cg{Ho, Wo, stride, pad, kw, C / kBK};
+    return bn == 64 ? launch_gemm<64, 4, true>(ta, tb, M, Cout, K, ep, cg, st) : launch_gemm<128, 3, true>(ta, tb, M, Cout, K, ep, cg, st);
 }
 
 }  // namespace ab
@@ -311,4 +392,24 @@ extern "C" int ab_gemm_bf16(int M, int N, int K, const void* A, int64_t lda, con
     ep.D = D; ep.ldd = ldd; ep.out_fp32 = out_fp32; ep.scale = scale; ep.bias = bias;
     ep.residual = (const __nv_bfloat16*)residual; ep.ldr = ldr; ep.relu = relu; ep.col_sum = col_sum; ep.col_sumsq = col_sumsq;
     return ab::gemm_bf16_tn(M, N, K, A, lda, B, ldb, ep, (cudaStream_t)stream);
+}
+
+extern "C" int ab_conv_bf16_nhwc(const void* x, int B, int H, int W, int C, const void* w_packed, int Cout, int kh, int kw,
+                                 int stride, int pad, void* D, int64_t ldd, int out_fp32, const float* scale,
+                                 const float* bias, const void* residual, int64_t ldr, int relu, float* col_sum,
+                                 float* col_sumsq, void* stream) {
+    AB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, "bad shape");
+    if (B == 0) return AB_OK;
+    AB_REQUIRE(C % 64 == 0, "implicit-GEMM convolution needs C % 64 == 0 (use ab_im2col_nhwc + ab_gemm_bf16 otherwise)");
+    AB_REQUIRE(kh <= 16 && kw <= 16 && pad < kh && pad < kw, "filter / padding out of range");
+    AB_REQUIRE(x && w_packed && D, "null pointer");
+    AB_REQUIRE(Cout % 8 == 0 && ldd % 8 == 0 && (!residual || ldr % 8 == 0), "Cout, ldd, ldr must be multiples of 8");
+    AB_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)D & 15) == 0 &&
+                   ((uintptr_t)residual & 15) == 0, "tensors must be 16-byte aligned");
+    AB_REQUIRE((col_sum == nullptr) == (col_sumsq == nullptr), "col_sum and col_sumsq go together");
+    AB_REQUIRE((long long)B * H * W < (1ll << 31), "too many pixels");
+    ab::GemmEpilogue ep;
+    ep.D = D; ep.ldd = ldd; ep.out_fp32 = out_fp32; ep.scale = scale; ep.bias = bias;
+    ep.residual = (const __nv_bfloat16*)residual; ep.ldr = ldr; ep.relu = relu; ep.col_sum = col_sum; ep.col_sumsq = col_sumsq;
+    return ab::conv_bf16_implicit(x, B, H, W, C, w_packed, Cout, kh, kw, stride, pad, ep, (cudaStream_t)stream);
 }

@@ -30,6 +30,7 @@ class Act:
 
 
 _cache = {}
+IMPLICIT_CONV = True  # False: materialise im2col rows (ab_im2col_nhwc) and run the plain GEMM, for A/B comparison
 
 
 def _cached(key, versions, build):
@@ -49,10 +50,14 @@ def _pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
-def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
-    """[Cout, Cin, kh, kw] fp32 -> bf16 [Cout, Kp], K order (ky, kx, ci), zero padded to a multiple of 8."""
+def pack_conv_weight(w: torch.Tensor, cin_pad: int = 0) -> torch.Tensor:
+    """[Cout, Cin, kh, kw] fp32 -> bf16 [Cout, Kp], K order (ky, kx, ci), zero padded to a multiple of 8.
+    cin_pad > Cin pads the input-channel axis with zeros first (the 3-channel image travels as 4 channels)."""
     cout = w.shape[0]
-    m = w.detach().permute(0, 2, 3, 1).reshape(cout, -1)
+    m = w.detach().permute(0, 2, 3, 1)
+    if cin_pad > m.shape[3]:
+        m = torch.nn.functional.pad(m, (0, cin_pad - m.shape[3]))
+    m = m.reshape(cout, -1)
     kp = _pad8(m.shape[1])
     out = torch.zeros((cout, kp), dtype=torch.bfloat16, device=w.device)
     out[:, :m.shape[1]] = m.to(torch.bfloat16)
@@ -77,14 +82,16 @@ def bn_affine(bn, training: bool):
 
 
 def image_to_act(image: torch.Tensor) -> Act:
+    """f32 NCHW image -> bf16 NHWC with the channel count padded to a multiple of 4 (RGB -> 8 bytes per pixel)."""
     lib.require_cuda(image, "image")
     B, C, H, W = image.shape
+    cp = (C + 3) // 4 * 4
     img = image.contiguous().float()
-    out = torch.empty((B * H * W, C), dtype=torch.bfloat16, device=image.device)
+    out = torch.empty((B * H * W, cp), dtype=torch.bfloat16, device=image.device)
     with torch.cuda.device(image.device):
-        rc = lib.load().ab_image_to_nhwc(img.data_ptr(), B, C, H, W, C, out.data_ptr(), lib.stream_ptr(image.device))
+        rc = lib.load().ab_image_to_nhwc(img.data_ptr(), B, C, H, W, cp, out.data_ptr(), lib.stream_ptr(image.device))
     lib.check(rc, "ab_image_to_nhwc")
-    return Act(out, B, H, W, C)
+    return Act(out, B, H, W, cp)
 
 
 def conv_bn_act(x: Act, conv: nn.Conv2d, bn=None, relu: bool = False, residual: Optional[Act] = None,
@@ -94,13 +101,24 @@ def conv_bn_act(x: Act, conv: nn.Conv2d, bn=None, relu: bool = False, residual: 
     stride, pad = conv.stride[0], conv.padding[0]
     cout = conv.out_channels
     assert conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1] and conv.groups == 1
-    wp = _cached(("w", id(conv)), _ver(conv.weight), lambda: pack_conv_weight(conv.weight))
+    wp = _cached(("w", id(conv), x.C), _ver(conv.weight), lambda: pack_conv_weight(conv.weight, x.C))
     scale, bias = bn_affine(bn, training)
     if conv.bias is not None:
         cb = conv.bias.detach().float()
         bias = cb if bias is None else bias + cb * scale
     Ho, Wo = (x.H + 2 * pad - kh) // stride + 1, (x.W + 2 * pad - kw) // stride + 1
     dev = x.data.device
+    if IMPLICIT_CONV and x.C % 64 == 0 and not (kh == 1 and kw == 1 and stride == 1):
+        # implicit GEMM: the activation is the A operand, gathered by TMA in im2col mode
+        out = torch.empty((x.B * Ho * Wo, cout), dtype=torch.float32 if out_fp32 else torch.bfloat16, device=dev)
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        with torch.cuda.device(dev):
+            rc = lib.load().ab_conv_bf16_nhwc(x.data.data_ptr(), x.B, x.H, x.W, x.C, wp.data_ptr(), cout, kh, kw, stride, pad,
+                                              out.data_ptr(), cout, int(out_fp32), p(scale), p(bias),
+                                              None if residual is None else residual.data.data_ptr(), cout, int(relu),
+                                              None, None, lib.stream_ptr(dev))
+        lib.check(rc, "ab_conv_bf16_nhwc")
+        return out if out_fp32 else Act(out, x.B, Ho, Wo, cout)
     if kh == 1 and kw == 1 and stride == 1 and pad == 0 and x.C % 8 == 0:
         a = x.data
     else:

@@ -256,9 +256,101 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
+    if world == 1 and not args.no_network:
+        try:
+            line["extras"] = {"network_forward_configs2": network_forward_bench(dev)}
+        except Exception as e:  # the secondary workload must never cost the headline line
+            line["extras"] = {"network_forward_configs2": {"error": repr(e)}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------ secondary workload: network forward
+def torch_forward(model, inputs):
+    """Plain torch.nn / cuDNN evaluation of the same clasbased modules (the reference's own path: fp32 NCHW,
+    anakin/models/resnet.py:199-221, simplebaseline.py:177-190, mlp.py:24).  Baseline leg only."""
+    import torch
+    import torch.nn.functional as F
+    hb = model.model_list[0]
+    bb, head = hb.backbone, hb.hybrid_head
+    x = inputs["image"]
+    x = bb.maxpool(bb.relu(bb.bn1(bb.conv1(x))))
+    for name in ("layer1", "layer2", "layer3", "layer4"):
+        for blk in getattr(bb, name):
+            r = x if blk.downsample is None else blk.downsample(x)
+            if hasattr(blk, "conv3"):
+                o = blk.relu(blk.bn1(blk.conv1(x)))
+                o = blk.relu(blk.bn2(blk.conv2(o)))
+                o = blk.bn3(blk.conv3(o))
+            else:
+                o = blk.relu(blk.bn1(blk.conv1(x)))
+                o = blk.bn2(blk.conv2(o))
+            x = blk.relu(o + r)
+    mean = x.mean(3).mean(2)
+    h = head.final_layer(head.deconv_layers(x))
+    h = F.softmax(h.reshape(h.shape[0], head.nclasses, -1), 2)
+    confd = h.max(-1).values
+    h = (h / (h.sum(-1, keepdim=True) + 1e-7)).view(h.shape[0], head.nclasses, head.depth_res, head.height_res, head.width_res)
+    u = (h.sum(dim=[2, 3]) * (torch.arange(head.width_res, device=h.device) / head.width_res)).sum(-1)
+    v = (h.sum(dim=[2, 4]) * (torch.arange(head.height_res, device=h.device) / head.height_res)).sum(-1)
+    d = (h.sum(dim=[3, 4]) * (torch.arange(head.depth_res, device=h.device) / head.depth_res)).sum(-1)
+    rot6d = hb.box_head.layers(mean)
+    return torch.stack([u, v, d], -1), confd, rot6d
+
+
+def network_forward_bench(dev, batch=128, steps=10, warmup=3):
+    """BASELINE.json configs[2]: clasbased forward-only, synthetic 256x256 batch, tensor-core conv path; with the
+    reference's torch.nn / cuDNN path (fp32, and bf16 autocast as a stronger baseline) timed beside it."""
+    import torch
+
+    import artiboost_b200.models as M
+    from artiboost_b200 import lib
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import netcfg
+    out = {}
+    flops = {"ResNet34": 10.70e9, "ResNet50": 12.61e9}  # fwd FLOPs / image at 256^2, measured on the reference (BASELINE.md)
+    for backbone in ("ResNet50", "ResNet34"):
+        arch, preset = netcfg.arch_cfg(backbone)
+        torch.manual_seed(1)
+        model = M.Arch({"ARCH": arch}, M.build_arch_model_list(arch, preset_cfg=preset)).eval()
+        netcfg.randomise_bn(model)
+        model = model.to(dev)
+        inp = {k: v.to(dev) for k, v in netcfg.make_inputs(batch).items()}
+
+        def timed(fn):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / steps
+
+        with torch.no_grad():
+            lib.profile_enable(True)
+            ms = timed(lambda: model(inp))
+            lib.profile_enable(False)
+            stages = lib.profile_collect()
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            ms_fp32 = timed(lambda: torch_forward(model, inp))
+            ci = dict(inp, image=inp["image"].contiguous(memory_format=torch.channels_last))
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                ms_bf16 = timed(lambda: torch_forward(model, ci))
+        gemm_ms = stages.get("gemm_bf16_tn_kernel", (0.0, 0))[0] / (steps + warmup)
+        out[backbone] = {
+            "batch": batch, "images_per_s": batch / ms * 1e3, "ms_per_step": ms,
+            "tflops": batch * flops[backbone] / ms / 1e9, "frac_of_bf16_sustained_peak": batch * flops[backbone] / ms / 1e9 / 1364.6,
+            "stage_ms_per_step": {k: v[0] / (steps + warmup) for k, v in stages.items()},
+            "gemm_tflops_in_kernel": batch * flops[backbone] / gemm_ms / 1e9 if gemm_ms else None,
+            "torch_cudnn_fp32_images_per_s": batch / ms_fp32 * 1e3, "torch_cudnn_bf16_autocast_images_per_s": batch / ms_bf16 * 1e3,
+        }
+        del model
+    return out
 
 
 def main():
@@ -269,6 +361,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-network", action="store_true", help="skip the secondary network-forward measurement")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: `python bench.py --gpus N` re-launches itself as one rank per GPU like the driver does

@@ -57,6 +57,7 @@ AB_API uint64_t ab_launch_count(void);
 #define AB_STAGE_IM2COL 8
 #define AB_STAGE_ELEMENTWISE 9
 #define AB_STAGE_HEAD_DECODE 10
+#define AB_STAGE_CONV_IMPLICIT 11
 #define AB_STAGE_COUNT 16
 AB_API int ab_profile_enable(int on);
 AB_API int ab_profile_collect(double* ms_per_stage, int64_t* launches_per_stage, int n_stages);
@@ -162,6 +163,14 @@ AB_API int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int batc
 AB_API int ab_gemm_bf16(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
                         int out_fp32, const float* scale, const float* bias, const void* residual, int64_t ldr, int relu,
                         float* col_sum, float* col_sumsq, void* stream);
+
+/* Convolution as implicit GEMM (anakin/models/resnet.py:72-152 conv3x3 / 1x1 stride-2 downsample): x bf16 NHWC
+ * [B,H,W,C] with C % 64 == 0, w_packed bf16 [Cout, kh*kw*C] with K order (ky, kx, c).  The A operand is fetched by TMA
+ * in im2col mode (one filter tap x 64 channels per k-block, padding zero-filled by the TMA unit), so no im2col matrix
+ * is ever materialised.  D [B*Ho*Wo, Cout] and the epilogue arguments as in ab_gemm_bf16.                     */
+AB_API int ab_conv_bf16_nhwc(const void* x, int B, int H, int W, int C, const void* w_packed, int Cout, int kh, int kw,
+                             int stride, int pad, void* D, int64_t ldd, int out_fp32, const float* scale, const float* bias,
+                             const void* residual, int64_t ldr, int relu, float* col_sum, float* col_sumsq, void* stream);
 
 /* ------------------------------------------------------------------- data movement around the contraction (NHWC bf16)
  * Activations are bf16 NHWC ([B,H,W,C], C contiguous) between layers; the reference keeps fp32 NCHW and lets cuDNN

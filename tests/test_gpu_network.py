@@ -80,12 +80,14 @@ def test_gemm_argument_errors():
 
 # ------------------------------------------------------------------------------------------------- primitives
 def to_act(x_nchw):
-    from artiboost_b200.models.nhwc import Act
+    from artiboost_b200.models.nhwc import Act, image_to_act
     B, C, H, W = x_nchw.shape
+    if C == 3:
+        return image_to_act(x_nchw)  # the stem's path: padded to 4 channels
     return Act(bf(x_nchw).permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous(), B, H, W, C)
 
 
-@pytest.mark.parametrize("cin,cout,k,s,p,hw", [(3, 64, 7, 2, 3, 64), (64, 64, 3, 1, 1, 32), (64, 128, 3, 2, 1, 32),
+@pytest.mark.parametrize("cin,cout,k,s,p,hw", [(3, 64, 7, 2, 3, 64), (3, 64, 7, 2, 3, 37), (40, 64, 3, 1, 1, 16), (64, 64, 3, 1, 1, 32), (64, 128, 3, 2, 1, 32),
                                                (64, 128, 1, 2, 0, 32), (256, 64, 1, 1, 0, 16), (128, 128, 3, 1, 1, 15)])
 def test_conv_bn_relu_residual_matches_torch(cin, cout, k, s, p, hw):
     from artiboost_b200.models import nhwc
