@@ -58,6 +58,7 @@ AB_API uint64_t ab_launch_count(void);
 #define AB_STAGE_ELEMENTWISE 9
 #define AB_STAGE_HEAD_DECODE 10
 #define AB_STAGE_CONV_IMPLICIT 11
+#define AB_STAGE_WGRAD 12
 #define AB_STAGE_COUNT 16
 AB_API int ab_profile_enable(int on);
 AB_API int ab_profile_collect(double* ms_per_stage, int64_t* launches_per_stage, int n_stages);
@@ -171,6 +172,16 @@ AB_API int ab_gemm_bf16(int M, int N, int K, const void* A, int64_t lda, const v
 AB_API int ab_conv_bf16_nhwc(const void* x, int B, int H, int W, int C, const void* w_packed, int Cout, int kh, int kw,
                              int stride, int pad, void* D, int64_t ldd, int out_fp32, const float* scale, const float* bias,
                              const void* residual, int64_t ldr, int relu, float* col_sum, float* col_sumsq, void* stream);
+
+/* Weight gradients (the wgrad half of loss.backward() at train/train_artiboost.py:91-93, cuDNN wgrad in the
+ * reference).  D[Mo,No] += sum_p G[p,mo] * X[p,no], fp32 atomic accumulation into a caller-zeroed D (pitch ldd):
+ * G = dY bf16 [P,Mo], X bf16 [P,No] (ab_wgrad_bf16), or X = the NHWC activation read through TMA im2col
+ * (ab_conv_wgrad_bf16_nhwc: dw_packed f32 [Cout, kh*kw*C], K order (ky,kx,c), C % 64 == 0).  The reduction runs
+ * over operand rows: both operands are MN-major for tcgen05; the pixel axis is split across CTAs.               */
+AB_API int ab_wgrad_bf16(int P, int Mo, int No, const void* G, int64_t ldg, const void* X, int64_t ldx, float* D, int64_t ldd,
+                         void* stream);
+AB_API int ab_conv_wgrad_bf16_nhwc(const void* x, int B, int H, int W, int C, const void* dy, int Cout, int kh, int kw,
+                                   int stride, int pad, float* dw_packed, void* stream);
 
 /* ------------------------------------------------------------------- data movement around the contraction (NHWC bf16)
  * Activations are bf16 NHWC ([B,H,W,C], C contiguous) between layers; the reference keeps fp32 NCHW and lets cuDNN
