@@ -1,0 +1,561 @@
+// Training-side kernels of the clasbased network (NHWC bf16 activations, fp32 statistics / parameter gradients):
+// what torch.nn.BatchNorm2d / ReLU / MaxPool2d / autograd do around the convolutions in the reference's train step
+// (anakin/models/resnet.py:72-152, simplebaseline.py:161-190, train/train_artiboost.py:91-96).
+//
+//   ab_col_stats          per-column sum / sum of squares of a [M,C] bf16 or fp32 matrix (BN batch statistics, bias grads)
+//   ab_bn_finalize        mean / biased var -> (scale, shift) for the apply pass, saved mean / invstd, running-stat update
+//   ab_bn_apply           y = relu(raw * scale + shift (+ residual))
+//   ab_bn_bwd_reduce      dy' = dy * (y > 0);  sum(dy'), sum(dy' * xhat)   (= dbeta, dgamma)
+//   ab_bn_bwd_apply       dx = gamma * invstd * (dy' - mean(dy') - xhat * mean(dy' * xhat));  optional copy of dy'
+//   ab_maxpool3x3s2_bwd, ab_avgpool_bwd, ab_dilate2x (zero insertion for stride-2 data gradients),
+//   ab_deconv4x4s2_gather (transpose of the col2im gather), ab_head_decode_bwd (softmax / soft-argmax backward),
+//   ab_adam_step + ab_sumsq (fused multi-tensor Adam with gradient-norm clipping, train_artiboost.py:94-96)
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ab {
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& v, float* f) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 t = __bfloat1622float2(p[j]);
+        f[2 * j] = t.x; f[2 * j + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 float_to_bf16x8(const float* f) {
+    uint4 v;
+    __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    return v;
+}
+
+constexpr int kRedThreads = 256;
+constexpr int kRedRows = 512;  // rows per CTA in the column reductions
+
+// Column reduction skeleton: thread t owns column group g = t % C8 and visits rows r0 + t / C8 + k * (256 / C8); the
+// CTA's partial sums are combined in shared memory and issued as one atomic per (CTA, column).
+template <int NACC, class RowFn>
+__device__ __forceinline__ void column_reduce(int M, int C8, float* const* out, RowFn fn) {
+    __shared__ float red[kRedThreads][8 * NACC + 1];
+    const int t = threadIdx.x;
+    const int tpr = min(C8, kRedThreads);       // threads per row
+    const int rows_par = kRedThreads / tpr;     // rows visited in parallel
+    const int g0 = t % tpr, rl = t / tpr;
+    const long long r_begin = (long long)blockIdx.x * kRedRows;
+    const long long r_end = min((long long)M, r_begin + kRedRows);
+    for (int g = g0; g < C8; g += tpr) {
+        float acc[8 * NACC];
+#pragma unroll
+        for (int j = 0; j < 8 * NACC; ++j) acc[j] = 0.0f;
+        if (rl < rows_par)
+            for (long long r = r_begin + rl; r < r_end; r += rows_par) fn(r, g, acc);
+#pragma unroll
+        for (int j = 0; j < 8 * NACC; ++j) red[t][j] = acc[j];
+        __syncthreads();
+        if (rl == 0) {
+            for (int k = 1; k < rows_par; ++k)
+#pragma unroll
+                for (int j = 0; j < 8 * NACC; ++j) acc[j] += red[t + k * tpr][j];
+#pragma unroll
+            for (int a = 0; a < NACC; ++a)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) atomicAdd(out[a] + 8 * g + j, acc[8 * a + j]);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+col_stats_bf16_kernel(const uint4* __restrict__ x, int M, int C8, long long ld8, float* sum, float* sumsq) {
+    float* outs[2] = {sum, sumsq};
+    if (sumsq) {
+        column_reduce<2>(M, C8, outs, [&](long long r, int g, float* acc) {
+            float f[8];
+            bf16x8_to_float(__ldg(x + r * ld8 + g), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[j] += f[j]; acc[8 + j] += f[j] * f[j]; }
+        });
+    } else {
+        column_reduce<1>(M, C8, outs, [&](long long r, int g, float* acc) {
+            float f[8];
+            bf16x8_to_float(__ldg(x + r * ld8 + g), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        });
+    }
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+col_stats_f32_kernel(const float4* __restrict__ x, int M, int C8, long long ld4, float* sum, float* sumsq) {
+    float* outs[2] = {sum, sumsq};
+    auto load = [&](long long r, int g, float* f) {
+        const float4 a = __ldg(x + r * ld4 + 2 * g), b = __ldg(x + r * ld4 + 2 * g + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    };
+    if (sumsq) {
+        column_reduce<2>(M, C8, outs, [&](long long r, int g, float* acc) {
+            float f[8];
+            load(r, g, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[j] += f[j]; acc[8 + j] += f[j] * f[j]; }
+        });
+    } else {
+        column_reduce<1>(M, C8, outs, [&](long long r, int g, float* acc) {
+            float f[8];
+            load(r, g, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        });
+    }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, int C, float count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                                   float* scale, float* shift, float* save_mean, float* save_invstd, float* running_mean,
+                                   float* running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float mean = sum[c] / count;
+    const float var = fmaxf(sumsq[c] / count - mean * mean, 0.0f);  // biased, as used for normalisation
+    const float invstd = rsqrtf(var + eps);
+    const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+    scale[c] = g * invstd;
+    shift[c] = b - mean * g * invstd;
+    save_mean[c] = mean;
+    save_invstd[c] = invstd;
+    if (running_mean) {
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean;
+        const float unbiased = count > 1.0f ? var * count / (count - 1.0f) : var;
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * unbiased;
+    }
+}
+
+__global__ void bn_apply_kernel(const uint4* __restrict__ raw, long long n8, int C8, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const uint4* __restrict__ residual, int relu,
+                                uint4* __restrict__ y) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const int g = (int)(i % C8);
+    float f[8], r[8];
+    bf16x8_to_float(__ldg(raw + i), f);
+    if (residual) bf16x8_to_float(__ldg(residual + i), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float v = fmaf(f[j], scale[8 * g + j], shift[8 * g + j]);
+        if (residual) v += r[j];
+        f[j] = relu ? fmaxf(v, 0.0f) : v;
+    }
+    y[i] = float_to_bf16x8(f);
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ raw, int M, int C8,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu, float* sum_dy,
+                     float* sum_dy_xhat) {
+    float* outs[2] = {sum_dy, sum_dy_xhat};
+    column_reduce<2>(M, C8, outs, [&](long long r, int g, float* acc) {
+        float d[8], yy[8], x[8];
+        bf16x8_to_float(__ldg(dy + r * C8 + g), d);
+        bf16x8_to_float(__ldg(raw + r * C8 + g), x);
+        if (relu) bf16x8_to_float(__ldg(y + r * C8 + g), yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float dd = (relu && !(yy[j] > 0.0f)) ? 0.0f : d[j];
+            acc[j] += dd;
+            acc[8 + j] += dd * (x[j] - mean[8 * g + j]) * invstd[8 * g + j];
+        }
+    });
+}
+
+__global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ raw,
+                                    long long n8, int C8, float inv_count, const float* __restrict__ gamma,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ sum_dy, const float* __restrict__ sum_dy_xhat, int relu,
+                                    uint4* __restrict__ dx, uint4* __restrict__ dres) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const int g = (int)(i % C8);
+    float d[8], yy[8], x[8], o[8];
+    bf16x8_to_float(__ldg(dy + i), d);
+    bf16x8_to_float(__ldg(raw + i), x);
+    if (relu) bf16x8_to_float(__ldg(y + i), yy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = 8 * g + j;
+        const float dd = (relu && !(yy[j] > 0.0f)) ? 0.0f : d[j];
+        d[j] = dd;
+        const float xhat = (x[j] - mean[c]) * invstd[c];
+        const float gm = gamma ? gamma[c] : 1.0f;
+        o[j] = gm * invstd[c] * (dd - sum_dy[c] * inv_count - xhat * sum_dy_xhat[c] * inv_count);
+    }
+    dx[i] = float_to_bf16x8(o);
+    if (dres) dres[i] = float_to_bf16x8(d);
+}
+
+// eval-mode / frozen BN inside a training graph, or plain ReLU: dx = dy * (y > 0) * scale
+__global__ void affine_relu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, long long n8, int C8,
+                                       const float* __restrict__ scale, int relu, uint4* __restrict__ dx,
+                                       uint4* __restrict__ dres) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const int g = (int)(i % C8);
+    float d[8], yy[8], o[8];
+    bf16x8_to_float(__ldg(dy + i), d);
+    if (relu) bf16x8_to_float(__ldg(y + i), yy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        d[j] = (relu && !(yy[j] > 0.0f)) ? 0.0f : d[j];
+        o[j] = d[j] * (scale ? scale[8 * g + j] : 1.0f);
+    }
+    dx[i] = float_to_bf16x8(o);
+    if (dres) dres[i] = float_to_bf16x8(d);
+}
+
+// MaxPool2d(3, 2, 1) backward, gather form: input pixel (iy, ix) receives dy of every window whose FIRST maximum (scan
+// order ky, kx -- torch's tie-break) it is.  bf16 activations tie often enough for the rule to matter.
+__global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const uint4* __restrict__ dy,
+                                   int B, int H, int W, int C8, int Ho, int Wo, uint4* __restrict__ dx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * H * W * C8;
+    if (i >= total) return;
+    const int g = (int)(i % C8);
+    long long t = i / C8;
+    const int ix = (int)(t % W);
+    t /= W;
+    const int iy = (int)(t % H);
+    const int b = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    // windows oy with 2*oy - 1 <= iy <= 2*oy + 1
+    for (int oy = max(iy / 2, 0); oy <= min((iy + 1) / 2, Ho - 1); ++oy)
+        for (int ox = max(ix / 2, 0); ox <= min((ix + 1) / 2, Wo - 1); ++ox) {
+            const long long o = (((long long)b * Ho + oy) * Wo + ox) * C8 + g;
+            float yv[8], dv[8];
+            bf16x8_to_float(__ldg(y + o), yv);
+            bf16x8_to_float(__ldg(dy + o), dv);
+            bool taken[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) taken[j] = false;
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int wy = 2 * oy - 1 + ky, wx = 2 * ox - 1 + kx;
+                    if (wy < 0 || wy >= H || wx < 0 || wx >= W) continue;
+                    float xv[8];
+                    bf16x8_to_float(__ldg(x + (((long long)b * H + wy) * W + wx) * C8 + g), xv);
+                    const bool me = (wy == iy && wx == ix);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (!taken[j] && xv[j] == yv[j]) {
+                            taken[j] = true;
+                            if (me) acc[j] += dv[j];
+                        }
+                    }
+                }
+        }
+    dx[i] = float_to_bf16x8(acc);
+}
+
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dmean, int B, int HW, int C8, uint4* __restrict__ dx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * HW * C8;
+    if (i >= total) return;
+    const int g = (int)(i % C8);
+    const int b = (int)(i / ((long long)HW * C8));
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = dmean[(long long)b * C8 * 8 + 8 * g + j] / (float)HW;
+    dx[i] = float_to_bf16x8(f);
+}
+
+// out[b, 2*oy, 2*ox, :] = in[b, oy, ox, :], zeros elsewhere; out is [B, H, W, C] (H, W of the stride-2 conv's input)
+__global__ void dilate2x_kernel(const uint4* __restrict__ in, int B, int Ho, int Wo, int H, int W, int C8, uint4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * H * W * C8;
+    if (i >= total) return;
+    const int g = (int)(i % C8);
+    long long t = i / C8;
+    const int x = (int)(t % W);
+    t /= W;
+    const int y = (int)(t % H);
+    const int b = (int)(t / H);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!(x & 1) && !(y & 1) && (y >> 1) < Ho && (x >> 1) < Wo) v = __ldg(in + (((long long)b * Ho + (y >> 1)) * Wo + (x >> 1)) * C8 + g);
+    out[i] = v;
+}
+
+// dycol[b, iy, ix, (ky, kx, co)] = dy[b, 2*iy - 1 + ky, 2*ix - 1 + kx, co] (0 outside): transpose of the col2im gather
+__global__ void deconv_gather_kernel(const uint4* __restrict__ dy, int B, int H, int W, int C8, uint4* __restrict__ dycol) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * H * W * 16 * C8;
+    if (i >= total) return;
+    const int g = (int)(i % C8);
+    long long t = i / C8;
+    const int tap = (int)(t % 16);
+    t /= 16;
+    const int ix = (int)(t % W);
+    t /= W;
+    const int iy = (int)(t % H);
+    const int b = (int)(t / H);
+    const int oy = 2 * iy - 1 + (tap >> 2), ox = 2 * ix - 1 + (tap & 3);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (oy >= 0 && oy < 2 * H && ox >= 0 && ox < 2 * W) v = __ldg(dy + (((long long)b * 2 * H + oy) * 2 * W + ox) * C8 + g);
+    dycol[i] = v;
+}
+
+// Backward of ab_head_decode w.r.t. the logits: p = softmax(l); u = sum p * w / W ...; dl_i = p_i * (g_i - sum_j p_j g_j)
+// with g_i = du * w_i / W + dv * h_i / H + dd * d_i / D (the 1 / (1 + 1e-7) re-normalisation factor included).
+constexpr int kDecodeThreads = 256;
+__global__ void __launch_bounds__(kDecodeThreads)
+head_decode_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ dkp3d, int ncls, int D, int H, int W,
+                       __nv_bfloat16* __restrict__ dlogits) {
+    __shared__ float red[2][kDecodeThreads / 32];
+    const int b = blockIdx.x / ncls, cls = blockIdx.x % ncls;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int HW = H * W, n = HW * D, ldc = ncls * D;
+    const float* base = logits + (long long)b * HW * ldc + cls * D;
+    __nv_bfloat16* obase = dlogits + (long long)b * HW * ldc + cls * D;
+    const float renorm = 1.0f / (1.0f + 1e-7f);
+    const float gu = dkp3d[((long long)b * ncls + cls) * 3] * renorm / (float)W;
+    const float gv = dkp3d[((long long)b * ncls + cls) * 3 + 1] * renorm / (float)H;
+    const float gd = dkp3d[((long long)b * ncls + cls) * 3 + 2] * renorm / (float)D;
+    float mx = -INFINITY;
+    for (int i = tid; i < n; i += kDecodeThreads) {
+        const int p = i / D, d = i - p * D;
+        mx = fmaxf(mx, base[(long long)p * ldc + d]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[0][wid] = mx;
+    __syncthreads();
+    mx = red[0][0];
+#pragma unroll
+    for (int w = 1; w < kDecodeThreads / 32; ++w) mx = fmaxf(mx, red[0][w]);
+    __syncthreads();
+    float s = 0.f, sg = 0.f;
+    for (int i = tid; i < n; i += kDecodeThreads) {
+        const int p = i / D, d = i - p * D;
+        const int h = p / W, w = p - h * W;
+        const float e = expf(base[(long long)p * ldc + d] - mx);
+        s += e;
+        sg += e * (gu * (float)w + gv * (float)h + gd * (float)d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        sg += __shfl_xor_sync(0xffffffffu, sg, o);
+    }
+    if (lane == 0) { red[0][wid] = s; red[1][wid] = sg; }
+    __syncthreads();
+    float S = 0.f, SG = 0.f;
+    for (int w = 0; w < kDecodeThreads / 32; ++w) { S += red[0][w]; SG += red[1][w]; }
+    const float inv = 1.0f / S, gbar = SG * inv;
+    for (int i = tid; i < n; i += kDecodeThreads) {
+        const int p = i / D, d = i - p * D;
+        const int h = p / W, w = p - h * W;
+        const float pr = expf(base[(long long)p * ldc + d] - mx) * inv;
+        obase[(long long)p * ldc + d] = __float2bfloat16(pr * (gu * (float)w + gv * (float)h + gd * (float)d - gbar));
+    }
+}
+
+// ---- optimiser: sum of squares of the flat gradient (for clip_grad_norm_) and the fused Adam update
+__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* out) {
+    __shared__ float red[32];
+    float s = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += g[i] * g[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(out, s);
+    }
+}
+
+// torch.optim.Adam (no amsgrad, weight_decay added to the gradient) on one flat fp32 buffer.  grad_sumsq (device scalar):
+// total squared norm of the gradient; the clip coefficient min(1, max_norm / (norm + 1e-6)) of clip_grad_norm_ is
+// applied on the fly (max_norm <= 0: no clipping).
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float beta1, float beta2, float eps, float weight_decay, float bias1,
+                            float bias2, const float* __restrict__ grad_sumsq, float max_norm, float grad_scale) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float clip = 1.0f;
+    if (max_norm > 0.0f) clip = fminf(1.0f, max_norm / (sqrtf(*grad_sumsq) * grad_scale + 1e-6f));
+    float gi = g[i] * grad_scale * clip + weight_decay * p[i];
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bias2) + eps;
+    p[i] -= lr / bias1 * mi / denom;
+}
+
+static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace ab
+
+using namespace ab;
+
+#define AB_LAUNCH_END(name)      \
+    count_launch();              \
+    return check_launch(name)
+
+extern "C" int ab_col_stats(const void* x, int is_f32, int M, int C, int64_t ld, float* sum, float* sumsq, void* stream) {
+    AB_REQUIRE(M >= 0 && C > 0 && C % 8 == 0 && ld % 8 == 0, "bad shape (C and ld multiples of 8)");
+    if (M == 0) return AB_OK;
+    AB_REQUIRE(x && sum, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    if (is_f32) col_stats_f32_kernel<<<nblk(M, kRedRows), kRedThreads, 0, st>>>((const float4*)x, M, C / 8, ld / 4, sum, sumsq);
+    else col_stats_bf16_kernel<<<nblk(M, kRedRows), kRedThreads, 0, st>>>((const uint4*)x, M, C / 8, ld / 8, sum, sumsq);
+    AB_LAUNCH_END("col_stats_kernel");
+}
+
+extern "C" int ab_bn_finalize(const float* sum, const float* sumsq, int C, float count, const float* gamma, const float* beta,
+                              float eps, float momentum, float* scale, float* shift, float* save_mean, float* save_invstd,
+                              float* running_mean, float* running_var, void* stream) {
+    AB_REQUIRE(C > 0 && count > 0, "bad shape");
+    AB_REQUIRE(sum && sumsq && scale && shift && save_mean && save_invstd, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    bn_finalize_kernel<<<nblk(C, 128), 128, 0, st>>>(sum, sumsq, C, count, gamma, beta, eps, momentum, scale, shift, save_mean,
+                                                     save_invstd, running_mean, running_var);
+    AB_LAUNCH_END("bn_finalize_kernel");
+}
+
+extern "C" int ab_bn_apply(const void* raw, int64_t M, int C, const float* scale, const float* shift, const void* residual,
+                           int relu, void* y, void* stream) {
+    AB_REQUIRE(M >= 0 && C > 0 && C % 8 == 0, "bad shape");
+    if (M == 0) return AB_OK;
+    AB_REQUIRE(raw && scale && shift && y, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    const long long n8 = M * (C / 8);
+    bn_apply_kernel<<<nblk(n8, 256), 256, 0, st>>>((const uint4*)raw, n8, C / 8, scale, shift, (const uint4*)residual, relu, (uint4*)y);
+    AB_LAUNCH_END("bn_apply_kernel");
+}
+
+extern "C" int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, int M, int C, const float* mean,
+                                const float* invstd, int relu, float* sum_dy, float* sum_dy_xhat, void* stream) {
+    AB_REQUIRE(M >= 0 && C > 0 && C % 8 == 0, "bad shape");
+    if (M == 0) return AB_OK;
+    AB_REQUIRE(dy && raw && mean && invstd && sum_dy && sum_dy_xhat && (!relu || y), "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    bn_bwd_reduce_kernel<<<nblk(M, kRedRows), kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M, C / 8,
+                                                                    mean, invstd, relu, sum_dy, sum_dy_xhat);
+    AB_LAUNCH_END("bn_bwd_reduce_kernel");
+}
+
+extern "C" int ab_bn_bwd_apply(const void* dy, const void* y, const void* raw, int64_t M, int C, const float* gamma,
+                               const float* mean, const float* invstd, const float* sum_dy, const float* sum_dy_xhat,
+                               int relu, void* dx, void* dres, void* stream) {
+    AB_REQUIRE(M >= 0 && C > 0 && C % 8 == 0, "bad shape");
+    if (M == 0) return AB_OK;
+    AB_REQUIRE(dy && raw && mean && invstd && sum_dy && sum_dy_xhat && dx && (!relu || y), "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    const long long n8 = M * (C / 8);
+    bn_bwd_apply_kernel<<<nblk(n8, 256), 256, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, n8, C / 8,
+                                                       1.0f / (float)M, gamma, mean, invstd, sum_dy, sum_dy_xhat, relu,
+                                                       (uint4*)dx, (uint4*)dres);
+    AB_LAUNCH_END("bn_bwd_apply_kernel");
+}
+
+extern "C" int ab_affine_relu_bwd(const void* dy, const void* y, int64_t M, int C, const float* scale, int relu, void* dx,
+                                  void* dres, void* stream) {
+    AB_REQUIRE(M >= 0 && C > 0 && C % 8 == 0, "bad shape");
+    if (M == 0) return AB_OK;
+    AB_REQUIRE(dy && dx && (!relu || y), "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    const long long n8 = M * (C / 8);
+    affine_relu_bwd_kernel<<<nblk(n8, 256), 256, 0, st>>>((const uint4*)dy, (const uint4*)y, n8, C / 8, scale, relu, (uint4*)dx,
+                                                          (uint4*)dres);
+    AB_LAUNCH_END("affine_relu_bwd_kernel");
+}
+
+extern "C" int ab_maxpool3x3s2_bwd(const void* x, const void* y, const void* dy, int B, int H, int W, int C, void* dx,
+                                   void* stream) {
+    AB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad shape");
+    if (B == 0) return AB_OK;
+    AB_REQUIRE(x && y && dy && dx, "null pointer");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    maxpool_bwd_kernel<<<nblk((long long)B * H * W * (C / 8), 256), 256, 0, st>>>((const uint4*)x, (const uint4*)y, (const uint4*)dy,
+                                                                                  B, H, W, C / 8, Ho, Wo, (uint4*)dx);
+    AB_LAUNCH_END("maxpool_bwd_kernel");
+}
+
+extern "C" int ab_avgpool_bwd(const float* dmean, int B, int HW, int C, void* dx, void* stream) {
+    AB_REQUIRE(B >= 0 && HW > 0 && C > 0 && C % 8 == 0, "bad shape");
+    if (B == 0) return AB_OK;
+    AB_REQUIRE(dmean && dx, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    avgpool_bwd_kernel<<<nblk((long long)B * HW * (C / 8), 256), 256, 0, st>>>(dmean, B, HW, C / 8, (uint4*)dx);
+    AB_LAUNCH_END("avgpool_bwd_kernel");
+}
+
+extern "C" int ab_dilate2x(const void* in, int B, int Ho, int Wo, int H, int W, int C, void* out, void* stream) {
+    AB_REQUIRE(B >= 0 && Ho > 0 && Wo > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad shape");
+    if (B == 0) return AB_OK;
+    AB_REQUIRE(in && out, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    dilate2x_kernel<<<nblk((long long)B * H * W * (C / 8), 256), 256, 0, st>>>((const uint4*)in, B, Ho, Wo, H, W, C / 8, (uint4*)out);
+    AB_LAUNCH_END("dilate2x_kernel");
+}
+
+extern "C" int ab_deconv4x4s2_gather(const void* dy, int B, int H, int W, int C, void* dycol, void* stream) {
+    AB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad shape");
+    if (B == 0) return AB_OK;
+    AB_REQUIRE(dy && dycol, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    deconv_gather_kernel<<<nblk((long long)B * H * W * 16 * (C / 8), 256), 256, 0, st>>>((const uint4*)dy, B, H, W, C / 8, (uint4*)dycol);
+    AB_LAUNCH_END("deconv_gather_kernel");
+}
+
+extern "C" int ab_head_decode_bwd(const float* logits, const float* dkp3d, int B, int ncls, int D, int H, int W, void* dlogits,
+                                  void* stream) {
+    AB_REQUIRE(B >= 0 && ncls > 0 && D > 0 && H > 0 && W > 0, "bad shape");
+    if (B == 0) return AB_OK;
+    AB_REQUIRE(logits && dkp3d && dlogits, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_HEAD_DECODE, st);
+    head_decode_bwd_kernel<<<B * ncls, kDecodeThreads, 0, st>>>(logits, dkp3d, ncls, D, H, W, (__nv_bfloat16*)dlogits);
+    AB_LAUNCH_END("head_decode_bwd_kernel");
+}
+
+extern "C" int ab_sumsq(const float* g, int64_t n, float* out, void* stream) {
+    AB_REQUIRE(n >= 0, "negative size");
+    if (n == 0) return AB_OK;
+    AB_REQUIRE(g && out, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_OPTIMIZER, st);
+    sumsq_kernel<<<(unsigned)min((long long)148 * 8, (long long)nblk(n, 256)), 256, 0, st>>>(g, n, out);
+    AB_LAUNCH_END("sumsq_kernel");
+}
+
+extern "C" int ab_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                            float weight_decay, int step, const float* grad_sumsq, float max_norm, float grad_scale,
+                            void* stream) {
+    AB_REQUIRE(n >= 0 && step >= 1, "bad arguments");
+    if (n == 0) return AB_OK;
+    AB_REQUIRE(p && g && m && v && (max_norm <= 0.0f || grad_sumsq), "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_OPTIMIZER, st);
+    const float bias1 = 1.0f - powf(beta1, (float)step), bias2 = 1.0f - powf(beta2, (float)step);
+    adam_kernel<<<nblk(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias1, bias2, grad_sumsq,
+                                              max_norm, grad_scale);
+    AB_LAUNCH_END("adam_kernel");
+}

@@ -69,6 +69,24 @@ EXPORTS = {
     "ab_deconv4x4s2_col2im": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                                       C.c_void_p, C.c_void_p]),
     "ab_head_decode": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_col_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_bn_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_float]
+                       + [C.c_void_p] * 7),
+    "ab_bn_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ab_bn_bwd_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_bn_bwd_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
+                        + [C.c_void_p] * 3),
+    "ab_affine_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "ab_maxpool3x3s2_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
+    "ab_avgpool_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ab_dilate2x": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
+    "ab_deconv4x4s2_gather": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
+    "ab_head_decode_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    "ab_sumsq": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ab_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int, C.c_void_p, C.c_float, C.c_float,
+                                                                                  C.c_void_p]),
 }
 
 _lib = None
@@ -121,7 +139,7 @@ def launch_count() -> int:
 
 STAGES = {0: "raster_vertex_kernel", 1: "raster_triangle_kernel", 2: "raster_resolve_kernel", 3: "mano_lbs_kernel",
           4: "posegen_prelude_kernel", 5: "ccv_cdf+draw_kernels", 6: "view_kernel", 7: "gemm_bf16_tn_kernel",
-          8: "im2col_kernel", 9: "elementwise_kernels", 10: "head_decode_kernel", 11: "gemm_bf16_tn_kernel<im2col TMA>", 12: "wgrad_bf16_kernel"}
+          8: "im2col_kernel", 9: "elementwise_kernels", 10: "head_decode_kernel", 11: "gemm_bf16_tn_kernel<im2col TMA>", 12: "wgrad_bf16_kernel", 13: "train_elementwise_kernels", 14: "optimizer_kernels"}
 
 
 def profile_enable(on: bool) -> None:

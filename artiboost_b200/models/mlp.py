@@ -2,7 +2,7 @@
 import torch
 import torch.nn as nn
 
-from . import nhwc
+from . import nhwc, train_ops
 from .registry import MODEL
 
 
@@ -20,10 +20,14 @@ class MLP_O(nn.Module):
         layers.append(nn.Linear(layers_n[-1], out_channel))
         self.layers = nn.Sequential(*layers)
 
-    @torch.no_grad()
     def forward(self, x):
-        h = x.to(torch.bfloat16).contiguous()
         fcs = [m for m in self.layers if isinstance(m, nn.Linear)]
+        if torch.is_grad_enabled():
+            h = x
+            for fc in fcs[:-1]:
+                h = train_ops.linear(h, fc, relu=True)
+            return train_ops.linear(h, fcs[-1], relu=False, out_fp32=True)
+        h = x.to(torch.bfloat16).contiguous()
         for fc in fcs[:-1]:
             h = nhwc.linear(h, fc, relu=True).contiguous()
         return nhwc.linear(h, fcs[-1], relu=False, out_fp32=True)

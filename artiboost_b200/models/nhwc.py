@@ -69,8 +69,8 @@ def bn_affine(bn, training: bool):
     if bn is None:
         return None, None
     if training and isinstance(bn, nn.BatchNorm2d):
-        raise NotImplementedError("training-mode BatchNorm (batch statistics) is not on the tensor-core path yet; "
-                                  "call .eval() or build the backbone with FREEZE_BATCHNORM: true")
+        raise NotImplementedError("training-mode BatchNorm needs batch statistics: run the model with gradients enabled "
+                                  "(the training graph), or call .eval() / use FREEZE_BATCHNORM: true under torch.no_grad()")
 
     def build():
         eps = getattr(bn, "eps", 1e-5)
@@ -155,7 +155,7 @@ def avgpool(x: Act):
     return f, h
 
 
-def deconv4x4s2_bn_relu(x: Act, deconv: nn.ConvTranspose2d, bn, relu: bool = True, training: bool = False) -> Act:
+def deconv4x4s2_bn_relu(x: Act, deconv: nn.ConvTranspose2d, bn, training: bool = False, relu: bool = True) -> Act:
     """ConvTranspose2d(k=4, s=2, p=1) + BN + ReLU (simplebaseline.py:152-175): X . W -> [B*H*W, 16*Cout], then the
     gather form of col2im with the BN affine and ReLU fused."""
     if deconv.kernel_size != (4, 4) or deconv.stride != (2, 2) or deconv.padding != (1, 1) or deconv.output_padding != (0, 0):

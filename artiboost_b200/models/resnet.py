@@ -6,7 +6,7 @@ from typing import Dict
 import torch
 import torch.nn as nn
 
-from . import nhwc
+from . import nhwc, train_ops
 from .registry import BACKBONE, enable_lower_param
 
 
@@ -27,6 +27,11 @@ class FrozenBatchNorm2d(nn.Module):
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
 
 
+def _prims():
+    """Inference primitives under torch.no_grad(), differentiable ones (forward + backward kernels) otherwise."""
+    return train_ops if torch.is_grad_enabled() else nhwc
+
+
 def conv3x3(in_planes, out_planes, stride=1):
     return nn.Conv2d(in_planes, out_planes, kernel_size=3, stride=stride, padding=1, bias=False)
 
@@ -45,10 +50,10 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
     def forward_act(self, x: nhwc.Act) -> nhwc.Act:
-        tr = self.training
-        residual = x if self.downsample is None else nhwc.conv_bn_act(x, self.downsample[0], self.downsample[1], training=tr)
-        out = nhwc.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=tr)
-        return nhwc.conv_bn_act(out, self.conv2, self.bn2, relu=True, residual=residual, training=tr)
+        tr, ops_ = self.training, _prims()
+        residual = x if self.downsample is None else ops_.conv_bn_act(x, self.downsample[0], self.downsample[1], training=tr)
+        out = ops_.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=tr)
+        return ops_.conv_bn_act(out, self.conv2, self.bn2, relu=True, residual=residual, training=tr)
 
 
 class Bottleneck(nn.Module):
@@ -67,11 +72,11 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward_act(self, x: nhwc.Act) -> nhwc.Act:
-        tr = self.training
-        residual = x if self.downsample is None else nhwc.conv_bn_act(x, self.downsample[0], self.downsample[1], training=tr)
-        out = nhwc.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=tr)
-        out = nhwc.conv_bn_act(out, self.conv2, self.bn2, relu=True, training=tr)
-        return nhwc.conv_bn_act(out, self.conv3, self.bn3, relu=True, residual=residual, training=tr)
+        tr, ops_ = self.training, _prims()
+        residual = x if self.downsample is None else ops_.conv_bn_act(x, self.downsample[0], self.downsample[1], training=tr)
+        out = ops_.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=tr)
+        out = ops_.conv_bn_act(out, self.conv2, self.bn2, relu=True, training=tr)
+        return ops_.conv_bn_act(out, self.conv3, self.bn3, relu=True, residual=residual, training=tr)
 
 
 class ResNet(nn.Module):
@@ -119,18 +124,22 @@ class ResNet(nn.Module):
     def load_pretrained(self):
         raise RuntimeError("ImageNet weights cannot be downloaded here (no network): load a state_dict instead")
 
-    @torch.no_grad()
     def forward_acts(self, image: torch.Tensor) -> Dict[str, object]:
         """NHWC bf16 feature maps (what the head consumes without a layout round trip)."""
+        ops_ = _prims()
         x = nhwc.image_to_act(image)
-        x = nhwc.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=self.training)
-        x = nhwc.maxpool3x3s2(x)
+        x = ops_.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=self.training)
+        x = ops_.maxpool3x3s2(x)
         feats = OrderedDict()
         for name in ("layer1", "layer2", "layer3", "layer4"):
             for blk in getattr(self, name):
                 x = blk.forward_act(x)
             feats["res_" + name] = x
-        feats["res_layer4_mean"], feats["res_layer4_mean_bf16"] = nhwc.avgpool(x)
+        if ops_ is nhwc:
+            feats["res_layer4_mean"], feats["res_layer4_mean_bf16"] = nhwc.avgpool(x)
+        else:
+            feats["res_layer4_mean"] = train_ops.avgpool(x)
+            feats["res_layer4_mean_bf16"] = feats["res_layer4_mean"]  # LinearFn casts (and routes the gradient) itself
         return feats
 
     def forward(self, **kwargs) -> Dict:

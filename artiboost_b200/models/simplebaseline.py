@@ -6,7 +6,7 @@ from typing import Dict
 import torch
 import torch.nn as nn
 
-from . import nhwc
+from . import nhwc, train_ops
 from .registry import HEAD, enable_lower_param
 
 
@@ -69,16 +69,16 @@ class IntegralDeconvHead(nn.Module):
             self.inplanes = planes
         return nn.Sequential(*layers)
 
-    @torch.no_grad()
     def forward_act(self, x: nhwc.Act) -> Dict[str, torch.Tensor]:
+        ops_ = train_ops if torch.is_grad_enabled() else nhwc
         mods = list(self.deconv_layers)
         for i in range(0, len(mods), 3):
-            x = nhwc.deconv4x4s2_bn_relu(x, mods[i], mods[i + 1], relu=True, training=self.training)
+            x = ops_.deconv4x4s2_bn_relu(x, mods[i], mods[i + 1], training=self.training)
         if (x.H, x.W) != (self.height_res, self.width_res):
             # the reference's view_to_bcdhw would raise on this mismatch too (simplebaseline.py:120-135)
             raise RuntimeError(f"heatmap is {x.H}x{x.W} but HEATMAP_SIZE is {self.height_res}x{self.width_res}")
-        logits = nhwc.conv_bn_act(x, self.final_layer, None, relu=False, out_fp32=True)  # [B*H*W, ncls*D], conv bias fused
-        kp3d, confd = nhwc.head_decode(logits, x.B, self.nclasses, self.depth_res, x.H, x.W)
+        logits = ops_.conv_bn_act(x, self.final_layer, None, relu=False, out_fp32=True)  # [B*H*W, ncls*D], conv bias fused
+        kp3d, confd = ops_.head_decode(logits, x.B, self.nclasses, self.depth_res, x.H, x.W)
         return {"kp3d": kp3d, "kp3d_confd": confd}
 
     def forward(self, **kwargs) -> Dict[str, torch.Tensor]:

@@ -1,0 +1,408 @@
+"""Differentiable layer primitives of the clasbased network: forward AND backward on the C-ABI kernels.
+
+Each `torch.autograd.Function` below is one fused layer of the reference graph (conv + BatchNorm + ReLU (+ residual),
+max-pool, global mean, transposed conv + BatchNorm + ReLU, linear, heatmap decode).  autograd only orders the calls and
+sums fan-out gradients; the arithmetic of `loss.backward()` (train/train_artiboost.py:91-93: cuDNN dgrad / wgrad,
+BatchNorm / ReLU / pooling backward in the reference) runs in:
+
+  data gradients    stride-1 k x k : the implicit-GEMM conv kernel on dy with flipped, transposed filters
+                    stride-2       : ab_dilate2x (zero insertion) + the same kernel;  1x1: plain GEMM (+ dilation)
+  weight gradients  ab_conv_wgrad_bf16_nhwc / ab_wgrad_bf16 (MN-major tcgen05, split over pixels)
+  BatchNorm         statistics from the conv epilogue, ab_bn_finalize / ab_bn_apply; ab_bn_bwd_reduce / ab_bn_bwd_apply
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import lib, ops
+from . import nhwc
+from .nhwc import Act, _cached, _pad8, _ver
+
+P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+
+
+def _call(name, *args):
+    lib.check(getattr(lib.load(), name)(*args), name)
+
+
+def _stream(dev):
+    return lib.stream_ptr(dev)
+
+
+# --------------------------------------------------------------------------------------------- packed filters
+def _pack_dgrad_weight(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, kh, kw] -> bf16 [Cin, (ky', kx', co)] with the taps flipped: the filter matrix of the data gradient."""
+    cin = w.shape[1]
+    return w.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(cin, -1).to(torch.bfloat16).contiguous()
+
+
+def _unpack_wgrad(dw_packed: torch.Tensor, w: torch.Tensor, cin_pad: int) -> torch.Tensor:
+    cout, cin, kh, kw = w.shape
+    return dw_packed[:, :kh * kw * cin_pad].view(cout, kh, kw, cin_pad)[..., :cin].permute(0, 3, 1, 2).contiguous()
+
+
+def _conv_raw(x: Act, wp, cout, kh, kw, stride, pad, col_stats=None, scale=None, bias=None, relu=False, out_fp32=False,
+              residual=None):
+    """Convolution on the tensor cores; returns the [M_out, Cout] matrix and (Ho, Wo)."""
+    Ho, Wo = (x.H + 2 * pad - kh) // stride + 1, (x.W + 2 * pad - kw) // stride + 1
+    dev = x.data.device
+    cs, cq = col_stats if col_stats is not None else (None, None)
+    if x.C % 64 == 0 and not (kh == 1 and kw == 1 and stride == 1):
+        out = torch.empty((x.B * Ho * Wo, cout), dtype=torch.float32 if out_fp32 else torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            _call("ab_conv_bf16_nhwc", x.data.data_ptr(), x.B, x.H, x.W, x.C, wp.data_ptr(), cout, kh, kw, stride, pad,
+                  out.data_ptr(), cout, int(out_fp32), P(scale), P(bias), P(residual), cout, int(relu), P(cs), P(cq), _stream(dev))
+        return out, Ho, Wo, None
+    if kh == 1 and kw == 1 and stride == 1 and pad == 0 and x.C % 8 == 0:
+        a = x.data
+    else:
+        kp = wp.shape[1]
+        a = torch.empty((x.B * Ho * Wo, kp), dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            _call("ab_im2col_nhwc", x.data.data_ptr(), x.B, x.H, x.W, x.C, kh, kw, stride, pad, kp, a.data_ptr(), _stream(dev))
+    out = ops.gemm_bf16(a, wp, scale=scale, bias=bias, residual=residual, relu=relu, out_fp32=out_fp32, col_stats=col_stats)
+    return out, Ho, Wo, (a if a is not x.data else None)
+
+
+class _BNState:
+    """What the backward pass needs from a training-mode BatchNorm."""
+    __slots__ = ("mean", "invstd", "scale")
+
+
+def _bn_forward_train(raw, M, C, bn, sums, residual, relu):
+    dev = raw.device
+    scale, shift = torch.empty(C, device=dev), torch.empty(C, device=dev)
+    st = _BNState()
+    st.mean, st.invstd = torch.empty(C, device=dev), torch.empty(C, device=dev)
+    track = bn.track_running_stats and bn.running_mean is not None
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    with torch.cuda.device(dev):
+        _call("ab_bn_finalize", sums[0].data_ptr(), sums[1].data_ptr(), C, float(M), P(bn.weight), P(bn.bias), float(bn.eps),
+              float(momentum), scale.data_ptr(), shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
+              P(bn.running_mean) if track else None, P(bn.running_var) if track else None, _stream(dev))
+        y = torch.empty_like(raw)
+        _call("ab_bn_apply", raw.data_ptr(), M, C, scale.data_ptr(), shift.data_ptr(), P(residual), int(relu), y.data_ptr(),
+              _stream(dev))
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return y, st
+
+
+def _norm_backward(dy, y, raw, M, C, bn, st, relu, want_res):
+    """-> (draw bf16 [M,C], dgamma, dbeta, dres).  st: _BNState (batch statistics) or a frozen scale tensor or None."""
+    dev = dy.device
+    dx = torch.empty((M, C), dtype=torch.bfloat16, device=dev)
+    dres = torch.empty((M, C), dtype=torch.bfloat16, device=dev) if want_res else None
+    dgamma = dbeta = None
+    with torch.cuda.device(dev):
+        if isinstance(st, _BNState):
+            dbeta, dgamma = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+            _call("ab_bn_bwd_reduce", dy.data_ptr(), P(y), raw.data_ptr(), M, C, st.mean.data_ptr(), st.invstd.data_ptr(), int(relu),
+                  dbeta.data_ptr(), dgamma.data_ptr(), _stream(dev))
+            _call("ab_bn_bwd_apply", dy.data_ptr(), P(y), raw.data_ptr(), M, C, P(bn.weight), st.mean.data_ptr(),
+                  st.invstd.data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), int(relu), dx.data_ptr(), P(dres), _stream(dev))
+        else:
+            _call("ab_affine_relu_bwd", dy.data_ptr(), P(y), M, C, P(st), int(relu), dx.data_ptr(), P(dres), _stream(dev))
+    return dx, dgamma, dbeta, dres
+
+
+def _col_sum(mat, is_f32=False):
+    M, C = mat.shape
+    out = torch.zeros(C, device=mat.device)
+    with torch.cuda.device(mat.device):
+        _call("ab_col_stats", mat.data_ptr(), int(is_f32), M, C, mat.stride(0), out.data_ptr(), None, _stream(mat.device))
+    return out
+
+
+def _conv_dgrad(dy: Act, conv_w, kh, kw, stride, pad, H, W, key) -> torch.Tensor:
+    """Data gradient of a convolution whose input was [B, H, W, Cin]; dy is [B, Ho, Wo, Cout]."""
+    cout, cin = conv_w.shape[0], conv_w.shape[1]
+    dev = dy.data.device
+    if kh == 1 and kw == 1:
+        wt = _cached(("wt",) + key, _ver(conv_w), lambda: conv_w.detach().view(cout, cin).t().to(torch.bfloat16).contiguous())
+        dx = ops.gemm_bf16(dy.data, wt)  # [M_out, Cin]
+        if stride == 1:
+            return dx
+        out = torch.empty((dy.B * H * W, cin), dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            _call("ab_dilate2x", dx.data_ptr(), dy.B, dy.H, dy.W, H, W, cin, out.data_ptr(), _stream(dev))
+        return out
+    wd = _cached(("wd",) + key, _ver(conv_w), lambda: _pack_dgrad_weight(conv_w))
+    g = dy
+    if stride == 2:
+        d = torch.empty((dy.B * H * W, cout), dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            _call("ab_dilate2x", dy.data.data_ptr(), dy.B, dy.H, dy.W, H, W, cout, d.data_ptr(), _stream(dev))
+        g = Act(d, dy.B, H, W, cout)
+    elif stride != 1:
+        raise NotImplementedError("stride must be 1 or 2")
+    dx, Ho, Wo, _ = _conv_raw(g, wd, cin, kh, kw, 1, kh - 1 - pad)
+    assert (Ho, Wo) == (H, W)
+    return dx
+
+
+def _conv_wgrad(x: Act, xcol, dy_mat, conv_w, kh, kw, stride, pad) -> torch.Tensor:
+    cout = conv_w.shape[0]
+    dev = dy_mat.device
+    with torch.cuda.device(dev):
+        if x.C % 64 == 0:
+            dwp = torch.zeros((cout, kh * kw * x.C), device=dev)
+            _call("ab_conv_wgrad_bf16_nhwc", x.data.data_ptr(), x.B, x.H, x.W, x.C, dy_mat.data_ptr(), cout, kh, kw, stride, pad,
+                  dwp.data_ptr(), _stream(dev))
+        else:
+            if xcol is None:  # 1x1 stride-1 on a narrow activation: the activation is the matrix
+                xcol = x.data
+            dwp = torch.zeros((cout, xcol.shape[1]), device=dev)
+            _call("ab_wgrad_bf16", dy_mat.shape[0], cout, xcol.shape[1], dy_mat.data_ptr(), dy_mat.stride(0), xcol.data_ptr(),
+                  xcol.stride(0), dwp.data_ptr(), dwp.stride(0), _stream(dev))
+    return _unpack_wgrad(dwp, conv_w, x.C)
+
+
+# ------------------------------------------------------------------------------------------------ Functions
+class ConvBNActFn(torch.autograd.Function):
+    """y = relu?(BN(conv(x)) (+ residual)); BN uses batch statistics when `bn_train`, running statistics otherwise."""
+
+    @staticmethod
+    def forward(ctx, x_data, weight, bias, gamma, beta, residual, geom, conv, bn, relu, bn_train, out_fp32):
+        B, H, W, C = geom
+        x = Act(x_data, B, H, W, C)
+        kh, kw = conv.kernel_size
+        stride, pad, cout = conv.stride[0], conv.padding[0], conv.out_channels
+        wp = _cached(("w", id(conv), C), _ver(weight), lambda: nhwc.pack_conv_weight(weight, C))
+        ctx.meta = (geom, conv, bn, relu, kh, kw, stride, pad, cout, out_fp32)
+        ctx.has_res = residual is not None
+        empty = x_data.new_empty(0)
+        if bn is not None and bn_train:
+            if bias is not None:
+                raise NotImplementedError("conv bias followed by training-mode BatchNorm does not occur in the clasbased network")
+            sums = (torch.zeros(cout, device=x_data.device), torch.zeros(cout, device=x_data.device))
+            raw, Ho, Wo, xcol = _conv_raw(x, wp, cout, kh, kw, stride, pad, col_stats=sums)
+            y, st = _bn_forward_train(raw, raw.shape[0], cout, bn, sums, residual, relu)
+            ctx.save_for_backward(x_data, weight, raw, y, xcol if xcol is not None else empty)
+            ctx.st = st
+        else:
+            scale, shift = nhwc.bn_affine(bn, False) if bn is not None else (None, None)
+            if bias is not None:
+                cb = bias.detach().float()
+                shift = cb if shift is None else shift + cb * scale
+            y, Ho, Wo, xcol = _conv_raw(x, wp, cout, kh, kw, stride, pad, scale=scale, bias=shift, relu=relu, out_fp32=out_fp32,
+                                        residual=residual)
+            ctx.save_for_backward(x_data, weight, empty, y, xcol if xcol is not None else empty)
+            ctx.st = scale
+        ctx.out_hw = (Ho, Wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_data, weight, raw, y, xcol = ctx.saved_tensors
+        geom, conv, bn, relu, kh, kw, stride, pad, cout, out_fp32 = ctx.meta
+        B, H, W, C = geom
+        Ho, Wo = ctx.out_hw
+        M = B * Ho * Wo
+        dy = dy.to(torch.bfloat16).contiguous()
+        draw, dgamma, dbeta, dres = _norm_backward(dy, y if relu else None, raw if raw.numel() else y, M, cout, bn, ctx.st, relu,
+                                                   ctx.has_res)
+        dbias = _col_sum(draw) if (conv.bias is not None and ctx.needs_input_grad[2]) else None
+        x = Act(x_data, B, H, W, C)
+        dw = _conv_wgrad(x, xcol if xcol.numel() else None, draw, weight, kh, kw, stride, pad) if ctx.needs_input_grad[1] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _conv_dgrad(Act(draw, B, Ho, Wo, cout), weight, kh, kw, stride, pad, H, W, (id(conv),))
+        if not isinstance(ctx.st, _BNState):
+            dgamma = dbeta = None  # frozen / eval-mode statistics carry no parameter gradient here
+        return dx, dw, dbias, dgamma, dbeta, dres, None, None, None, None, None, None
+
+
+def conv_bn_act(x: Act, conv: nn.Conv2d, bn=None, relu=False, residual: Act = None, training=False, out_fp32=False):
+    bn_train = training and isinstance(bn, nn.BatchNorm2d)
+    y = ConvBNActFn.apply(x.data, conv.weight, conv.bias, getattr(bn, "weight", None) if bn_train else None,
+                          getattr(bn, "bias", None) if bn_train else None, None if residual is None else residual.data,
+                          (x.B, x.H, x.W, x.C), conv, bn, relu, bn_train, out_fp32)
+    kh, kw = conv.kernel_size
+    Ho = (x.H + 2 * conv.padding[0] - kh) // conv.stride[0] + 1
+    Wo = (x.W + 2 * conv.padding[0] - kw) // conv.stride[0] + 1
+    return y if out_fp32 else Act(y, x.B, Ho, Wo, conv.out_channels)
+
+
+class MaxPoolFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x_data, geom):
+        B, H, W, C = geom
+        y = nhwc.maxpool3x3s2(Act(x_data, B, H, W, C))
+        ctx.save_for_backward(x_data, y.data)
+        ctx.geom = geom
+        return y.data
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_data, y = ctx.saved_tensors
+        B, H, W, C = ctx.geom
+        dx = torch.empty_like(x_data)
+        dy = dy.to(torch.bfloat16).contiguous()
+        with torch.cuda.device(dy.device):
+            _call("ab_maxpool3x3s2_bwd", x_data.data_ptr(), y.data_ptr(), dy.data_ptr(), B, H, W, C, dx.data_ptr(), _stream(dy.device))
+        return dx, None
+
+
+def maxpool3x3s2(x: Act) -> Act:
+    y = MaxPoolFn.apply(x.data, (x.B, x.H, x.W, x.C))
+    return Act(y, x.B, (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1, x.C)
+
+
+class AvgPoolFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x_data, geom):
+        B, H, W, C = geom
+        f, _ = nhwc.avgpool(Act(x_data, B, H, W, C))
+        ctx.geom = geom
+        return f
+
+    @staticmethod
+    def backward(ctx, dmean):
+        B, H, W, C = ctx.geom
+        dx = torch.empty((B * H * W, C), dtype=torch.bfloat16, device=dmean.device)
+        dmean = dmean.float().contiguous()
+        with torch.cuda.device(dmean.device):
+            _call("ab_avgpool_bwd", dmean.data_ptr(), B, H * W, C, dx.data_ptr(), _stream(dmean.device))
+        return dx, None
+
+
+def avgpool(x: Act) -> torch.Tensor:
+    return AvgPoolFn.apply(x.data, (x.B, x.H, x.W, x.C))
+
+
+class DeconvBNReluFn(torch.autograd.Function):
+    """ConvTranspose2d(4, 2, 1) + BatchNorm + ReLU (simplebaseline.py:161-172)."""
+
+    @staticmethod
+    def forward(ctx, x_data, weight, gamma, beta, geom, deconv, bn, bn_train):
+        B, H, W, C = geom
+        cout = deconv.out_channels
+        dev = x_data.device
+        wp = _cached(("dw", id(deconv)), _ver(weight),
+                     lambda: weight.detach().permute(2, 3, 1, 0).reshape(16 * cout, -1).to(torch.bfloat16).contiguous())
+        ycol = ops.gemm_bf16(x_data, wp, out_fp32=True)
+        M = B * 4 * H * W
+        ctx.meta = (geom, deconv, bn, cout)
+        if bn_train:
+            raw32 = torch.empty((M, cout), device=dev)
+            with torch.cuda.device(dev):
+                _call("ab_deconv4x4s2_col2im", ycol.data_ptr(), B, H, W, cout, None, None, 0, None, raw32.data_ptr(), _stream(dev))
+                sums = (torch.zeros(cout, device=dev), torch.zeros(cout, device=dev))
+                _call("ab_col_stats", raw32.data_ptr(), 1, M, cout, cout, sums[0].data_ptr(), sums[1].data_ptr(), _stream(dev))
+            raw = raw32.to(torch.bfloat16)
+            y, st = _bn_forward_train(raw, M, cout, bn, sums, None, True)
+            ctx.st = st
+            ctx.save_for_backward(x_data, weight, raw, y)
+        else:
+            scale, shift = nhwc.bn_affine(bn, False)
+            y = torch.empty((M, cout), dtype=torch.bfloat16, device=dev)
+            with torch.cuda.device(dev):
+                _call("ab_deconv4x4s2_col2im", ycol.data_ptr(), B, H, W, cout, P(scale), P(shift), 1, y.data_ptr(), None, _stream(dev))
+            ctx.st = scale
+            ctx.save_for_backward(x_data, weight, x_data.new_empty(0), y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_data, weight, raw, y = ctx.saved_tensors
+        (B, H, W, C), deconv, bn, cout = ctx.meta
+        dev = dy.device
+        M = B * 4 * H * W
+        dy = dy.to(torch.bfloat16).contiguous()
+        draw, dgamma, dbeta, _ = _norm_backward(dy, y, raw if raw.numel() else y, M, cout, bn, ctx.st, True, False)
+        dycol = torch.empty((B * H * W, 16 * cout), dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            _call("ab_deconv4x4s2_gather", draw.data_ptr(), B, H, W, cout, dycol.data_ptr(), _stream(dev))
+        dw = dx = None
+        if ctx.needs_input_grad[1]:
+            dwp = torch.zeros((16 * cout, C), device=dev)  # [(ky,kx,co), ci]
+            with torch.cuda.device(dev):
+                _call("ab_wgrad_bf16", B * H * W, 16 * cout, C, dycol.data_ptr(), 16 * cout, x_data.data_ptr(), C, dwp.data_ptr(), C,
+                      _stream(dev))
+            dw = dwp.view(4, 4, cout, C).permute(3, 2, 0, 1).contiguous()  # -> [Cin, Cout, ky, kx]
+        if ctx.needs_input_grad[0]:
+            wt = _cached(("dwt", id(deconv)), _ver(weight),
+                         lambda: weight.detach().permute(0, 2, 3, 1).reshape(C, 16 * cout).to(torch.bfloat16).contiguous())
+            dx = ops.gemm_bf16(dycol, wt)
+        if not isinstance(ctx.st, _BNState):
+            dgamma = dbeta = None
+        return dx, dw, dgamma, dbeta, None, None, None, None
+
+
+def deconv4x4s2_bn_relu(x: Act, deconv, bn, training=False) -> Act:
+    if deconv.kernel_size != (4, 4) or deconv.stride != (2, 2) or deconv.padding != (1, 1) or deconv.bias is not None:
+        raise NotImplementedError("only ConvTranspose2d(kernel 4, stride 2, padding 1, bias=False) (the shipped head config)")
+    bn_train = training and isinstance(bn, nn.BatchNorm2d)
+    y = DeconvBNReluFn.apply(x.data, deconv.weight, bn.weight if bn_train else None, bn.bias if bn_train else None,
+                             (x.B, x.H, x.W, x.C), deconv, bn, bn_train)
+    return Act(y, x.B, 2 * x.H, 2 * x.W, deconv.out_channels)
+
+
+class HeadDecodeFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, logits, dims):
+        B, ncls, D, H, W = dims
+        kp3d, confd = nhwc.head_decode(logits, B, ncls, D, H, W)
+        ctx.save_for_backward(logits)
+        ctx.dims = dims
+        ctx.mark_non_differentiable(confd)
+        return kp3d, confd
+
+    @staticmethod
+    def backward(ctx, dkp3d, _dconfd):
+        (logits,) = ctx.saved_tensors
+        B, ncls, D, H, W = ctx.dims
+        dl = torch.empty(logits.shape, dtype=torch.bfloat16, device=logits.device)
+        dk = dkp3d.float().contiguous()
+        with torch.cuda.device(logits.device):
+            _call("ab_head_decode_bwd", logits.data_ptr(), dk.data_ptr(), B, ncls, D, H, W, dl.data_ptr(), _stream(logits.device))
+        return dl, None
+
+
+def head_decode(logits, B, ncls, D, H, W):
+    return HeadDecodeFn.apply(logits, (B, ncls, D, H, W))
+
+
+class LinearFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, fc, relu, out_fp32):
+        xb = x.to(torch.bfloat16).contiguous()
+        y = nhwc.linear(xb, fc, relu=relu, out_fp32=out_fp32)
+        ctx.save_for_backward(xb, weight, y)
+        ctx.meta = (fc, relu)
+        return y.contiguous()
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, weight, y = ctx.saved_tensors
+        fc, relu = ctx.meta
+        dev = dy.device
+        n, k = weight.shape
+        npad = _pad8(n)
+        g = torch.zeros((dy.shape[0], npad), dtype=torch.bfloat16, device=dev)
+        g[:, :n] = (dy.float() * (y.float() > 0)) if relu else dy
+        dwp = torch.zeros((npad, _pad8(k)), device=dev)
+        with torch.cuda.device(dev):
+            _call("ab_wgrad_bf16", g.shape[0], npad, xb.shape[1], g.data_ptr(), npad, xb.data_ptr(), xb.stride(0), dwp.data_ptr(),
+                  dwp.stride(0), _stream(dev))
+        dw = dwp[:n, :k].contiguous()
+        db = _col_sum(g)[:n] if fc.bias is not None else None
+        wt = _cached(("fct", id(fc)), _ver(weight), lambda: _pad_rows(weight.detach().t().to(torch.bfloat16), _pad8(k), npad))
+        dx = ops.gemm_bf16(g, wt)[:, :k] if ctx.needs_input_grad[0] else None
+        return dx, dw, db, None, None, None
+
+
+def _pad_rows(m, rows, cols):
+    out = torch.zeros((rows, cols), dtype=m.dtype, device=m.device)
+    out[:m.shape[0], :m.shape[1]] = m
+    return out
+
+
+def linear(x, fc: nn.Linear, relu=False, out_fp32=False):
+    return LinearFn.apply(x, fc.weight, fc.bias, fc, relu, out_fp32)

@@ -59,6 +59,8 @@ AB_API uint64_t ab_launch_count(void);
 #define AB_STAGE_HEAD_DECODE 10
 #define AB_STAGE_CONV_IMPLICIT 11
 #define AB_STAGE_WGRAD 12
+#define AB_STAGE_TRAIN_ELEMENTWISE 13
+#define AB_STAGE_OPTIMIZER 14
 #define AB_STAGE_COUNT 16
 AB_API int ab_profile_enable(int on);
 AB_API int ab_profile_collect(double* ms_per_stage, int64_t* launches_per_stage, int n_stages);
@@ -203,6 +205,45 @@ AB_API int ab_deconv4x4s2_col2im(const float* ycol, int B, int H, int W, int Cou
                                  int relu, void* out_bf16, float* out_raw, void* stream);
 AB_API int ab_head_decode(const float* logits, int B, int ncls, int D, int H, int W, float* kp3d, float* confd,
                           void* stream);
+
+/* ------------------------------------------------------------------------------------------ training-side kernels
+ * What nn.BatchNorm2d (training mode), ReLU, MaxPool2d and autograd do around the convolutions in the reference's
+ * train step (anakin/models/resnet.py:72-152, simplebaseline.py:161-190, train/train_artiboost.py:91-96).
+ * Activations / activation gradients bf16 [M,C] (NHWC rows), statistics and parameter gradients fp32.
+ * ab_col_stats: sum[c] += sum_r x[r,c], sumsq[c] += sum_r x^2 (sumsq may be NULL); caller zeroes the accumulators.
+ * ab_bn_finalize: mean, biased var -> scale = gamma*invstd, shift = beta - mean*scale, saved mean / invstd, and the
+ *   running-stat update running = (1-momentum)*running + momentum*{mean, unbiased var} (running_* may be NULL).
+ * ab_bn_apply: y = relu?(raw*scale + shift (+ residual)).
+ * ab_bn_bwd_reduce / ab_bn_bwd_apply: dy' = dy*(y>0) when relu; sum_dy = dbeta, sum_dy_xhat = dgamma;
+ *   dx = gamma*invstd*(dy' - sum_dy/M - xhat*sum_dy_xhat/M); dres (optional) receives dy' for the residual branch.
+ * ab_affine_relu_bwd: dx = dy*(y>0)*scale for frozen / eval-mode BatchNorm.
+ * ab_dilate2x: zero insertion, turns the data gradient of a stride-2 conv into a stride-1 conv of the dilated dy.
+ * ab_deconv4x4s2_gather: dycol[b,iy,ix,(ky,kx,co)] = dy[b,2iy-1+ky,2ix-1+kx,co], the transpose of ab_deconv4x4s2_col2im.
+ * ab_head_decode_bwd: gradient of ab_head_decode's kp3d w.r.t. the logits (bf16 [B*H*W, ncls*D]).
+ * ab_sumsq / ab_adam_step: clip_grad_norm_(max_norm) + torch.optim.Adam on one flat fp32 parameter buffer;
+ *   grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).                              */
+AB_API int ab_col_stats(const void* x, int is_f32, int M, int C, int64_t ld, float* sum, float* sumsq, void* stream);
+AB_API int ab_bn_finalize(const float* sum, const float* sumsq, int C, float count, const float* gamma, const float* beta,
+                          float eps, float momentum, float* scale, float* shift, float* save_mean, float* save_invstd,
+                          float* running_mean, float* running_var, void* stream);
+AB_API int ab_bn_apply(const void* raw, int64_t M, int C, const float* scale, const float* shift, const void* residual,
+                       int relu, void* y, void* stream);
+AB_API int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, int M, int C, const float* mean,
+                            const float* invstd, int relu, float* sum_dy, float* sum_dy_xhat, void* stream);
+AB_API int ab_bn_bwd_apply(const void* dy, const void* y, const void* raw, int64_t M, int C, const float* gamma,
+                           const float* mean, const float* invstd, const float* sum_dy, const float* sum_dy_xhat, int relu,
+                           void* dx, void* dres, void* stream);
+AB_API int ab_affine_relu_bwd(const void* dy, const void* y, int64_t M, int C, const float* scale, int relu, void* dx,
+                              void* dres, void* stream);
+AB_API int ab_maxpool3x3s2_bwd(const void* x, const void* y, const void* dy, int B, int H, int W, int C, void* dx, void* stream);
+AB_API int ab_avgpool_bwd(const float* dmean, int B, int HW, int C, void* dx, void* stream);
+AB_API int ab_dilate2x(const void* in, int B, int Ho, int Wo, int H, int W, int C, void* out, void* stream);
+AB_API int ab_deconv4x4s2_gather(const void* dy, int B, int H, int W, int C, void* dycol, void* stream);
+AB_API int ab_head_decode_bwd(const float* logits, const float* dkp3d, int B, int ncls, int D, int H, int W, void* dlogits,
+                              void* stream);
+AB_API int ab_sumsq(const float* g, int64_t n, float* out, void* stream);
+AB_API int ab_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, int step, const float* grad_sumsq, float max_norm, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

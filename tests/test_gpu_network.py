@@ -211,5 +211,5 @@ def test_registry_and_checkpoint_names_follow_the_reference():
         assert k in keys, k
     model.train()
     inp = {k: v.to(DEV) for k, v in netcfg.make_inputs(1).items()}
-    with pytest.raises(NotImplementedError):
-        model(inp)  # training-mode BatchNorm is refused loudly rather than silently using running statistics
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        model(inp)  # train mode without a graph is refused loudly rather than silently using running statistics
