@@ -7,6 +7,7 @@ rebuilt when a parameter's version counter changes.
 """
 from __future__ import annotations
 
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -29,21 +30,32 @@ class Act:
         return self.data.view(self.B, self.H, self.W, self.C).permute(0, 3, 1, 2).to(dtype)
 
 
-_cache = {}
+_cache = weakref.WeakKeyDictionary()  # module -> {tag: (versions, packed value)}; dies with the module (no id() reuse)
+_param_epoch = [0]
 IMPLICIT_CONV = True  # False: materialise im2col rows (ab_im2col_nhwc) and run the plain GEMM, for A/B comparison
 
 
-def _cached(key, versions, build):
-    hit = _cache.get(key)
+def _cached(owner, tag, versions, build):
+    """Packed copy of `owner`'s parameters, rebuilt when a parameter's storage / version / the parameter epoch changes."""
+    slot = _cache.get(owner)
+    if slot is None:
+        slot = _cache[owner] = {}
+    hit = slot.get(tag)
     if hit is not None and hit[0] == versions:
         return hit[1]
     val = build()
-    _cache[key] = (versions, val)
+    slot[tag] = (versions, val)
     return val
 
 
+def bump_params():
+    """Parameters were rewritten behind autograd's back (the fused Adam kernel writes the flat buffer): invalidate
+    every packed copy."""
+    _param_epoch[0] += 1
+
+
 def _ver(*tensors):
-    return tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+    return (_param_epoch[0],) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors if t is not None)
 
 
 def _pad8(n: int) -> int:
@@ -78,7 +90,7 @@ def bn_affine(bn, training: bool):
         bias = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
         return scale.contiguous(), bias.contiguous()
 
-    return _cached(("bn", id(bn)), _ver(bn.weight, bn.bias, bn.running_mean, bn.running_var), build)
+    return _cached(bn, "bn", _ver(bn.weight, bn.bias, bn.running_mean, bn.running_var), build)
 
 
 def image_to_act(image: torch.Tensor) -> Act:
@@ -101,7 +113,7 @@ def conv_bn_act(x: Act, conv: nn.Conv2d, bn=None, relu: bool = False, residual: 
     stride, pad = conv.stride[0], conv.padding[0]
     cout = conv.out_channels
     assert conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1] and conv.groups == 1
-    wp = _cached(("w", id(conv), x.C), _ver(conv.weight), lambda: pack_conv_weight(conv.weight, x.C))
+    wp = _cached(conv, ("w", x.C), _ver(conv.weight), lambda: pack_conv_weight(conv.weight, x.C))
     scale, bias = bn_affine(bn, training)
     if conv.bias is not None:
         cb = conv.bias.detach().float()
@@ -165,7 +177,7 @@ def deconv4x4s2_bn_relu(x: Act, deconv: nn.ConvTranspose2d, bn, training: bool =
     def build():  # [Cin, Cout, ky, kx] -> [(ky, kx, co), ci]
         return deconv.weight.detach().permute(2, 3, 1, 0).reshape(16 * cout, -1).to(torch.bfloat16).contiguous()
 
-    wp = _cached(("dw", id(deconv)), _ver(deconv.weight), build)
+    wp = _cached(deconv, "dw", _ver(deconv.weight), build)
     scale, bias = bn_affine(bn, training)
     if deconv.bias is not None:
         db = deconv.bias.detach().float()
@@ -194,7 +206,7 @@ def linear(x_bf16: torch.Tensor, fc: nn.Linear, relu: bool = False, out_fp32: bo
             b[:n] = fc.bias.detach().float()
         return w, b
 
-    w, b = _cached(("fc", id(fc)), _ver(fc.weight, fc.bias), build)
+    w, b = _cached(fc, "fc", _ver(fc.weight, fc.bias), build)
     out = ops.gemm_bf16(x_bf16, w, bias=b, relu=relu, out_fp32=out_fp32)
     return out[:, :n]
 

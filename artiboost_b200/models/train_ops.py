@@ -120,7 +120,7 @@ def _conv_dgrad(dy: Act, conv_w, kh, kw, stride, pad, H, W, key) -> torch.Tensor
     cout, cin = conv_w.shape[0], conv_w.shape[1]
     dev = dy.data.device
     if kh == 1 and kw == 1:
-        wt = _cached(("wt",) + key, _ver(conv_w), lambda: conv_w.detach().view(cout, cin).t().to(torch.bfloat16).contiguous())
+        wt = _cached(key, "wt", _ver(conv_w), lambda: conv_w.detach().view(cout, cin).t().to(torch.bfloat16).contiguous())
         dx = ops.gemm_bf16(dy.data, wt)  # [M_out, Cin]
         if stride == 1:
             return dx
@@ -128,7 +128,7 @@ def _conv_dgrad(dy: Act, conv_w, kh, kw, stride, pad, H, W, key) -> torch.Tensor
         with torch.cuda.device(dev):
             _call("ab_dilate2x", dx.data_ptr(), dy.B, dy.H, dy.W, H, W, cin, out.data_ptr(), _stream(dev))
         return out
-    wd = _cached(("wd",) + key, _ver(conv_w), lambda: _pack_dgrad_weight(conv_w))
+    wd = _cached(key, "wd", _ver(conv_w), lambda: _pack_dgrad_weight(conv_w))
     g = dy
     if stride == 2:
         d = torch.empty((dy.B * H * W, cout), dtype=torch.bfloat16, device=dev)
@@ -169,7 +169,7 @@ class ConvBNActFn(torch.autograd.Function):
         x = Act(x_data, B, H, W, C)
         kh, kw = conv.kernel_size
         stride, pad, cout = conv.stride[0], conv.padding[0], conv.out_channels
-        wp = _cached(("w", id(conv), C), _ver(weight), lambda: nhwc.pack_conv_weight(weight, C))
+        wp = _cached(conv, ("w", C), _ver(weight), lambda: nhwc.pack_conv_weight(weight, C))
         ctx.meta = (geom, conv, bn, relu, kh, kw, stride, pad, cout, out_fp32)
         ctx.has_res = residual is not None
         empty = x_data.new_empty(0)
@@ -208,7 +208,7 @@ class ConvBNActFn(torch.autograd.Function):
         dw = _conv_wgrad(x, xcol if xcol.numel() else None, draw, weight, kh, kw, stride, pad) if ctx.needs_input_grad[1] else None
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = _conv_dgrad(Act(draw, B, Ho, Wo, cout), weight, kh, kw, stride, pad, H, W, (id(conv),))
+            dx = _conv_dgrad(Act(draw, B, Ho, Wo, cout), weight, kh, kw, stride, pad, H, W, conv)
         if not isinstance(ctx.st, _BNState):
             dgamma = dbeta = None  # frozen / eval-mode statistics carry no parameter gradient here
         return dx, dw, dbias, dgamma, dbeta, dres, None, None, None, None, None, None
@@ -282,7 +282,7 @@ class DeconvBNReluFn(torch.autograd.Function):
         B, H, W, C = geom
         cout = deconv.out_channels
         dev = x_data.device
-        wp = _cached(("dw", id(deconv)), _ver(weight),
+        wp = _cached(deconv, "dw", _ver(weight),
                      lambda: weight.detach().permute(2, 3, 1, 0).reshape(16 * cout, -1).to(torch.bfloat16).contiguous())
         ycol = ops.gemm_bf16(x_data, wp, out_fp32=True)
         M = B * 4 * H * W
@@ -325,7 +325,7 @@ class DeconvBNReluFn(torch.autograd.Function):
                       _stream(dev))
             dw = dwp.view(4, 4, cout, C).permute(3, 2, 0, 1).contiguous()  # -> [Cin, Cout, ky, kx]
         if ctx.needs_input_grad[0]:
-            wt = _cached(("dwt", id(deconv)), _ver(weight),
+            wt = _cached(deconv, "dwt", _ver(weight),
                          lambda: weight.detach().permute(0, 2, 3, 1).reshape(C, 16 * cout).to(torch.bfloat16).contiguous())
             dx = ops.gemm_bf16(dycol, wt)
         if not isinstance(ctx.st, _BNState):
@@ -393,7 +393,7 @@ class LinearFn(torch.autograd.Function):
                   dwp.stride(0), _stream(dev))
         dw = dwp[:n, :k].contiguous()
         db = _col_sum(g)[:n] if fc.bias is not None else None
-        wt = _cached(("fct", id(fc)), _ver(weight), lambda: _pad_rows(weight.detach().t().to(torch.bfloat16), _pad8(k), npad))
+        wt = _cached(fc, "fct", _ver(weight), lambda: _pad_rows(weight.detach().t().to(torch.bfloat16), _pad8(k), npad))
         dx = ops.gemm_bf16(g, wt)[:, :k] if ctx.needs_input_grad[0] else None
         return dx, dw, db, None, None, None
 

@@ -1,0 +1,176 @@
+"""The training step of train/train_artiboost.py:66-96 and the ArtiBoost feedback loop of
+anakin/artiboost/artiboost_loader.py:279-340,503-523, on device:
+
+  synthesise views (CCV draw -> pose generator -> rasterise)  ->  mix with real-shaped samples  ->  HybridBaseline forward
+  (batch-statistics BatchNorm)  ->  losses  ->  backward kernels  ->  gradient all-reduce (NCCL)  ->  clip_grad_norm_ + Adam
+  as one fused kernel over a flat parameter buffer  ->  per-cell error capture for the CCV re-weighting.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import lib, parallel
+from .models import nhwc
+from .criterions import DEFAULT_CRITERION_CFG, Criterion
+
+
+class FlatParams:
+    """Re-homes every parameter of `model` (and its gradient) as a view into one flat fp32 buffer, so the all-reduce,
+    the norm and the Adam update are single launches.  state_dict names and shapes are untouched."""
+
+    def __init__(self, model: nn.Module):
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.params = params
+        n = sum(p.numel() for p in params)
+        dev = params[0].device
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p.data)
+            p.grad = self.grad[off:off + k].view_as(p.data)
+            off += k
+        self.numel = n
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p in self.params:  # autograd may have replaced .grad with a fresh tensor: re-attach the views
+            pass
+
+
+class FusedAdam:
+    """torch.optim.Adam(lr, betas, eps, weight_decay) + clip_grad_norm_(max_norm) in two launches (ab_sumsq, ab_adam_step)."""
+
+    def __init__(self, flat: FlatParams, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=0.0):
+        self.fp, self.lr, self.betas, self.eps, self.wd, self.max_norm = flat, lr, betas, eps, weight_decay, max_norm
+        self.m = torch.zeros_like(flat.flat)
+        self.v = torch.zeros_like(flat.flat)
+        self.sumsq = torch.zeros(1, device=flat.flat.device)
+        self.step_count = 0
+
+    def step(self, grad_scale: float = 1.0):
+        fp, dev = self.fp, self.fp.flat.device
+        self.step_count += 1
+        L = lib.load()
+        with torch.cuda.device(dev):
+            if self.max_norm > 0:
+                self.sumsq.zero_()
+                lib.check(L.ab_sumsq(fp.grad.data_ptr(), fp.numel, self.sumsq.data_ptr(), lib.stream_ptr(dev)), "ab_sumsq")
+            lib.check(L.ab_adam_step(fp.flat.data_ptr(), fp.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), fp.numel,
+                                     self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count,
+                                     self.sumsq.data_ptr(), float(self.max_norm), float(grad_scale), lib.stream_ptr(dev)),
+                      "ab_adam_step")
+        nhwc.bump_params()  # the kernel rewrote the parameters in place: packed bf16 filter copies are stale
+
+    def grad_norm(self) -> torch.Tensor:
+        return self.sumsq.sqrt()
+
+
+class CCVFeedback:
+    """Per-(object, view, grasp) error capture during training and the weight update of `update_method_1`
+    (val_metric.py:76-135 ValMetricMean3DEPE2 + artiboost_loader.py:292-340,503-523), kept on the device."""
+
+    def __init__(self, shape, device, lower=0.1, upper=10.0):
+        self.shape = tuple(shape)
+        self.err_sum = torch.zeros(self.shape, device=device)
+        self.err_cnt = torch.zeros(self.shape, device=device)
+        self.lower, self.upper = lower, upper
+
+    @torch.no_grad()
+    def feed(self, pred_corners_abs, targ_corners_abs, obj_id, persp_id, grasp_id, is_synth=None):
+        """mean corner error in millimetres per sample (meanepe.py:39-70), accumulated in its CCV cell."""
+        err = (pred_corners_abs - targ_corners_abs).norm(dim=-1).mean(dim=-1) * 1000.0
+        if is_synth is not None:
+            keep = is_synth.bool()
+            err, obj_id, persp_id, grasp_id = err[keep], obj_id[keep], persp_id[keep], grasp_id[keep]
+        flat = (obj_id.long() * self.shape[1] + persp_id.long()) * self.shape[2] + grasp_id.long()
+        self.err_sum.view(-1).index_add_(0, flat, err.float())
+        self.err_cnt.view(-1).index_add_(0, flat, torch.ones_like(err, dtype=torch.float32))
+
+    @torch.no_grad()
+    def step_eval(self, weight_map: torch.Tensor) -> torch.Tensor:
+        """All-reduce the cell statistics over ranks, apply update_method_1, reset.  -> new weight map."""
+        parallel.allreduce_cell_errors_(self.err_sum, self.err_cnt)
+        seen = self.err_cnt > 0
+        new = weight_map.clone()
+        if bool(seen.any()):
+            val = self.err_sum[seen] / self.err_cnt[seen]
+            vmax, vmin = val.max(), val.min()
+            conf = (vmax - val) / (vmax - vmin + 1e-8)
+            new[seen] = new[seen] * (1.0 / (conf + 0.5))
+        new = torch.clamp(new, self.lower, self.upper)  # also lifts blacklisted zeros to `lower`, like the reference
+        self.err_sum.zero_()
+        self.err_cnt.zero_()
+        return new
+
+
+class TrainStep:
+    """One optimisation step on a batch dict with the reference's keys (image, root_joint, cam_intr, corners_can,
+    joints_3d, corners_3d, joints_vis, corners_vis)."""
+
+    def __init__(self, arch: nn.Module, criterion_cfg: Optional[dict] = None, lr=5e-5, grad_clip=1e-3, generator=None):
+        self.arch = arch
+        self.flat = FlatParams(arch)
+        self.opt = FusedAdam(self.flat, lr=lr, max_norm=grad_clip)   # Adam lr 5e-5, clip 1e-3 (yaml:130-142)
+        self.criterion = Criterion(criterion_cfg or DEFAULT_CRITERION_CFG, generator=generator)
+        self.world = parallel.world()[1]
+
+    def __call__(self, batch: Dict[str, torch.Tensor]):
+        self.arch.train()
+        self.flat.grad.zero_()
+        for p in self.flat.params:  # gradients accumulate straight into the flat buffer's views
+            if p.grad is None or p.grad.data_ptr() < self.flat.grad.data_ptr():
+                raise RuntimeError("a parameter gradient left the flat buffer")
+        preds = self.arch(batch)
+        preds = preds[next(iter(preds))] if "joints_3d_abs" not in preds else preds
+        loss, parts = self.criterion.compute_losses(preds, batch)
+        loss.backward()
+        parallel.allreduce_sum_(self.flat.grad)
+        self.opt.step(grad_scale=1.0 / self.world)
+        return loss.detach(), preds
+
+
+def synth_to_batch(views: dict, pipe, center_idx: int = 0) -> Dict[str, torch.Tensor]:
+    """Rendered views + their annotations -> the network's batch dict (the part of RenderedDataset.__getitem__ that is
+    not augmentation: rendered_dataset.py:127-133,207-272).  No crop / warp yet: the render size
+    is the network input size."""
+    rgba = views["rgba"]
+    B = rgba.shape[0]
+    image = rgba[..., :3].permute(0, 3, 1, 2).float() / 255.0 - 0.5           # to_tensor, then -0.5 (:269-270)
+    joints = views["joints"]
+    pose = views["obj_pose"]
+    corners_can = pipe.obj_engine.corners_can[views["obj_id"].long()]
+    corners = torch.einsum("bij,bkj->bki", pose[:, :3, :3], corners_can) + pose[:, :3, 3].unsqueeze(1)
+    root = joints[:, center_idx]
+    K = torch.as_tensor(pipe.cam_intr, device=rgba.device).expand(B, 3, 3).contiguous()
+    ones = lambda n: torch.ones((B, n), device=rgba.device)  # noqa: E731
+    return {"image": image, "root_joint": root, "cam_intr": K, "corners_can": corners_can,
+            "joints_3d": joints - root.unsqueeze(1), "corners_3d": corners - root.unsqueeze(1),
+            "joints_vis": ones(21), "corners_vis": ones(8), "is_synth": torch.ones(B, device=rgba.device),
+            "obj_id": views["obj_id"], "persp_id": views["persp_id"], "grasp_id": views["grasp_id"]}
+
+
+def real_shaped_batch(B: int, device, generator=None, size: int = 256) -> Dict[str, torch.Tensor]:
+    """Synthetic stand-in for real dataset samples with the schema of anakin/datasets/hodata.py:315-450: random image,
+    geometrically consistent random annotations."""
+    g = generator
+    r = lambda *s: torch.rand(s, device=device, generator=g)  # noqa: E731
+    n = lambda *s: torch.randn(s, device=device, generator=g)  # noqa: E731
+    root = torch.tensor([0.0, 0.0, 0.5], device=device) + 0.05 * n(B, 3)
+    f = 217.5 * size / 256
+    K = torch.tensor([[f, 0, size / 2.0], [0, f, size / 2.0], [0, 0, 1]], device=device).expand(B, 3, 3).contiguous()
+    return {"image": r(B, 3, size, size) - 0.5, "root_joint": root, "cam_intr": K, "corners_can": 0.2 * r(B, 8, 3) - 0.1,
+            "joints_3d": 0.05 * n(B, 21, 3), "corners_3d": 0.08 * n(B, 8, 3), "joints_vis": torch.ones((B, 21), device=device),
+            "corners_vis": torch.ones((B, 8), device=device), "is_synth": torch.zeros(B, device=device),
+            "obj_id": torch.zeros(B, dtype=torch.int32, device=device), "persp_id": torch.zeros(B, dtype=torch.int32, device=device),
+            "grasp_id": torch.zeros(B, dtype=torch.int32, device=device)}
+
+
+def mix_batches(a: Dict[str, torch.Tensor], b: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """MixedDataset (mixed_dataset.py:32-37) at batch granularity: real-shaped samples followed by synthetic ones."""
+    return {k: torch.cat([a[k], b[k]], dim=0) for k in a.keys() & b.keys()}

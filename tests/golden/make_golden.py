@@ -9,7 +9,8 @@ The fixtures pin oracle/ (tests/test_oracle_golden.py); the GPU parity tests the
   preprocessor.npz   anakin/artiboost/preprocessor.py       PreProcessorPoseGenerator.forward + refiner.NullRefine
                      (third-party MANO / pytorch3d underneath are oracle shims: pins the composition)
   ortho6d.npz        anakin/utils/transform.py              compute_rotation_matrix_from_ortho6d, batch_uvd2xyz
-  update_method.npz  anakin/artiboost/artiboost_loader.py   update_method_1 arithmetic (:503-523, run on a bare object)
+  update_method.npz  anakin/artiboost/artiboost_loader.py   update_method_1 arithmetic (:503-523)
+  losses.npz         anakin/criterions/{criterion,jointloss,ordinal}.py  Criterion.compute_losses with pinned random draws
 """
 import os
 import sys
@@ -188,6 +189,39 @@ def gen_update_method():
     save("update_method.npz", w0=w0.numpy(), cells=cells, vals=vals, w1=w1.numpy())
 
 
+def gen_losses():
+    """anakin/criterions/{jointloss,ordinal,criterion}.py with the random draws pinned: random.shuffle -> identity (the
+    first third of the pairs is kept), sample_view_vectors -> a recorded set of view vectors."""
+    import random as pyrandom
+    from anakin.criterions import ordinal
+    from anakin.criterions.criterion import Criterion
+    from anakin.criterions.jointloss import JointsLoss
+    rng = np.random.RandomState(6)
+    B = 5
+    t = lambda a: torch.from_numpy(np.asarray(a, np.float32))  # noqa: E731
+    preds = {"joints_3d_abs": t(rng.normal(0, 0.05, (B, 21, 3)) + [0, 0, 0.5]), "corners_3d_abs": t(rng.normal(0, 0.08, (B, 8, 3)) + [0, 0, 0.5])}
+    jv, cv = np.ones((B, 21), np.float32), np.ones((B, 8), np.float32)
+    jv[1, 3:7] = 0
+    cv[2, :] = 0
+    targs = {"joints_3d": t(rng.normal(0, 0.05, (B, 21, 3))), "corners_3d": t(rng.normal(0, 0.08, (B, 8, 3))),
+             "root_joint": t(rng.normal(0, 0.05, (B, 3)) + [0, 0, 0.5]), "joints_vis": t(jv), "corners_vis": t(cv)}
+    vv = {20: ordinal.sample_view_vectors(20), 40: ordinal.sample_view_vectors(40)}
+    orig_shuffle, orig_svv = pyrandom.shuffle, ordinal.sample_view_vectors
+    pyrandom.shuffle = lambda x: None
+    ordinal.random.shuffle = lambda x: None
+    ordinal.sample_view_vectors = lambda n=20: vv[n]
+    try:
+        crit = Criterion({"LAMBDAS": [0.5, 0.2, 0.1]}, [JointsLoss(LAMBDA_JOINTS_3D=1.0, LAMBDA_CORNERS_3D=0.2),
+                                                          ordinal.HandOrdLoss(), ordinal.SceneOrdLoss()])
+        total, parts = crit.compute_losses(preds, targs)
+    finally:
+        pyrandom.shuffle, ordinal.sample_view_vectors = orig_shuffle, orig_svv
+        ordinal.random.shuffle = orig_shuffle
+    save("losses.npz", vv20=vv[20].numpy(), vv40=vv[40].numpy(), total=total.numpy(),
+         **{"pred_" + k: v.numpy() for k, v in preds.items()}, **{"targ_" + k: v.numpy() for k, v in targs.items()},
+         **{"part_" + k: (v.numpy() if v is not None else np.zeros(())) for k, v in parts.items()})
+
+
 if __name__ == "__main__":
     model = assets.make_synthetic_mano(seed=0)
     gen_mano(model)
@@ -196,3 +230,4 @@ if __name__ == "__main__":
     gen_scrambler_and_preprocessor(model)
     gen_transform()
     gen_update_method()
+    gen_losses()

@@ -179,9 +179,13 @@ def test_hybridbaseline_matches_reference_modules(backbone):
     model = build(backbone)
     assert sum(p.numel() for p in model.parameters()) == int(g["n_params"])
     inp = {k: v.to(DEV) for k, v in netcfg.make_inputs(2).items()}
-    out = model(inp)["HybridBaseline"]
+    with torch.no_grad():
+        out = model(inp)["HybridBaseline"]
     for k in ("joints_3d_abs", "corners_3d_abs", "joints_3d", "corners_3d", "2d_uvd", "boxroot_3d_abs", "box_rot_rotmat"):
         assert tuple(out[k].shape) == g[k].shape, k
+    graph_out = model(inp)["HybridBaseline"]  # same eval-mode arithmetic when autograd records the graph
+    assert graph_out["joints_3d_abs"].requires_grad
+    torch.testing.assert_close(graph_out["joints_3d_abs"].detach(), out["joints_3d_abs"], rtol=0, atol=1e-4)
     err_j = np.abs(out["joints_3d_abs"].cpu().numpy() - g["joints_3d_abs"]).max()
     err_c = np.abs(out["corners_3d_abs"].cpu().numpy() - g["corners_3d_abs"]).max()
     err_uvd = np.abs(out["2d_uvd"].cpu().numpy() - g["2d_uvd"]).max()
@@ -190,7 +194,8 @@ def test_hybridbaseline_matches_reference_modules(backbone):
     assert err_j < 3e-3 and err_c < 3e-3, "3 mm bound on absolute keypoints / corners"
     assert err_uvd < 5e-3 and err_R < 3e-2
     # intermediate features follow the fp32 reference statistically and point-wise on the pooled feature
-    feats = model.model_list[0].backbone(image=inp["image"])
+    with torch.no_grad():
+        feats = model.model_list[0].backbone(image=inp["image"])
     l4m = feats["res_layer4_mean"].cpu().numpy()
     rel = np.abs(l4m - g["res_layer4_mean"]).max() / np.abs(g["res_layer4_mean"]).max()
     assert rel < 3e-2, rel

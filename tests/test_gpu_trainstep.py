@@ -1,0 +1,76 @@
+"""GPU: fused Adam + gradient clipping vs torch.optim.Adam + clip_grad_norm_; the full synth -> train step runs, learns
+and feeds the CCV re-weighting."""
+import sys
+
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+sys.path.insert(0, GOLDEN)
+import netcfg  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_fused_adam_matches_torch_adam_with_clipping(lib_built):
+    from artiboost_b200.train import FlatParams, FusedAdam
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Linear(19, 5)).to(DEV)
+    ref = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Linear(19, 5)).to(DEV)
+    ref.load_state_dict(net.state_dict())
+    flat = FlatParams(net)
+    opt = FusedAdam(flat, lr=1e-3, max_norm=0.05, weight_decay=0.0)
+    topt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    for it in range(5):
+        x = torch.randn((16, 37), device=DEV)
+        flat.grad.zero_()
+        net(x).pow(2).mean().backward()
+        opt.step()
+        topt.zero_grad()
+        ref(x).pow(2).mean().backward()
+        total = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05)
+        topt.step()
+        torch.testing.assert_close(opt.grad_norm()[0], total, rtol=1e-5, atol=1e-8)
+    for p, q in zip(net.parameters(), ref.parameters()):
+        torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-7)
+    assert net[0].weight.data_ptr() >= flat.flat.data_ptr()  # parameters live inside the flat buffer
+
+
+def test_synth_train_step_runs_learns_and_feeds_ccv(lib_built):
+    import artiboost_b200.models as M
+    from artiboost_b200.synth import SynthPipeline
+    from artiboost_b200.train import CCVFeedback, TrainStep, mix_batches, real_shaped_batch, synth_to_batch
+    arch, preset = netcfg.arch_cfg("ResNet34")
+    torch.manual_seed(1)
+    model = M.Arch({"ARCH": arch}, M.build_arch_model_list(arch, preset_cfg=preset)).to(DEV)
+    pipe = SynthPipeline(device=DEV, seed=1, n_hand_tex=4, n_bg=2)
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    step = TrainStep(model, lr=1e-3, grad_clip=1.0, generator=gen)
+    fb = CCVFeedback(pipe.sample_weight_map.shape, DEV)
+    views = pipe.synthesise(6)
+    batch = mix_batches(real_shaped_batch(10, DEV, gen), synth_to_batch(views, pipe))
+    assert batch["image"].shape == (16, 3, 256, 256) and float(batch["is_synth"].sum()) == 6
+    w0 = model.model_list[0].backbone.conv1.weight.detach().clone()
+    losses = []
+    for it in range(6):
+        loss, preds = step(batch)
+        if it == 0:
+            first = preds["joints_3d_abs"].detach().clone()
+        if it == 1:  # the packed bf16 filters followed the in-place Adam update (no stale copies)
+            assert not torch.equal(first, preds["joints_3d_abs"].detach())
+        losses.append(float(loss))
+        targ = batch["corners_3d"] + batch["root_joint"].unsqueeze(1)
+        fb.feed(preds["corners_3d_abs"].detach(), targ, batch["obj_id"], batch["persp_id"], batch["grasp_id"], batch["is_synth"])
+    assert all(l == l for l in losses) and losses[-1] < losses[0], losses   # finite, decreasing on a fixed batch
+    assert not torch.equal(w0, model.model_list[0].backbone.conv1.weight)
+    assert float(fb.err_cnt.sum()) == 36.0
+    new_w = fb.step_eval(pipe.sample_weight_map)
+    assert new_w.shape == pipe.sample_weight_map.shape and float(new_w.min()) >= 0.1 and float(new_w.max()) <= 10.0
+    assert int((new_w != 1.0).sum()) >= 1
+    # BatchNorm running statistics moved, and eval-mode inference still works afterwards
+    assert float(model.model_list[0].backbone.bn1.running_mean.abs().sum()) > 0
+    with torch.no_grad():
+        out = model.eval()(batch)["HybridBaseline"]
+    assert torch.isfinite(out["joints_3d_abs"]).all()

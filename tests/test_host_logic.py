@@ -1,0 +1,129 @@
+"""CPU tests of the host-side logic: losses vs the reference's own criterions (fixture), CCV feedback vs the oracle,
+multi-process plumbing on the gloo backend (world_size 2), registries."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import golden
+
+
+def test_criterion_matches_reference_losses(monkeypatch):
+    """artiboost_b200/criterions.py vs anakin/criterions/* (tests/golden/losses.npz, random draws pinned)."""
+    from artiboost_b200 import criterions as C
+    g = golden("losses.npz")
+    t = torch.from_numpy
+    preds = {"joints_3d_abs": t(g["pred_joints_3d_abs"]), "corners_3d_abs": t(g["pred_corners_3d_abs"])}
+    targs = {k: t(g["targ_" + k]) for k in ("joints_3d", "corners_3d", "root_joint", "joints_vis", "corners_vis")}
+    vv = {20: t(g["vv20"]), 40: t(g["vv40"])}
+    monkeypatch.setattr(C, "sample_view_vectors", lambda n, device, generator=None: vv[n])
+    monkeypatch.setattr(C, "_subsample", lambda n, device, generator: torch.arange(n // 3))
+    crit = C.Criterion(C.DEFAULT_CRITERION_CFG)
+    total, parts = crit.compute_losses(preds, targs)
+    np.testing.assert_allclose(total.numpy(), g["total"].reshape(()), rtol=1e-5)
+    for k in ("joints_3d_loss", "corners_3d_loss", "joint_ord_loss", "part_ord_loss", "scene_ord_loss"):
+        np.testing.assert_allclose(parts[k].numpy(), g["part_" + k], rtol=1e-5, atol=1e-9, err_msg=k)
+    # unpinned draws: finite, differentiable
+    crit = C.Criterion(C.DEFAULT_CRITERION_CFG, generator=torch.Generator().manual_seed(0))
+    p = {k: v.clone().requires_grad_(True) for k, v in preds.items()}
+    total, _ = crit.compute_losses(p, targs)
+    total.backward()
+    assert torch.isfinite(total) and all(torch.isfinite(v.grad).all() for v in p.values())
+
+
+def test_ccv_feedback_matches_oracle_update_method_1():
+    from artiboost_b200.train import CCVFeedback
+    from oracle import ccv
+    g = golden("update_method.npz")
+    fb = CCVFeedback(g["w0"].shape, "cpu")
+    cells, vals = torch.from_numpy(g["cells"]), torch.from_numpy(g["vals"]).float()
+    # feed every cell twice with errors whose mean is the recorded value (in metres: feed() converts to millimetres)
+    for delta in (-1.0, 1.0):
+        err = (vals + delta) / 1000.0
+        pred = torch.zeros((len(vals), 8, 3))
+        pred[:, :, 0] = err[:, None]
+        fb.feed(pred, torch.zeros_like(pred), cells[:, 0], cells[:, 1], cells[:, 2])
+    w1 = fb.step_eval(torch.from_numpy(g["w0"]))
+    np.testing.assert_allclose(w1.numpy(), g["w1"], rtol=2e-5)  # the reference's own update_method_1 output
+    np.testing.assert_allclose(w1.numpy(), ccv.update_method_1(g["w0"], g["cells"], g["vals"]), rtol=2e-5)
+    assert float(fb.err_cnt.sum()) == 0.0
+
+
+def test_shard_range_is_a_partition():
+    from artiboost_b200.parallel import shard_range
+    for n in (0, 1, 7, 512, 1000):
+        for w in (1, 2, 3, 8):
+            cuts = [shard_range(n, r, w) for r in range(w)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from artiboost_b200 import parallel
+    from artiboost_b200.train import CCVFeedback
+    assert parallel.world() == (rank, world)
+    # gradient all-reduce on a flat buffer, bucketed
+    g = torch.full((1000,), float(rank + 1))
+    parallel.allreduce_sum_(g, bucket_elems=256)
+    assert torch.equal(g, torch.full((1000,), 3.0))
+    # CCV feedback: each rank feeds its own shard of the samples; step_eval must equal the single-process result
+    rng = np.random.RandomState(0)
+    shape = (4, 12, 5)
+    n = 200
+    cells = np.stack([rng.randint(s, size=n) for s in shape], 1)
+    err = rng.uniform(0.005, 0.06, size=n).astype(np.float32)
+    lo, hi = parallel.shard_range(n)
+    fb = CCVFeedback(shape, "cpu")
+    pred = torch.zeros((hi - lo, 8, 3))
+    pred[:, :, 2] = torch.from_numpy(err[lo:hi])[:, None]
+    c = torch.from_numpy(cells[lo:hi])
+    fb.feed(pred, torch.zeros_like(pred), c[:, 0], c[:, 1], c[:, 2])
+    occ = torch.zeros(shape, dtype=torch.bool)
+    occ[c[:, 0], c[:, 1], c[:, 2]] = True
+    _, _, occ = parallel.allreduce_cell_errors_(torch.zeros(shape), torch.zeros(shape), occ)
+    w = fb.step_eval(torch.ones(shape))
+    torch.save({"w": w, "occ": occ}, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_allreduce_and_ccv_feedback(tmp_path):
+    from artiboost_b200.train import CCVFeedback
+    port = 29500 + os.getpid() % 400
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
+    assert torch.equal(r0["w"], r1["w"]) and torch.equal(r0["occ"], r1["occ"])
+    rng = np.random.RandomState(0)
+    shape, n = (4, 12, 5), 200
+    cells = np.stack([rng.randint(s, size=n) for s in shape], 1)
+    err = rng.uniform(0.005, 0.06, size=n).astype(np.float32)
+    fb = CCVFeedback(shape, "cpu")
+    pred = torch.zeros((n, 8, 3))
+    pred[:, :, 2] = torch.from_numpy(err)[:, None]
+    c = torch.from_numpy(cells)
+    fb.feed(pred, torch.zeros_like(pred), c[:, 0], c[:, 1], c[:, 2])
+    torch.testing.assert_close(fb.step_eval(torch.ones(shape)), r0["w"], rtol=1e-5, atol=1e-6)
+    occ = torch.zeros(shape, dtype=torch.bool)
+    occ[c[:, 0], c[:, 1], c[:, 2]] = True
+    assert torch.equal(occ, r0["occ"])
+
+
+def test_model_registry_builds_the_reference_config_on_cpu():
+    import artiboost_b200.models as M
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import netcfg
+    arch, preset = netcfg.arch_cfg("ResNet34")
+    g = golden("network_resnet34.npz")
+    torch.manual_seed(netcfg.SEED)
+    model = M.Arch({"ARCH": arch}, M.build_arch_model_list(arch, preset_cfg=preset))
+    assert sum(p.numel() for p in model.parameters()) == int(g["n_params"]) == 25267734
+    from artiboost_b200.lib import AbError
+    with torch.no_grad(), pytest.raises(AbError):
+        model.eval()(netcfg.make_inputs(1))  # host tensors: there is no CPU path
