@@ -99,18 +99,10 @@ __global__ void im2col_c4_kernel(const uint2* __restrict__ in, int B, int H, int
         for (int k = kh * kw; k < Kp4; ++k) out[m * Kp4 + k] = make_uint2(0, 0);
 }
 
-__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
-    uint4 r;
-    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
-    __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) pr[j] = __hmax2(pa[j], pb[j]);
-    return r;
-}
-
+// idx (optional, training): uint8 per output element = ky*3 + kx of the FIRST maximum in scan order (torch's tie-break),
+// consumed by ab_maxpool3x3s2_bwd.
 __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int B, int H, int W, int C8, int Ho, int Wo,
-                                    uint4* __restrict__ out) {
+                                    uint4* __restrict__ out, uint2* __restrict__ idx) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * Ho * Wo * C8;
     if (i >= total) return;
@@ -120,8 +112,10 @@ __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int B, int H, 
     t /= Wo;
     const int oy = (int)(t % Ho);
     const int b = (int)(t / Ho);
-    bool any = false;
-    uint4 best = make_uint4(0, 0, 0, 0);
+    float best[8];
+    uint32_t tap[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; tap[j] = 4; }
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -129,10 +123,21 @@ __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int B, int H, 
             const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
             if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
             const uint4 v = __ldg(in + (((long long)b * H + iy) * W + ix) * C8 + c8);
-            best = any ? bf16x8_max(best, v) : v;
-            any = true;
+            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(pv[j]);
+                if (f.x > best[2 * j]) { best[2 * j] = f.x; tap[2 * j] = ky * 3 + kx; }
+                if (f.y > best[2 * j + 1]) { best[2 * j + 1] = f.y; tap[2 * j + 1] = ky * 3 + kx; }
+            }
         }
-    out[i] = best;
+    uint4 o;
+    __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) po[j] = __floats2bfloat162_rn(best[2 * j], best[2 * j + 1]);  // exact: values are bf16
+    out[i] = o;
+    if (idx) idx[i] = make_uint2(tap[0] | (tap[1] << 8) | (tap[2] << 16) | (tap[3] << 24),
+                                 tap[4] | (tap[5] << 8) | (tap[6] << 16) | (tap[7] << 24));
 }
 
 // [B, HW, C] bf16 -> mean over HW: fp32 [B, C] and bf16 [B, C].  One thread per (b, c); consecutive threads read
@@ -294,7 +299,7 @@ extern "C" int ab_im2col_nhwc(const void* in, int B, int H, int W, int C, int kh
     return check_launch("im2col_kernel");
 }
 
-extern "C" int ab_maxpool3x3s2_nhwc(const void* in, int B, int H, int W, int C, void* out, void* stream) {
+extern "C" int ab_maxpool3x3s2_nhwc(const void* in, int B, int H, int W, int C, void* out, void* idx, void* stream) {
     AB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad shape (C must be a multiple of 8)");
     if (B == 0) return AB_OK;
     AB_REQUIRE(in && out, "null pointer");
@@ -302,7 +307,7 @@ extern "C" int ab_maxpool3x3s2_nhwc(const void* in, int B, int H, int W, int C, 
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_ELEMENTWISE, st);
     maxpool3x3s2_kernel<<<blocks_for((long long)B * Ho * Wo * (C / 8), 256), 256, 0, st>>>((const uint4*)in, B, H, W, C / 8,
-                                                                                           Ho, Wo, (uint4*)out);
+                                                                                           Ho, Wo, (uint4*)out, (uint2*)idx);
     count_launch();
     return check_launch("maxpool3x3s2_kernel");
 }

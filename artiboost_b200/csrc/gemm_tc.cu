@@ -37,8 +37,8 @@ struct GemmEpilogue {
     const __nv_bfloat16* residual;  // [M, ldr] or null
     long long ldr;
     int relu;
-    float* col_sum;          // [N] or null: += sum over rows of the PRE-epilogue accumulator
-    float* col_sumsq;        // [N] or null
+    float* col_sum;          // [ceil(M/128), N] or null: per-row-tile column sums of the PRE-epilogue accumulator
+    float* col_sumsq;        // [ceil(M/128), N] or null   (plain stores, no atomics: deterministic; see ab_bn_finalize)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -122,7 +122,27 @@ struct GemmSmem {
     __nv_bfloat16 b[STAGES][BN * kBK];
     uint64_t full[STAGES], empty[STAGES], tmem_full;
     uint32_t tmem_base;
+    float stat[2][4][BN];    // per-epilogue-warp column sums / sums of squares of this tile
 };
+
+// Column sums of a 32 x 16 fragment held one row per lane: butterfly that halves the columns a lane owns at every
+// step (8 + 4 + 2 + 1 + 1 shuffles instead of 16 x 5).  The result is the sum of column
+// 8*bit4(lane) + 4*bit3(lane) + 2*bit2(lane) + bit1(lane), present on both lanes of each even/odd pair.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    bool hi = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = (hi ? v[j + 8] : v[j]) + __shfl_xor_sync(0xffffffffu, hi ? v[j] : v[j + 8], 16);
+    hi = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = (hi ? a[j + 4] : a[j]) + __shfl_xor_sync(0xffffffffu, hi ? a[j] : a[j + 4], 8);
+    hi = lane & 4;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) c[j] = (hi ? b[j + 2] : b[j]) + __shfl_xor_sync(0xffffffffu, hi ? b[j] : b[j + 2], 4);
+    hi = lane & 2;
+    float d = (hi ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, hi ? c[0] : c[1], 2);
+    return d + __shfl_xor_sync(0xffffffffu, d, 1);
+}
 
 template <int BN, int STAGES, bool IM2COL>
 __global__ void __launch_bounds__(kGemmThreads)
@@ -207,18 +227,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
             if (ep.col_sum) {  // training-mode BatchNorm statistics of the raw convolution output
+                float s1[16], s2[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float s1 = row_ok ? v[j] : 0.0f, s2 = s1 * s1;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                    }
-                    if (lane == 0 && col + j < N) {
-                        atomicAdd(ep.col_sum + col + j, s1);
-                        atomicAdd(ep.col_sumsq + col + j, s2);
-                    }
+                for (int j = 0; j < 16; ++j) { s1[j] = row_ok ? v[j] : 0.0f; s2[j] = s1[j] * s1[j]; }
+                const float t1 = warp_colsum16(s1, lane), t2 = warp_colsum16(s2, lane);
+                if (!(lane & 1)) {
+                    const int cj = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    sm.stat[0][q][cj] = t1;
+                    sm.stat[1][q][cj] = t2;
                 }
             }
             if (!row_ok) continue;
@@ -256,6 +272,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 4; ++j) pp[j] = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
                     *reinterpret_cast<uint4*>((__nv_bfloat16*)ep.D + (size_t)row * ep.ldd + cc) = pk;
+                }
+            }
+        }
+        if (ep.col_sum) {  // combine the four epilogue warps, one plain store per (row tile, column)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int c = threadIdx.x - 128; c < BN; c += 128) {
+                const int col = tile_n * BN + c;
+                if (col < N) {
+                    ep.col_sum[(size_t)tile_m * N + col] = (sm.stat[0][0][c] + sm.stat[0][1][c]) + (sm.stat[0][2][c] + sm.stat[0][3][c]);
+                    ep.col_sumsq[(size_t)tile_m * N + col] = (sm.stat[1][0][c] + sm.stat[1][1][c]) + (sm.stat[1][2][c] + sm.stat[1][3][c]);
                 }
             }
         }

@@ -33,25 +33,27 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float* f) {
 }
 
 constexpr int kRedThreads = 256;
-constexpr int kRedRows = 512;  // rows per CTA in the column reductions
 
-// Column reduction skeleton: thread t owns column group g = t % C8 and visits rows r0 + t / C8 + k * (256 / C8); the
-// CTA's partial sums are combined in shared memory and issued as one atomic per (CTA, column).
+// Column reduction skeleton, deterministic (no atomics): CTA b of gridDim.x visits row slices b, b + grid, ...; thread t
+// owns column group g = t % C8 and row t / C8 of each slice (a warp reads whole contiguous rows).  The CTA's sums are
+// combined in shared memory and stored as row b of the partial matrices part[a] ([gridDim.x, C] each); the small
+// partial_sum_kernel below adds the rows up.
 template <int NACC, class RowFn>
-__device__ __forceinline__ void column_reduce(int M, int C8, float* const* out, RowFn fn) {
+__device__ __forceinline__ void column_partial(int M, int C8, float* const* part, RowFn fn) {
     __shared__ float red[kRedThreads][8 * NACC + 1];
     const int t = threadIdx.x;
     const int tpr = min(C8, kRedThreads);       // threads per row
     const int rows_par = kRedThreads / tpr;     // rows visited in parallel
     const int g0 = t % tpr, rl = t / tpr;
-    const long long r_begin = (long long)blockIdx.x * kRedRows;
-    const long long r_end = min((long long)M, r_begin + kRedRows);
+    const int C = 8 * C8;
     for (int g = g0; g < C8; g += tpr) {
         float acc[8 * NACC];
 #pragma unroll
         for (int j = 0; j < 8 * NACC; ++j) acc[j] = 0.0f;
-        if (rl < rows_par)
-            for (long long r = r_begin + rl; r < r_end; r += rows_par) fn(r, g, acc);
+        if (rl < rows_par) {
+#pragma unroll 4
+            for (long long r = (long long)blockIdx.x * rows_par + rl; r < M; r += (long long)gridDim.x * rows_par) fn(r, g, acc);
+        }
 #pragma unroll
         for (int j = 0; j < 8 * NACC; ++j) red[t][j] = acc[j];
         __syncthreads();
@@ -60,26 +62,53 @@ __device__ __forceinline__ void column_reduce(int M, int C8, float* const* out, 
 #pragma unroll
                 for (int j = 0; j < 8 * NACC; ++j) acc[j] += red[t + k * tpr][j];
 #pragma unroll
-            for (int a = 0; a < NACC; ++a)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) atomicAdd(out[a] + 8 * g + j, acc[8 * a + j]);
+            for (int a = 0; a < NACC; ++a) {
+                float4* o = reinterpret_cast<float4*>(part[a] + (size_t)blockIdx.x * C + 8 * g);
+                o[0] = make_float4(acc[8 * a], acc[8 * a + 1], acc[8 * a + 2], acc[8 * a + 3]);
+                o[1] = make_float4(acc[8 * a + 4], acc[8 * a + 5], acc[8 * a + 6], acc[8 * a + 7]);
+            }
         }
         __syncthreads();
     }
 }
 
+// out_a[c] = sum_p part_a[p, c]  for a = 0, 1 (part1 / out1 may be null).  Block = 8 columns x 32 partial rows.
+__global__ void __launch_bounds__(256)
+partial_sum_kernel(const float* __restrict__ part0, const float* __restrict__ part1, int n_part, int C, float* out0, float* out1) {
+    __shared__ float red[2][8][8];
+    const int cx = threadIdx.x & 7, pr = threadIdx.x >> 3, c = blockIdx.x * 8 + cx;
+    float s0 = 0.0f, s1 = 0.0f;
+    if (c < C)
+        for (int p = pr; p < n_part; p += 32) {
+            s0 += part0[(size_t)p * C + c];
+            if (part1) s1 += part1[(size_t)p * C + c];
+        }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane < 8) { red[0][wid][lane] = s0; red[1][wid][lane] = s1; }
+    __syncthreads();
+    if (threadIdx.x < 8 && c < C) {
+        float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a0 += red[0][w][threadIdx.x]; a1 += red[1][w][threadIdx.x]; }
+        out0[c] = a0;
+        if (out1) out1[c] = a1;
+    }
+}
+
 __global__ void __launch_bounds__(kRedThreads)
-col_stats_bf16_kernel(const uint4* __restrict__ x, int M, int C8, long long ld8, float* sum, float* sumsq) {
-    float* outs[2] = {sum, sumsq};
-    if (sumsq) {
-        column_reduce<2>(M, C8, outs, [&](long long r, int g, float* acc) {
+col_stats_bf16_kernel(const uint4* __restrict__ x, int M, int C8, long long ld8, float* psum, float* psumsq) {
+    float* outs[2] = {psum, psumsq};
+    if (psumsq) {
+        column_partial<2>(M, C8, outs, [&](long long r, int g, float* acc) {
             float f[8];
             bf16x8_to_float(__ldg(x + r * ld8 + g), f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { acc[j] += f[j]; acc[8 + j] += f[j] * f[j]; }
         });
     } else {
-        column_reduce<1>(M, C8, outs, [&](long long r, int g, float* acc) {
+        column_partial<1>(M, C8, outs, [&](long long r, int g, float* acc) {
             float f[8];
             bf16x8_to_float(__ldg(x + r * ld8 + g), f);
 #pragma unroll
@@ -89,21 +118,21 @@ col_stats_bf16_kernel(const uint4* __restrict__ x, int M, int C8, long long ld8,
 }
 
 __global__ void __launch_bounds__(kRedThreads)
-col_stats_f32_kernel(const float4* __restrict__ x, int M, int C8, long long ld4, float* sum, float* sumsq) {
-    float* outs[2] = {sum, sumsq};
+col_stats_f32_kernel(const float4* __restrict__ x, int M, int C8, long long ld4, float* psum, float* psumsq) {
+    float* outs[2] = {psum, psumsq};
     auto load = [&](long long r, int g, float* f) {
         const float4 a = __ldg(x + r * ld4 + 2 * g), b = __ldg(x + r * ld4 + 2 * g + 1);
         f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
     };
-    if (sumsq) {
-        column_reduce<2>(M, C8, outs, [&](long long r, int g, float* acc) {
+    if (psumsq) {
+        column_partial<2>(M, C8, outs, [&](long long r, int g, float* acc) {
             float f[8];
             load(r, g, f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { acc[j] += f[j]; acc[8 + j] += f[j] * f[j]; }
         });
     } else {
-        column_reduce<1>(M, C8, outs, [&](long long r, int g, float* acc) {
+        column_partial<1>(M, C8, outs, [&](long long r, int g, float* acc) {
             float f[8];
             load(r, g, f);
 #pragma unroll
@@ -112,14 +141,35 @@ col_stats_f32_kernel(const float4* __restrict__ x, int M, int C8, long long ld4,
     }
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, int C, float count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
-                                   float* scale, float* shift, float* save_mean, float* save_invstd, float* running_mean,
-                                   float* running_var) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const float mean = sum[c] / count;
-    const float var = fmaxf(sumsq[c] / count - mean * mean, 0.0f);  // biased, as used for normalisation
+// Batch statistics from the per-row-tile partial sums of the convolution epilogue (ab_gemm_bf16 / ab_conv_bf16_nhwc),
+// then mean / biased variance -> folded (scale, shift), saved mean / invstd, running statistics.
+// Block = 8 channels x 128 partial rows.
+__global__ void __launch_bounds__(1024)
+bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psumsq, int n_part, int C, float count,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                   float* scale, float* shift, float* save_mean, float* save_invstd, float* running_mean,
+                   float* running_var) {
+    __shared__ float red[2][32][8];
+    const int cx = threadIdx.x & 7, pr = threadIdx.x >> 3, c = blockIdx.x * 8 + cx;
+    float s0 = 0.0f, s1 = 0.0f;
+    if (c < C) {
+#pragma unroll 4
+        for (int p = pr; p < n_part; p += 128) {
+            s0 += __ldg(psum + (size_t)p * C + c);
+            s1 += __ldg(psumsq + (size_t)p * C + c);
+        }
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane < 8) { red[0][wid][lane] = s0; red[1][wid][lane] = s1; }
+    __syncthreads();
+    if (threadIdx.x >= 8 || c >= C) return;
+    float sum = 0.0f, sumsq = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) { sum += red[0][w][threadIdx.x]; sumsq += red[1][w][threadIdx.x]; }
+    const float mean = sum / count;
+    const float var = fmaxf(sumsq / count - mean * mean, 0.0f);  // biased, as used for normalisation
     const float invstd = rsqrtf(var + eps);
     const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
     scale[c] = g * invstd;
@@ -156,7 +206,7 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, 
                      const float* __restrict__ mean, const float* __restrict__ invstd, int relu, float* sum_dy,
                      float* sum_dy_xhat) {
     float* outs[2] = {sum_dy, sum_dy_xhat};
-    column_reduce<2>(M, C8, outs, [&](long long r, int g, float* acc) {
+    column_partial<2>(M, C8, outs, [&](long long r, int g, float* acc) {
         float d[8], yy[8], x[8];
         bf16x8_to_float(__ldg(dy + r * C8 + g), d);
         bf16x8_to_float(__ldg(raw + r * C8 + g), x);
@@ -214,10 +264,10 @@ __global__ void affine_relu_bwd_kernel(const uint4* __restrict__ dy, const uint4
     if (dres) dres[i] = float_to_bf16x8(d);
 }
 
-// MaxPool2d(3, 2, 1) backward, gather form: input pixel (iy, ix) receives dy of every window whose FIRST maximum (scan
-// order ky, kx -- torch's tie-break) it is.  bf16 activations tie often enough for the rule to matter.
-__global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const uint4* __restrict__ dy,
-                                   int B, int H, int W, int C8, int Ho, int Wo, uint4* __restrict__ dx) {
+// MaxPool2d(3, 2, 1) backward, gather form: input pixel (iy, ix) receives dy of every window (at most 4) whose recorded
+// argmax tap (ky*3 + kx of the FIRST maximum in scan order -- torch's tie-break, written by the forward kernel) it is.
+__global__ void maxpool_bwd_kernel(const uint2* __restrict__ idx, const uint4* __restrict__ dy, int B, int H, int W, int C8,
+                                   int Ho, int Wo, uint4* __restrict__ dx) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * H * W * C8;
     if (i >= total) return;
@@ -231,30 +281,18 @@ __global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __r
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
     // windows oy with 2*oy - 1 <= iy <= 2*oy + 1
-    for (int oy = max(iy / 2, 0); oy <= min((iy + 1) / 2, Ho - 1); ++oy)
-        for (int ox = max(ix / 2, 0); ox <= min((ix + 1) / 2, Wo - 1); ++ox) {
+    for (int oy = iy / 2; oy <= min((iy + 1) / 2, Ho - 1); ++oy)
+        for (int ox = ix / 2; ox <= min((ix + 1) / 2, Wo - 1); ++ox) {
             const long long o = (((long long)b * Ho + oy) * Wo + ox) * C8 + g;
-            float yv[8], dv[8];
-            bf16x8_to_float(__ldg(y + o), yv);
+            const uint2 id = __ldg(idx + o);
+            const uint32_t me = (uint32_t)((iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1)));
+            float dv[8];
             bf16x8_to_float(__ldg(dy + o), dv);
-            bool taken[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) taken[j] = false;
-            for (int ky = 0; ky < 3; ++ky)
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int wy = 2 * oy - 1 + ky, wx = 2 * ox - 1 + kx;
-                    if (wy < 0 || wy >= H || wx < 0 || wx >= W) continue;
-                    float xv[8];
-                    bf16x8_to_float(__ldg(x + (((long long)b * H + wy) * W + wx) * C8 + g), xv);
-                    const bool me = (wy == iy && wx == ix);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (!taken[j] && xv[j] == yv[j]) {
-                            taken[j] = true;
-                            if (me) acc[j] += dv[j];
-                        }
-                    }
-                }
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t tap = ((j < 4 ? id.x : id.y) >> (8 * (j & 3))) & 0xffu;
+                if (tap == me) acc[j] += dv[j];
+            }
         }
     dx[i] = float_to_bf16x8(acc);
 }
@@ -407,26 +445,40 @@ using namespace ab;
     count_launch();              \
     return check_launch(name)
 
-extern "C" int ab_col_stats(const void* x, int is_f32, int M, int C, int64_t ld, float* sum, float* sumsq, void* stream) {
-    AB_REQUIRE(M >= 0 && C > 0 && C % 8 == 0 && ld % 8 == 0, "bad shape (C and ld multiples of 8)");
-    if (M == 0) return AB_OK;
-    AB_REQUIRE(x && sum, "null pointer");
-    cudaStream_t st = (cudaStream_t)stream;
-    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
-    if (is_f32) col_stats_f32_kernel<<<nblk(M, kRedRows), kRedThreads, 0, st>>>((const float4*)x, M, C / 8, ld / 4, sum, sumsq);
-    else col_stats_bf16_kernel<<<nblk(M, kRedRows), kRedThreads, 0, st>>>((const uint4*)x, M, C / 8, ld / 8, sum, sumsq);
-    AB_LAUNCH_END("col_stats_kernel");
+static inline int stat_parts(int M, int C8) {
+    const int rows_par = kRedThreads / min(C8, kRedThreads);
+    return max(1, min(AB_STAT_PARTS, (M + 4 * rows_par - 1) / (4 * rows_par)));
 }
 
-extern "C" int ab_bn_finalize(const float* sum, const float* sumsq, int C, float count, const float* gamma, const float* beta,
-                              float eps, float momentum, float* scale, float* shift, float* save_mean, float* save_invstd,
-                              float* running_mean, float* running_var, void* stream) {
-    AB_REQUIRE(C > 0 && count > 0, "bad shape");
-    AB_REQUIRE(sum && sumsq && scale && shift && save_mean && save_invstd, "null pointer");
+extern "C" int ab_col_stats(const void* x, int is_f32, int M, int C, int64_t ld, float* sum, float* sumsq, float* ws, void* stream) {
+    AB_REQUIRE(M >= 0 && C > 0 && C % 8 == 0 && ld % 8 == 0, "bad shape (C and ld multiples of 8)");
+    AB_REQUIRE(x && sum && ws, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (M == 0) {
+        AB_CUDA(cudaMemsetAsync(sum, 0, sizeof(float) * C, st));
+        if (sumsq) AB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * C, st));
+        return AB_OK;
+    }
+    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    const int parts = stat_parts(M, C / 8);
+    float* p0 = ws;
+    float* p1 = sumsq ? ws + (size_t)AB_STAT_PARTS * C : nullptr;
+    if (is_f32) col_stats_f32_kernel<<<parts, kRedThreads, 0, st>>>((const float4*)x, M, C / 8, ld / 4, p0, p1);
+    else col_stats_bf16_kernel<<<parts, kRedThreads, 0, st>>>((const uint4*)x, M, C / 8, ld / 8, p0, p1);
+    partial_sum_kernel<<<nblk(C, 8), 256, 0, st>>>(p0, p1, parts, C, sum, sumsq);
+    count_launch(2);
+    return check_launch("col_stats_kernel");
+}
+
+extern "C" int ab_bn_finalize(const float* sum_part, const float* sumsq_part, int n_part, int C, float count, const float* gamma,
+                              const float* beta, float eps, float momentum, float* scale, float* shift, float* save_mean,
+                              float* save_invstd, float* running_mean, float* running_var, void* stream) {
+    AB_REQUIRE(C > 0 && count > 0 && n_part > 0, "bad shape");
+    AB_REQUIRE(sum_part && sumsq_part && scale && shift && save_mean && save_invstd, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
-    bn_finalize_kernel<<<nblk(C, 128), 128, 0, st>>>(sum, sumsq, C, count, gamma, beta, eps, momentum, scale, shift, save_mean,
-                                                     save_invstd, running_mean, running_var);
+    bn_finalize_kernel<<<nblk(C, 8), 1024, 0, st>>>(sum_part, sumsq_part, n_part, C, count, gamma, beta, eps, momentum, scale,
+                                                    shift, save_mean, save_invstd, running_mean, running_var);
     AB_LAUNCH_END("bn_finalize_kernel");
 }
 
@@ -443,15 +495,19 @@ extern "C" int ab_bn_apply(const void* raw, int64_t M, int C, const float* scale
 }
 
 extern "C" int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, int M, int C, const float* mean,
-                                const float* invstd, int relu, float* sum_dy, float* sum_dy_xhat, void* stream) {
-    AB_REQUIRE(M >= 0 && C > 0 && C % 8 == 0, "bad shape");
-    if (M == 0) return AB_OK;
-    AB_REQUIRE(dy && raw && mean && invstd && sum_dy && sum_dy_xhat && (!relu || y), "null pointer");
+                                const float* invstd, int relu, float* sum_dy, float* sum_dy_xhat, float* ws, void* stream) {
+    AB_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "bad shape");
+    AB_REQUIRE(dy && raw && mean && invstd && sum_dy && sum_dy_xhat && ws && (!relu || y), "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
-    bn_bwd_reduce_kernel<<<nblk(M, kRedRows), kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M, C / 8,
-                                                                    mean, invstd, relu, sum_dy, sum_dy_xhat);
-    AB_LAUNCH_END("bn_bwd_reduce_kernel");
+    const int parts = stat_parts(M, C / 8);
+    float* p0 = ws;
+    float* p1 = ws + (size_t)AB_STAT_PARTS * C;
+    bn_bwd_reduce_kernel<<<parts, kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M, C / 8, mean,
+                                                        invstd, relu, p0, p1);
+    partial_sum_kernel<<<nblk(C, 8), 256, 0, st>>>(p0, p1, parts, C, sum_dy, sum_dy_xhat);
+    count_launch(2);
+    return check_launch("bn_bwd_reduce_kernel");
 }
 
 extern "C" int ab_bn_bwd_apply(const void* dy, const void* y, const void* raw, int64_t M, int C, const float* gamma,
@@ -482,16 +538,15 @@ extern "C" int ab_affine_relu_bwd(const void* dy, const void* y, int64_t M, int 
     AB_LAUNCH_END("affine_relu_bwd_kernel");
 }
 
-extern "C" int ab_maxpool3x3s2_bwd(const void* x, const void* y, const void* dy, int B, int H, int W, int C, void* dx,
-                                   void* stream) {
+extern "C" int ab_maxpool3x3s2_bwd(const void* idx, const void* dy, int B, int H, int W, int C, void* dx, void* stream) {
     AB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad shape");
     if (B == 0) return AB_OK;
-    AB_REQUIRE(x && y && dy && dx, "null pointer");
+    AB_REQUIRE(idx && dy && dx, "null pointer");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
-    maxpool_bwd_kernel<<<nblk((long long)B * H * W * (C / 8), 256), 256, 0, st>>>((const uint4*)x, (const uint4*)y, (const uint4*)dy,
-                                                                                  B, H, W, C / 8, Ho, Wo, (uint4*)dx);
+    maxpool_bwd_kernel<<<nblk((long long)B * H * W * (C / 8), 256), 256, 0, st>>>((const uint2*)idx, (const uint4*)dy, B, H, W, C / 8,
+                                                                                  Ho, Wo, (uint4*)dx);
     AB_LAUNCH_END("maxpool_bwd_kernel");
 }
 

@@ -64,22 +64,22 @@ EXPORTS = {
     "ab_conv_wgrad_bf16_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "ab_image_to_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "ab_im2col_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]),
-    "ab_maxpool3x3s2_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
+    "ab_maxpool3x3s2_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_avgpool_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 3 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_deconv4x4s2_col2im": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                                       C.c_void_p, C.c_void_p]),
     "ab_head_decode": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "ab_col_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "ab_bn_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_float]
+    "ab_col_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_bn_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_float]
                        + [C.c_void_p] * 7),
     "ab_bn_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ab_bn_bwd_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
-                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_bn_bwd_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
                         + [C.c_void_p] * 3),
     "ab_affine_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
-    "ab_maxpool3x3s2_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
+    "ab_maxpool3x3s2_bwd": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
     "ab_avgpool_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ab_dilate2x": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
     "ab_deconv4x4s2_gather": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
@@ -89,6 +89,7 @@ EXPORTS = {
                                                                                   C.c_void_p]),
 }
 
+STAT_PARTS = 296  # AB_STAT_PARTS: rows of the column-reduction workspace (2 * STAT_PARTS * C floats)
 _lib = None
 
 

@@ -145,12 +145,13 @@ def conv_bn_act(x: Act, conv: nn.Conv2d, bn=None, relu: bool = False, residual: 
     return out if out_fp32 else Act(out, x.B, Ho, Wo, cout)
 
 
-def maxpool3x3s2(x: Act) -> Act:
+def maxpool3x3s2(x: Act, idx: Optional[torch.Tensor] = None) -> Act:
+    """idx: optional uint8 [B*Ho*Wo, C] that receives the argmax tap of every output (for the backward kernel)."""
     Ho, Wo = (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1
     out = torch.empty((x.B * Ho * Wo, x.C), dtype=torch.bfloat16, device=x.data.device)
     with torch.cuda.device(x.data.device):
         rc = lib.load().ab_maxpool3x3s2_nhwc(x.data.data_ptr(), x.B, x.H, x.W, x.C, out.data_ptr(),
-                                             lib.stream_ptr(x.data.device))
+                                             None if idx is None else idx.data_ptr(), lib.stream_ptr(x.data.device))
     lib.check(rc, "ab_maxpool3x3s2_nhwc")
     return Act(out, x.B, Ho, Wo, x.C)
 

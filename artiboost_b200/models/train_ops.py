@@ -70,7 +70,18 @@ class _BNState:
     __slots__ = ("mean", "invstd", "scale")
 
 
+def _stat_ws(C, dev):
+    """Workspace of the deterministic column reductions (2 * AB_STAT_PARTS * C floats)."""
+    return torch.empty(2 * lib.STAT_PARTS * C, device=dev)
+
+
+def _stat_partials(M, C, dev):
+    """Per-row-tile partial sums / sums of squares written by the convolution epilogue: [2, ceil(M/128), C]."""
+    return torch.empty((2, (M + 127) // 128, C), device=dev)
+
+
 def _bn_forward_train(raw, M, C, bn, sums, residual, relu):
+    """sums: [2, n_part, C] partial column sums / sums of squares of `raw`."""
     dev = raw.device
     scale, shift = torch.empty(C, device=dev), torch.empty(C, device=dev)
     st = _BNState()
@@ -78,7 +89,7 @@ def _bn_forward_train(raw, M, C, bn, sums, residual, relu):
     track = bn.track_running_stats and bn.running_mean is not None
     momentum = 0.1 if bn.momentum is None else bn.momentum
     with torch.cuda.device(dev):
-        _call("ab_bn_finalize", sums[0].data_ptr(), sums[1].data_ptr(), C, float(M), P(bn.weight), P(bn.bias), float(bn.eps),
+        _call("ab_bn_finalize", sums[0].data_ptr(), sums[1].data_ptr(), sums.shape[1], C, float(M), P(bn.weight), P(bn.bias), float(bn.eps),
               float(momentum), scale.data_ptr(), shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
               P(bn.running_mean) if track else None, P(bn.running_var) if track else None, _stream(dev))
         y = torch.empty_like(raw)
@@ -97,9 +108,9 @@ def _norm_backward(dy, y, raw, M, C, bn, st, relu, want_res):
     dgamma = dbeta = None
     with torch.cuda.device(dev):
         if isinstance(st, _BNState):
-            dbeta, dgamma = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+            dbeta, dgamma = torch.empty(C, device=dev), torch.empty(C, device=dev)
             _call("ab_bn_bwd_reduce", dy.data_ptr(), P(y), raw.data_ptr(), M, C, st.mean.data_ptr(), st.invstd.data_ptr(), int(relu),
-                  dbeta.data_ptr(), dgamma.data_ptr(), _stream(dev))
+                  dbeta.data_ptr(), dgamma.data_ptr(), _stat_ws(C, dev).data_ptr(), _stream(dev))
             _call("ab_bn_bwd_apply", dy.data_ptr(), P(y), raw.data_ptr(), M, C, P(bn.weight), st.mean.data_ptr(),
                   st.invstd.data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), int(relu), dx.data_ptr(), P(dres), _stream(dev))
         else:
@@ -109,9 +120,10 @@ def _norm_backward(dy, y, raw, M, C, bn, st, relu, want_res):
 
 def _col_sum(mat, is_f32=False):
     M, C = mat.shape
-    out = torch.zeros(C, device=mat.device)
+    out = torch.empty(C, device=mat.device)
     with torch.cuda.device(mat.device):
-        _call("ab_col_stats", mat.data_ptr(), int(is_f32), M, C, mat.stride(0), out.data_ptr(), None, _stream(mat.device))
+        _call("ab_col_stats", mat.data_ptr(), int(is_f32), M, C, mat.stride(0), out.data_ptr(), None,
+              _stat_ws(C, mat.device).data_ptr(), _stream(mat.device))
     return out
 
 
@@ -176,8 +188,9 @@ class ConvBNActFn(torch.autograd.Function):
         if bn is not None and bn_train:
             if bias is not None:
                 raise NotImplementedError("conv bias followed by training-mode BatchNorm does not occur in the clasbased network")
-            sums = (torch.zeros(cout, device=x_data.device), torch.zeros(cout, device=x_data.device))
-            raw, Ho, Wo, xcol = _conv_raw(x, wp, cout, kh, kw, stride, pad, col_stats=sums)
+            Ho_, Wo_ = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+            sums = _stat_partials(B * Ho_ * Wo_, cout, x_data.device)
+            raw, Ho, Wo, xcol = _conv_raw(x, wp, cout, kh, kw, stride, pad, col_stats=(sums[0], sums[1]))
             y, st = _bn_forward_train(raw, raw.shape[0], cout, bn, sums, residual, relu)
             ctx.save_for_backward(x_data, weight, raw, y, xcol if xcol is not None else empty)
             ctx.st = st
@@ -230,19 +243,21 @@ class MaxPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_data, geom):
         B, H, W, C = geom
-        y = nhwc.maxpool3x3s2(Act(x_data, B, H, W, C))
-        ctx.save_for_backward(x_data, y.data)
+        Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+        idx = torch.empty((B * Ho * Wo, C), dtype=torch.uint8, device=x_data.device)
+        y = nhwc.maxpool3x3s2(Act(x_data, B, H, W, C), idx=idx)
+        ctx.save_for_backward(idx)
         ctx.geom = geom
         return y.data
 
     @staticmethod
     def backward(ctx, dy):
-        x_data, y = ctx.saved_tensors
+        (idx,) = ctx.saved_tensors
         B, H, W, C = ctx.geom
-        dx = torch.empty_like(x_data)
+        dx = torch.empty((B * H * W, C), dtype=torch.bfloat16, device=dy.device)
         dy = dy.to(torch.bfloat16).contiguous()
         with torch.cuda.device(dy.device):
-            _call("ab_maxpool3x3s2_bwd", x_data.data_ptr(), y.data_ptr(), dy.data_ptr(), B, H, W, C, dx.data_ptr(), _stream(dy.device))
+            _call("ab_maxpool3x3s2_bwd", idx.data_ptr(), dy.data_ptr(), B, H, W, C, dx.data_ptr(), _stream(dy.device))
         return dx, None
 
 
@@ -291,8 +306,9 @@ class DeconvBNReluFn(torch.autograd.Function):
             raw32 = torch.empty((M, cout), device=dev)
             with torch.cuda.device(dev):
                 _call("ab_deconv4x4s2_col2im", ycol.data_ptr(), B, H, W, cout, None, None, 0, None, raw32.data_ptr(), _stream(dev))
-                sums = (torch.zeros(cout, device=dev), torch.zeros(cout, device=dev))
-                _call("ab_col_stats", raw32.data_ptr(), 1, M, cout, cout, sums[0].data_ptr(), sums[1].data_ptr(), _stream(dev))
+                sums = torch.empty((2, 1, cout), device=dev)
+                _call("ab_col_stats", raw32.data_ptr(), 1, M, cout, cout, sums[0].data_ptr(), sums[1].data_ptr(),
+                      _stat_ws(cout, dev).data_ptr(), _stream(dev))
             raw = raw32.to(torch.bfloat16)
             y, st = _bn_forward_train(raw, M, cout, bn, sums, None, True)
             ctx.st = st

@@ -174,3 +174,37 @@ def real_shaped_batch(B: int, device, generator=None, size: int = 256) -> Dict[s
 def mix_batches(a: Dict[str, torch.Tensor], b: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """MixedDataset (mixed_dataset.py:32-37) at batch granularity: real-shaped samples followed by synthetic ones."""
     return {k: torch.cat([a[k], b[k]], dim=0) for k in a.keys() & b.keys()}
+
+
+class ArtiBoostLoop:
+    """The per-iteration loop of train/train_artiboost.py:204-227 with ArtiBoostLoader's synthesis inlined
+    (artiboost_loader.py:279-340): every step draws `n_synth` CCV cells with the current weights, poses and rasterises
+    them on this rank's GPU, mixes them with `n_real` real(-shaped) samples (MixedDataset: N real + SYNTH_FACTOR * N
+    synthetic, yaml:2), runs the optimisation step and records the per-cell corner error; `end_epoch()` turns the
+    recorded errors into the next epoch's sampling weights (all-reduced over ranks)."""
+
+    def __init__(self, arch: nn.Module, pipe, batch_size: int = 128, synth_factor: float = 0.6, real_source=None,
+                 criterion_cfg: Optional[dict] = None, lr=5e-5, grad_clip=1e-3, generator=None):
+        self.pipe, self.batch_size = pipe, batch_size
+        self.n_synth = int(round(batch_size * synth_factor / (1.0 + synth_factor)))
+        self.n_real = batch_size - self.n_synth
+        self.generator = generator
+        self.real_source = real_source or (lambda n: real_shaped_batch(n, pipe.device, self.generator, pipe.renderer.width))
+        self.train_step = TrainStep(arch, criterion_cfg, lr=lr, grad_clip=grad_clip, generator=generator)
+        self.feedback = CCVFeedback(pipe.sample_weight_map.shape, pipe.device)
+
+    def make_batch(self) -> Dict[str, torch.Tensor]:
+        synth = synth_to_batch(self.pipe.synthesise(self.n_synth), self.pipe)
+        return mix_batches(self.real_source(self.n_real), synth) if self.n_real else synth
+
+    def step(self, batch: Optional[Dict[str, torch.Tensor]] = None):
+        batch = batch if batch is not None else self.make_batch()
+        loss, preds = self.train_step(batch)
+        targ = batch["corners_3d"] + batch["root_joint"].unsqueeze(1)
+        self.feedback.feed(preds["corners_3d_abs"].detach(), targ, batch["obj_id"], batch["persp_id"], batch["grasp_id"],
+                           batch["is_synth"])
+        return loss
+
+    def end_epoch(self):
+        self.pipe.sample_weight_map = self.feedback.step_eval(self.pipe.sample_weight_map)
+        return self.pipe.sample_weight_map

@@ -39,7 +39,7 @@ def load_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -211,6 +211,16 @@ def run_ours(args):
     d2h = sum(x.numel() * x.element_size() for x in h_out.values())
     same = all(torch.equal(h_out[k], out[k].cpu()) for k in out)
 
+    train = None
+    if not args.no_train:
+        del h_out, h_in
+        try:
+            train = train_bench(dev, world, rank)
+        except Exception as e:  # the secondary workload must never cost the headline line
+            if world > 1:
+                raise
+            train = {"error": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -256,11 +266,14 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
+    line["extras"] = {}
+    if train is not None:
+        line["extras"]["train_loop_configs3"] = train
     if world == 1 and not args.no_network:
         try:
-            line["extras"] = {"network_forward_configs2": network_forward_bench(dev)}
+            line["extras"]["network_forward_configs2"] = network_forward_bench(dev)
         except Exception as e:  # the secondary workload must never cost the headline line
-            line["extras"] = {"network_forward_configs2": {"error": repr(e)}}
+            line["extras"]["network_forward_configs2"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -353,6 +366,110 @@ def network_forward_bench(dev, batch=128, steps=10, warmup=3):
     return out
 
 
+# --------------------------------------------------------- secondary workload: full loop, train images/s (configs[3])
+def torch_train_forward(model, batch):
+    """The reference's own training graph (torch.nn / cuDNN fp32 NCHW modules + autograd) on the same parameters:
+    anakin/models/hybridbaseline.py:41-96.  Baseline leg only."""
+    import torch
+    from artiboost_b200.models.transform import batch_uvd2xyz, compute_rotation_matrix_from_ortho6d
+    hb = model.model_list[0]
+    kp3d, _, rot6d = torch_forward(model, batch)
+    xyz = batch_uvd2xyz(uvd=kp3d, root_joint=batch["root_joint"], intr=batch["cam_intr"], inp_res=hb.inp_res)
+    R = compute_rotation_matrix_from_ortho6d(rot6d)
+    corners = torch.matmul(R, batch["corners_can"].permute(0, 2, 1)).permute(0, 2, 1) + xyz[:, 21:22]
+    return {"joints_3d_abs": xyz[:, :21], "corners_3d_abs": corners}
+
+
+def train_bench(dev, world, rank, steps=8, warmup=3, batch=128, backbone="ResNet34"):
+    """BASELINE.json configs[3]: CCV sample -> pose -> rasterise -> mix -> clasbased train step (batch-statistics BN,
+    JointsLoss + HandOrdLoss + SceneOrdLoss, clip 1e-3, Adam 5e-5), gradient all-reduce over ranks; per-GPU batch 128
+    (yaml:131), synthetic share 0.6 / 1.6 (yaml:2).  Beside it on rank 0 at N=1: the same modules through torch.nn /
+    cuDNN fp32 + autograd + torch.optim.Adam (the reference's single-GPU PyTorch path) and bf16 autocast."""
+    import copy
+
+    import torch
+    import torch.distributed as dist
+
+    import artiboost_b200.models as M
+    from artiboost_b200 import criterions, lib
+    from artiboost_b200.synth import SynthPipeline
+    from artiboost_b200.train import ArtiBoostLoop
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import netcfg
+    flops = {"ResNet34": 31.8e9, "ResNet50": 37.5e9}[backbone]   # fwd+bwd FLOPs / image at 256^2 (SURVEY.md 8d)
+    arch, preset = netcfg.arch_cfg(backbone)
+    torch.manual_seed(1)
+    model = M.Arch({"ARCH": arch}, M.build_arch_model_list(arch, preset_cfg=preset)).to(dev)
+    ref_model = copy.deepcopy(model) if world == 1 else None
+    pipe = SynthPipeline(device=dev, seed=11 + rank)
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    loop = ArtiBoostLoop(model, pipe, batch_size=batch, generator=gen)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, n, w):
+        for _ in range(w):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n
+
+    ms_synth = timed(lambda: loop.make_batch(), steps, warmup)
+    fixed = loop.make_batch()
+    l0 = lib.launch_count()
+    ms_step = timed(lambda: loop.step(), steps, warmup)
+    launches = (lib.launch_count() - l0) / (steps + warmup)
+    ms_net = timed(lambda: loop.step(fixed), steps, 1)
+    lib.profile_enable(True)   # stage breakdown from a separate, event-bracketed pass (not the timed one)
+    for _ in range(2):
+        loop.step()
+    torch.cuda.synchronize(dev)
+    lib.profile_enable(False)
+    stages = lib.profile_collect()
+    out = {"backbone": backbone, "per_gpu_batch": batch, "synthetic_per_batch": loop.n_synth, "real_shaped_per_batch": loop.n_real,
+           "images_per_s": world * batch / ms_step * 1e3, "ms_per_step": ms_step, "ms_synthesis_and_batching": ms_synth,
+           "ms_train_step_only": ms_net, "launches_per_step": launches,
+           "tflops_fwd_bwd": batch * flops / ms_net / 1e9, "frac_of_bf16_sustained_peak": batch * flops / ms_net / 1e9 / 1364.6,
+           "stage_ms_per_step": {k: v[0] / 2 for k, v in stages.items()},
+           "stage_launches_per_step": {k: v[1] / 2 for k, v in stages.items()}}
+    if ref_model is not None and rank == 0:
+        crit = criterions.Criterion(criterions.DEFAULT_CRITERION_CFG, generator=gen)
+        opt = torch.optim.Adam([p for p in ref_model.parameters() if p.requires_grad], lr=5e-5)
+        ref_model.train()
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+        def ref_step(autocast):
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                preds = torch_train_forward(ref_model, fixed)
+            loss, _ = crit.compute_losses({k: v.float() for k, v in preds.items()}, fixed)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(ref_model.parameters(), 1e-3)
+            opt.step()
+
+        ms_ref = timed(lambda: ref_step(False), max(3, steps // 2), 2)
+        out["torch_cudnn_fp32_train_images_per_s"] = batch / ms_ref * 1e3
+        cl = dict(fixed, image=fixed["image"].contiguous(memory_format=torch.channels_last))
+        fixed_nchw, fixed = fixed, cl
+        ms_ref16 = timed(lambda: ref_step(True), max(3, steps // 2), 2)
+        fixed = fixed_nchw
+        out["torch_cudnn_bf16_autocast_train_images_per_s"] = batch / ms_ref16 * 1e3
+        out["train_step_only_images_per_s"] = batch / ms_net * 1e3
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -361,6 +478,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary full-loop train images/s measurement")
     ap.add_argument("--no-network", action="store_true", help="skip the secondary network-forward measurement")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:

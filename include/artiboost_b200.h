@@ -160,8 +160,9 @@ AB_API int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int batc
  * D[M,N] = epilogue(A[M,K] . B[N,K]^T): A, B bf16 row-major (K contiguous, pitches lda / ldb in elements), fp32
  * accumulation in tensor memory (tcgen05).  epilogue: y = acc * scale[n] + bias[n] (+ residual[m,n]) (ReLU) -> bf16
  * (out_fp32 = 0) or fp32 store with pitch ldd.  scale / bias / residual may be NULL.  col_sum / col_sumsq (both or
- * neither): fp32 [N] accumulators that receive the per-column sum and sum of squares of the raw accumulator (the
- * batch statistics of training-mode BatchNorm); the caller zeroes them.
+ * neither): fp32 [ceil(M/128), N] matrices; row t receives the per-column sum / sum of squares of the raw accumulator
+ * over output rows 128t .. 128t+127 (the batch statistics of training-mode BatchNorm, summed by ab_bn_finalize).
+ * Plain stores, no atomics: nothing to zero, bit-reproducible.
  * K, N, lda, ldb, ldd, ldr multiples of 8; pointers 16-byte aligned.                                           */
 AB_API int ab_gemm_bf16(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
                         int out_fp32, const float* scale, const float* bias, const void* residual, int64_t ldr, int relu,
@@ -190,7 +191,8 @@ AB_API int ab_conv_wgrad_bf16_nhwc(const void* x, int B, int H, int W, int C, co
  * pick layouts (anakin/models/resnet.py:199-221).
  * ab_image_to_nhwc: f32 [B,C,H,W] -> bf16 [B,H,W,Cp], channels C..Cp-1 zero.
  * ab_im2col_nhwc:   -> rows [B*Ho*Wo, Kp] with K order (ky, kx, c), columns kh*kw*C..Kp-1 zero; Ho = (H+2*pad-kh)/stride+1.
- * ab_maxpool3x3s2_nhwc: nn.MaxPool2d(3, 2, 1) (resnet.py:157).  ab_avgpool_nhwc: mean over H*W (resnet.py:219).
+ * ab_maxpool3x3s2_nhwc: nn.MaxPool2d(3, 2, 1) (resnet.py:157); idx (optional, u8 [B,Ho,Wo,C]) receives the argmax tap
+ *   ky*3+kx of each output (first maximum in scan order) for ab_maxpool3x3s2_bwd.  ab_avgpool_nhwc: mean over H*W (resnet.py:219).
  * ab_deconv4x4s2_col2im: ycol f32 [B*H*W, 16*Cout] (column order ky, kx, co) = X . W of a ConvTranspose2d(4, 2, 1)
  *   (simplebaseline.py:161-170) -> out[b, 2H, 2W, Cout] = sum of the 4 contributing taps, * scale + bias, ReLU, bf16;
  *   out_raw (optional) receives the un-normalised f32 sums for training-mode batch statistics.
@@ -199,7 +201,7 @@ AB_API int ab_conv_wgrad_bf16_nhwc(const void* x, int B, int H, int W, int C, co
 AB_API int ab_image_to_nhwc(const float* image, int B, int C, int H, int W, int Cp, void* out, void* stream);
 AB_API int ab_im2col_nhwc(const void* in, int B, int H, int W, int C, int kh, int kw, int stride, int pad, int Kp,
                           void* out, void* stream);
-AB_API int ab_maxpool3x3s2_nhwc(const void* in, int B, int H, int W, int C, void* out, void* stream);
+AB_API int ab_maxpool3x3s2_nhwc(const void* in, int B, int H, int W, int C, void* out, void* idx, void* stream);
 AB_API int ab_avgpool_nhwc(const void* in, int B, int HW, int C, float* out_f32, void* out_bf16, void* stream);
 AB_API int ab_deconv4x4s2_col2im(const float* ycol, int B, int H, int W, int Cout, const float* scale, const float* bias,
                                  int relu, void* out_bf16, float* out_raw, void* stream);
@@ -210,8 +212,11 @@ AB_API int ab_head_decode(const float* logits, int B, int ncls, int D, int H, in
  * What nn.BatchNorm2d (training mode), ReLU, MaxPool2d and autograd do around the convolutions in the reference's
  * train step (anakin/models/resnet.py:72-152, simplebaseline.py:161-190, train/train_artiboost.py:91-96).
  * Activations / activation gradients bf16 [M,C] (NHWC rows), statistics and parameter gradients fp32.
- * ab_col_stats: sum[c] += sum_r x[r,c], sumsq[c] += sum_r x^2 (sumsq may be NULL); caller zeroes the accumulators.
- * ab_bn_finalize: mean, biased var -> scale = gamma*invstd, shift = beta - mean*scale, saved mean / invstd, and the
+ * Column reductions are deterministic: CTAs write partial rows into a caller-owned workspace ws of
+ *   2 * AB_STAT_PARTS * C floats and a second small kernel adds them up; outputs are overwritten, never accumulated.
+ * ab_col_stats: sum[c] = sum_r x[r,c], sumsq[c] = sum_r x^2 (sumsq may be NULL).
+ * ab_bn_finalize: adds the n_part partial rows ([n_part, C] each; n_part = ceil(M/128) after a convolution, 1 after
+ *   ab_col_stats), then mean, biased var -> scale = gamma*invstd, shift = beta - mean*scale, saved mean / invstd, and the
  *   running-stat update running = (1-momentum)*running + momentum*{mean, unbiased var} (running_* may be NULL).
  * ab_bn_apply: y = relu?(raw*scale + shift (+ residual)).
  * ab_bn_bwd_reduce / ab_bn_bwd_apply: dy' = dy*(y>0) when relu; sum_dy = dbeta, sum_dy_xhat = dgamma;
@@ -222,20 +227,21 @@ AB_API int ab_head_decode(const float* logits, int B, int ncls, int D, int H, in
  * ab_head_decode_bwd: gradient of ab_head_decode's kp3d w.r.t. the logits (bf16 [B*H*W, ncls*D]).
  * ab_sumsq / ab_adam_step: clip_grad_norm_(max_norm) + torch.optim.Adam on one flat fp32 parameter buffer;
  *   grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).                              */
-AB_API int ab_col_stats(const void* x, int is_f32, int M, int C, int64_t ld, float* sum, float* sumsq, void* stream);
-AB_API int ab_bn_finalize(const float* sum, const float* sumsq, int C, float count, const float* gamma, const float* beta,
-                          float eps, float momentum, float* scale, float* shift, float* save_mean, float* save_invstd,
-                          float* running_mean, float* running_var, void* stream);
+#define AB_STAT_PARTS 296
+AB_API int ab_col_stats(const void* x, int is_f32, int M, int C, int64_t ld, float* sum, float* sumsq, float* ws, void* stream);
+AB_API int ab_bn_finalize(const float* sum_part, const float* sumsq_part, int n_part, int C, float count, const float* gamma,
+                          const float* beta, float eps, float momentum, float* scale, float* shift, float* save_mean,
+                          float* save_invstd, float* running_mean, float* running_var, void* stream);
 AB_API int ab_bn_apply(const void* raw, int64_t M, int C, const float* scale, const float* shift, const void* residual,
                        int relu, void* y, void* stream);
 AB_API int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, int M, int C, const float* mean,
-                            const float* invstd, int relu, float* sum_dy, float* sum_dy_xhat, void* stream);
+                            const float* invstd, int relu, float* sum_dy, float* sum_dy_xhat, float* ws, void* stream);
 AB_API int ab_bn_bwd_apply(const void* dy, const void* y, const void* raw, int64_t M, int C, const float* gamma,
                            const float* mean, const float* invstd, const float* sum_dy, const float* sum_dy_xhat, int relu,
                            void* dx, void* dres, void* stream);
 AB_API int ab_affine_relu_bwd(const void* dy, const void* y, int64_t M, int C, const float* scale, int relu, void* dx,
                               void* dres, void* stream);
-AB_API int ab_maxpool3x3s2_bwd(const void* x, const void* y, const void* dy, int B, int H, int W, int C, void* dx, void* stream);
+AB_API int ab_maxpool3x3s2_bwd(const void* idx, const void* dy, int B, int H, int W, int C, void* dx, void* stream);
 AB_API int ab_avgpool_bwd(const float* dmean, int B, int HW, int C, void* dx, void* stream);
 AB_API int ab_dilate2x(const void* in, int B, int Ho, int Wo, int H, int W, int C, void* out, void* stream);
 AB_API int ab_deconv4x4s2_gather(const void* dy, int B, int H, int W, int C, void* dycol, void* stream);

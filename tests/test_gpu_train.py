@@ -242,3 +242,43 @@ def test_whole_model_gradients_follow_torch_autograd(backbone):
     bn, bn_r = model.model_list[0].backbone.bn1, ref32.model_list[0].backbone.bn1
     close(bn.running_mean, bn_r.running_mean, 2e-2, "stem running_mean")
     close(bn.running_var, bn_r.running_var, 2e-2, "stem running_var")
+
+
+@pytest.mark.parametrize("M,C,f32", [(1, 8, False), (777, 64, False), (70001, 64, True), (4099, 256, False), (300, 2304, True)])
+def test_column_statistics_are_exact_sums_and_reproducible(M, C, f32):
+    """ab_col_stats (deterministic partial rows + second pass) vs fp64 sums; ragged M, C above the CTA width."""
+    from artiboost_b200 import lib
+    from artiboost_b200.models.train_ops import _stat_ws
+    g = torch.Generator(device=DEV).manual_seed(M + C)
+    x = torch.randn((M, C), device=DEV, generator=g)
+    x = x if f32 else bf(x)
+    L = lib.load()
+
+    def run():
+        s, q = torch.full((C,), float("nan"), device=DEV), torch.full((C,), float("nan"), device=DEV)
+        lib.check(L.ab_col_stats(x.data_ptr(), int(f32), M, C, C, s.data_ptr(), q.data_ptr(), _stat_ws(C, DEV).data_ptr(),
+                                 lib.stream_ptr(DEV)), "ab_col_stats")
+        return s, q
+
+    s, q = run()
+    xd = x.double()
+    torch.testing.assert_close(s.double(), xd.sum(0), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(q.double(), (xd * xd).sum(0), rtol=1e-5, atol=1e-3)
+    s2, q2 = run()
+    assert torch.equal(s, s2) and torch.equal(q, q2)
+
+
+def test_maxpool_argmax_index_and_backward_match_torch():
+    """First-maximum tie-break (bf16 activations tie often after ReLU): dx equals torch's max_pool2d backward."""
+    from artiboost_b200.models import train_ops
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.relu(torch.randn((3, 16, 37, 41), device=DEV, generator=g)).mul(4).round().div(4)  # many exact ties
+    a = act_of(x, requires_grad=True)
+    y = train_ops.maxpool3x3s2(a)
+    xr = bf(x).float().requires_grad_(True)
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    torch.testing.assert_close(nchw(y.data, 3, y.H, y.W), yr, rtol=0, atol=0)
+    dy = bf(torch.randn(yr.shape, device=DEV, generator=g))
+    y.data.backward(dy.permute(0, 2, 3, 1).reshape(-1, 16).contiguous())
+    yr.backward(dy.float())
+    close(nchw(a.data.grad, 3, 37, 41), xr.grad, tol=4e-3, name="maxpool dx")
