@@ -411,6 +411,15 @@ int conv_bf16_implicit(const void* x, int B, int H, int W, int C, const void* w,
 // [64 rows (k) x 64 contiguous elements] TMA boxes with 128-byte swizzle -- byte-identical to the forward pass's A tile
 // -- and described to tcgen05 with a_major = b_major = MN (instruction-descriptor bits 15/16), LBO = 8 KB between the
 // two 64-wide MN atoms of a 128-wide tile, SBO = 1 KB between 8-row groups, +2 KB per K=16 step.
+// Where element (row, col) of the [Mo, No] product lands: rows / columns are split as (hi, lo) = (i / div, i % div) and
+//   offset = row_hi * s_rh + row_lo * s_rl + col_hi * s_ch + col_lo * s_cl,   skipped unless col_lo < cl_valid,
+// so the gradient is accumulated straight into the parameter's own layout (conv [Cout,Cin,kh,kw], deconv
+// [Cin,Cout,kh,kw], linear [N,K]) with no packed intermediate.
+struct WgradOutMap {
+    int rdiv, cdiv, cl_valid;
+    long long s_rh, s_rl, s_ch, s_cl;
+};
+
 constexpr int kWgStages = 3;
 struct WgradSmem {
     __nv_bfloat16 a[kWgStages][2][64 * 64];
@@ -426,7 +435,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(const void* smem_tile) {
 template <bool IM2COL>
 __global__ void __launch_bounds__(kGemmThreads)
 wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, int P, int Mo, int No,
-                  float* __restrict__ D, long long ldd, int kblocks_per_split, const ConvGeom cg, int taps) {
+                  float* __restrict__ D, const WgradOutMap om, int kblocks_per_split, const ConvGeom cg, int taps) {
     extern __shared__ uint8_t smem_raw[];
     auto& sm = *reinterpret_cast<WgradSmem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -509,9 +518,13 @@ wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             uint32_t r[16];
             tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             if (row < Mo) {
+                float* drow = D + (long long)(row / om.rdiv) * om.s_rh + (long long)(row % om.rdiv) * om.s_rl;
+                int chi = col / om.cdiv, clo = col - chi * om.cdiv;
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (col + j < No) atomicAdd(D + (size_t)row * ldd + col + j, __uint_as_float(r[j]));
+                for (int j = 0; j < 16; ++j) {
+                    if (col + j < No && clo < om.cl_valid) atomicAdd(drow + chi * om.s_ch + clo * om.s_cl, __uint_as_float(r[j]));
+                    if (++clo == om.cdiv) { clo = 0; ++chi; }
+                }
             }
         }
     }
@@ -555,7 +568,7 @@ static int make_im2col_map_px(CUtensorMap* m, const void* ptr, int B, int H, int
 }
 
 template <bool IM2COL>
-static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, int P, int Mo, int No, float* D, long long ldd,
+static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, int P, int Mo, int No, float* D, const WgradOutMap& om,
                         const ConvGeom& cg, int taps, cudaStream_t st) {
     const size_t smem = sizeof(WgradSmem) + 1024;
     static bool configured = false;
@@ -568,7 +581,7 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, int P, int
     const int per = cdiv(total_kb, splits);
     splits = cdiv(total_kb, per);
     StageTimer tm(AB_STAGE_WGRAD, st);
-    wgrad_bf16_kernel<IM2COL><<<dim3(mt, nt, splits), kGemmThreads, smem, st>>>(tg, tx, P, Mo, No, D, ldd, per, cg, taps);
+    wgrad_bf16_kernel<IM2COL><<<dim3(mt, nt, splits), kGemmThreads, smem, st>>>(tg, tx, P, Mo, No, D, om, per, cg, taps);
     count_launch();
     return check_launch("wgrad_bf16_kernel");
 }
@@ -613,35 +626,40 @@ extern "C" int ab_conv_bf16_nhwc(const void* x, int B, int H, int W, int C, cons
     return ab::conv_bf16_implicit(x, B, H, W, C, w_packed, Cout, kh, kw, stride, pad, ep, (cudaStream_t)stream);
 }
 
-extern "C" int ab_wgrad_bf16(int P, int Mo, int No, const void* G, int64_t ldg, const void* X, int64_t ldx, float* D, int64_t ldd,
-                             void* stream) {
+extern "C" int ab_wgrad_bf16(int P, int Mo, int No, const void* G, int64_t ldg, const void* X, int64_t ldx, float* D,
+                             const ab_wgrad_map* map, void* stream) {
     AB_REQUIRE(P >= 0 && Mo > 0 && No > 0, "bad shape");
     if (P == 0) return AB_OK;
-    AB_REQUIRE(G && X && D, "null pointer");
-    AB_REQUIRE(Mo % 8 == 0 && No % 8 == 0 && ldg % 8 == 0 && ldx % 8 == 0, "Mo, No, ldg, ldx must be multiples of 8");
+    AB_REQUIRE(G && X && D && map, "null pointer");
+    AB_REQUIRE(map->row_div > 0 && map->col_div > 0 && map->col_lo_valid > 0, "bad output map");
+    AB_REQUIRE(ldg % 8 == 0 && ldx % 8 == 0 && Mo <= ldg && No <= ldx, "ldg, ldx must be multiples of 8 (16-byte rows) and cover Mo, No");
     AB_REQUIRE(((uintptr_t)G & 15) == 0 && ((uintptr_t)X & 15) == 0, "operands must be 16-byte aligned");
     CUtensorMap tg, tx;
     int rc = ab::make_map_mn(&tg, G, P, Mo, ldg);
     if (rc) return rc;
     rc = ab::make_map_mn(&tx, X, P, No, ldx);
     if (rc) return rc;
-    return ab::launch_wgrad<false>(tg, tx, P, Mo, No, D, ldd, ab::ConvGeom{}, 0, (cudaStream_t)stream);
+    const ab::WgradOutMap om{map->row_div, map->col_div, map->col_lo_valid, map->s_row_hi, map->s_row_lo, map->s_col_hi, map->s_col_lo};
+    return ab::launch_wgrad<false>(tg, tx, P, Mo, No, D, om, ab::ConvGeom{}, 0, (cudaStream_t)stream);
 }
 
 extern "C" int ab_conv_wgrad_bf16_nhwc(const void* x, int B, int H, int W, int C, const void* dy, int Cout, int kh, int kw,
-                                       int stride, int pad, float* dw_packed, void* stream) {
+                                       int stride, int pad, float* dw, int param_layout, void* stream) {
     AB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, "bad shape");
     if (B == 0) return AB_OK;
     AB_REQUIRE(C % 64 == 0 && Cout % 8 == 0, "implicit weight gradient needs C % 64 == 0 and Cout % 8 == 0");
-    AB_REQUIRE(x && dy && dw_packed, "null pointer");
+    AB_REQUIRE(x && dy && dw, "null pointer");
     AB_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0, "tensors must be 16-byte aligned");
     const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
-    const int P = B * Ho * Wo;
+    const int P = B * Ho * Wo, taps = kh * kw;
     CUtensorMap tg, tx;
     int rc = ab::make_map_mn(&tg, dy, P, Cout, Cout);
     if (rc) return rc;
     rc = ab::make_im2col_map_px(&tx, x, B, H, W, C, kh, kw, stride, pad, 64);
     if (rc) return rc;
     const ab::ConvGeom cg{Ho, Wo, stride, pad, kw, C / 64};
-    return ab::launch_wgrad<true>(tg, tx, P, Cout, kh * kw * C, dw_packed, (long long)kh * kw * C, cg, kh * kw, (cudaStream_t)stream);
+    // columns are (tap, c): packed [Cout, taps*C] keeps them; the parameter layout [Cout, C, kh, kw] swaps them
+    const ab::WgradOutMap om = param_layout ? ab::WgradOutMap{1 << 30, C, C, 0, (long long)C * taps, 1, taps}
+                                            : ab::WgradOutMap{1 << 30, C, C, 0, (long long)C * taps, C, 1};
+    return ab::launch_wgrad<true>(tg, tx, P, Cout, taps * C, dw, om, cg, taps, (cudaStream_t)stream);
 }

@@ -183,29 +183,50 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psu
     }
 }
 
-__global__ void bn_apply_kernel(const uint4* __restrict__ raw, long long n8, int C8, const float* __restrict__ scale,
-                                const float* __restrict__ shift, const uint4* __restrict__ residual, int relu,
-                                uint4* __restrict__ y) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n8) return;
-    const int g = (int)(i % C8);
-    float f[8], r[8];
-    bf16x8_to_float(__ldg(raw + i), f);
-    if (residual) bf16x8_to_float(__ldg(residual + i), r);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float v = fmaf(f[j], scale[8 * g + j], shift[8 * g + j]);
-        if (residual) v += r[j];
-        f[j] = relu ? fmaxf(v, 0.0f) : v;
+// Streaming skeleton shared by the BatchNorm apply / backward-apply passes: thread t owns column group t % C8 (its
+// per-channel coefficients stay in registers) and walks rows blockIdx.x * rows_par + t / C8 (+ grid stride).
+template <class Setup, class Body>
+__device__ __forceinline__ void stream_rows(long long M, int C8, Setup setup, Body body) {
+    const int t = threadIdx.x;
+    const int tpr = min(C8, kRedThreads), rows_par = kRedThreads / tpr;
+    const int g0 = t % tpr, rl = t / tpr;
+    if (rl >= rows_par) return;
+    for (int g = g0; g < C8; g += tpr) {
+        setup(g);
+#pragma unroll 4
+        for (long long r = (long long)blockIdx.x * rows_par + rl; r < M; r += (long long)gridDim.x * rows_par) body(r * C8 + g);
     }
-    y[i] = float_to_bf16x8(f);
+}
+
+__device__ __forceinline__ void load8(const float* p, float* f) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
 __global__ void __launch_bounds__(kRedThreads)
+bn_apply_kernel(const uint4* __restrict__ raw, long long M, int C8, const float* __restrict__ scale,
+                const float* __restrict__ shift, const uint4* __restrict__ residual, int relu, uint4* __restrict__ y) {
+    float sc[8], sh[8];
+    stream_rows(M, C8, [&](int g) { load8(scale + 8 * g, sc); load8(shift + 8 * g, sh); },
+                [&](long long i) {
+                    float f[8], r[8];
+                    bf16x8_to_float(__ldg(raw + i), f);
+                    if (residual) bf16x8_to_float(__ldg(residual + i), r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float v = fmaf(f[j], sc[j], sh[j]);
+                        if (residual) v += r[j];
+                        f[j] = relu ? fmaxf(v, 0.0f) : v;
+                    }
+                    y[i] = float_to_bf16x8(f);
+                });
+}
+
+// dy' = dy * (y > 0);  partial column sums of dy' and dy' * raw (the x-hat form follows in bn_bwd_finalize_kernel)
+__global__ void __launch_bounds__(kRedThreads)
 bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ raw, int M, int C8,
-                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu, float* sum_dy,
-                     float* sum_dy_xhat) {
-    float* outs[2] = {sum_dy, sum_dy_xhat};
+                     int relu, float* psum_dy, float* psum_dy_x) {
+    float* outs[2] = {psum_dy, psum_dy_x};
     column_partial<2>(M, C8, outs, [&](long long r, int g, float* acc) {
         float d[8], yy[8], x[8];
         bf16x8_to_float(__ldg(dy + r * C8 + g), d);
@@ -215,34 +236,66 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, 
         for (int j = 0; j < 8; ++j) {
             const float dd = (relu && !(yy[j] > 0.0f)) ? 0.0f : d[j];
             acc[j] += dd;
-            acc[8 + j] += dd * (x[j] - mean[8 * g + j]) * invstd[8 * g + j];
+            acc[8 + j] = fmaf(dd, x[j], acc[8 + j]);
         }
     });
 }
 
-__global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ raw,
-                                    long long n8, int C8, float inv_count, const float* __restrict__ gamma,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ sum_dy, const float* __restrict__ sum_dy_xhat, int relu,
-                                    uint4* __restrict__ dx, uint4* __restrict__ dres) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n8) return;
-    const int g = (int)(i % C8);
-    float d[8], yy[8], x[8], o[8];
-    bf16x8_to_float(__ldg(dy + i), d);
-    bf16x8_to_float(__ldg(raw + i), x);
-    if (relu) bf16x8_to_float(__ldg(y + i), yy);
+// Adds the partial rows, then: dbeta = sum dy', dgamma = sum dy' * xhat = (sum dy'x - mean * sum dy') * invstd, written
+// or accumulated into the parameter gradients, and the three per-channel coefficients of the apply pass
+//   dx = gamma*invstd*(dy' - dbeta/M - xhat*dgamma/M) = A*dy' + B*raw + K,
+//   A = gamma*invstd, B = -A*invstd*dgamma/M, K = A*(mean*invstd*dgamma - dbeta)/M.            coef: [3, C]
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ part0, const float* __restrict__ part1, int n_part, int C, float inv_count,
+                       const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
+                       float* dgamma, float* dbeta, int accumulate, float* coef) {
+    __shared__ float red[2][8][8];
+    const int cx = threadIdx.x & 7, pr = threadIdx.x >> 3, c = blockIdx.x * 8 + cx;
+    float s0 = 0.0f, s1 = 0.0f;
+    if (c < C)
+        for (int p = pr; p < n_part; p += 32) {
+            s0 += part0[(size_t)p * C + c];
+            s1 += part1[(size_t)p * C + c];
+        }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane < 8) { red[0][wid][lane] = s0; red[1][wid][lane] = s1; }
+    __syncthreads();
+    if (threadIdx.x >= 8 || c >= C) return;
+    float sdy = 0.0f, sdyx = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = 8 * g + j;
-        const float dd = (relu && !(yy[j] > 0.0f)) ? 0.0f : d[j];
-        d[j] = dd;
-        const float xhat = (x[j] - mean[c]) * invstd[c];
-        const float gm = gamma ? gamma[c] : 1.0f;
-        o[j] = gm * invstd[c] * (dd - sum_dy[c] * inv_count - xhat * sum_dy_xhat[c] * inv_count);
-    }
-    dx[i] = float_to_bf16x8(o);
-    if (dres) dres[i] = float_to_bf16x8(d);
+    for (int w = 0; w < 8; ++w) { sdy += red[0][w][threadIdx.x]; sdyx += red[1][w][threadIdx.x]; }
+    const float mu = mean[c], is = invstd[c], gm = gamma ? gamma[c] : 1.0f;
+    const float dg = (sdyx - mu * sdy) * is;
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + sdy : sdy;
+    const float A = gm * is;
+    coef[c] = A;
+    coef[C + c] = -A * is * dg * inv_count;
+    coef[2 * C + c] = A * (mu * is * dg - sdy) * inv_count;
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ raw, long long M,
+                    int C8, const float* __restrict__ coef, int relu, uint4* __restrict__ dx, uint4* __restrict__ dres) {
+    float A[8], Bc[8], K[8];
+    const int C = 8 * C8;
+    stream_rows(M, C8, [&](int g) { load8(coef + 8 * g, A); load8(coef + C + 8 * g, Bc); load8(coef + 2 * C + 8 * g, K); },
+                [&](long long i) {
+                    float d[8], yy[8], x[8], o[8];
+                    bf16x8_to_float(__ldg(dy + i), d);
+                    bf16x8_to_float(__ldg(raw + i), x);
+                    if (relu) bf16x8_to_float(__ldg(y + i), yy);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float dd = (relu && !(yy[j] > 0.0f)) ? 0.0f : d[j];
+                        d[j] = dd;
+                        o[j] = fmaf(A[j], dd, fmaf(Bc[j], x[j], K[j]));
+                    }
+                    dx[i] = float_to_bf16x8(o);
+                    if (dres) dres[i] = float_to_bf16x8(d);
+                });
 }
 
 // eval-mode / frozen BN inside a training graph, or plain ReLU: dx = dy * (y > 0) * scale
@@ -482,6 +535,11 @@ extern "C" int ab_bn_finalize(const float* sum_part, const float* sumsq_part, in
     AB_LAUNCH_END("bn_finalize_kernel");
 }
 
+static inline unsigned stream_grid(long long M, int C8) {
+    const int rows_par = kRedThreads / min(C8, kRedThreads);
+    return (unsigned)max(1ll, min((long long)148 * 8, (M + rows_par - 1) / rows_par));
+}
+
 extern "C" int ab_bn_apply(const void* raw, int64_t M, int C, const float* scale, const float* shift, const void* residual,
                            int relu, void* y, void* stream) {
     AB_REQUIRE(M >= 0 && C > 0 && C % 8 == 0, "bad shape");
@@ -489,39 +547,37 @@ extern "C" int ab_bn_apply(const void* raw, int64_t M, int C, const float* scale
     AB_REQUIRE(raw && scale && shift && y, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
-    const long long n8 = M * (C / 8);
-    bn_apply_kernel<<<nblk(n8, 256), 256, 0, st>>>((const uint4*)raw, n8, C / 8, scale, shift, (const uint4*)residual, relu, (uint4*)y);
+    bn_apply_kernel<<<stream_grid(M, C / 8), kRedThreads, 0, st>>>((const uint4*)raw, M, C / 8, scale, shift, (const uint4*)residual,
+                                                                   relu, (uint4*)y);
     AB_LAUNCH_END("bn_apply_kernel");
 }
 
-extern "C" int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, int M, int C, const float* mean,
-                                const float* invstd, int relu, float* sum_dy, float* sum_dy_xhat, float* ws, void* stream) {
+extern "C" int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, int M, int C, const float* gamma,
+                                const float* mean, const float* invstd, int relu, float* dgamma, float* dbeta, int accumulate,
+                                float* coef, float* ws, void* stream) {
     AB_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "bad shape");
-    AB_REQUIRE(dy && raw && mean && invstd && sum_dy && sum_dy_xhat && ws && (!relu || y), "null pointer");
+    AB_REQUIRE(dy && raw && mean && invstd && coef && ws && (!relu || y), "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
     const int parts = stat_parts(M, C / 8);
     float* p0 = ws;
     float* p1 = ws + (size_t)AB_STAT_PARTS * C;
-    bn_bwd_reduce_kernel<<<parts, kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M, C / 8, mean,
-                                                        invstd, relu, p0, p1);
-    partial_sum_kernel<<<nblk(C, 8), 256, 0, st>>>(p0, p1, parts, C, sum_dy, sum_dy_xhat);
+    bn_bwd_reduce_kernel<<<parts, kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M, C / 8, relu, p0, p1);
+    bn_bwd_finalize_kernel<<<nblk(C, 8), 256, 0, st>>>(p0, p1, parts, C, 1.0f / (float)M, gamma, mean, invstd, dgamma, dbeta,
+                                                       accumulate, coef);
     count_launch(2);
     return check_launch("bn_bwd_reduce_kernel");
 }
 
-extern "C" int ab_bn_bwd_apply(const void* dy, const void* y, const void* raw, int64_t M, int C, const float* gamma,
-                               const float* mean, const float* invstd, const float* sum_dy, const float* sum_dy_xhat,
-                               int relu, void* dx, void* dres, void* stream) {
+extern "C" int ab_bn_bwd_apply(const void* dy, const void* y, const void* raw, int64_t M, int C, const float* coef, int relu,
+                               void* dx, void* dres, void* stream) {
     AB_REQUIRE(M >= 0 && C > 0 && C % 8 == 0, "bad shape");
     if (M == 0) return AB_OK;
-    AB_REQUIRE(dy && raw && mean && invstd && sum_dy && sum_dy_xhat && dx && (!relu || y), "null pointer");
+    AB_REQUIRE(dy && raw && coef && dx && (!relu || y), "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
-    const long long n8 = M * (C / 8);
-    bn_bwd_apply_kernel<<<nblk(n8, 256), 256, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, n8, C / 8,
-                                                       1.0f / (float)M, gamma, mean, invstd, sum_dy, sum_dy_xhat, relu,
-                                                       (uint4*)dx, (uint4*)dres);
+    bn_bwd_apply_kernel<<<stream_grid(M, C / 8), kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M,
+                                                                       C / 8, coef, relu, (uint4*)dx, (uint4*)dres);
     AB_LAUNCH_END("bn_bwd_apply_kernel");
 }
 

@@ -34,6 +34,18 @@ class CameraStruct(C.Structure):
                 ("diffuse", C.c_float), ("bg_r", C.c_int32), ("bg_g", C.c_int32), ("bg_b", C.c_int32)]
 
 
+class WgradMapStruct(C.Structure):
+    _fields_ = [("row_div", C.c_int32), ("col_div", C.c_int32), ("col_lo_valid", C.c_int32), ("s_row_hi", C.c_int64),
+                ("s_row_lo", C.c_int64), ("s_col_hi", C.c_int64), ("s_col_lo", C.c_int64)]
+
+
+BIG = 1 << 30
+
+
+def wgrad_map(row_div=BIG, col_div=BIG, col_lo_valid=BIG, s_row_hi=0, s_row_lo=0, s_col_hi=0, s_col_lo=1):
+    return WgradMapStruct(row_div, col_div, col_lo_valid, s_row_hi, s_row_lo, s_col_hi, s_col_lo)
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "ab_version": (C.c_int, []),
@@ -60,8 +72,9 @@ EXPORTS = {
                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "ab_wgrad_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
-                                C.c_int64, C.c_void_p]),
-    "ab_conv_wgrad_bf16_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+                                C.POINTER(WgradMapStruct), C.c_void_p]),
+    "ab_conv_wgrad_bf16_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int,
+                                                                                                   C.c_void_p]),
     "ab_image_to_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "ab_im2col_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]),
     "ab_maxpool3x3s2_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -73,10 +86,10 @@ EXPORTS = {
     "ab_bn_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_float]
                        + [C.c_void_p] * 7),
     "ab_bn_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
-    "ab_bn_bwd_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
-                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "ab_bn_bwd_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
-                        + [C.c_void_p] * 3),
+    "ab_bn_bwd_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_bn_bwd_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     "ab_affine_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
     "ab_maxpool3x3s2_bwd": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),

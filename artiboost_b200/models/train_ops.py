@@ -37,9 +37,15 @@ def _pack_dgrad_weight(w: torch.Tensor) -> torch.Tensor:
     return w.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(cin, -1).to(torch.bfloat16).contiguous()
 
 
-def _unpack_wgrad(dw_packed: torch.Tensor, w: torch.Tensor, cin_pad: int) -> torch.Tensor:
-    cout, cin, kh, kw = w.shape
-    return dw_packed[:, :kh * kw * cin_pad].view(cout, kh, kw, cin_pad)[..., :cin].permute(0, 3, 1, 2).contiguous()
+def _grad_target(param: torch.Tensor):
+    """-> (fp32 buffer the kernels accumulate into, in_place).  When the parameter already owns a dense fp32 .grad
+    (FlatParams views, or a previous backward) the kernels add into it directly and the Function returns None for that
+    input; otherwise a zeroed buffer is returned to autograd."""
+    g = param.grad
+    if (g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == param.shape and g.device == param.device
+            and not torch.is_grad_enabled()):
+        return g, True
+    return torch.zeros(param.shape, dtype=torch.float32, device=param.device), False
 
 
 def _conv_raw(x: Act, wp, cout, kh, kw, stride, pad, col_stats=None, scale=None, bias=None, relu=False, out_fp32=False,
@@ -101,18 +107,26 @@ def _bn_forward_train(raw, M, C, bn, sums, residual, relu):
 
 
 def _norm_backward(dy, y, raw, M, C, bn, st, relu, want_res):
-    """-> (draw bf16 [M,C], dgamma, dbeta, dres).  st: _BNState (batch statistics) or a frozen scale tensor or None."""
+    """-> (draw bf16 [M,C], dgamma, dbeta, dres).  st: _BNState (batch statistics) or a frozen scale tensor or None.
+    dgamma / dbeta are None when they were accumulated straight into bn.weight.grad / bn.bias.grad."""
     dev = dy.device
     dx = torch.empty((M, C), dtype=torch.bfloat16, device=dev)
     dres = torch.empty((M, C), dtype=torch.bfloat16, device=dev) if want_res else None
     dgamma = dbeta = None
     with torch.cuda.device(dev):
         if isinstance(st, _BNState):
-            dbeta, dgamma = torch.empty(C, device=dev), torch.empty(C, device=dev)
-            _call("ab_bn_bwd_reduce", dy.data_ptr(), P(y), raw.data_ptr(), M, C, st.mean.data_ptr(), st.invstd.data_ptr(), int(relu),
-                  dbeta.data_ptr(), dgamma.data_ptr(), _stat_ws(C, dev).data_ptr(), _stream(dev))
-            _call("ab_bn_bwd_apply", dy.data_ptr(), P(y), raw.data_ptr(), M, C, P(bn.weight), st.mean.data_ptr(),
-                  st.invstd.data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), int(relu), dx.data_ptr(), P(dres), _stream(dev))
+            (gbuf, g_in), (bbuf, b_in) = _grad_target(bn.weight), _grad_target(bn.bias)
+            in_place = g_in and b_in
+            if not in_place:
+                gbuf, bbuf = torch.empty(C, device=dev), torch.empty(C, device=dev)
+            coef = torch.empty(3 * C, device=dev)
+            _call("ab_bn_bwd_reduce", dy.data_ptr(), P(y), raw.data_ptr(), M, C, P(bn.weight), st.mean.data_ptr(),
+                  st.invstd.data_ptr(), int(relu), gbuf.data_ptr(), bbuf.data_ptr(), int(in_place), coef.data_ptr(),
+                  _stat_ws(C, dev).data_ptr(), _stream(dev))
+            _call("ab_bn_bwd_apply", dy.data_ptr(), P(y), raw.data_ptr(), M, C, coef.data_ptr(), int(relu), dx.data_ptr(), P(dres),
+                  _stream(dev))
+            if not in_place:
+                dgamma, dbeta = gbuf, bbuf
         else:
             _call("ab_affine_relu_bwd", dy.data_ptr(), P(y), M, C, P(st), int(relu), dx.data_ptr(), P(dres), _stream(dev))
     return dx, dgamma, dbeta, dres
@@ -154,21 +168,23 @@ def _conv_dgrad(dy: Act, conv_w, kh, kw, stride, pad, H, W, key) -> torch.Tensor
     return dx
 
 
-def _conv_wgrad(x: Act, xcol, dy_mat, conv_w, kh, kw, stride, pad) -> torch.Tensor:
-    cout = conv_w.shape[0]
+def _conv_wgrad(x: Act, xcol, dy_mat, conv_w, kh, kw, stride, pad):
+    """Weight gradient accumulated in the nn.Conv2d layout [Cout, Cin, kh, kw]; -> None when it went into conv_w.grad."""
+    cout, cin = conv_w.shape[0], conv_w.shape[1]
+    taps = kh * kw
     dev = dy_mat.device
+    dw, in_place = _grad_target(conv_w)
     with torch.cuda.device(dev):
         if x.C % 64 == 0:
-            dwp = torch.zeros((cout, kh * kw * x.C), device=dev)
             _call("ab_conv_wgrad_bf16_nhwc", x.data.data_ptr(), x.B, x.H, x.W, x.C, dy_mat.data_ptr(), cout, kh, kw, stride, pad,
-                  dwp.data_ptr(), _stream(dev))
+                  dw.data_ptr(), 1, _stream(dev))
         else:
             if xcol is None:  # 1x1 stride-1 on a narrow activation: the activation is the matrix
                 xcol = x.data
-            dwp = torch.zeros((cout, xcol.shape[1]), device=dev)
-            _call("ab_wgrad_bf16", dy_mat.shape[0], cout, xcol.shape[1], dy_mat.data_ptr(), dy_mat.stride(0), xcol.data_ptr(),
-                  xcol.stride(0), dwp.data_ptr(), dwp.stride(0), _stream(dev))
-    return _unpack_wgrad(dwp, conv_w, x.C)
+            m = lib.wgrad_map(col_div=x.C, col_lo_valid=cin, s_row_lo=cin * taps, s_col_hi=1, s_col_lo=taps)
+            _call("ab_wgrad_bf16", dy_mat.shape[0], cout, taps * x.C, dy_mat.data_ptr(), dy_mat.stride(0), xcol.data_ptr(),
+                  xcol.stride(0), dw.data_ptr(), m, _stream(dev))
+    return None if in_place else dw
 
 
 # ------------------------------------------------------------------------------------------------ Functions
@@ -218,7 +234,7 @@ class ConvBNActFn(torch.autograd.Function):
                                                    ctx.has_res)
         dbias = _col_sum(draw) if (conv.bias is not None and ctx.needs_input_grad[2]) else None
         x = Act(x_data, B, H, W, C)
-        dw = _conv_wgrad(x, xcol if xcol.numel() else None, draw, weight, kh, kw, stride, pad) if ctx.needs_input_grad[1] else None
+        dw = _conv_wgrad(x, xcol if xcol.numel() else None, draw, conv.weight, kh, kw, stride, pad) if ctx.needs_input_grad[1] else None
         dx = None
         if ctx.needs_input_grad[0]:
             dx = _conv_dgrad(Act(draw, B, Ho, Wo, cout), weight, kh, kw, stride, pad, H, W, conv)
@@ -335,11 +351,12 @@ class DeconvBNReluFn(torch.autograd.Function):
             _call("ab_deconv4x4s2_gather", draw.data_ptr(), B, H, W, cout, dycol.data_ptr(), _stream(dev))
         dw = dx = None
         if ctx.needs_input_grad[1]:
-            dwp = torch.zeros((16 * cout, C), device=dev)  # [(ky,kx,co), ci]
+            dwb, in_place = _grad_target(deconv.weight)  # rows (ky,kx,co), columns ci -> [Cin, Cout, ky, kx]
+            m = lib.wgrad_map(row_div=cout, s_row_hi=1, s_row_lo=16, s_col_lo=cout * 16)
             with torch.cuda.device(dev):
-                _call("ab_wgrad_bf16", B * H * W, 16 * cout, C, dycol.data_ptr(), 16 * cout, x_data.data_ptr(), C, dwp.data_ptr(), C,
+                _call("ab_wgrad_bf16", B * H * W, 16 * cout, C, dycol.data_ptr(), 16 * cout, x_data.data_ptr(), C, dwb.data_ptr(), m,
                       _stream(dev))
-            dw = dwp.view(4, 4, cout, C).permute(3, 2, 0, 1).contiguous()  # -> [Cin, Cout, ky, kx]
+            dw = None if in_place else dwb
         if ctx.needs_input_grad[0]:
             wt = _cached(deconv, "dwt", _ver(weight),
                          lambda: weight.detach().permute(0, 2, 3, 1).reshape(C, 16 * cout).to(torch.bfloat16).contiguous())
@@ -403,11 +420,11 @@ class LinearFn(torch.autograd.Function):
         npad = _pad8(n)
         g = torch.zeros((dy.shape[0], npad), dtype=torch.bfloat16, device=dev)
         g[:, :n] = (dy.float() * (y.float() > 0)) if relu else dy
-        dwp = torch.zeros((npad, _pad8(k)), device=dev)
+        dwb, in_place = _grad_target(fc.weight)
         with torch.cuda.device(dev):
-            _call("ab_wgrad_bf16", g.shape[0], npad, xb.shape[1], g.data_ptr(), npad, xb.data_ptr(), xb.stride(0), dwp.data_ptr(),
-                  dwp.stride(0), _stream(dev))
-        dw = dwp[:n, :k].contiguous()
+            _call("ab_wgrad_bf16", g.shape[0], n, k, g.data_ptr(), npad, xb.data_ptr(), xb.stride(0), dwb.data_ptr(),
+                  lib.wgrad_map(s_row_lo=k, s_col_lo=1), _stream(dev))
+        dw = None if in_place else dwb
         db = _col_sum(g)[:n] if fc.bias is not None else None
         wt = _cached(fc, "fct", _ver(weight), lambda: _pad_rows(weight.detach().t().to(torch.bfloat16), _pad8(k), npad))
         dx = ops.gemm_bf16(g, wt)[:, :k] if ctx.needs_input_grad[0] else None

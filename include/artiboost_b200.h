@@ -177,14 +177,23 @@ AB_API int ab_conv_bf16_nhwc(const void* x, int B, int H, int W, int C, const vo
                              const void* residual, int64_t ldr, int relu, float* col_sum, float* col_sumsq, void* stream);
 
 /* Weight gradients (the wgrad half of loss.backward() at train/train_artiboost.py:91-93, cuDNN wgrad in the
- * reference).  D[Mo,No] += sum_p G[p,mo] * X[p,no], fp32 atomic accumulation into a caller-zeroed D (pitch ldd):
+ * reference).  D(row, col) += sum_p G[p,row] * X[p,col], fp32 atomic accumulation into the caller's gradient buffer
+ * (which already holds whatever was accumulated before, like autograd's .grad):
  * G = dY bf16 [P,Mo], X bf16 [P,No] (ab_wgrad_bf16), or X = the NHWC activation read through TMA im2col
- * (ab_conv_wgrad_bf16_nhwc: dw_packed f32 [Cout, kh*kw*C], K order (ky,kx,c), C % 64 == 0).  The reduction runs
- * over operand rows: both operands are MN-major for tcgen05; the pixel axis is split across CTAs.               */
-AB_API int ab_wgrad_bf16(int P, int Mo, int No, const void* G, int64_t ldg, const void* X, int64_t ldx, float* D, int64_t ldd,
-                         void* stream);
+ * (ab_conv_wgrad_bf16_nhwc, columns (ky,kx,c), C % 64 == 0; param_layout = 1 writes the nn.Conv2d layout
+ * [Cout, C, kh, kw], 0 the packed [Cout, kh*kw*C]).  ab_wgrad_map places (row, col) anywhere: with (hi, lo) =
+ * (i / div, i % div), offset = row_hi*s_row_hi + row_lo*s_row_lo + col_hi*s_col_hi + col_lo*s_col_lo, and columns with
+ * col_lo >= col_lo_valid (channel padding) are dropped -- so conv, transposed-conv and linear gradients land directly
+ * in the parameter's own layout.  The reduction runs over operand rows: both operands are MN-major for tcgen05;
+ * the pixel axis is split across CTAs.                                                                          */
+typedef struct ab_wgrad_map {
+    int32_t row_div, col_div, col_lo_valid;
+    int64_t s_row_hi, s_row_lo, s_col_hi, s_col_lo;
+} ab_wgrad_map;
+AB_API int ab_wgrad_bf16(int P, int Mo, int No, const void* G, int64_t ldg, const void* X, int64_t ldx, float* D,
+                         const ab_wgrad_map* map, void* stream);
 AB_API int ab_conv_wgrad_bf16_nhwc(const void* x, int B, int H, int W, int C, const void* dy, int Cout, int kh, int kw,
-                                   int stride, int pad, float* dw_packed, void* stream);
+                                   int stride, int pad, float* dw, int param_layout, void* stream);
 
 /* ------------------------------------------------------------------- data movement around the contraction (NHWC bf16)
  * Activations are bf16 NHWC ([B,H,W,C], C contiguous) between layers; the reference keeps fp32 NCHW and lets cuDNN
@@ -219,8 +228,10 @@ AB_API int ab_head_decode(const float* logits, int B, int ncls, int D, int H, in
  *   ab_col_stats), then mean, biased var -> scale = gamma*invstd, shift = beta - mean*scale, saved mean / invstd, and the
  *   running-stat update running = (1-momentum)*running + momentum*{mean, unbiased var} (running_* may be NULL).
  * ab_bn_apply: y = relu?(raw*scale + shift (+ residual)).
- * ab_bn_bwd_reduce / ab_bn_bwd_apply: dy' = dy*(y>0) when relu; sum_dy = dbeta, sum_dy_xhat = dgamma;
- *   dx = gamma*invstd*(dy' - sum_dy/M - xhat*sum_dy_xhat/M); dres (optional) receives dy' for the residual branch.
+ * ab_bn_bwd_reduce: dy' = dy*(y>0) when relu; dbeta = sum dy', dgamma = sum dy'*xhat, stored (accumulate = 0) or added
+ *   (accumulate = 1) into dgamma / dbeta (either may be NULL), plus coef f32 [3, C] = the per-channel coefficients of
+ * ab_bn_bwd_apply: dx = gamma*invstd*(dy' - dbeta/M - xhat*dgamma/M) = coef0*dy' + coef1*raw + coef2; dres (optional)
+ *   receives dy' for the residual branch.
  * ab_affine_relu_bwd: dx = dy*(y>0)*scale for frozen / eval-mode BatchNorm.
  * ab_dilate2x: zero insertion, turns the data gradient of a stride-2 conv into a stride-1 conv of the dilated dy.
  * ab_deconv4x4s2_gather: dycol[b,iy,ix,(ky,kx,co)] = dy[b,2iy-1+ky,2ix-1+kx,co], the transpose of ab_deconv4x4s2_col2im.
@@ -234,10 +245,10 @@ AB_API int ab_bn_finalize(const float* sum_part, const float* sumsq_part, int n_
                           float* save_invstd, float* running_mean, float* running_var, void* stream);
 AB_API int ab_bn_apply(const void* raw, int64_t M, int C, const float* scale, const float* shift, const void* residual,
                        int relu, void* y, void* stream);
-AB_API int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, int M, int C, const float* mean,
-                            const float* invstd, int relu, float* sum_dy, float* sum_dy_xhat, float* ws, void* stream);
-AB_API int ab_bn_bwd_apply(const void* dy, const void* y, const void* raw, int64_t M, int C, const float* gamma,
-                           const float* mean, const float* invstd, const float* sum_dy, const float* sum_dy_xhat, int relu,
+AB_API int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, int M, int C, const float* gamma,
+                            const float* mean, const float* invstd, int relu, float* dgamma, float* dbeta, int accumulate,
+                            float* coef, float* ws, void* stream);
+AB_API int ab_bn_bwd_apply(const void* dy, const void* y, const void* raw, int64_t M, int C, const float* coef, int relu,
                            void* dx, void* dres, void* stream);
 AB_API int ab_affine_relu_bwd(const void* dy, const void* y, int64_t M, int C, const float* scale, int relu, void* dx,
                               void* dres, void* stream);
