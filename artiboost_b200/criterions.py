@@ -19,13 +19,26 @@ def _targets(targs, device):
     return targs["joints_3d"].to(device) + root.unsqueeze(1), targs["corners_3d"].to(device) + root.unsqueeze(1)
 
 
+_dev_cache = {}
+_CAMERA_AXIS = np.array([[0.0, 0.0, 1.0]], np.float32)
+
+
+def _on(arr, device):
+    """Constant index table on `device` (uploaded once, outside any graph capture)."""
+    key = (id(arr), str(device))
+    t = _dev_cache.get(key)
+    if t is None:
+        t = _dev_cache[key] = (arr, torch.as_tensor(arr, device=device))
+    return t[1]
+
+
 def sample_view_vectors(n_virtual_views, device, generator=None):
     """ordinal.py:59-72: the camera axis + n random directions on the upper hemisphere."""
     theta = torch.rand(n_virtual_views, device=device, generator=generator) * 2.0 * np.pi
     u = torch.rand(n_virtual_views, device=device, generator=generator)
     s = torch.sqrt(1.0 - u ** 2)
     nv = torch.stack([s * torch.cos(theta), s * torch.sin(theta), u], dim=1)
-    return torch.cat([torch.tensor([[0.0, 0.0, 1.0]], device=device), nv], dim=0)
+    return torch.cat([_on(_CAMERA_AXIS, device), nv], dim=0)
 
 
 def _subsample(n, device, generator):
@@ -68,6 +81,7 @@ class HandOrdLoss:
         self.n_virtual_views = int(cfg.get("N_VIRTUAL_VIEWS", 20))
         self.jp = np.array(list(combinations(range(21), 2)))
         self.pp = np.array(list(combinations(range(20), 2)))
+        self.parents = np.array(JOINTS_IDX_PARENTS)
         self.generator = None
 
     def __call__(self, preds, targs, **kw):
@@ -77,12 +91,12 @@ class HandOrdLoss:
         m = targs["joints_vis"].to(dev).unsqueeze(-1)
         pj, tj = pj * m, tj * m
         vv = sample_view_vectors(self.n_virtual_views, dev, self.generator)
-        jp = torch.as_tensor(self.jp, device=dev)[_subsample(len(self.jp), dev, self.generator)]
+        jp = _on(self.jp, dev)[_subsample(len(self.jp), dev, self.generator)]
         sign = torch.sign(_joint_ord(tj[:, jp[:, 0]], tj[:, jp[:, 1]], vv))
         joint_ord_loss = torch.log(1.0 + F.relu(-sign * _joint_ord(pj[:, jp[:, 0]], pj[:, jp[:, 1]], vv))).mean()
-        par = torch.as_tensor(JOINTS_IDX_PARENTS, device=dev)
+        par = _on(self.parents, dev)
         pparts, tparts = (pj - pj[:, par])[:, 1:], (tj - tj[:, par])[:, 1:]
-        pp = torch.as_tensor(self.pp, device=dev)[_subsample(len(self.pp), dev, self.generator)]
+        pp = _on(self.pp, dev)[_subsample(len(self.pp), dev, self.generator)]
         t_ord = torch.einsum("bpk,vk->bpv", torch.cross(tparts[:, pp[:, 0]], tparts[:, pp[:, 1]], dim=-1), vv)
         p_ord = torch.einsum("bpk,vk->bpv", torch.cross(pparts[:, pp[:, 0]], pparts[:, pp[:, 1]], dim=-1), vv)
         part_ord_loss = F.relu(-torch.sign(t_ord) * p_ord).mean()
@@ -106,7 +120,7 @@ class SceneOrdLoss:
         mj, mc = targs["joints_vis"].to(dev).unsqueeze(-1), targs["corners_vis"].to(dev).unsqueeze(-1)
         pj, tj, pc, tc = pj * mj, tj * mj, pc * mc, tc * mc
         vv = sample_view_vectors(self.n_virtual_views, dev, self.generator)
-        hp = torch.as_tensor(self.hp, device=dev)[_subsample(len(self.hp), dev, self.generator)]
+        hp = _on(self.hp, dev)[_subsample(len(self.hp), dev, self.generator)]
         sign = torch.sign(_joint_ord(tj[:, hp[:, 0]], tc[:, hp[:, 1]], vv))
         loss = torch.log(1.0 + F.relu(-sign * _joint_ord(pj[:, hp[:, 0]], pc[:, hp[:, 1]], vv))).mean()
         return self.lambda_scene_lev * loss, {"scene_ord_loss": loss}

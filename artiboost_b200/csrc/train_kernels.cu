@@ -471,21 +471,35 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* ou
 
 // torch.optim.Adam (no amsgrad, weight_decay added to the gradient) on one flat fp32 buffer.  grad_sumsq (device scalar):
 // total squared norm of the gradient; the clip coefficient min(1, max_norm / (norm + 1e-6)) of clip_grad_norm_ is
-// applied on the fly (max_norm <= 0: no clipping).
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long n, float lr, float beta1, float beta2, float eps, float weight_decay, float bias1,
-                            float bias2, const float* __restrict__ grad_sumsq, float max_norm, float grad_scale) {
+// applied on the fly (max_norm <= 0: no clipping).  state = {step count, 1 - beta1^t, 1 - beta2^t} lives on the device
+// and is advanced by adam_tick_kernel, so a captured CUDA graph of the step replays with the right bias corrections.
+__global__ void adam_tick_kernel(float* state, float beta1, float beta2) {
+    const float t = state[0] + 1.0f;
+    state[0] = t;
+    state[1] = 1.0f - powf(beta1, t);
+    state[2] = 1.0f - powf(beta2, t);
+}
+
+__global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                            long long n4, float lr, float beta1, float beta2, float eps, float weight_decay,
+                            const float* __restrict__ state, const float* __restrict__ grad_sumsq, float max_norm,
+                            float grad_scale) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n4) return;
+    const float bias1 = state[1], rsb2 = rsqrtf(state[2]);
     float clip = 1.0f;
     if (max_norm > 0.0f) clip = fminf(1.0f, max_norm / (sqrtf(*grad_sumsq) * grad_scale + 1e-6f));
-    float gi = g[i] * grad_scale * clip + weight_decay * p[i];
-    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / sqrtf(bias2) + eps;
-    p[i] -= lr / bias1 * mi / denom;
+    const float gs = grad_scale * clip, step = lr / bias1;
+    float4 P = p[i], G = __ldg(g + i), M = m[i], V = v[i];
+    float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float gi = gg[j] * gs + weight_decay * pp[j];
+        mm[j] = beta1 * mm[j] + (1.0f - beta1) * gi;
+        vv[j] = beta2 * vv[j] + (1.0f - beta2) * gi * gi;
+        pp[j] -= step * mm[j] / (sqrtf(vv[j]) * rsb2 + eps);
+    }
+    p[i] = P; m[i] = M; v[i] = V;
 }
 
 static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -658,15 +672,17 @@ extern "C" int ab_sumsq(const float* g, int64_t n, float* out, void* stream) {
 }
 
 extern "C" int ab_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                            float weight_decay, int step, const float* grad_sumsq, float max_norm, float grad_scale,
+                            float weight_decay, float* state, const float* grad_sumsq, float max_norm, float grad_scale,
                             void* stream) {
-    AB_REQUIRE(n >= 0 && step >= 1, "bad arguments");
+    AB_REQUIRE(n >= 0 && n % 4 == 0, "n must be a non-negative multiple of 4 (pad the flat buffer)");
     if (n == 0) return AB_OK;
-    AB_REQUIRE(p && g && m && v && (max_norm <= 0.0f || grad_sumsq), "null pointer");
+    AB_REQUIRE(p && g && m && v && state && (max_norm <= 0.0f || grad_sumsq), "null pointer");
+    AB_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_OPTIMIZER, st);
-    const float bias1 = 1.0f - powf(beta1, (float)step), bias2 = 1.0f - powf(beta2, (float)step);
-    adam_kernel<<<nblk(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias1, bias2, grad_sumsq,
-                                              max_norm, grad_scale);
-    AB_LAUNCH_END("adam_kernel");
+    adam_tick_kernel<<<1, 1, 0, st>>>(state, beta1, beta2);
+    adam_kernel<<<nblk(n / 4, 256), 256, 0, st>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, n / 4, lr, beta1, beta2, eps,
+                                                  weight_decay, state, grad_sumsq, max_norm, grad_scale);
+    count_launch(2);
+    return check_launch("adam_kernel");
 }

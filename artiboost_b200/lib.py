@@ -98,7 +98,7 @@ EXPORTS = {
     "ab_deconv4x4s2_gather": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
     "ab_head_decode_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "ab_sumsq": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "ab_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int, C.c_void_p, C.c_float, C.c_float,
+    "ab_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                                                                   C.c_void_p]),
 }
 

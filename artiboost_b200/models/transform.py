@@ -9,8 +9,8 @@ def batch_uvd2xyz(uvd: torch.Tensor, root_joint: torch.Tensor, intr: torch.Tenso
     """anakin/utils/transform.py:512-546."""
     if inp_res is None:
         inp_res = [256, 256]
-    res = torch.tensor(inp_res, dtype=uvd.dtype, device=uvd.device)
-    uv = uvd[:, :, :2] * res
+    # scalar multiplies (no host->device tensor): the step must stay capturable into a CUDA graph
+    uv = torch.stack((uvd[:, :, 0] * float(inp_res[0]), uvd[:, :, 1] * float(inp_res[1])), dim=-1)
     d = (uvd[:, :, 2] - 0.5) * depth_range
     if ref_bone_len is None:
         ref_bone_len = torch.ones((uvd.shape[0], 1), dtype=uvd.dtype, device=uvd.device)

@@ -26,8 +26,9 @@ class FlatParams:
         self.params = params
         n = sum(p.numel() for p in params)
         dev = params[0].device
-        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        n_pad = (n + 3) // 4 * 4  # the optimiser kernel works on float4
+        self.flat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         off = 0
         for p in params:
             k = p.numel()
@@ -35,12 +36,10 @@ class FlatParams:
             p.data = self.flat[off:off + k].view_as(p.data)
             p.grad = self.grad[off:off + k].view_as(p.data)
             off += k
-        self.numel = n
+        self.numel = n_pad
 
     def zero_grad(self):
         self.grad.zero_()
-        for p in self.params:  # autograd may have replaced .grad with a fresh tensor: re-attach the views
-            pass
 
 
 class FusedAdam:
@@ -51,18 +50,21 @@ class FusedAdam:
         self.m = torch.zeros_like(flat.flat)
         self.v = torch.zeros_like(flat.flat)
         self.sumsq = torch.zeros(1, device=flat.flat.device)
-        self.step_count = 0
+        self.state = torch.zeros(3, device=flat.flat.device)  # {step count, 1 - beta1^t, 1 - beta2^t}, advanced on device
+
+    @property
+    def step_count(self) -> int:
+        return int(self.state[0].item())
 
     def step(self, grad_scale: float = 1.0):
         fp, dev = self.fp, self.fp.flat.device
-        self.step_count += 1
         L = lib.load()
         with torch.cuda.device(dev):
             if self.max_norm > 0:
                 self.sumsq.zero_()
                 lib.check(L.ab_sumsq(fp.grad.data_ptr(), fp.numel, self.sumsq.data_ptr(), lib.stream_ptr(dev)), "ab_sumsq")
             lib.check(L.ab_adam_step(fp.flat.data_ptr(), fp.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), fp.numel,
-                                     self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count,
+                                     self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.state.data_ptr(),
                                      self.sumsq.data_ptr(), float(self.max_norm), float(grad_scale), lib.stream_ptr(dev)),
                       "ab_adam_step")
         nhwc.bump_params()  # the kernel rewrote the parameters in place: packed bf16 filter copies are stale
@@ -111,28 +113,73 @@ class CCVFeedback:
 
 class TrainStep:
     """One optimisation step on a batch dict with the reference's keys (image, root_joint, cam_intr, corners_can,
-    joints_3d, corners_3d, joints_vis, corners_vis)."""
+    joints_3d, corners_3d, joints_vis, corners_vis).
 
-    def __init__(self, arch: nn.Module, criterion_cfg: Optional[dict] = None, lr=5e-5, grad_clip=1e-3, generator=None):
+    use_graph: after `graph_warmup` eager steps the whole step (zero-grad, forward, losses, backward kernels, gradient
+    all-reduce, clip + Adam, filter re-packing) is captured ONCE into a CUDA graph and replayed: ~1400 launches become one
+    submission.  The batch is then copied into static input buffers, the returned loss / predictions are static
+    tensors that the next step overwrites, and the batch size and learning rate are fixed for the graph's lifetime."""
+
+    BATCH_KEYS = ("image", "root_joint", "cam_intr", "corners_can", "joints_3d", "corners_3d", "joints_vis", "corners_vis")
+
+    def __init__(self, arch: nn.Module, criterion_cfg: Optional[dict] = None, lr=5e-5, grad_clip=1e-3, generator=None,
+                 use_graph: bool = False, graph_warmup: int = 3):
         self.arch = arch
         self.flat = FlatParams(arch)
         self.opt = FusedAdam(self.flat, lr=lr, max_norm=grad_clip)   # Adam lr 5e-5, clip 1e-3 (yaml:130-142)
         self.criterion = Criterion(criterion_cfg or DEFAULT_CRITERION_CFG, generator=generator)
+        self.generator = generator
         self.world = parallel.world()[1]
+        self.use_graph, self.graph_warmup = use_graph, graph_warmup
+        self._graph, self._static, self._out, self._eager_steps = None, None, None, 0
 
-    def __call__(self, batch: Dict[str, torch.Tensor]):
+    def _eager(self, batch: Dict[str, torch.Tensor]):
         self.arch.train()
         self.flat.grad.zero_()
-        for p in self.flat.params:  # gradients accumulate straight into the flat buffer's views
-            if p.grad is None or p.grad.data_ptr() < self.flat.grad.data_ptr():
-                raise RuntimeError("a parameter gradient left the flat buffer")
         preds = self.arch(batch)
         preds = preds[next(iter(preds))] if "joints_3d_abs" not in preds else preds
         loss, parts = self.criterion.compute_losses(preds, batch)
         loss.backward()
         parallel.allreduce_sum_(self.flat.grad)
         self.opt.step(grad_scale=1.0 / self.world)
-        return loss.detach(), preds
+        return loss.detach(), {k: v.detach() for k, v in preds.items()}
+
+    def _check_grads(self):
+        lo, hi = self.flat.grad.data_ptr(), self.flat.grad.data_ptr() + 4 * self.flat.numel
+        for p in self.flat.params:  # gradients accumulate straight into the flat buffer's views
+            if p.grad is None or not lo <= p.grad.data_ptr() < hi:
+                raise RuntimeError("a parameter gradient left the flat buffer")
+
+    def _capture(self, batch):
+        dev = self.flat.flat.device
+        self._static = {k: batch[k].detach().clone() for k in self.BATCH_KEYS}
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        if self.generator is not None:
+            graph.register_generator_state(self.generator)
+        with torch.cuda.graph(graph):
+            self._out = self._eager(self._static)
+        self._graph = graph
+
+    def __call__(self, batch: Dict[str, torch.Tensor]):
+        self._check_grads()
+        if not self.use_graph:
+            return self._eager(batch)
+        if self._graph is None:
+            if self._eager_steps < self.graph_warmup:
+                self._eager_steps += 1
+                side = torch.cuda.Stream(self.flat.flat.device)   # warm up off the default stream, as capture will run
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    out = self._eager(batch)
+                torch.cuda.current_stream().wait_stream(side)
+                return out
+            self._capture(batch)
+        for k in self.BATCH_KEYS:
+            self._static[k].copy_(batch[k], non_blocking=True)
+        self._graph.replay()
+        nhwc.bump_params()  # the replayed Adam kernel rewrote the parameters: eager users must re-pack their filters
+        return self._out
 
 
 def synth_to_batch(views: dict, pipe, center_idx: int = 0) -> Dict[str, torch.Tensor]:
@@ -184,13 +231,13 @@ class ArtiBoostLoop:
     recorded errors into the next epoch's sampling weights (all-reduced over ranks)."""
 
     def __init__(self, arch: nn.Module, pipe, batch_size: int = 128, synth_factor: float = 0.6, real_source=None,
-                 criterion_cfg: Optional[dict] = None, lr=5e-5, grad_clip=1e-3, generator=None):
+                 criterion_cfg: Optional[dict] = None, lr=5e-5, grad_clip=1e-3, generator=None, use_graph: bool = False):
         self.pipe, self.batch_size = pipe, batch_size
         self.n_synth = int(round(batch_size * synth_factor / (1.0 + synth_factor)))
         self.n_real = batch_size - self.n_synth
         self.generator = generator
         self.real_source = real_source or (lambda n: real_shaped_batch(n, pipe.device, self.generator, pipe.renderer.width))
-        self.train_step = TrainStep(arch, criterion_cfg, lr=lr, grad_clip=grad_clip, generator=generator)
+        self.train_step = TrainStep(arch, criterion_cfg, lr=lr, grad_clip=grad_clip, generator=generator, use_graph=use_graph)
         self.feedback = CCVFeedback(pipe.sample_weight_map.shape, pipe.device)
 
     def make_batch(self) -> Dict[str, torch.Tensor]:

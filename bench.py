@@ -403,7 +403,9 @@ def train_bench(dev, world, rank, steps=8, warmup=3, batch=128, backbone="ResNet
     ref_model = copy.deepcopy(model) if world == 1 else None
     pipe = SynthPipeline(device=dev, seed=11 + rank)
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
-    loop = ArtiBoostLoop(model, pipe, batch_size=batch, generator=gen)
+    loop = ArtiBoostLoop(model, pipe, batch_size=batch, generator=gen, use_graph=True)
+    for _ in range(4):   # eager warm-up steps, then the one-time CUDA-graph capture of the optimisation step
+        loop.step()
 
     def barrier():
         if world > 1:

@@ -237,7 +237,9 @@ AB_API int ab_head_decode(const float* logits, int B, int ncls, int D, int H, in
  * ab_deconv4x4s2_gather: dycol[b,iy,ix,(ky,kx,co)] = dy[b,2iy-1+ky,2ix-1+kx,co], the transpose of ab_deconv4x4s2_col2im.
  * ab_head_decode_bwd: gradient of ab_head_decode's kp3d w.r.t. the logits (bf16 [B*H*W, ncls*D]).
  * ab_sumsq / ab_adam_step: clip_grad_norm_(max_norm) + torch.optim.Adam on one flat fp32 parameter buffer;
- *   grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).                              */
+ *   grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).  state f32 [3] = {step count,
+ *   1 - beta1^t, 1 - beta2^t} lives on the device (zero it once) and is advanced by the call itself, so a captured
+ *   CUDA graph of the training step replays with the right bias corrections.  n % 4 == 0.                       */
 #define AB_STAT_PARTS 296
 AB_API int ab_col_stats(const void* x, int is_f32, int M, int C, int64_t ld, float* sum, float* sumsq, float* ws, void* stream);
 AB_API int ab_bn_finalize(const float* sum_part, const float* sumsq_part, int n_part, int C, float count, const float* gamma,
@@ -260,7 +262,7 @@ AB_API int ab_head_decode_bwd(const float* logits, const float* dkp3d, int B, in
                               void* stream);
 AB_API int ab_sumsq(const float* g, int64_t n, float* out, void* stream);
 AB_API int ab_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                        float weight_decay, int step, const float* grad_sumsq, float max_norm, float grad_scale, void* stream);
+                        float weight_decay, float* state, const float* grad_sumsq, float max_norm, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,3 +74,44 @@ def test_synth_train_step_runs_learns_and_feeds_ccv(lib_built):
     with torch.no_grad():
         out = model.eval()(batch)["HybridBaseline"]
     assert torch.isfinite(out["joints_3d_abs"]).all()
+
+
+def test_cuda_graph_step_matches_eager_step(lib_built):
+    """The captured-and-replayed step performs the same arithmetic as the eager one.  lr = 0 keeps the two models'
+    parameters identical, so every step's loss (deterministic forward: bit-equal) and flat gradient (weight-gradient
+    atomics: order-dependent last bits) can be compared; then a graph-mode run with lr > 0 must learn."""
+    import copy
+
+    import artiboost_b200.models as M
+    from artiboost_b200.train import TrainStep, real_shaped_batch
+    arch, preset = netcfg.arch_cfg("ResNet34")
+    torch.manual_seed(1)
+    model_a = M.Arch({"ARCH": arch}, M.build_arch_model_list(arch, preset_cfg=preset)).to(DEV)
+    model_b = copy.deepcopy(model_a)
+    cfg = {"LAMBDAS": [1.0], "CRITERION": [{"TYPE": "JointsLoss", "LAMBDA_JOINTS_3D": 1.0, "LAMBDA_CORNERS_3D": 0.2}]}
+    eager = TrainStep(model_a, cfg, lr=0.0, grad_clip=1.0)
+    graphed = TrainStep(model_b, cfg, lr=0.0, grad_clip=1.0, use_graph=True, graph_warmup=2)
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    batches = [real_shaped_batch(8, DEV, gen) for _ in range(5)]
+    for i, b in enumerate(batches):
+        la, _ = eager(b)
+        lb, _ = graphed(b)
+        assert (graphed._graph is not None) == (i >= 2)
+        assert float(la) == float(lb), (i, float(la), float(lb))
+        ga, gb = eager.flat.grad, graphed.flat.grad
+        assert float((ga - gb).norm() / ga.norm()) < 1e-3
+        torch.testing.assert_close(eager.opt.grad_norm(), graphed.opt.grad_norm(), rtol=1e-4, atol=0)
+    assert graphed.opt.step_count == eager.opt.step_count == 5
+    bn_a, bn_b = model_a.model_list[0].backbone.bn1, model_b.model_list[0].backbone.bn1
+    torch.testing.assert_close(bn_a.running_var, bn_b.running_var, rtol=1e-6, atol=0)
+    assert int(bn_b.num_batches_tracked) == 5
+    # graph mode with the full (randomised) criterion learns, and eager eval afterwards sees the trained parameters
+    gen2 = torch.Generator(device=DEV).manual_seed(4)
+    learner = TrainStep(model_b, lr=1e-3, grad_clip=1.0, generator=gen2, use_graph=True, graph_warmup=1)
+    with torch.no_grad():
+        before = model_b.eval()(batches[0])["HybridBaseline"]["joints_3d_abs"].clone()
+    losses = [float(learner(batches[0])[0]) for _ in range(8)]
+    assert learner._graph is not None and losses[-1] < losses[0], losses
+    with torch.no_grad():
+        after = model_b.eval()(batches[0])["HybridBaseline"]["joints_3d_abs"]
+    assert float((after - before).abs().max()) > 1e-4
