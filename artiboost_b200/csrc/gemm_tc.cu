@@ -435,7 +435,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(const void* smem_tile) {
 template <bool IM2COL>
 __global__ void __launch_bounds__(kGemmThreads)
 wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, int P, int Mo, int No,
-                  float* __restrict__ D, const WgradOutMap om, int kblocks_per_split, const ConvGeom cg, int taps) {
+                  float* __restrict__ ws, int kblocks_per_split, const ConvGeom cg, int taps) {
     extern __shared__ uint8_t smem_raw[];
     auto& sm = *reinterpret_cast<WgradSmem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -514,23 +514,60 @@ wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 16) {
             const int col = tile_n * 128 + c0;
-            if (col >= No) break;
             uint32_t r[16];
             tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            if (row < Mo) {
-                float* drow = D + (long long)(row / om.rdiv) * om.s_rh + (long long)(row % om.rdiv) * om.s_rl;
-                int chi = col / om.cdiv, clo = col - chi * om.cdiv;
+            // this split's partial tile goes to the workspace [split][mt*128][nt*128] with plain 16-byte stores (whole
+            // tile, padding included: nothing to zero, no atomics); wgrad_reduce_kernel adds the splits up
+            float4* o = reinterpret_cast<float4*>(ws + ((size_t)blockIdx.z * gridDim.x * 128 + row) * ((size_t)gridDim.y * 128) + col);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (col + j < No && clo < om.cl_valid) atomicAdd(drow + chi * om.s_ch + clo * om.s_cl, __uint_as_float(r[j]));
-                    if (++clo == om.cdiv) { clo = 0; ++chi; }
-                }
-            }
+            for (int j = 0; j < 4; ++j)
+                o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                   __uint_as_float(r[4 * j + 3]));
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem, 128);
+}
+
+// D(row, col) += sum over splits of ws[split][row][col], placed through the output map.  One thread per element;
+// consecutive threads read consecutive columns (coalesced), single writer per destination (deterministic).
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int Mo, int No, int Mp, int Np, float* __restrict__ D,
+                                    const WgradOutMap om) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)Mo * No) return;
+    const int row = (int)(i / No), col = (int)(i - (long long)row * No);
+    const int chi = col / om.cdiv, clo = col - chi * om.cdiv;
+    if (clo >= om.cl_valid) return;
+    const float* p = ws + (size_t)row * Np + col;
+    float acc = 0.0f;
+#pragma unroll 4
+    for (int z = 0; z < splits; ++z) acc += __ldg(p + (size_t)z * Mp * Np);
+    float* d = D + (long long)(row / om.rdiv) * om.s_rh + (long long)(row % om.rdiv) * om.s_rl + (long long)chi * om.s_ch +
+               (long long)clo * om.s_cl;
+    *d += acc;
+}
+
+// Pixel-axis split: CTAs are 2 per SM, so cost ~ waves(tiles * s) * (k-blocks per split + epilogue), minimised over s.
+static int wgrad_splits(int P, int Mo, int No, int* per_out) {
+    const int tiles = cdiv(Mo, 128) * cdiv(No, 128), total_kb = cdiv(P, 64);
+    int best = 1;
+    long long best_cost = -1;
+    for (int sp = 1; sp <= min(total_kb, 1024); ++sp) {
+        const int per = cdiv(total_kb, sp);
+        if (cdiv(total_kb, per) != sp) continue;  // only split counts that leave no empty split
+        const long long cost = (long long)cdiv(tiles * sp, 2 * 148) * (per + 12);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sp; }
+    }
+    *per_out = cdiv(total_kb, best);
+    return best;
+}
+
+size_t wgrad_workspace_bytes(int P, int Mo, int No) {
+    if (P <= 0) return 0;
+    int per;
+    const int sp = wgrad_splits(P, Mo, No, &per);
+    return (size_t)sp * cdiv(Mo, 128) * 128 * cdiv(No, 128) * 128 * sizeof(float);
 }
 
 // box of 64 contiguous elements x 64 rows over a row-major [rows, cols] bf16 matrix
@@ -569,20 +606,21 @@ static int make_im2col_map_px(CUtensorMap* m, const void* ptr, int B, int H, int
 
 template <bool IM2COL>
 static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, int P, int Mo, int No, float* D, const WgradOutMap& om,
-                        const ConvGeom& cg, int taps, cudaStream_t st) {
+                        float* ws, const ConvGeom& cg, int taps, cudaStream_t st) {
     const size_t smem = sizeof(WgradSmem) + 1024;
     static bool configured = false;
     if (!configured) {
         AB_CUDA(cudaFuncSetAttribute(wgrad_bf16_kernel<IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const int mt = cdiv(Mo, 128), nt = cdiv(No, 128), total_kb = cdiv(P, 64);
-    int splits = max(1, min(total_kb, (2 * 148 + mt * nt - 1) / (mt * nt)));
-    const int per = cdiv(total_kb, splits);
-    splits = cdiv(total_kb, per);
+    const int mt = cdiv(Mo, 128), nt = cdiv(No, 128);
+    int per;
+    const int splits = wgrad_splits(P, Mo, No, &per);
     StageTimer tm(AB_STAGE_WGRAD, st);
-    wgrad_bf16_kernel<IM2COL><<<dim3(mt, nt, splits), kGemmThreads, smem, st>>>(tg, tx, P, Mo, No, D, om, per, cg, taps);
-    count_launch();
+    wgrad_bf16_kernel<IM2COL><<<dim3(mt, nt, splits), kGemmThreads, smem, st>>>(tg, tx, P, Mo, No, ws, per, cg, taps);
+    const long long n = (long long)Mo * No;
+    wgrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, splits, Mo, No, mt * 128, nt * 128, D, om);
+    count_launch(2);
     return check_launch("wgrad_bf16_kernel");
 }
 
@@ -626,11 +664,14 @@ extern "C" int ab_conv_bf16_nhwc(const void* x, int B, int H, int W, int C, cons
     return ab::conv_bf16_implicit(x, B, H, W, C, w_packed, Cout, kh, kw, stride, pad, ep, (cudaStream_t)stream);
 }
 
+extern "C" uint64_t ab_wgrad_workspace_bytes(int P, int Mo, int No) { return (uint64_t)ab::wgrad_workspace_bytes(P, Mo, No); }
+
 extern "C" int ab_wgrad_bf16(int P, int Mo, int No, const void* G, int64_t ldg, const void* X, int64_t ldx, float* D,
-                             const ab_wgrad_map* map, void* stream) {
+                             const ab_wgrad_map* map, void* ws, void* stream) {
     AB_REQUIRE(P >= 0 && Mo > 0 && No > 0, "bad shape");
     if (P == 0) return AB_OK;
-    AB_REQUIRE(G && X && D && map, "null pointer");
+    AB_REQUIRE(G && X && D && map && ws, "null pointer");
+    AB_REQUIRE(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
     AB_REQUIRE(map->row_div > 0 && map->col_div > 0 && map->col_lo_valid > 0, "bad output map");
     AB_REQUIRE(ldg % 8 == 0 && ldx % 8 == 0 && Mo <= ldg && No <= ldx, "ldg, ldx must be multiples of 8 (16-byte rows) and cover Mo, No");
     AB_REQUIRE(((uintptr_t)G & 15) == 0 && ((uintptr_t)X & 15) == 0, "operands must be 16-byte aligned");
@@ -640,16 +681,16 @@ extern "C" int ab_wgrad_bf16(int P, int Mo, int No, const void* G, int64_t ldg, 
     rc = ab::make_map_mn(&tx, X, P, No, ldx);
     if (rc) return rc;
     const ab::WgradOutMap om{map->row_div, map->col_div, map->col_lo_valid, map->s_row_hi, map->s_row_lo, map->s_col_hi, map->s_col_lo};
-    return ab::launch_wgrad<false>(tg, tx, P, Mo, No, D, om, ab::ConvGeom{}, 0, (cudaStream_t)stream);
+    return ab::launch_wgrad<false>(tg, tx, P, Mo, No, D, om, (float*)ws, ab::ConvGeom{}, 0, (cudaStream_t)stream);
 }
 
 extern "C" int ab_conv_wgrad_bf16_nhwc(const void* x, int B, int H, int W, int C, const void* dy, int Cout, int kh, int kw,
-                                       int stride, int pad, float* dw, int param_layout, void* stream) {
+                                       int stride, int pad, float* dw, int param_layout, void* ws, void* stream) {
     AB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, "bad shape");
     if (B == 0) return AB_OK;
     AB_REQUIRE(C % 64 == 0 && Cout % 8 == 0, "implicit weight gradient needs C % 64 == 0 and Cout % 8 == 0");
-    AB_REQUIRE(x && dy && dw, "null pointer");
-    AB_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0, "tensors must be 16-byte aligned");
+    AB_REQUIRE(x && dy && dw && ws, "null pointer");
+    AB_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)ws & 15) == 0, "tensors must be 16-byte aligned");
     const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
     const int P = B * Ho * Wo, taps = kh * kw;
     CUtensorMap tg, tx;
@@ -661,5 +702,5 @@ extern "C" int ab_conv_wgrad_bf16_nhwc(const void* x, int B, int H, int W, int C
     // columns are (tap, c): packed [Cout, taps*C] keeps them; the parameter layout [Cout, C, kh, kw] swaps them
     const ab::WgradOutMap om = param_layout ? ab::WgradOutMap{1 << 30, C, C, 0, (long long)C * taps, 1, taps}
                                             : ab::WgradOutMap{1 << 30, C, C, 0, (long long)C * taps, C, 1};
-    return ab::launch_wgrad<true>(tg, tx, P, Cout, taps * C, dw, om, cg, taps, (cudaStream_t)stream);
+    return ab::launch_wgrad<true>(tg, tx, P, Cout, taps * C, dw, om, (float*)ws, cg, taps, (cudaStream_t)stream);
 }

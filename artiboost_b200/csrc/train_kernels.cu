@@ -543,7 +543,7 @@ extern "C" int ab_bn_finalize(const float* sum_part, const float* sumsq_part, in
     AB_REQUIRE(C > 0 && count > 0 && n_part > 0, "bad shape");
     AB_REQUIRE(sum_part && sumsq_part && scale && shift && save_mean && save_invstd, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    StageTimer tm(AB_STAGE_BN_FINALIZE, st);
     bn_finalize_kernel<<<nblk(C, 8), 1024, 0, st>>>(sum_part, sumsq_part, n_part, C, count, gamma, beta, eps, momentum, scale,
                                                     shift, save_mean, save_invstd, running_mean, running_var);
     AB_LAUNCH_END("bn_finalize_kernel");
@@ -560,7 +560,7 @@ extern "C" int ab_bn_apply(const void* raw, int64_t M, int C, const float* scale
     if (M == 0) return AB_OK;
     AB_REQUIRE(raw && scale && shift && y, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    StageTimer tm(AB_STAGE_BN_APPLY, st);
     bn_apply_kernel<<<stream_grid(M, C / 8), kRedThreads, 0, st>>>((const uint4*)raw, M, C / 8, scale, shift, (const uint4*)residual,
                                                                    relu, (uint4*)y);
     AB_LAUNCH_END("bn_apply_kernel");
@@ -572,7 +572,7 @@ extern "C" int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, 
     AB_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "bad shape");
     AB_REQUIRE(dy && raw && mean && invstd && coef && ws && (!relu || y), "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    StageTimer tm(AB_STAGE_BN_BWD_REDUCE, st);
     const int parts = stat_parts(M, C / 8);
     float* p0 = ws;
     float* p1 = ws + (size_t)AB_STAT_PARTS * C;
@@ -589,7 +589,7 @@ extern "C" int ab_bn_bwd_apply(const void* dy, const void* y, const void* raw, i
     if (M == 0) return AB_OK;
     AB_REQUIRE(dy && raw && coef && dx && (!relu || y), "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
+    StageTimer tm(AB_STAGE_BN_BWD_APPLY, st);
     bn_bwd_apply_kernel<<<stream_grid(M, C / 8), kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M,
                                                                        C / 8, coef, relu, (uint4*)dx, (uint4*)dres);
     AB_LAUNCH_END("bn_bwd_apply_kernel");

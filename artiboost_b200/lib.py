@@ -71,10 +71,11 @@ EXPORTS = {
     "ab_conv_bf16_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int64,
                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "ab_wgrad_workspace_bytes": (C.c_uint64, [C.c_int, C.c_int, C.c_int]),
     "ab_wgrad_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
-                                C.POINTER(WgradMapStruct), C.c_void_p]),
+                                C.POINTER(WgradMapStruct), C.c_void_p, C.c_void_p]),
     "ab_conv_wgrad_bf16_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int,
-                                                                                                   C.c_void_p]),
+                                                                                                   C.c_void_p, C.c_void_p]),
     "ab_image_to_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "ab_im2col_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]),
     "ab_maxpool3x3s2_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -102,7 +103,7 @@ EXPORTS = {
                                                                                   C.c_void_p]),
 }
 
-STAT_PARTS = 296  # AB_STAT_PARTS: rows of the column-reduction workspace (2 * STAT_PARTS * C floats)
+STAT_PARTS = 1184  # AB_STAT_PARTS: rows of the column-reduction workspace (2 * STAT_PARTS * C floats)
 _lib = None
 
 
@@ -153,7 +154,8 @@ def launch_count() -> int:
 
 STAGES = {0: "raster_vertex_kernel", 1: "raster_triangle_kernel", 2: "raster_resolve_kernel", 3: "mano_lbs_kernel",
           4: "posegen_prelude_kernel", 5: "ccv_cdf+draw_kernels", 6: "view_kernel", 7: "gemm_bf16_tn_kernel",
-          8: "im2col_kernel", 9: "elementwise_kernels", 10: "head_decode_kernel", 11: "gemm_bf16_tn_kernel<im2col TMA>", 12: "wgrad_bf16_kernel", 13: "train_elementwise_kernels", 14: "optimizer_kernels"}
+          8: "im2col_kernel", 9: "elementwise_kernels", 10: "head_decode_kernel", 11: "gemm_bf16_tn_kernel<im2col TMA>", 12: "wgrad_bf16_kernel", 13: "train_elementwise_kernels", 14: "optimizer_kernels", 15: "bn_apply_kernel", 16: "bn_bwd_reduce_kernel",
+          17: "bn_bwd_apply_kernel", 18: "bn_finalize_kernel"}
 
 
 def profile_enable(on: bool) -> None:
@@ -162,7 +164,7 @@ def profile_enable(on: bool) -> None:
 
 def profile_collect() -> dict:
     """-> {stage name: (total ms, launches)} for everything launched since profiling was enabled / last collected."""
-    n = 16
+    n = 24
     ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
     check(load().ab_profile_collect(ms, cnt, n), "ab_profile_collect")
     return {STAGES.get(i, f"stage{i}"): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}

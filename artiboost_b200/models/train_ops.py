@@ -37,6 +37,11 @@ def _pack_dgrad_weight(w: torch.Tensor) -> torch.Tensor:
     return w.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(cin, -1).to(torch.bfloat16).contiguous()
 
 
+def _wgrad_ws(P_, Mo, No, dev):
+    """Workspace of the split-over-pixels weight-gradient kernel (partial tiles, summed by its second pass)."""
+    return torch.empty(int(lib.load().ab_wgrad_workspace_bytes(P_, Mo, No)) // 4, device=dev)
+
+
 def _grad_target(param: torch.Tensor):
     """-> (fp32 buffer the kernels accumulate into, in_place).  When the parameter already owns a dense fp32 .grad
     (FlatParams views, or a previous backward) the kernels add into it directly and the Function returns None for that
@@ -177,13 +182,13 @@ def _conv_wgrad(x: Act, xcol, dy_mat, conv_w, kh, kw, stride, pad):
     with torch.cuda.device(dev):
         if x.C % 64 == 0:
             _call("ab_conv_wgrad_bf16_nhwc", x.data.data_ptr(), x.B, x.H, x.W, x.C, dy_mat.data_ptr(), cout, kh, kw, stride, pad,
-                  dw.data_ptr(), 1, _stream(dev))
+                  dw.data_ptr(), 1, _wgrad_ws(dy_mat.shape[0], cout, taps * x.C, dev).data_ptr(), _stream(dev))
         else:
             if xcol is None:  # 1x1 stride-1 on a narrow activation: the activation is the matrix
                 xcol = x.data
             m = lib.wgrad_map(col_div=x.C, col_lo_valid=cin, s_row_lo=cin * taps, s_col_hi=1, s_col_lo=taps)
             _call("ab_wgrad_bf16", dy_mat.shape[0], cout, taps * x.C, dy_mat.data_ptr(), dy_mat.stride(0), xcol.data_ptr(),
-                  xcol.stride(0), dw.data_ptr(), m, _stream(dev))
+                  xcol.stride(0), dw.data_ptr(), m, _wgrad_ws(dy_mat.shape[0], cout, taps * x.C, dev).data_ptr(), _stream(dev))
     return None if in_place else dw
 
 
@@ -355,7 +360,7 @@ class DeconvBNReluFn(torch.autograd.Function):
             m = lib.wgrad_map(row_div=cout, s_row_hi=1, s_row_lo=16, s_col_lo=cout * 16)
             with torch.cuda.device(dev):
                 _call("ab_wgrad_bf16", B * H * W, 16 * cout, C, dycol.data_ptr(), 16 * cout, x_data.data_ptr(), C, dwb.data_ptr(), m,
-                      _stream(dev))
+                      _wgrad_ws(B * H * W, 16 * cout, C, dev).data_ptr(), _stream(dev))
             dw = None if in_place else dwb
         if ctx.needs_input_grad[0]:
             wt = _cached(deconv, "dwt", _ver(weight),
@@ -423,7 +428,7 @@ class LinearFn(torch.autograd.Function):
         dwb, in_place = _grad_target(fc.weight)
         with torch.cuda.device(dev):
             _call("ab_wgrad_bf16", g.shape[0], n, k, g.data_ptr(), npad, xb.data_ptr(), xb.stride(0), dwb.data_ptr(),
-                  lib.wgrad_map(s_row_lo=k, s_col_lo=1), _stream(dev))
+                  lib.wgrad_map(s_row_lo=k, s_col_lo=1), _wgrad_ws(g.shape[0], n, k, dev).data_ptr(), _stream(dev))
         dw = None if in_place else dwb
         db = _col_sum(g)[:n] if fc.bias is not None else None
         wt = _cached(fc, "fct", _ver(weight), lambda: _pad_rows(weight.detach().t().to(torch.bfloat16), _pad8(k), npad))

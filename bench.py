@@ -433,15 +433,22 @@ def train_bench(dev, world, rank, steps=8, warmup=3, batch=128, backbone="ResNet
     ms_step = timed(lambda: loop.step(), steps, warmup)
     launches = (lib.launch_count() - l0) / (steps + warmup)
     ms_net = timed(lambda: loop.step(fixed), steps, 1)
-    lib.profile_enable(True)   # stage breakdown from a separate, event-bracketed pass (not the timed one)
+    # stage breakdown from a separate, event-bracketed EAGER pass (events cannot be recorded inside the replayed graph)
+    loop.train_step.use_graph = False
+    loop.step()
+    lib.profile_enable(True)
+    l1 = lib.launch_count()
     for _ in range(2):
         loop.step()
     torch.cuda.synchronize(dev)
+    kernels_in_step = (lib.launch_count() - l1) / 2
     lib.profile_enable(False)
     stages = lib.profile_collect()
+    loop.train_step.use_graph = True
     out = {"backbone": backbone, "per_gpu_batch": batch, "synthetic_per_batch": loop.n_synth, "real_shaped_per_batch": loop.n_real,
            "images_per_s": world * batch / ms_step * 1e3, "ms_per_step": ms_step, "ms_synthesis_and_batching": ms_synth,
-           "ms_train_step_only": ms_net, "launches_per_step": launches,
+           "ms_train_step_only": ms_net, "host_submissions_per_step": launches,
+           "our_kernels_per_step": kernels_in_step, "cuda_graph": True,
            "tflops_fwd_bwd": batch * flops / ms_net / 1e9, "frac_of_bf16_sustained_peak": batch * flops / ms_net / 1e9 / 1364.6,
            "stage_ms_per_step": {k: v[0] / 2 for k, v in stages.items()},
            "stage_launches_per_step": {k: v[1] / 2 for k, v in stages.items()}}

@@ -61,7 +61,11 @@ AB_API uint64_t ab_launch_count(void);
 #define AB_STAGE_WGRAD 12
 #define AB_STAGE_TRAIN_ELEMENTWISE 13
 #define AB_STAGE_OPTIMIZER 14
-#define AB_STAGE_COUNT 16
+#define AB_STAGE_BN_APPLY 15
+#define AB_STAGE_BN_BWD_REDUCE 16
+#define AB_STAGE_BN_BWD_APPLY 17
+#define AB_STAGE_BN_FINALIZE 18
+#define AB_STAGE_COUNT 24
 AB_API int ab_profile_enable(int on);
 AB_API int ab_profile_collect(double* ms_per_stage, int64_t* launches_per_stage, int n_stages);
 
@@ -177,8 +181,10 @@ AB_API int ab_conv_bf16_nhwc(const void* x, int B, int H, int W, int C, const vo
                              const void* residual, int64_t ldr, int relu, float* col_sum, float* col_sumsq, void* stream);
 
 /* Weight gradients (the wgrad half of loss.backward() at train/train_artiboost.py:91-93, cuDNN wgrad in the
- * reference).  D(row, col) += sum_p G[p,row] * X[p,col], fp32 atomic accumulation into the caller's gradient buffer
- * (which already holds whatever was accumulated before, like autograd's .grad):
+ * reference).  D(row, col) += sum_p G[p,row] * X[p,col], added into the caller's gradient buffer (which already holds
+ * whatever was accumulated before, like autograd's .grad).  The pixel axis is split across CTAs; each split stores its
+ * partial tile in the caller-owned workspace ws (ab_wgrad_workspace_bytes(P, Mo, No); for a convolution P = B*Ho*Wo,
+ * Mo = Cout, No = kh*kw*C) and a second kernel adds the splits: no atomics, bit-reproducible.
  * G = dY bf16 [P,Mo], X bf16 [P,No] (ab_wgrad_bf16), or X = the NHWC activation read through TMA im2col
  * (ab_conv_wgrad_bf16_nhwc, columns (ky,kx,c), C % 64 == 0; param_layout = 1 writes the nn.Conv2d layout
  * [Cout, C, kh, kw], 0 the packed [Cout, kh*kw*C]).  ab_wgrad_map places (row, col) anywhere: with (hi, lo) =
@@ -190,10 +196,11 @@ typedef struct ab_wgrad_map {
     int32_t row_div, col_div, col_lo_valid;
     int64_t s_row_hi, s_row_lo, s_col_hi, s_col_lo;
 } ab_wgrad_map;
+AB_API uint64_t ab_wgrad_workspace_bytes(int P, int Mo, int No);
 AB_API int ab_wgrad_bf16(int P, int Mo, int No, const void* G, int64_t ldg, const void* X, int64_t ldx, float* D,
-                         const ab_wgrad_map* map, void* stream);
+                         const ab_wgrad_map* map, void* ws, void* stream);
 AB_API int ab_conv_wgrad_bf16_nhwc(const void* x, int B, int H, int W, int C, const void* dy, int Cout, int kh, int kw,
-                                   int stride, int pad, float* dw, int param_layout, void* stream);
+                                   int stride, int pad, float* dw, int param_layout, void* ws, void* stream);
 
 /* ------------------------------------------------------------------- data movement around the contraction (NHWC bf16)
  * Activations are bf16 NHWC ([B,H,W,C], C contiguous) between layers; the reference keeps fp32 NCHW and lets cuDNN
@@ -240,7 +247,7 @@ AB_API int ab_head_decode(const float* logits, int B, int ncls, int D, int H, in
  *   grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).  state f32 [3] = {step count,
  *   1 - beta1^t, 1 - beta2^t} lives on the device (zero it once) and is advanced by the call itself, so a captured
  *   CUDA graph of the training step replays with the right bias corrections.  n % 4 == 0.                       */
-#define AB_STAT_PARTS 296
+#define AB_STAT_PARTS 1184
 AB_API int ab_col_stats(const void* x, int is_f32, int M, int C, int64_t ld, float* sum, float* sumsq, float* ws, void* stream);
 AB_API int ab_bn_finalize(const float* sum_part, const float* sumsq_part, int n_part, int C, float count, const float* gamma,
                           const float* beta, float eps, float momentum, float* scale, float* shift, float* save_mean,

@@ -78,8 +78,8 @@ def test_synth_train_step_runs_learns_and_feeds_ccv(lib_built):
 
 def test_cuda_graph_step_matches_eager_step(lib_built):
     """The captured-and-replayed step performs the same arithmetic as the eager one.  lr = 0 keeps the two models'
-    parameters identical, so every step's loss (deterministic forward: bit-equal) and flat gradient (weight-gradient
-    atomics: order-dependent last bits) can be compared; then a graph-mode run with lr > 0 must learn."""
+    parameters identical, so every step's loss and flat gradient can be compared -- bit for bit, since no kernel of the
+    step uses atomics (column statistics, weight gradients and BatchNorm reductions are two-pass); then a graph-mode run with lr > 0 must learn."""
     import copy
 
     import artiboost_b200.models as M
@@ -99,8 +99,8 @@ def test_cuda_graph_step_matches_eager_step(lib_built):
         assert (graphed._graph is not None) == (i >= 2)
         assert float(la) == float(lb), (i, float(la), float(lb))
         ga, gb = eager.flat.grad, graphed.flat.grad
-        assert float((ga - gb).norm() / ga.norm()) < 1e-3
-        torch.testing.assert_close(eager.opt.grad_norm(), graphed.opt.grad_norm(), rtol=1e-4, atol=0)
+        assert torch.equal(ga, gb), "the step has no atomics: gradients are bit-reproducible, eager or replayed"
+        assert torch.equal(eager.opt.grad_norm(), graphed.opt.grad_norm())
     assert graphed.opt.step_count == eager.opt.step_count == 5
     bn_a, bn_b = model_a.model_list[0].backbone.bn1, model_b.model_list[0].backbone.bn1
     torch.testing.assert_close(bn_a.running_var, bn_b.running_var, rtol=1e-6, atol=0)
