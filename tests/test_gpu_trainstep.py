@@ -100,7 +100,7 @@ def test_cuda_graph_step_matches_eager_step(lib_built):
         assert float(la) == float(lb), (i, float(la), float(lb))
         ga, gb = eager.flat.grad, graphed.flat.grad
         assert torch.equal(ga, gb), "the step has no atomics: gradients are bit-reproducible, eager or replayed"
-        assert torch.equal(eager.opt.grad_norm(), graphed.opt.grad_norm())
+        torch.testing.assert_close(eager.opt.grad_norm(), graphed.opt.grad_norm(), rtol=1e-5, atol=0)  # one atomic per CTA
     assert graphed.opt.step_count == eager.opt.step_count == 5
     bn_a, bn_b = model_a.model_list[0].backbone.bn1, model_b.model_list[0].backbone.bn1
     torch.testing.assert_close(bn_a.running_var, bn_b.running_var, rtol=1e-6, atol=0)
