@@ -222,8 +222,7 @@ def run_ours(args):
             train = {"error": repr(e)}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world, dev)
         return
 
     # ---- roofline of the dominant kernel (largest share of the timed region)
@@ -275,8 +274,21 @@ def run_ours(args):
         except Exception as e:  # the secondary workload must never cost the headline line
             line["extras"]["network_forward_configs2"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
+    finish(world, dev)
+
+
+def finish(world, dev):
+    """Leave together.  With N > 1 the captured training graph still references NCCL work, and
+    destroy_process_group() can wait on it forever: synchronise, meet at a barrier, then exit without the teardown."""
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------ secondary workload: network forward
