@@ -12,3 +12,4 @@ from .grasp_engine import GraspEngine  # noqa: E402,F401
 from .object_engine import ObjEngine  # noqa: E402,F401
 from .renderer import Renderer, PointLight, DirectionalLight, make_mesh  # noqa: E402,F401
 from .render_infra import RendererProvider  # noqa: E402,F401
+from .rendered_dataset import RenderedDataset  # noqa: E402,F401

@@ -20,7 +20,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr"]
 # The rasteriser's rule set requires individually rounded fp32 operations (see oracle/raster.c header).
-PER_FILE = {"raster.cu": ["-fmad=false"]}
+# augment.cu reproduces Pillow's fp32 / fp64 arithmetic operation by operation (oracle/augment.py): no FMA contraction.
+PER_FILE = {"raster.cu": ["-fmad=false"], "augment.cu": ["-fmad=false"]}
 
 
 def _nvcc() -> str:

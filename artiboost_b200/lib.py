@@ -34,6 +34,11 @@ class CameraStruct(C.Structure):
                 ("diffuse", C.c_float), ("bg_r", C.c_int32), ("bg_g", C.c_int32), ("bg_b", C.c_int32)]
 
 
+class AugmentCfgStruct(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("raw_w", "raw_h", "out_w", "out_h", "center_idx", "crop_model", "full_image", "aug")] + \
+               [("bbox_expand_ratio", C.c_float), ("center_jit", C.c_float), ("scale_jit", C.c_float), ("K", C.c_float * 9)]
+
+
 class WgradMapStruct(C.Structure):
     _fields_ = [("row_div", C.c_int32), ("col_div", C.c_int32), ("col_lo_valid", C.c_int32), ("s_row_hi", C.c_int64),
                 ("s_row_lo", C.c_int64), ("s_col_hi", C.c_int64), ("s_col_lo", C.c_int64)]
@@ -98,6 +103,8 @@ EXPORTS = {
     "ab_dilate2x": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
     "ab_deconv4x4s2_gather": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
     "ab_head_decode_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    "ab_augment_workspace_bytes": (C.c_uint64, [C.POINTER(AugmentCfgStruct), C.c_int]),
+    "ab_crop_augment": (C.c_int, [C.POINTER(AugmentCfgStruct), C.c_int] + [C.c_void_p] * 21),
     "ab_sumsq": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ab_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                                                                   C.c_void_p]),
@@ -155,7 +162,7 @@ def launch_count() -> int:
 STAGES = {0: "raster_vertex_kernel", 1: "raster_triangle_kernel", 2: "raster_resolve_kernel", 3: "mano_lbs_kernel",
           4: "posegen_prelude_kernel", 5: "ccv_cdf+draw_kernels", 6: "view_kernel", 7: "gemm_bf16_tn_kernel",
           8: "im2col_kernel", 9: "elementwise_kernels", 10: "head_decode_kernel", 11: "gemm_bf16_tn_kernel<im2col TMA>", 12: "wgrad_bf16_kernel", 13: "train_elementwise_kernels", 14: "optimizer_kernels", 15: "bn_apply_kernel", 16: "bn_bwd_reduce_kernel",
-          17: "bn_bwd_apply_kernel", 18: "bn_finalize_kernel"}
+          17: "bn_bwd_apply_kernel", 18: "bn_finalize_kernel", 19: "augment_kernels"}
 
 
 def profile_enable(on: bool) -> None:

@@ -65,6 +65,7 @@ AB_API uint64_t ab_launch_count(void);
 #define AB_STAGE_BN_BWD_REDUCE 16
 #define AB_STAGE_BN_BWD_APPLY 17
 #define AB_STAGE_BN_FINALIZE 18
+#define AB_STAGE_AUGMENT 19
 #define AB_STAGE_COUNT 24
 AB_API int ab_profile_enable(int on);
 AB_API int ab_profile_collect(double* ms_per_stage, int64_t* launches_per_stage, int n_stages);
@@ -270,6 +271,36 @@ AB_API int ab_head_decode_bwd(const float* logits, const float* dkp3d, int B, in
 AB_API int ab_sumsq(const float* g, int64_t n, float* out, void* stream);
 AB_API int ab_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                         float weight_decay, float* state, const float* grad_sumsq, float max_norm, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------- crop / augment
+ * RenderedDataset.__getitem__ for a batch of rendered views (anakin/artiboost/rendered_dataset.py:127-133,155-274;
+ * utils/transform.py:425-470; utils/img_augment.py:6-80; datasets/hodata.py:161-186), which the reference runs per
+ * sample on the CPU with PIL inside the DataLoader workers.  rgba u8 [B,raw_h,raw_w,4] (the rasteriser's output),
+ * joints f32 [B,21,3] and obj_pose f32 [B,4,4] in camera space, corners_can f32 [B,8,3] -> image f32 [B,3,out_h,out_w]
+ * (x/255 - 0.5) and the transformed annotations with the reference's sample keys.  Every random draw is an input:
+ * draws f32 [B, AB_AUG_DRAWS] = {centre jitter x, y in U(-1,1); scale jitter ~ N(0, scale_jit/3); cos, sin of the in-plane
+ * rotation; GaussianBlur radius (<= 0.1 in the reference); brightness, contrast, saturation factors; hue factor} and
+ * order i32 [B,4] = execution order of the colour operations as indices into {brightness, saturation, hue, contrast}.
+ * Byte-exact Pillow arithmetic (blur, enhancers, HSV round trip, NEAREST AFFINE warp): see oracle/augment.py.
+ * affine / inv_affine (optional, f32 [B,6]) return the forward / inverse 2x3 matrices; status (optional, device i32):
+ * bit 0 = a blur radius outside the supported range (box radius >= 1), bit 1 = warp outside Pillow's fixed-point range.
+ * ws: ab_augment_workspace_bytes(cfg, B), 256-byte aligned.                                                        */
+#define AB_AUG_DRAWS 10
+typedef struct ab_augment_cfg {
+    int32_t raw_w, raw_h, out_w, out_h;
+    int32_t center_idx;     /* DATA_PRESET.CENTER_IDX */
+    int32_t crop_model;     /* 0 root_obj, 1 hand_obj, 2 hand (DATA_PRESET.CROP_MODEL) */
+    int32_t full_image;     /* DATA_PRESET.FULL_IMAGE */
+    int32_t aug;            /* cfg_dataset.AUG */
+    float bbox_expand_ratio, center_jit, scale_jit;
+    float K[9];             /* render camera intrinsics, row-major */
+} ab_augment_cfg;
+AB_API uint64_t ab_augment_workspace_bytes(const ab_augment_cfg* cfg, int B);
+AB_API int ab_crop_augment(const ab_augment_cfg* cfg, int B, const uint8_t* rgba, const float* joints, const float* obj_pose,
+                           const float* corners_can, const float* draws, const int32_t* order, float* image, float* cam_intr,
+                           float* root_joint, float* joints_3d, float* joints_2d, float* joints_vis, float* corners_3d,
+                           float* corners_2d, float* corners_vis, float* obj_transf, float* affine, float* inv_affine,
+                           int32_t* status, void* ws, void* stream);
 
 #ifdef __cplusplus
 }

@@ -222,31 +222,35 @@ def color_jitter(img, draws):
 
 
 # ------------------------------------------------------------------------------------------------ geometry (fp64)
+# Written as individually rounded scalar operations in a fixed order (no BLAS: its FMA use is not defined), so that
+# csrc/augment.cu (compiled with -fmad=false) reproduces every integer decision (bbox centre, jitter truncation).
+def _dot3(a0, a1, a2, b0, b1, b2):
+    return (a0 * b0 + a1 * b1) + a2 * b2
+
+
 def affine_no_rot(center, scale, res):
-    """transform.py:462-470 get_affine_trans_no_rot."""
-    m = np.zeros((3, 3))
+    """transform.py:462-470 get_affine_trans_no_rot -> (m00, m11, m02, m12); the other entries are 0 / 1."""
     ratio = float(res[0]) / float(res[1])
-    m[0, 0] = float(res[0]) / scale
-    m[1, 1] = float(res[1]) / scale * ratio
-    m[0, 2] = res[0] * (-float(center[0]) / scale + 0.5)
-    m[1, 2] = res[1] * (-float(center[1]) / scale * ratio + 0.5)
-    m[2, 2] = 1
-    return m
+    m00 = float(res[0]) / scale
+    m11 = float(res[1]) / scale * ratio
+    m02 = res[0] * (-float(center[0]) / scale + 0.5)
+    m12 = res[1] * (-float(center[1]) / scale * ratio + 0.5)
+    return m00, m11, m02, m12
 
 
 def get_affine_transform(center, scale, optical_center, out_res, cs, sn):
-    """transform.py:434-460 with cos / sin supplied.  -> (total fp32 [3,3], post-rotation fp32 [3,3])."""
+    """transform.py:434-460 with cos / sin supplied.  -> (total fp32 [3,3], post-rotation fp32 [3,3]).
+    total = no_rot(R c) . R and post = no_rot(T^-1 R T c): products with the exact zeros / ones of R, T are dropped."""
     cs, sn = float(cs), float(sn)
-    rot = np.array([[cs, -sn, 0.0], [sn, cs, 0.0], [0.0, 0.0, 1.0]])
-    c = np.array([float(center[0]), float(center[1]), 1.0])
-    origin_rot_center = rot.dot(c)[:2]
-    t_mat = np.eye(3)
-    t_mat[0, 2], t_mat[1, 2] = -float(optical_center[0]), -float(optical_center[1])
-    t_inv = t_mat.copy()
-    t_inv[:2, 2] *= -1
-    transformed_center = t_inv.dot(rot).dot(t_mat).dot(c)
-    total = affine_no_rot(origin_rot_center, scale, out_res).dot(rot)
-    post = affine_no_rot(transformed_center[:2], scale, out_res)
+    cx, cy = float(center[0]), float(center[1])
+    ox, oy = float(optical_center[0]), float(optical_center[1])
+    orc = (cs * cx + (-sn) * cy, sn * cx + cs * cy)
+    dx, dy = cx - ox, cy - oy
+    tc = ((cs * dx + (-sn) * dy) + ox, (sn * dx + cs * dy) + oy)
+    m00, m11, m02, m12 = affine_no_rot(orc, scale, out_res)
+    total = np.array([[m00 * cs, m00 * (-sn), m02], [m11 * sn, m11 * cs, m12], [0, 0, 1]])
+    p00, p11, p02, p12 = affine_no_rot(tc, scale, out_res)
+    post = np.array([[p00, 0, p02], [0, p11, p12], [0, 0, 1]])
     return total.astype(np.float32), post.astype(np.float32)
 
 
@@ -264,8 +268,9 @@ def invert_affine(m32):
 def project(K, pts):
     """rendered_dataset.py:127-133: uv = (K . X)[:2] / (Z + 1e-8), fp64."""
     K, pts = np.asarray(K, np.float64), np.asarray(pts, np.float64)
-    h = pts @ K.T
-    return h[:, :2] / (h[:, 2:3] + 1e-8)
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    hz = _dot3(K[2, 0], K[2, 1], K[2, 2], x, y, z) + 1e-8
+    return np.stack([_dot3(K[0, 0], K[0, 1], K[0, 2], x, y, z) / hz, _dot3(K[1, 0], K[1, 1], K[1, 2], x, y, z) / hz], 1)
 
 
 def crop_params(joints_2d, corners_2d, draws, cfg):
@@ -279,11 +284,12 @@ def crop_params(joints_2d, corners_2d, draws, cfg):
         mn, mx = pts.min(0), pts.max(0)
         center = np.array([int((mx[0] + mn[0]) / 2), int((mx[1] + mn[1]) / 2)])
         scale = float(max(mx[0] - mn[0], mx[1] - mn[1]))
-    scale *= cfg.get("bbox_expand_ratio", 1.2) if not cfg.get("full_image", False) else 1.0
+    f32 = lambda v: float(np.float32(v))  # noqa: E731  configuration factors travel as fp32 (ab_augment_cfg)
+    scale *= f32(cfg.get("bbox_expand_ratio", 1.2)) if not cfg.get("full_image", False) else 1.0
     if cfg.get("aug", True):
-        off = cfg["center_jit"] * scale * np.asarray(draws["center_jit"], np.float64)
+        off = f32(cfg["center_jit"]) * scale * np.asarray(draws["center_jit"], np.float64)
         center = center + off.astype(int)  # truncation toward zero (rendered_dataset.py:180)
-        jit = float(np.clip(float(draws["scale_jit"]) + 1.0, 1 - cfg["scale_jit"], 1 + cfg["scale_jit"]))
+        jit = float(np.clip(float(draws["scale_jit"]) + 1.0, 1 - f32(cfg["scale_jit"]), 1 + f32(cfg["scale_jit"])))
         scale = scale * jit
     return center, scale
 
@@ -298,20 +304,31 @@ def rendered_sample(img, joints, obj_pose, corners_can, cam_intr, draws, cfg):
     joints = np.asarray(joints, np.float32)
     pose = np.asarray(obj_pose, np.float32)
     corners_can = np.asarray(corners_can, np.float32)
-    corners_3d = (pose[:3, :3].astype(np.float64) @ corners_can.astype(np.float64).T).T + pose[:3, 3].astype(np.float64)
+    R, t, cc = pose[:3, :3].astype(np.float64), pose[:3, 3].astype(np.float64), corners_can.astype(np.float64)
+    corners_3d = np.stack([_dot3(R[i, 0], R[i, 1], R[i, 2], cc[:, 0], cc[:, 1], cc[:, 2]) + t[i] for i in range(3)], 1)
     j2d, c2d = project(K, joints), project(K, corners_3d)
     center, scale = crop_params(j2d, c2d, draws, cfg)
     cs, sn = (np.float32(draws["rot_cs"][0]), np.float32(draws["rot_cs"][1])) if aug else (np.float32(1), np.float32(0))
     total, post = get_affine_transform(center, scale, (K[0, 2], K[1, 2]), (wo, ho), cs, sn)
     rot3 = np.array([[cs, -sn, 0], [sn, cs, 0], [0, 0, 1]], np.float32)
-    out = {"cam_intr": (post.astype(np.float64) @ K).astype(np.float32)}
-    j3 = (rot3.astype(np.float64) @ joints.astype(np.float64).T).T
+    P = post.astype(np.float64)
+    out = {"cam_intr": np.array([[_dot3(P[i, 0], P[i, 1], P[i, 2], K[0, j], K[1, j], K[2, j]) for j in range(3)]
+                                 for i in range(3)]).astype(np.float32)}
+    c64, s64 = float(cs), float(sn)
+
+    def rotz(p):
+        p = p.astype(np.float64)
+        return np.stack([c64 * p[:, 0] + (-s64) * p[:, 1], s64 * p[:, 0] + c64 * p[:, 1], p[:, 2]], 1)
+
+    j3 = rotz(joints)
     root = j3[cfg.get("center_idx", 0)]
     out["root_joint"] = root.astype(np.float32)
     out["joints_3d"] = (j3 - root).astype(np.float32)
 
+    T = total.astype(np.float64)
+
     def warp_pts(p):
-        return (np.concatenate([p, np.ones((len(p), 1))], 1) @ total.astype(np.float64).T)[:, :2].astype(np.float32)
+        return np.stack([(T[0, 0] * p[:, 0] + T[0, 1] * p[:, 1]) + T[0, 2], (T[1, 0] * p[:, 0] + T[1, 1] * p[:, 1]) + T[1, 2]], 1).astype(np.float32)
 
     def vis(raw2d, aug2d, n):
         rw, rh = cfg["raw_size"]
@@ -323,14 +340,13 @@ def rendered_sample(img, joints, obj_pose, corners_can, cam_intr, draws, cfg):
 
     out["joints_2d"] = warp_pts(j2d)
     out["joints_vis"] = vis(j2d, out["joints_2d"], 21)
-    c3 = (rot3.astype(np.float64) @ corners_3d.T).T
+    c3 = rotz(corners_3d)
     out["corners_3d"] = (c3 - root).astype(np.float32)
     out["corners_2d"] = warp_pts(c2d)
     out["corners_vis"] = vis(c2d, out["corners_2d"], 8)
     out["corners_can"] = corners_can
     transf = np.eye(4, dtype=np.float32)
-    transf[:3, :3] = rot3 @ pose[:3, :3]
-    transf[:3, 3] = rot3 @ pose[:3, 3]
+    transf[:3, :4] = np.stack([c64 * pose[0, :4] + (-s64) * pose[1, :4], s64 * pose[0, :4] + c64 * pose[1, :4], pose[2, :4]]).astype(np.float32)
     out["obj_transf"] = transf
     out["affine"] = total
     out["inv_affine"] = invert_affine(total)
