@@ -99,6 +99,29 @@ __global__ void im2col_c4_kernel(const uint2* __restrict__ in, int B, int H, int
         for (int k = kh * kw; k < Kp4; ++k) out[m * Kp4 + k] = make_uint2(0, 0);
 }
 
+// Packed bf16 copies of a convolution filter [Cout, Cin, kh, kw] (fp32 parameter layout), one launch per layer:
+//   wp [Cout, Kp]           forward / implicit-GEMM operand, K order (ky, kx, ci) with ci padded to cin_pad, zero tail
+//   wd [Cin, kh*kw*Cout]    data-gradient operand: taps flipped, (ky', kx', co) order           (optional)
+__global__ void pack_conv_filters_kernel(const float* __restrict__ w, int Cout, int Cin, int kh, int kw, int cin_pad, int Kp,
+                                         __nv_bfloat16* __restrict__ wp, __nv_bfloat16* __restrict__ wd) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int taps = kh * kw;
+    const long long n_wp = (long long)Cout * Kp, n_wd = wd ? (long long)Cin * taps * Cout : 0;
+    if (i < n_wp) {
+        const int co = (int)(i / Kp), k = (int)(i - (long long)co * Kp);
+        const int tap = k / cin_pad, ci = k - tap * cin_pad;
+        float v = 0.0f;
+        if (tap < taps && ci < Cin) v = w[((size_t)co * Cin + ci) * taps + tap];
+        wp[i] = __float2bfloat16(v);
+    } else if (i < n_wp + n_wd) {
+        const long long j = i - n_wp;
+        const int co = (int)(j % Cout);
+        const long long r = j / Cout;
+        const int tap = (int)(r % taps), ci = (int)(r / taps);
+        wd[j] = __float2bfloat16(w[((size_t)co * Cin + ci) * taps + (taps - 1 - tap)]);  // flip(ky) & flip(kx) = reversed tap
+    }
+}
+
 // idx (optional, training): uint8 per output element = ky*3 + kx of the FIRST maximum in scan order (torch's tie-break),
 // consumed by ab_maxpool3x3s2_bwd.
 __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int B, int H, int W, int C8, int Ho, int Wo,
@@ -297,6 +320,19 @@ extern "C" int ab_im2col_nhwc(const void* in, int B, int H, int W, int C, int kh
     }
     count_launch();
     return check_launch("im2col_kernel");
+}
+
+extern "C" int ab_pack_conv_filters(const float* w, int Cout, int Cin, int kh, int kw, int cin_pad, int Kp, void* wp, void* wd,
+                                    void* stream) {
+    AB_REQUIRE(Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && cin_pad >= Cin && Kp >= kh * kw * cin_pad, "bad shape");
+    AB_REQUIRE(w && wp, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_ELEMENTWISE, st);
+    const long long n = (long long)Cout * Kp + (wd ? (long long)Cin * kh * kw * Cout : 0);
+    pack_conv_filters_kernel<<<blocks_for(n, 256), 256, 0, st>>>(w, Cout, Cin, kh, kw, cin_pad, Kp, (__nv_bfloat16*)wp,
+                                                                 (__nv_bfloat16*)wd);
+    count_launch();
+    return check_launch("pack_conv_filters_kernel");
 }
 
 extern "C" int ab_maxpool3x3s2_nhwc(const void* in, int B, int H, int W, int C, void* out, void* idx, void* stream) {

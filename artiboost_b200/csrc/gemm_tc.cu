@@ -548,6 +548,26 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
     *d += acc;
 }
 
+// The same for the convolution parameter layout [Cout, C, taps] (columns arrive as (tap, c)): one CTA per (row, 32 channels),
+// thread (tap, cc) reads 32 consecutive columns per tap (coalesced), the tile is transposed through shared memory and
+// written as 32 * taps consecutive floats of the destination.
+__global__ void wgrad_reduce_conv_kernel(const float* __restrict__ ws, int splits, int C, int taps, int Mp, int Np,
+                                         float* __restrict__ D) {
+    extern __shared__ float tile[];  // [32 * taps]
+    const int row = blockIdx.x, c0 = blockIdx.y * 32, t = threadIdx.x;
+    const int tap = t >> 5, cc = t & 31;
+    const float* p = ws + (size_t)row * Np + (size_t)tap * C + c0 + cc;
+    float acc = 0.0f;
+    if (c0 + cc < C) {
+#pragma unroll 4
+        for (int z = 0; z < splits; ++z) acc += __ldg(p + (size_t)z * Mp * Np);
+    }
+    tile[cc * taps + tap] = acc;
+    __syncthreads();
+    const int n = min(32, C - c0) * taps;
+    if (t < n) D[((size_t)row * C + c0) * taps + t] += tile[t];
+}
+
 // Pixel-axis split: CTAs are 2 per SM, so cost ~ waves(tiles * s) * (k-blocks per split + epilogue), minimised over s.
 static int wgrad_splits(int P, int Mo, int No, int* per_out) {
     const int tiles = cdiv(Mo, 128) * cdiv(No, 128), total_kb = cdiv(P, 64);
@@ -606,7 +626,7 @@ static int make_im2col_map_px(CUtensorMap* m, const void* ptr, int B, int H, int
 
 template <bool IM2COL>
 static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, int P, int Mo, int No, float* D, const WgradOutMap& om,
-                        float* ws, const ConvGeom& cg, int taps, cudaStream_t st) {
+                        float* ws, const ConvGeom& cg, int taps, cudaStream_t st, int conv_param_C = 0) {
     const size_t smem = sizeof(WgradSmem) + 1024;
     static bool configured = false;
     if (!configured) {
@@ -618,8 +638,13 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, int P, int
     const int splits = wgrad_splits(P, Mo, No, &per);
     StageTimer tm(AB_STAGE_WGRAD, st);
     wgrad_bf16_kernel<IM2COL><<<dim3(mt, nt, splits), kGemmThreads, smem, st>>>(tg, tx, P, Mo, No, ws, per, cg, taps);
-    const long long n = (long long)Mo * No;
-    wgrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, splits, Mo, No, mt * 128, nt * 128, D, om);
+    if (conv_param_C > 0 && taps <= 32) {
+        wgrad_reduce_conv_kernel<<<dim3(Mo, cdiv(conv_param_C, 32)), 32 * taps, 32 * taps * sizeof(float), st>>>(
+            ws, splits, conv_param_C, taps, mt * 128, nt * 128, D);
+    } else {
+        const long long n = (long long)Mo * No;
+        wgrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, splits, Mo, No, mt * 128, nt * 128, D, om);
+    }
     count_launch(2);
     return check_launch("wgrad_bf16_kernel");
 }
@@ -702,5 +727,5 @@ extern "C" int ab_conv_wgrad_bf16_nhwc(const void* x, int B, int H, int W, int C
     // columns are (tap, c): packed [Cout, taps*C] keeps them; the parameter layout [Cout, C, kh, kw] swaps them
     const ab::WgradOutMap om = param_layout ? ab::WgradOutMap{1 << 30, C, C, 0, (long long)C * taps, 1, taps}
                                             : ab::WgradOutMap{1 << 30, C, C, 0, (long long)C * taps, C, 1};
-    return ab::launch_wgrad<true>(tg, tx, P, Cout, taps * C, dw, om, (float*)ws, cg, taps, (cudaStream_t)stream);
+    return ab::launch_wgrad<true>(tg, tx, P, Cout, taps * C, dw, om, (float*)ws, cg, taps, (cudaStream_t)stream, param_layout ? C : 0);
 }

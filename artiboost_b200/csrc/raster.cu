@@ -369,46 +369,96 @@ __device__ __forceinline__ PixelOut shade_pixel(const RasterParams& P, int view,
     return r;
 }
 
-// One thread per pixel: a warp covers 32 consecutive pixels of a row, so background warps (most of the frame)
-// never enter the shading path, and the RGBA / depth stores are full 128-byte lines per warp.
+// Phase 1, one thread per PX consecutive pixels of a row (PX = 4 when W % 4 == 0, else 1): 32-byte key loads; background
+// pixels are finished here -- crop fetch with 32-bit divisions (operands < 2^30), one 16-byte RGBA store, one 16-byte
+// depth store and one 4-byte seg store per thread, i.e. 512 + 512 + 128 contiguous bytes per warp; covered pixels are
+// appended to a CTA-local list.  Phase 2: the CTA's covered pixels are dealt one per thread, so the long shading path runs
+// on fully populated warps instead of on the few lanes of each row segment that touch the hand or the object
+// (~9 % of the frame); their outputs overwrite the placeholders of phase 1 after the barrier.
+template <int PX>
 __global__ void __launch_bounds__(256)
 raster_resolve_kernel(const __grid_constant__ RasterParams P) {
+    __shared__ unsigned hit_prim[256 * PX];
+    __shared__ unsigned short hit_px[256 * PX];
+    __shared__ int n_hit;
     const int view = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cta_p0 = blockIdx.x * 256 * PX;
+    const int p0 = cta_p0 + threadIdx.x * PX;
     const int npx = P.W * P.H;
-    if (p >= npx) return;
-    unsigned long long* kp = P.keys + (size_t)view * npx + p;
-    const unsigned long long k = *kp;
-    const int py = p / P.W, px = p - py * P.W;
-    uchar4 c;
-    float z;
-    uint8_t s;
-    if (k == kEmptyKey) {
-        c = make_uchar4((uint8_t)P.bg_r, (uint8_t)P.bg_g, (uint8_t)P.bg_b, 0);
+    if (threadIdx.x == 0) n_hit = 0;
+    __syncthreads();
+    unsigned long long* kbase = P.keys + (size_t)view * npx;
+    const size_t obase = (size_t)view * npx;
+    if (p0 < npx) {
+        unsigned long long k[PX];
+        if constexpr (PX == 4) {
+            const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(kbase + p0), k23 = *reinterpret_cast<const ulonglong2*>(kbase + p0 + 2);
+            k[0] = k01.x; k[1] = k01.y; k[2] = k23.x; k[3] = k23.y;
+        } else {
+            k[0] = kbase[p0];
+        }
+        const int py = p0 / P.W, px0 = p0 - py * P.W;
         const int32_t* sel = P.bg_sel ? P.bg_sel + 5 * (size_t)view : nullptr;
-        if (sel && P.bgs && sel[0] >= 0) {
-            const int sx = sel[1] + (int)(((long long)(2 * px + 1) * sel[3]) / (2 * P.W));
-            const int sy = sel[2] + (int)(((long long)(2 * py + 1) * sel[4]) / (2 * P.H));
-            const uint8_t* src = P.bgs + 3 * (((size_t)sel[0] * P.bg_h + sy) * P.bg_w + sx);
-            c = make_uchar4(src[0], src[1], src[2], 0);
+        const bool has_bg = sel && P.bgs && sel[0] >= 0;
+        const uint8_t* bg_row = nullptr;
+        unsigned bg_x0 = 0, bg_cw = 0;
+        if (has_bg) {
+            const unsigned sy = (unsigned)sel[2] + ((unsigned)(2 * py + 1) * (unsigned)sel[4]) / (unsigned)(2 * P.H);
+            bg_row = P.bgs + 3 * (((size_t)sel[0] * P.bg_h + sy) * P.bg_w);
+            bg_x0 = (unsigned)sel[1];
+            bg_cw = (unsigned)sel[3];
         }
-        z = 0.0f;
-        s = 0;
-    } else {
-        const int oid = P.obj_id[view];
-        int n_of = 0, n_ov = 0;
-        if (oid >= 0) {
-            n_of = P.face_off[oid + 1] - P.face_off[oid];
-            n_ov = P.vert_off[oid + 1] - P.vert_off[oid];
+        uchar4 c[PX];
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            c[j] = make_uchar4((uint8_t)P.bg_r, (uint8_t)P.bg_g, (uint8_t)P.bg_b, 0);
+            if (k[j] == kEmptyKey) {
+                if (has_bg) {
+                    const unsigned sx = bg_x0 + ((unsigned)(2 * (px0 + j) + 1) * bg_cw) / (unsigned)(2 * P.W);
+                    const uint8_t* src = bg_row + 3 * (size_t)sx;
+                    c[j] = make_uchar4(src[0], src[1], src[2], 0);
+                }
+            } else {
+                const int slot = atomicAdd(&n_hit, 1);
+                hit_px[slot] = (unsigned short)(threadIdx.x * PX + j);
+                hit_prim[slot] = (unsigned)(k[j] & 0xffffffffull);
+            }
         }
-        const PixelOut r = shade_pixel(P, view, oid, n_ov, n_of, px, py, (unsigned)(k & 0xffffffffull));
-        c = r.rgba; z = r.depth; s = r.seg;
-        *kp = kEmptyKey;  // leave the key buffer empty for the next chunk
+        const size_t o = obase + p0;
+        if constexpr (PX == 4) {
+            if (P.rgba) {
+                uint4 v;
+                v.x = *reinterpret_cast<unsigned*>(&c[0]); v.y = *reinterpret_cast<unsigned*>(&c[1]);
+                v.z = *reinterpret_cast<unsigned*>(&c[2]); v.w = *reinterpret_cast<unsigned*>(&c[3]);
+                *reinterpret_cast<uint4*>(P.rgba + 4 * o) = v;
+            }
+            if (P.depth) *reinterpret_cast<float4*>(P.depth + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (P.seg) *reinterpret_cast<unsigned*>(P.seg + o) = 0u;
+        } else {
+            if (P.rgba) reinterpret_cast<uchar4*>(P.rgba)[o] = c[0];
+            if (P.depth) P.depth[o] = 0.0f;
+            if (P.seg) P.seg[o] = 0;
+        }
     }
-    const size_t o = (size_t)view * npx + p;
-    if (P.rgba) __stcs(reinterpret_cast<uchar4*>(P.rgba) + o, c);
-    if (P.depth) __stcs(P.depth + o, z);
-    if (P.seg) P.seg[o] = s;
+    __syncthreads();
+    const int total = n_hit;
+    if (total == 0) return;
+    const int oid = P.obj_id[view];
+    int n_of = 0, n_ov = 0;
+    if (oid >= 0) {
+        n_of = P.face_off[oid + 1] - P.face_off[oid];
+        n_ov = P.vert_off[oid + 1] - P.vert_off[oid];
+    }
+    for (int i = threadIdx.x; i < total; i += 256) {
+        const int p = cta_p0 + hit_px[i];
+        const int py = p / P.W, px = p - py * P.W;
+        const PixelOut r = shade_pixel(P, view, oid, n_ov, n_of, px, py, hit_prim[i]);
+        kbase[p] = kEmptyKey;  // leave the key buffer empty for the next chunk
+        const size_t o = obase + p;
+        if (P.rgba) reinterpret_cast<uchar4*>(P.rgba)[o] = r.rgba;
+        if (P.depth) P.depth[o] = r.depth;
+        if (P.seg) P.seg[o] = r.seg;
+    }
 }
 
 static int max_hand_obj_verts(const ab_scene* s) {
@@ -441,6 +491,7 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
     AB_REQUIRE(scene->n_obj >= 0 && scene->n_obj <= kMaxObjects, "n_obj out of range (max 64)");
     AB_REQUIRE(scene->n_obj == 0 || (scene->obj_verts && scene->obj_faces && scene->obj_colors &&
                                      scene->obj_vert_off_host && scene->obj_face_off_host), "null object arrays");
+    AB_REQUIRE(!scene->bgs || (scene->bg_w > 0 && scene->bg_h > 0 && scene->bg_w <= 65535 && scene->bg_h <= 65535), "bad background size");
     AB_REQUIRE(scene->n_hand_verts > 0 && scene->n_hand_faces > 0 && scene->n_hand_tex > 0 && scene->hand_faces &&
                    scene->hand_colors, "bad hand mesh");
     if (batch == 0) return AB_OK;
@@ -514,7 +565,11 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
         }
         {
             StageTimer tm(AB_STAGE_RASTER_RESOLVE, st);
-            raster_resolve_kernel<<<dim3(cdiv(npx, 256), n), 256, 0, st>>>(P);
+            // 4 pixels per thread needs 16-byte aligned output rows: W % 4 == 0 and 16 / 16 / 4-byte aligned bases
+            const bool vec = (P.W % 4 == 0) && (((uintptr_t)P.rgba & 15) == 0) && (((uintptr_t)P.depth & 15) == 0) &&
+                             (((uintptr_t)P.seg & 3) == 0);
+            if (vec) raster_resolve_kernel<4><<<dim3(cdiv(npx, 1024), n), 256, 0, st>>>(P);
+            else raster_resolve_kernel<1><<<dim3(cdiv(npx, 256), n), 256, 0, st>>>(P);
         }
         count_launch(3);
         int rc = check_launch("ab_render_batch");

@@ -72,17 +72,20 @@ __device__ __forceinline__ void column_partial(int M, int C8, float* const* part
     }
 }
 
-// out_a[c] = sum_p part_a[p, c]  for a = 0, 1 (part1 / out1 may be null).  Block = 8 columns x 32 partial rows.
-__global__ void __launch_bounds__(256)
+// out_a[c] = sum_p part_a[p, c]  for a = 0, 1 (part1 / out1 may be null).  Block = 8 columns x 128 partial rows
+// (independent loads, unrolled: the kernel is pure latency).
+__global__ void __launch_bounds__(1024)
 partial_sum_kernel(const float* __restrict__ part0, const float* __restrict__ part1, int n_part, int C, float* out0, float* out1) {
-    __shared__ float red[2][8][8];
+    __shared__ float red[2][32][8];
     const int cx = threadIdx.x & 7, pr = threadIdx.x >> 3, c = blockIdx.x * 8 + cx;
     float s0 = 0.0f, s1 = 0.0f;
-    if (c < C)
-        for (int p = pr; p < n_part; p += 32) {
-            s0 += part0[(size_t)p * C + c];
-            if (part1) s1 += part1[(size_t)p * C + c];
+    if (c < C) {
+#pragma unroll 4
+        for (int p = pr; p < n_part; p += 128) {
+            s0 += __ldg(part0 + (size_t)p * C + c);
+            if (part1) s1 += __ldg(part1 + (size_t)p * C + c);
         }
+    }
     s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
     s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -91,7 +94,7 @@ partial_sum_kernel(const float* __restrict__ part0, const float* __restrict__ pa
     if (threadIdx.x < 8 && c < C) {
         float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { a0 += red[0][w][threadIdx.x]; a1 += red[1][w][threadIdx.x]; }
+        for (int w = 0; w < 32; ++w) { a0 += red[0][w][threadIdx.x]; a1 += red[1][w][threadIdx.x]; }
         out0[c] = a0;
         if (out1) out1[c] = a1;
     }
@@ -245,18 +248,20 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, 
 // or accumulated into the parameter gradients, and the three per-channel coefficients of the apply pass
 //   dx = gamma*invstd*(dy' - dbeta/M - xhat*dgamma/M) = A*dy' + B*raw + K,
 //   A = gamma*invstd, B = -A*invstd*dgamma/M, K = A*(mean*invstd*dgamma - dbeta)/M.            coef: [3, C]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ part0, const float* __restrict__ part1, int n_part, int C, float inv_count,
                        const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
                        float* dgamma, float* dbeta, int accumulate, float* coef) {
-    __shared__ float red[2][8][8];
+    __shared__ float red[2][32][8];
     const int cx = threadIdx.x & 7, pr = threadIdx.x >> 3, c = blockIdx.x * 8 + cx;
     float s0 = 0.0f, s1 = 0.0f;
-    if (c < C)
-        for (int p = pr; p < n_part; p += 32) {
-            s0 += part0[(size_t)p * C + c];
-            s1 += part1[(size_t)p * C + c];
+    if (c < C) {
+#pragma unroll 4
+        for (int p = pr; p < n_part; p += 128) {
+            s0 += __ldg(part0 + (size_t)p * C + c);
+            s1 += __ldg(part1 + (size_t)p * C + c);
         }
+    }
     s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
     s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -265,7 +270,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ part0, const float* __restrict_
     if (threadIdx.x >= 8 || c >= C) return;
     float sdy = 0.0f, sdyx = 0.0f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { sdy += red[0][w][threadIdx.x]; sdyx += red[1][w][threadIdx.x]; }
+    for (int w = 0; w < 32; ++w) { sdy += red[0][w][threadIdx.x]; sdyx += red[1][w][threadIdx.x]; }
     const float mu = mean[c], is = invstd[c], gm = gamma ? gamma[c] : 1.0f;
     const float dg = (sdyx - mu * sdy) * is;
     if (dgamma) dgamma[c] = accumulate ? dgamma[c] + dg : dg;
@@ -532,7 +537,7 @@ extern "C" int ab_col_stats(const void* x, int is_f32, int M, int C, int64_t ld,
     float* p1 = sumsq ? ws + (size_t)AB_STAT_PARTS * C : nullptr;
     if (is_f32) col_stats_f32_kernel<<<parts, kRedThreads, 0, st>>>((const float4*)x, M, C / 8, ld / 4, p0, p1);
     else col_stats_bf16_kernel<<<parts, kRedThreads, 0, st>>>((const uint4*)x, M, C / 8, ld / 8, p0, p1);
-    partial_sum_kernel<<<nblk(C, 8), 256, 0, st>>>(p0, p1, parts, C, sum, sumsq);
+    partial_sum_kernel<<<nblk(C, 8), 1024, 0, st>>>(p0, p1, parts, C, sum, sumsq);
     count_launch(2);
     return check_launch("col_stats_kernel");
 }
@@ -577,7 +582,7 @@ extern "C" int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, 
     float* p0 = ws;
     float* p1 = ws + (size_t)AB_STAT_PARTS * C;
     bn_bwd_reduce_kernel<<<parts, kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M, C / 8, relu, p0, p1);
-    bn_bwd_finalize_kernel<<<nblk(C, 8), 256, 0, st>>>(p0, p1, parts, C, 1.0f / (float)M, gamma, mean, invstd, dgamma, dbeta,
+    bn_bwd_finalize_kernel<<<nblk(C, 8), 1024, 0, st>>>(p0, p1, parts, C, 1.0f / (float)M, gamma, mean, invstd, dgamma, dbeta,
                                                        accumulate, coef);
     count_launch(2);
     return check_launch("bn_bwd_reduce_kernel");

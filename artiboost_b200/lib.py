@@ -81,6 +81,7 @@ EXPORTS = {
                                 C.POINTER(WgradMapStruct), C.c_void_p, C.c_void_p]),
     "ab_conv_wgrad_bf16_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int,
                                                                                                    C.c_void_p, C.c_void_p]),
+    "ab_pack_conv_filters": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_image_to_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "ab_im2col_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]),
     "ab_maxpool3x3s2_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -76,6 +76,28 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: int = 0) -> torch.Tensor:
     return out
 
 
+def packed_filters(conv: nn.Conv2d, cin_pad: int, with_dgrad: bool = False):
+    """bf16 operand copies of conv.weight, cached per module and rebuilt by ONE kernel when the parameter changes:
+    -> (wp [Cout, Kp] forward filter matrix, wd [Cin, kh*kw*Cout] data-gradient filter matrix or None)."""
+    w = conv.weight
+    cout, cin, kh, kw = w.shape
+    cin_pad = max(cin_pad, cin)
+
+    def build():
+        lib.require_cuda(w, "conv.weight")
+        kp = _pad8(kh * kw * cin_pad)
+        wp = torch.empty((cout, kp), dtype=torch.bfloat16, device=w.device)
+        wd = torch.empty((cin, kh * kw * cout), dtype=torch.bfloat16, device=w.device) if with_dgrad else None
+        src = w.detach().float().contiguous()
+        with torch.cuda.device(w.device):
+            rc = lib.load().ab_pack_conv_filters(src.data_ptr(), cout, cin, kh, kw, cin_pad, kp, wp.data_ptr(),
+                                                 None if wd is None else wd.data_ptr(), lib.stream_ptr(w.device))
+        lib.check(rc, "ab_pack_conv_filters")
+        return wp, wd
+
+    return _cached(conv, ("packed", cin_pad, with_dgrad), _ver(w), build)
+
+
 def bn_affine(bn, training: bool):
     """Folded (scale, bias) of an eval-mode / frozen BatchNorm (resnet.py:44-69, nn.BatchNorm2d eval)."""
     if bn is None:
@@ -113,7 +135,7 @@ def conv_bn_act(x: Act, conv: nn.Conv2d, bn=None, relu: bool = False, residual: 
     stride, pad = conv.stride[0], conv.padding[0]
     cout = conv.out_channels
     assert conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1] and conv.groups == 1
-    wp = _cached(conv, ("w", x.C), _ver(conv.weight), lambda: pack_conv_weight(conv.weight, x.C))
+    wp, _ = packed_filters(conv, x.C)
     scale, bias = bn_affine(bn, training)
     if conv.bias is not None:
         cb = conv.bias.detach().float()

@@ -31,12 +31,6 @@ def _stream(dev):
 
 
 # --------------------------------------------------------------------------------------------- packed filters
-def _pack_dgrad_weight(w: torch.Tensor) -> torch.Tensor:
-    """[Cout, Cin, kh, kw] -> bf16 [Cin, (ky', kx', co)] with the taps flipped: the filter matrix of the data gradient."""
-    cin = w.shape[1]
-    return w.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(cin, -1).to(torch.bfloat16).contiguous()
-
-
 def _wgrad_ws(P_, Mo, No, dev):
     """Workspace of the split-over-pixels weight-gradient kernel (partial tiles, summed by its second pass)."""
     return torch.empty(int(lib.load().ab_wgrad_workspace_bytes(P_, Mo, No)) // 4, device=dev)
@@ -146,20 +140,19 @@ def _col_sum(mat, is_f32=False):
     return out
 
 
-def _conv_dgrad(dy: Act, conv_w, kh, kw, stride, pad, H, W, key) -> torch.Tensor:
-    """Data gradient of a convolution whose input was [B, H, W, Cin]; dy is [B, Ho, Wo, Cout]."""
+def _conv_dgrad(dy: Act, conv_w, kh, kw, stride, pad, H, W, key, in_c) -> torch.Tensor:
+    """Data gradient of a convolution whose input was [B, H, W, in_c]; dy is [B, Ho, Wo, Cout].  key: the conv module."""
     cout, cin = conv_w.shape[0], conv_w.shape[1]
     dev = dy.data.device
+    _, wd = nhwc.packed_filters(key, in_c, with_dgrad=True)  # built together with the forward copy, one launch per step
     if kh == 1 and kw == 1:
-        wt = _cached(key, "wt", _ver(conv_w), lambda: conv_w.detach().view(cout, cin).t().to(torch.bfloat16).contiguous())
-        dx = ops.gemm_bf16(dy.data, wt)  # [M_out, Cin]
+        dx = ops.gemm_bf16(dy.data, wd)  # [M_out, Cin]
         if stride == 1:
             return dx
         out = torch.empty((dy.B * H * W, cin), dtype=torch.bfloat16, device=dev)
         with torch.cuda.device(dev):
             _call("ab_dilate2x", dx.data_ptr(), dy.B, dy.H, dy.W, H, W, cin, out.data_ptr(), _stream(dev))
         return out
-    wd = _cached(key, "wd", _ver(conv_w), lambda: _pack_dgrad_weight(conv_w))
     g = dy
     if stride == 2:
         d = torch.empty((dy.B * H * W, cout), dtype=torch.bfloat16, device=dev)
@@ -202,7 +195,7 @@ class ConvBNActFn(torch.autograd.Function):
         x = Act(x_data, B, H, W, C)
         kh, kw = conv.kernel_size
         stride, pad, cout = conv.stride[0], conv.padding[0], conv.out_channels
-        wp = _cached(conv, ("w", C), _ver(weight), lambda: nhwc.pack_conv_weight(weight, C))
+        wp, _ = nhwc.packed_filters(conv, C, with_dgrad=True)
         ctx.meta = (geom, conv, bn, relu, kh, kw, stride, pad, cout, out_fp32)
         ctx.has_res = residual is not None
         empty = x_data.new_empty(0)
@@ -242,7 +235,7 @@ class ConvBNActFn(torch.autograd.Function):
         dw = _conv_wgrad(x, xcol if xcol.numel() else None, draw, conv.weight, kh, kw, stride, pad) if ctx.needs_input_grad[1] else None
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = _conv_dgrad(Act(draw, B, Ho, Wo, cout), weight, kh, kw, stride, pad, H, W, conv)
+            dx = _conv_dgrad(Act(draw, B, Ho, Wo, cout), weight, kh, kw, stride, pad, H, W, conv, C)
         if not isinstance(ctx.st, _BNState):
             dgamma = dbeta = None  # frozen / eval-mode statistics carry no parameter gradient here
         return dx, dw, dbias, dgamma, dbeta, dres, None, None, None, None, None, None

@@ -182,10 +182,28 @@ class TrainStep:
         return self._out
 
 
-def synth_to_batch(views: dict, pipe, center_idx: int = 0) -> Dict[str, torch.Tensor]:
-    """Rendered views + their annotations -> the network's batch dict (the part of RenderedDataset.__getitem__ that is
-    not augmentation: rendered_dataset.py:127-133,207-272).  No crop / warp yet: the render size
-    is the network input size."""
+# AUG / AUG_PARAM of the HO3D training config (config/ho3dv2_clasbased_jlol_artiboost2.yaml:85-88) and its DATA_PRESET
+# (:98-128) at the 256 x 256 network input of BASELINE.json (the shipped config uses 224 x 224)
+DEFAULT_AUG_CFG = {"AUG": True, "AUG_PARAM": {"SCALE_JIT": 0.1, "CENTER_JIT": 0.1, "MAX_ROT": 0.2}}
+DEFAULT_PRESET = {"IMAGE_SIZE": [256, 256], "CENTER_IDX": 0, "BBOX_EXPAND_RATIO": 1.2, "FULL_IMAGE": False, "CROP_MODEL": "root_obj"}
+
+
+def make_augmenter(pipe, cfg_dataset: Optional[dict] = None, cfg_preset: Optional[dict] = None, generator=None):
+    """The crop / augment stage that follows the rasteriser (artiboost.RenderedDataset on this pipeline's camera)."""
+    from .artiboost import RenderedDataset
+    r = pipe.renderer
+    return RenderedDataset(pipe.obj_engine.corners_can.cpu().numpy(), pipe.cam_intr, cfg_dataset or DEFAULT_AUG_CFG,
+                           cfg_preset or DEFAULT_PRESET, raw_size=(r.width, r.height), device=pipe.device, generator=generator)
+
+
+def synth_to_batch(views: dict, pipe, center_idx: int = 0, augmenter=None) -> Dict[str, torch.Tensor]:
+    """Rendered views + their annotations -> the network's batch dict.  With an `augmenter` (artiboost.RenderedDataset):
+    the full RenderedDataset.__getitem__ (crop box, jitter, blur, colour jitter, affine warp, transformed annotations;
+    rendered_dataset.py:155-274) on the device.  Without: only the un-augmented part (:127-133,207-272), render size =
+    network input size."""
+    if augmenter is not None:
+        return augmenter({"rgba": views["rgba"], "joints": views["joints"], "obj_pose": views["obj_pose"], "obj_id": views["obj_id"],
+                          "persp_id": views["persp_id"], "grasp_id": views["grasp_id"]})
     rgba = views["rgba"]
     B = rgba.shape[0]
     image = rgba[..., :3].permute(0, 3, 1, 2).float() / 255.0 - 0.5           # to_tensor, then -0.5 (:269-270)
@@ -231,8 +249,11 @@ class ArtiBoostLoop:
     recorded errors into the next epoch's sampling weights (all-reduced over ranks)."""
 
     def __init__(self, arch: nn.Module, pipe, batch_size: int = 128, synth_factor: float = 0.6, real_source=None,
-                 criterion_cfg: Optional[dict] = None, lr=5e-5, grad_clip=1e-3, generator=None, use_graph: bool = False):
+                 criterion_cfg: Optional[dict] = None, lr=5e-5, grad_clip=1e-3, generator=None, use_graph: bool = False,
+                 augment: bool = True, prefetch: bool = True):
         self.pipe, self.batch_size = pipe, batch_size
+        self.prefetch, self._prefetched = prefetch, None
+        self.augmenter = make_augmenter(pipe, generator=generator) if augment else None
         self.n_synth = int(round(batch_size * synth_factor / (1.0 + synth_factor)))
         self.n_real = batch_size - self.n_synth
         self.generator = generator
@@ -241,17 +262,26 @@ class ArtiBoostLoop:
         self.feedback = CCVFeedback(pipe.sample_weight_map.shape, pipe.device)
 
     def make_batch(self) -> Dict[str, torch.Tensor]:
-        synth = synth_to_batch(self.pipe.synthesise(self.n_synth), self.pipe)
+        synth = synth_to_batch(self.pipe.synthesise(self.n_synth), self.pipe, augmenter=self.augmenter)
         return mix_batches(self.real_source(self.n_real), synth) if self.n_real else synth
 
     def step(self, batch: Optional[Dict[str, torch.Tensor]] = None):
-        batch = batch if batch is not None else self.make_batch()
+        """One iteration.  Without an explicit batch the loop is software-pipelined: the step consumes the batch that was
+        synthesised while the previous step's graph was running, then immediately issues the synthesis of the next one --
+        the host-side launch work of ~60 small kernels hides behind the ~16 ms the GPU spends in the training graph."""
+        own = batch is None
+        if own:
+            batch = self._prefetched if self._prefetched is not None else self.make_batch()
+            self._prefetched = None
         loss, preds = self.train_step(batch)
         targ = batch["corners_3d"] + batch["root_joint"].unsqueeze(1)
         self.feedback.feed(preds["corners_3d_abs"].detach(), targ, batch["obj_id"], batch["persp_id"], batch["grasp_id"],
                            batch["is_synth"])
+        if own and self.prefetch:
+            self._prefetched = self.make_batch()
         return loss
 
     def end_epoch(self):
+        self._prefetched = None  # it was drawn with the old weights
         self.pipe.sample_weight_map = self.feedback.step_eval(self.pipe.sample_weight_map)
         return self.pipe.sample_weight_map

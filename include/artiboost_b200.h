@@ -215,6 +215,11 @@ AB_API int ab_conv_wgrad_bf16_nhwc(const void* x, int B, int H, int W, int C, co
  *   out_raw (optional) receives the un-normalised f32 sums for training-mode batch statistics.
  * ab_head_decode: logits f32 [B, H*W, ncls*D] (channel = cls*D + d) -> kp3d f32 [B,ncls,3] = (u,v,d) in [0,1),
  *   confd f32 [B,ncls]: IntegralDeconvHead.forward after the final conv (simplebaseline.py:182-190).            */
+/* ab_pack_conv_filters: bf16 operand copies of an nn.Conv2d weight f32 [Cout,Cin,kh,kw] in one launch: wp [Cout,Kp]
+ *   (K order (ky,kx,ci), ci padded to cin_pad, zero tail: the forward / implicit-GEMM filter matrix) and, optionally,
+ *   wd [Cin, kh*kw*Cout] (taps flipped, (ky,kx,co) order: the filter matrix of the data gradient).               */
+AB_API int ab_pack_conv_filters(const float* w, int Cout, int Cin, int kh, int kw, int cin_pad, int Kp, void* wp, void* wd,
+                                void* stream);
 AB_API int ab_image_to_nhwc(const float* image, int B, int C, int H, int W, int Cp, void* out, void* stream);
 AB_API int ab_im2col_nhwc(const void* in, int B, int H, int W, int C, int kh, int kw, int stride, int pad, int Kp,
                           void* out, void* stream);

@@ -115,3 +115,32 @@ def test_cuda_graph_step_matches_eager_step(lib_built):
     with torch.no_grad():
         after = model_b.eval()(batches[0])["HybridBaseline"]["joints_3d_abs"]
     assert float((after - before).abs().max()) > 1e-4
+
+
+def test_artiboost_loop_synthesises_augments_trains_and_reweights(lib_built):
+    """CCV draw -> pose -> rasterise -> crop / augment -> mix -> train step -> per-cell errors -> new sampling weights."""
+    import artiboost_b200.models as M
+    from artiboost_b200.synth import SynthPipeline
+    from artiboost_b200.train import ArtiBoostLoop
+    arch, preset = netcfg.arch_cfg("ResNet34")
+    torch.manual_seed(1)
+    model = M.Arch({"ARCH": arch}, M.build_arch_model_list(arch, preset_cfg=preset)).to(DEV)
+    pipe = SynthPipeline(device=DEV, seed=2, n_hand_tex=4, n_bg=2)
+    gen = torch.Generator(device=DEV).manual_seed(6)
+    loop = ArtiBoostLoop(model, pipe, batch_size=16, generator=gen, lr=1e-3, grad_clip=1.0)
+    assert (loop.n_synth, loop.n_real) == (6, 10)
+    batch = loop.make_batch()
+    assert batch["image"].shape == (16, 3, 256, 256) and float(batch["is_synth"].sum()) == 6
+    synth_img = batch["image"][10:]
+    assert float(synth_img.min()) >= -0.5 and float(synth_img.max()) <= 0.5 and float(synth_img.std()) > 0.05
+    assert set(batch["joints_vis"].unique().tolist()) <= {0.0, 1.0}
+    # the crop keeps the grasp in frame: the root joint projects inside the network input with the NEW intrinsics
+    K, root = batch["cam_intr"][10:], batch["root_joint"][10:]
+    uv = torch.einsum("bij,bj->bi", K, root)
+    uv = uv[:, :2] / uv[:, 2:3]
+    assert bool(((uv > -32) & (uv < 288)).all())
+    losses = [float(loop.step()) for _ in range(3)]
+    assert all(l == l for l in losses)
+    assert float(loop.feedback.err_cnt.sum()) == 18.0
+    w = loop.end_epoch()
+    assert w.shape == pipe.sample_weight_map.shape and float(w.min()) >= 0.1 and float(w.max()) <= 10.0

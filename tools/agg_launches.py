@@ -11,7 +11,8 @@ pat = sys.argv[sys.argv.index("--list") + 1] if "--list" in sys.argv else None
 with open(path) as f:
     rows = list(csv.DictReader(l for l in f if not l.startswith("==")))
 idx = [i for i, r in enumerate(rows) if marker in r["Kernel Name"]]
-step = rows[idx[-1]:] if idx else rows
+# the loop prefetches the next batch's synthesis at the end of a step: a full step is the span between the last two markers
+step = rows[idx[-2]:idx[-1]] if len(idx) >= 2 else (rows[idx[-1]:] if idx else rows)
 
 
 def us(r):
