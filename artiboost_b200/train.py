@@ -87,12 +87,11 @@ class CCVFeedback:
     def feed(self, pred_corners_abs, targ_corners_abs, obj_id, persp_id, grasp_id, is_synth=None):
         """mean corner error in millimetres per sample (meanepe.py:39-70), accumulated in its CCV cell."""
         err = (pred_corners_abs - targ_corners_abs).norm(dim=-1).mean(dim=-1) * 1000.0
-        if is_synth is not None:
-            keep = is_synth.bool()
-            err, obj_id, persp_id, grasp_id = err[keep], obj_id[keep], persp_id[keep], grasp_id[keep]
+        # real samples are weighted out instead of masked out: boolean indexing would force a host sync every step
+        w = torch.ones_like(err) if is_synth is None else is_synth.to(err.dtype)
         flat = (obj_id.long() * self.shape[1] + persp_id.long()) * self.shape[2] + grasp_id.long()
-        self.err_sum.view(-1).index_add_(0, flat, err.float())
-        self.err_cnt.view(-1).index_add_(0, flat, torch.ones_like(err, dtype=torch.float32))
+        self.err_sum.view(-1).index_add_(0, flat, err.float() * w)
+        self.err_cnt.view(-1).index_add_(0, flat, w.float())
 
     @torch.no_grad()
     def step_eval(self, weight_map: torch.Tensor) -> torch.Tensor:
@@ -252,7 +251,7 @@ class ArtiBoostLoop:
                  criterion_cfg: Optional[dict] = None, lr=5e-5, grad_clip=1e-3, generator=None, use_graph: bool = False,
                  augment: bool = True, prefetch: bool = True):
         self.pipe, self.batch_size = pipe, batch_size
-        self.prefetch, self._prefetched = prefetch, None
+        self.prefetch, self._prefetched, self._side = prefetch, None, None
         self.augmenter = make_augmenter(pipe, generator=generator) if augment else None
         self.n_synth = int(round(batch_size * synth_factor / (1.0 + synth_factor)))
         self.n_real = batch_size - self.n_synth
@@ -267,21 +266,42 @@ class ArtiBoostLoop:
 
     def step(self, batch: Optional[Dict[str, torch.Tensor]] = None):
         """One iteration.  Without an explicit batch the loop is software-pipelined: the step consumes the batch that was
-        synthesised while the previous step's graph was running, then immediately issues the synthesis of the next one --
-        the host-side launch work of ~60 small kernels hides behind the ~16 ms the GPU spends in the training graph."""
+        synthesised while the previous step's graph was running, then issues the synthesis of the next one on a second
+        stream -- its ~60 small kernels (and their host-side launch work) run beside the training graph instead of
+        after it.  The only ordering between the two streams: synthesis k+1 starts after everything enqueued before
+        step k's graph, and step k+1 waits for synthesis k+1."""
         own = batch is None
+        dev = self.pipe.device
+        main = torch.cuda.current_stream(dev)
         if own:
-            batch = self._prefetched if self._prefetched is not None else self.make_batch()
+            if self._prefetched is not None:
+                batch, done = self._prefetched
+                main.wait_event(done)
+            else:
+                batch = self.make_batch()
             self._prefetched = None
+        fence = torch.cuda.Event()
+        fence.record(main)  # before the step is enqueued: the side stream must not wait for the step itself
         loss, preds = self.train_step(batch)
         targ = batch["corners_3d"] + batch["root_joint"].unsqueeze(1)
         self.feedback.feed(preds["corners_3d_abs"].detach(), targ, batch["obj_id"], batch["persp_id"], batch["grasp_id"],
                            batch["is_synth"])
         if own and self.prefetch:
-            self._prefetched = self.make_batch()
+            if self._side is None:
+                self._side = torch.cuda.Stream(dev)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(fence)
+                nxt = self.make_batch()
+                for t in nxt.values():
+                    t.record_stream(main)  # allocated on the side stream, consumed on the main one
+                done = torch.cuda.Event()
+                done.record(self._side)
+            self._prefetched = (nxt, done)
         return loss
 
     def end_epoch(self):
         self._prefetched = None  # it was drawn with the old weights
+        if self._side is not None:
+            torch.cuda.current_stream(self.pipe.device).wait_stream(self._side)
         self.pipe.sample_weight_map = self.feedback.step_eval(self.pipe.sample_weight_map)
         return self.pipe.sample_weight_map
