@@ -21,11 +21,14 @@ CROP_MODELS = {"root_obj": 0, "hand_obj": 1, "hand": 2}
 class RenderedDataset:
 
     def __init__(self, obj_corners, cam_intr, cfg_dataset: dict, cfg_preset: dict, crop_image: Optional[dict] = None,
-                 raw_size=None, device="cuda", generator: Optional[torch.Generator] = None):
+                 raw_size=None, device="cuda", generator: Optional[torch.Generator] = None, obj_class_ids=None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise lib.AbError("RenderedDataset runs on a CUDA device only: artiboost_b200 has no CPU path")
         self.obj_corners = torch.as_tensor(np.asarray(obj_corners, np.float32), device=self.device).contiguous()  # [n_obj, 8, 3]
+        # Queries.OBJ_IDX is the 1-based YCB class id of the object (rendered_dataset.py:38,236: obj_map[objname])
+        ids = np.arange(1, len(self.obj_corners) + 1) if obj_class_ids is None else np.asarray(obj_class_ids)
+        self.obj_class_ids = torch.as_tensor(ids, dtype=torch.int32, device=self.device)
         self.cam_intr = np.asarray(cam_intr, np.float32).reshape(3, 3)
         self.image_size = tuple(cfg_preset["IMAGE_SIZE"])  # (W, H)
         self.raw_size = tuple(raw_size) if raw_size is not None else self.image_size
@@ -104,7 +107,7 @@ class RenderedDataset:
                                    P(aff[0]), P(aff[1]), status.data_ptr(), ws_ptr, lib.stream_ptr(dev))
         lib.check(rc, "ab_crop_augment")
         out["corners_can"] = corners_can
-        out["obj_idx"] = views["obj_id"]
+        out["obj_idx"] = self.obj_class_ids[views["obj_id"].long()]
         out["is_synth"] = torch.ones(B, device=dev)
         for k in ("obj_id", "persp_id", "grasp_id"):
             if k in views:

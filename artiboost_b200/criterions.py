@@ -126,7 +126,70 @@ class SceneOrdLoss:
         return self.lambda_scene_lev * loss, {"scene_ord_loss": loss}
 
 
-LOSSES = {"JointsLoss": JointsLoss, "HandOrdLoss": HandOrdLoss, "SceneOrdLoss": SceneOrdLoss}
+def get_symmetry_transformations(model_info: Dict, max_sym_disc_step: float):
+    """anakin/utils/bop_toolkit/bop_misc.py:18-65: the identity + discrete symmetries, each combined with the discretised
+    continuous ones (rotation about `axis` through `offset` in steps of 2 pi / ceil(pi / max_sym_disc_step))."""
+    disc = [(np.eye(3), np.zeros((3, 1)))]
+    for sym in model_info.get("symmetries_discrete", []):
+        m = np.reshape(sym, (4, 4))
+        disc.append((m[:3, :3], m[:3, 3].reshape(3, 1)))
+    cont = []
+    for sym in model_info.get("symmetries_continuous", []):
+        axis = np.asarray(sym["axis"], np.float64)
+        offset = np.asarray(sym["offset"], np.float64).reshape(3, 1)
+        steps = int(np.ceil(np.pi / max_sym_disc_step))
+        d = axis / np.linalg.norm(axis)
+        for i in range(1, steps):
+            ang = i * 2.0 * np.pi / steps
+            sa, ca = np.sin(ang), np.cos(ang)  # bop_toolkit/transform.py:302-343 rotation_matrix
+            R = np.diag([ca, ca, ca]) + np.outer(d, d) * (1.0 - ca) + sa * np.array([[0.0, -d[2], d[1]], [d[2], 0.0, -d[0]], [-d[1], d[0], 0.0]])
+            cont.append((R, -R.dot(offset) + offset))
+    if not cont:
+        return disc
+    return [(Rc.dot(Rd), Rc.dot(td) + tc) for Rd, td in disc for Rc, tc in cont]
+
+
+class SymCornerLoss:
+    """Symmetry-aware corner loss of the DexYCB config (symcornerloss.py:18-108, eval_dexycb_clasbased_sym_artiboost.yaml:
+    89-91): the MSE to the closest of the object's symmetric corner sets.  `MODEL_INFO` (dict) or `MODEL_INFO_PATH` (json,
+    BOP models_info layout keyed "1".."N"); translations in millimetres like the reference."""
+
+    def __init__(self, **cfg):
+        import json
+        self.lambda_sym_corners_3d = cfg.get("LAMBDA_SYM_CORNERS_3D", 0.0)
+        info = cfg["MODEL_INFO"] if "MODEL_INFO" in cfg else json.load(open(cfg["MODEL_INFO_PATH"], "r"))
+        self.max_sym_disc_step = cfg.get("MAX_SYM_DISC_STEP", 0.01)
+        self.use_ho3d_ycb = cfg.get("USE_HO3D_YCB", False)
+        syms = [get_symmetry_transformations(info[str(i)], self.max_sym_disc_step) for i in range(1, len(info) + 1)]
+        k = max(len(s_) for s_ in syms)
+        R = np.stack([np.stack([s_[j][0] if j < len(s_) else np.eye(3) for j in range(k)]) for s_ in syms])
+        t = np.stack([np.stack([s_[j][1] if j < len(s_) else np.zeros((3, 1)) for j in range(k)]) for s_ in syms]) / 1000.0
+        self.R, self.t = R.astype(np.float32), t.astype(np.float32)  # [N, K, 3, 3], [N, K, 3, 1]
+
+    def __call__(self, preds, targs, **kw):
+        pc = preds["corners_3d_abs"]
+        dev = pc.device
+        if not self.lambda_sym_corners_3d:
+            return torch.zeros((), device=dev), {"sym_corners_3d_loss": None}
+        idx = targs["obj_idx"].to(dev).long() - 1  # device gather (the reference goes through .tolist())
+        sym_R, sym_t = _on(self.R, dev)[idx], _on(self.t, dev)[idx]
+        cc = targs["corners_can"].to(dev)
+        transf = targs["obj_transf"].to(dev)
+        if not self.use_ho3d_ycb:
+            sym_can = (torch.einsum("bkmn,bcn->bkmc", sym_R, cc) + sym_t).transpose(-2, -1)
+        else:
+            ext = _on(_CAM_EXTR, dev)
+            sym_can = (ext @ (torch.einsum("bkmn,bnc->bkmc", sym_R, ext @ cc.transpose(-2, -1)) + sym_t)).transpose(-2, -1)
+        sym_abs = (torch.einsum("bij,bklj->bkil", transf[:, :3, :3], sym_can) + transf[:, None, :3, 3:]).transpose(-2, -1)
+        vis = targs["corners_vis"].to(dev)
+        pcm = pc * vis.unsqueeze(-1)
+        sym_abs = sym_abs * vis[:, None, :, None]
+        loss = ((sym_abs - pcm[:, None]) ** 2).mean(-1).mean(-1).min(dim=-1)[0].mean()
+        return self.lambda_sym_corners_3d * loss, {"sym_corners_3d_loss": loss}
+
+
+_CAM_EXTR = np.array([[1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, -1.0]], np.float32)
+LOSSES = {"JointsLoss": JointsLoss, "HandOrdLoss": HandOrdLoss, "SceneOrdLoss": SceneOrdLoss, "SymCornerLoss": SymCornerLoss}
 
 
 class Criterion:

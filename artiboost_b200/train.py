@@ -151,7 +151,11 @@ class TrainStep:
 
     def _capture(self, batch):
         dev = self.flat.flat.device
-        self._static = {k: batch[k].detach().clone() for k in self.BATCH_KEYS}
+        # every tensor of the batch gets a static twin (the losses may read more than BATCH_KEYS, e.g. obj_idx / obj_transf)
+        self._static = {k: v.detach().clone() for k, v in batch.items() if torch.is_tensor(v)}
+        missing = [k for k in self.BATCH_KEYS if k not in self._static]
+        if missing:
+            raise KeyError(f"batch lacks {missing}")
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         if self.generator is not None:
@@ -174,8 +178,8 @@ class TrainStep:
                 torch.cuda.current_stream().wait_stream(side)
                 return out
             self._capture(batch)
-        for k in self.BATCH_KEYS:
-            self._static[k].copy_(batch[k], non_blocking=True)
+        for k, buf in self._static.items():
+            buf.copy_(batch[k], non_blocking=True)
         self._graph.replay()
         nhwc.bump_params()  # the replayed Adam kernel rewrote the parameters: eager users must re-pack their filters
         return self._out
@@ -232,7 +236,8 @@ def real_shaped_batch(B: int, device, generator=None, size: int = 256) -> Dict[s
             "joints_3d": 0.05 * n(B, 21, 3), "corners_3d": 0.08 * n(B, 8, 3), "joints_vis": torch.ones((B, 21), device=device),
             "corners_vis": torch.ones((B, 8), device=device), "is_synth": torch.zeros(B, device=device),
             "obj_id": torch.zeros(B, dtype=torch.int32, device=device), "persp_id": torch.zeros(B, dtype=torch.int32, device=device),
-            "grasp_id": torch.zeros(B, dtype=torch.int32, device=device)}
+            "grasp_id": torch.zeros(B, dtype=torch.int32, device=device), "obj_idx": torch.ones(B, dtype=torch.int32, device=device),
+            "obj_transf": torch.cat([torch.eye(4, device=device)[:, :3].expand(B, 4, 3), torch.cat([root, torch.ones((B, 1), device=device)], 1).unsqueeze(-1)], 2)}
 
 
 def mix_batches(a: Dict[str, torch.Tensor], b: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:

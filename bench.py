@@ -366,6 +366,13 @@ def network_forward_bench(dev, batch=128, steps=10, warmup=3):
             ci = dict(inp, image=inp["image"].contiguous(memory_format=torch.channels_last))
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 ms_bf16 = timed(lambda: torch_forward(model, ci))
+            # MPCPE parity (SURVEY.md 8d iii): Mean3DEPE between the reference arithmetic (torch.nn / cuDNN fp32) and ours on the
+            # same synthetic inputs and identical weights, on `corners_3d_abs` (and joints), in millimetres
+            ours = model(inp)
+            ours = ours[next(iter(ours))]
+            ref = torch_train_forward(model, inp)
+            mpcpe = (ours["corners_3d_abs"].float() - ref["corners_3d_abs"]).norm(dim=-1).mean().item() * 1e3
+            mpjpe = (ours["joints_3d_abs"].float() - ref["joints_3d_abs"]).norm(dim=-1).mean().item() * 1e3
         gemm_ms = stages.get("gemm_bf16_tn_kernel", (0.0, 0))[0] / (steps + warmup)
         out[backbone] = {
             "batch": batch, "images_per_s": batch / ms * 1e3, "ms_per_step": ms,
@@ -373,6 +380,7 @@ def network_forward_bench(dev, batch=128, steps=10, warmup=3):
             "stage_ms_per_step": {k: v[0] / (steps + warmup) for k, v in stages.items()},
             "gemm_tflops_in_kernel": batch * flops[backbone] / gemm_ms / 1e9 if gemm_ms else None,
             "torch_cudnn_fp32_images_per_s": batch / ms_fp32 * 1e3, "torch_cudnn_bf16_autocast_images_per_s": batch / ms_bf16 * 1e3,
+            "mpcpe_vs_torch_fp32_mm": mpcpe, "mpjpe_vs_torch_fp32_mm": mpjpe,
         }
         del model
     return out

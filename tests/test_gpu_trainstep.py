@@ -144,3 +144,35 @@ def test_artiboost_loop_synthesises_augments_trains_and_reweights(lib_built):
     assert float(loop.feedback.err_cnt.sum()) == 18.0
     w = loop.end_epoch()
     assert w.shape == pipe.sample_weight_map.shape and float(w.min()) >= 0.1 and float(w.max()) <= 10.0
+
+
+def test_dexycb_style_config_21_objects_sym_corner_loss(lib_built):
+    """BASELINE.json configs[4] in miniature: 21-object CCV space, CENTER_IDX 9, JointsLoss (corners off) + HandOrdLoss +
+    SymCornerLoss (config_eval/eval_dexycb_clasbased_sym_artiboost.yaml:39,84-91) through the graph-captured loop."""
+    import artiboost_b200.models as M
+    from artiboost_b200 import assets
+    from artiboost_b200.synth import SynthPipeline
+    from artiboost_b200.train import DEFAULT_PRESET, ArtiBoostLoop, make_augmenter
+    arch, preset = netcfg.arch_cfg("ResNet34")
+    arch["DATA_PRESET"] = dict(preset, CENTER_IDX=9)
+    torch.manual_seed(1)
+    model = M.Arch({"ARCH": arch}, M.build_arch_model_list(arch, preset_cfg=dict(preset, CENTER_IDX=9))).to(DEV)
+    pipe = SynthPipeline(obj_names=list(assets.YCB_NAMES), device=DEV, seed=4, n_hand_tex=4, n_bg=2)
+    assert tuple(pipe.sample_weight_map.shape) == (21, 288, 50)
+    info = {str(i + 1): ({"symmetries_continuous": [{"axis": [0, 0, 1], "offset": [0, 0, 0]}]} if i % 3 == 0 else
+                         {"symmetries_discrete": [[-1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]]} if i % 3 == 1 else {}) for i in range(21)}
+    crit = {"LAMBDAS": [1.0, 0.1, 1.0],
+            "CRITERION": [{"TYPE": "JointsLoss", "LAMBDA_JOINTS_3D": 1.0, "LAMBDA_CORNERS_3D": 0.0}, {"TYPE": "HandOrdLoss"},
+                          {"TYPE": "SymCornerLoss", "LAMBDA_SYM_CORNERS_3D": 1.0, "MODEL_INFO": info, "MAX_SYM_DISC_STEP": 0.05}]}
+    gen = torch.Generator(device=DEV).manual_seed(8)
+    loop = ArtiBoostLoop(model, pipe, batch_size=8, criterion_cfg=crit, generator=gen, lr=1e-3, grad_clip=1.0, use_graph=True)
+    loop.train_step.graph_warmup = 1
+    loop.augmenter = make_augmenter(pipe, cfg_preset=dict(DEFAULT_PRESET, CENTER_IDX=9), generator=gen)
+    batch = loop.make_batch()
+    assert {"obj_idx", "obj_transf"} <= set(batch) and int(batch["obj_idx"].min()) >= 1 and int(batch["obj_idx"].max()) <= 21
+    losses = [float(loop.step()) for _ in range(4)]
+    assert loop.train_step._graph is not None and all(l == l for l in losses)
+    seen = loop.feedback.err_cnt.sum(dim=(1, 2))
+    assert float(seen.sum()) == 4 * loop.n_synth and int((seen > 0).sum()) >= 2   # several of the 21 objects were drawn
+    w = loop.end_epoch()
+    assert tuple(w.shape) == (21, 288, 50)

@@ -127,3 +127,29 @@ def test_model_registry_builds_the_reference_config_on_cpu():
     from artiboost_b200.lib import AbError
     with torch.no_grad(), pytest.raises(AbError):
         model.eval()(netcfg.make_inputs(1))  # host tensors: there is no CPU path
+
+
+def test_sym_corner_loss_matches_reference():
+    """artiboost_b200.criterions.SymCornerLoss vs anakin/criterions/symcornerloss.py (tests/golden/symloss.npz):
+    symmetry tables (identity / discrete / discretised continuous, combined) and the min-over-symmetries loss."""
+    import json
+
+    from artiboost_b200 import criterions as C
+    g = golden("symloss.npz")
+    info = json.loads(str(g["model_info"]))
+    t = torch.from_numpy
+    targs = {"obj_idx": t(g["obj_idx"]), "corners_can": t(g["corners_can"]), "obj_transf": t(g["obj_transf"]), "corners_vis": t(g["corners_vis"])}
+    for flag in (0, 1):
+        loss = C.SymCornerLoss(LAMBDA_SYM_CORNERS_3D=1.0, MODEL_INFO=info, MAX_SYM_DISC_STEP=0.05, USE_HO3D_YCB=bool(flag))
+        np.testing.assert_allclose(loss.R, g[f"R{flag}"], atol=1e-6)
+        np.testing.assert_allclose(loss.t, g[f"t{flag}"], atol=1e-7)
+        pred = t(g["pred"]).clone().requires_grad_(True)
+        final, parts = loss({"corners_3d_abs": pred}, targs)
+        np.testing.assert_allclose(parts["sym_corners_3d_loss"].detach().numpy(), g[f"loss_ho3d{flag}"], rtol=1e-5)
+        final.backward()
+        assert torch.isfinite(pred.grad).all() and float(pred.grad.abs().sum()) > 0
+    off = C.SymCornerLoss(LAMBDA_SYM_CORNERS_3D=0.0, MODEL_INFO=info)
+    assert off({"corners_3d_abs": t(g["pred"])}, targs)[1]["sym_corners_3d_loss"] is None
+    crit = C.Criterion({"LAMBDAS": [1.0, 1.0], "CRITERION": [{"TYPE": "JointsLoss", "LAMBDA_JOINTS_3D": 1.0, "LAMBDA_CORNERS_3D": 0.0},
+                                                            {"TYPE": "SymCornerLoss", "LAMBDA_SYM_CORNERS_3D": 1.0, "MODEL_INFO": info}]})
+    assert [type(l).__name__ for l in crit.loss_list] == ["JointsLoss", "SymCornerLoss"]
