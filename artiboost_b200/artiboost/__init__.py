@@ -4,8 +4,9 @@ reference modules of the same file names; everything heavy goes through the C-AB
 DUMMY = "dummy"  # CONST.DUMMY, anakin/utils/misc.py:70
 
 from .view_engine import ViewEngine  # noqa: E402,F401
-from .scrambler import Scrambler, RandomScrambler, NaiveScrambler, NullScrambler  # noqa: E402,F401
-from .refiner import Refiner, NullRefine  # noqa: E402,F401
+from .scrambler import (Scrambler, RandomScrambler, RandomScrambler2, RandomScrambler3, NaiveScrambler, NullScrambler,
+                        AxisLayer)  # noqa: E402,F401
+from .refiner import Refiner, NullRefine, HORefiner  # noqa: E402,F401
 from .preprocessor import PreProcessorPoseGenerator  # noqa: E402,F401
 from .ovg_set import OVGSet  # noqa: E402,F401
 from .grasp_engine import GraspEngine  # noqa: E402,F401

@@ -11,8 +11,11 @@ __device__ __constant__ const int kJointReorder[21] = {0, 13, 14, 15, 16, 1, 2, 
                                                         6, 18, 10, 11, 12, 19, 7, 8, 9, 20};
 // fingertip vertex ids appended as joints 16..20 (iknet/manolayer.py:266).
 __device__ __constant__ const int kTipVerts[5] = {745, 317, 444, 556, 673};
-// transforms_abs order of manotorch's MANOOutput: the 21-order without tips.
-__device__ __constant__ const int kTransfReorder[16] = {0, 13, 14, 15, 1, 2, 3, 4, 5, 6, 10, 11, 12, 7, 8, 9};
+// transforms_abs order of manotorch's MANOOutput: the MANO chain order (wrist, index, middle, little, ring, thumb).
+// manotorch is absent; the order is fixed by its consumers in the reference: AxisLayer pairs transforms_abs[:, 1:]
+// with the chain-ordered keypoint list [5,6,7, 9,10,11, 17,18,19, 13,14,15, 1,2,3], and scrambler.py:124-181 indexes
+// the resulting axes with chain-order pose indices (1,4,7,10 knuckles; 13 thumb base).
+__device__ __constant__ const int kTransfReorder[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15};
 
 // Axis-angle -> rotation matrix (row-major 3x3), exact Rodrigues form.
 __device__ __forceinline__ void rodrigues(float ax, float ay, float az, float* R) {

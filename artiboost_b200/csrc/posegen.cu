@@ -18,7 +18,8 @@ __global__ void posegen_prelude_kernel(ab_mano_model m, int batch, const float* 
                                        const float* __restrict__ persp_rotmat, const float* __restrict__ free_transf,
                                        const float* __restrict__ z_offset, const float* __restrict__ noise_tsl,
                                        const float* __restrict__ noise_angle, float* __restrict__ obj_pose,
-                                       float* __restrict__ pose_out, float* __restrict__ post_rt) {
+                                       float* __restrict__ pose_out, float* __restrict__ post_rt,
+                                       float* __restrict__ tsl_out, float* __restrict__ cso_out) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     const float* pose = hand_pose + (size_t)b * 48;
@@ -100,6 +101,10 @@ __global__ void posegen_prelude_kernel(ab_mano_model m, int batch, const float* 
 #pragma unroll
         for (int d = 0; d < 3; ++d) nt[d] += noise_tsl[(size_t)b * 3 + d];
     }
+    if (tsl_out) {  // the refiner's inputs when it is not the fused NullRefine (preprocessor.py:76-81)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { tsl_out[(size_t)b * 3 + d] = nt[d]; cso_out[(size_t)b * 3 + d] = cso[d]; }
+    }
     // rigid map applied by the LBS store: x' = Rf (x + nt + cso)               (refiner.py:139-140, preprocessor.py:84-88)
     float* q = post_rt + (size_t)b * 12;
     float sh[3] = {nt[0] + cso[0], nt[1] + cso[1], nt[2] + cso[2]};
@@ -135,11 +140,36 @@ extern "C" int ab_pose_generate(const ab_mano_model* model, int batch, const flo
     ab::StageTimer tm(AB_STAGE_POSEGEN_PRELUDE, st);
     ab::posegen_prelude_kernel<<<ab::cdiv(batch, 64), 64, 0, st>>>(*model, batch, hand_pose, hand_shape, hand_tsl,
                                                                   persp_rotmat, camera_free_transf, z_offset,
-                                                                  noise_tsl, noise_angle, final_obj_pose, pose2, post);
+                                                                  noise_tsl, noise_angle, final_obj_pose, pose2, post,
+                                                                  nullptr, nullptr);
     }
     ab::count_launch();
     int rc = ab::check_launch("posegen_prelude_kernel");
     if (rc) return rc;
     // NullRefine decodes with betas=None (refiner.py:138)
     return ab::launch_mano(model, batch, pose2, nullptr, post, -1, final_hand_verts, final_joints, nullptr, st);
+}
+
+/* The prelude on its own, for the refiners / scramblers that are not fused into ab_pose_generate. */
+extern "C" int ab_pose_prelude(const ab_mano_model* model, int batch, const float* hand_pose, const float* hand_shape,
+                               const float* hand_tsl, const float* persp_rotmat, const float* camera_free_transf,
+                               const float* z_offset, const float* noise_tsl, const float* noise_angle,
+                               float* final_obj_pose, float* pose_out, float* tsl_out, float* cam_sys_offset,
+                               float* post_rt, void* stream) {
+    AB_REQUIRE(model && model->j_template && model->j_shapedirs, "null model array");
+    AB_REQUIRE(batch >= 0, "negative batch");
+    if (batch == 0) return AB_OK;
+    AB_REQUIRE(hand_pose && hand_tsl && persp_rotmat && camera_free_transf && z_offset, "null input");
+    AB_REQUIRE(final_obj_pose && pose_out && tsl_out && cam_sys_offset && post_rt, "null output");
+    AB_REQUIRE((noise_tsl == nullptr) == (noise_angle == nullptr), "noise_tsl and noise_angle go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+    ab::StageTimer tm(AB_STAGE_POSEGEN_PRELUDE, st);
+    ab::posegen_prelude_kernel<<<ab::cdiv(batch, 64), 64, 0, st>>>(*model, batch, hand_pose, hand_shape, hand_tsl,
+                                                                  persp_rotmat, camera_free_transf, z_offset,
+                                                                  noise_tsl, noise_angle, final_obj_pose, pose_out, post_rt,
+                                                                  tsl_out, cam_sys_offset);
+    }
+    ab::count_launch();
+    return ab::check_launch("posegen_prelude_kernel");
 }

@@ -1,0 +1,450 @@
+// Hand-object refiner and anatomical scramblers (sm_100a): the pieces of anakin/artiboost/refiner.py:150-285
+// (HORefiner + _RefineNet, the shipped config's REFINER.TYPE "hand_obj") and scrambler.py:84-260 (random_2 / random_3)
+// that sit between the pose-generator prelude and the final LBS launch.
+//
+//   chamfer_nn_kernel       point2point_signed (refiner.py:21-85): nearest object point of every hand vertex.  The
+//                           reference calls the third-party chamfer_distance CUDA kernel on 778 x 10 000 points and
+//                           materialises the rotated object cloud per sample (refiner.py:190-191); here the rotation
+//                           is applied while the object tile is staged into shared memory, every thread scans the
+//                           tile for two hand vertices held in registers, and the BatchNorm1d(778) of
+//                           _RefineNet.forward (:266) is folded into the store.
+//   linear_f32_kernel       the RefineNet MLP (ResBlock, :288-319) in fp32 on the FMA pipe: y = act(x W^T + b (+ res)).
+//                           fp32 on purpose: the 1e-4 bar on vertex positions leaves no room for bf16 / tf32 operands
+//                           across three refinement iterations, and the MLP is ~5 % of the refiner's arithmetic.
+//   refine_encode_kernel    aa -> first two rotation-matrix columns ("CRot" 6D), refiner.py:253-257
+//   refine_decode_kernel    CRot2rotmat + rotmat_to_aa (parms_decode, :88-107) + the rigid map of the next LBS launch
+//   scramble_axis_kernel    manotorch AxisLayer + RandomScrambler2/3.forward
+#include "mano_math.cuh"
+
+namespace ab {
+
+// ---------------------------------------------------------------------------------------------- nearest neighbour
+constexpr int kNnThreads = 416;  // 13 warps x 2 queries = 832 slots for the 778 hand vertices
+constexpr int kNnQ = 2;
+constexpr int kNnTile = 2048;    // object points per shared-memory tile (32 KB of float4)
+constexpr int kNnChunk = 8;      // points per running-minimum update
+
+// d = fma(dz,dz, fma(dy,dy, dx*dx)): the arithmetic oracle/refiner.py restates (first minimum wins, like the
+// sequential strict `<` scan of the chamfer_distance kernel).
+__device__ __forceinline__ float nn_d2(float qx, float qy, float qz, float px, float py, float pz) {
+    float dx = qx - px, dy = qy - py, dz = qz - pz;
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+// Blackwell packed fp32 (FADD2 / FMUL2 / FFMA2): two IEEE fp32 lanes per instruction, each rounded exactly like the
+// scalar form above, so the scan below costs ~4 issue slots per (vertex, point) pair instead of ~7.5.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// y = R o with every operation individually rounded (matches the oracle's fp32 order)
+__device__ __forceinline__ void nn_rotate(const float* R, bool rot, const float* o, float& px, float& py, float& pz) {
+    float ox = o[0], oy = o[1], oz = o[2];
+    if (rot) {
+        px = __fadd_rn(__fadd_rn(__fmul_rn(R[0], ox), __fmul_rn(R[1], oy)), __fmul_rn(R[2], oz));
+        py = __fadd_rn(__fadd_rn(__fmul_rn(R[3], ox), __fmul_rn(R[4], oy)), __fmul_rn(R[5], oz));
+        pz = __fadd_rn(__fadd_rn(__fmul_rn(R[6], ox), __fmul_rn(R[7], oy)), __fmul_rn(R[8], oz));
+    } else {
+        px = ox; py = oy; pz = oz;
+    }
+}
+
+__global__ void __launch_bounds__(kNnThreads)
+chamfer_nn_kernel(int n_x, const float* __restrict__ x, int n_y, const float* __restrict__ y_points,
+                  const int32_t* __restrict__ obj_id, const float* __restrict__ rot, int rot_stride,
+                  const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ dist,
+                  long long dist_stride, int32_t* __restrict__ idx) {
+    __shared__ __align__(16) float sx[kNnTile], sy[kNnTile], sz[kNnTile];  // SoA: one LDS.128 = 4 points of one axis
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int q0 = blockIdx.x * (kNnThreads * kNnQ);
+    const float* yb = y_points + (size_t)(obj_id ? obj_id[b] : b) * n_y * 3;
+    float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+    if (rot) {
+        const int rs = rot_stride == 16 ? 4 : 3;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) R[3 * i + j] = rot[(size_t)b * rot_stride + rs * i + j];
+    }
+    float qx[kNnQ], qy[kNnQ], qz[kNnQ], best[kNnQ];
+    f32x2 qx2[kNnQ], qy2[kNnQ], qz2[kNnQ];
+    int bchunk[kNnQ];
+#pragma unroll
+    for (int k = 0; k < kNnQ; ++k) {
+        int qi = q0 + tid + k * kNnThreads;
+        const float* p = x + ((size_t)b * n_x + (qi < n_x ? qi : 0)) * 3;
+        qx[k] = p[0]; qy[k] = p[1]; qz[k] = p[2];
+        qx2[k] = pack2(qx[k], qx[k]); qy2[k] = pack2(qy[k], qy[k]); qz2[k] = pack2(qz[k], qz[k]);
+        best[k] = __int_as_float(0x7f800000);
+        bchunk[k] = 0;
+    }
+    for (int t0 = 0; t0 < n_y; t0 += kNnTile) {
+        const int tn = min(kNnTile, n_y - t0);
+        const int tn_pad = (tn + kNnChunk - 1) / kNnChunk * kNnChunk;
+        __syncthreads();
+        for (int i = tid; i < tn_pad; i += kNnThreads) {
+            float px = 1e18f, py = 1e18f, pz = 1e18f;  // padding of the last chunk: never the minimum
+            if (i < tn) nn_rotate(R, rot != nullptr, yb + (size_t)(t0 + i) * 3, px, py, pz);
+            sx[i] = px; sy[i] = py; sz[i] = pz;
+        }
+        __syncthreads();
+        for (int c = 0; c < tn_pad; c += kNnChunk) {
+            float m[kNnQ];
+#pragma unroll
+            for (int k = 0; k < kNnQ; ++k) m[k] = __int_as_float(0x7f800000);
+#pragma unroll
+            for (int h = 0; h < kNnChunk; h += 4) {
+                const float4 X = *reinterpret_cast<const float4*>(&sx[c + h]);
+                const float4 Y = *reinterpret_cast<const float4*>(&sy[c + h]);
+                const float4 Z = *reinterpret_cast<const float4*>(&sz[c + h]);
+                const f32x2 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
+                const f32x2 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
+                const f32x2 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
+#pragma unroll
+                for (int k = 0; k < kNnQ; ++k) {
+                    f32x2 dx = sub2(qx2[k], x01), dy = sub2(qy2[k], y01), dz = sub2(qz2[k], z01);
+                    f32x2 d01 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                    dx = sub2(qx2[k], x23); dy = sub2(qy2[k], y23); dz = sub2(qz2[k], z23);
+                    f32x2 d23 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                    float d0, d1, d2, d3;
+                    unpack2(d01, d0, d1);
+                    unpack2(d23, d2, d3);
+                    m[k] = fminf(fminf(m[k], fminf(d0, d1)), fminf(d2, d3));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kNnQ; ++k)
+                if (m[k] < best[k]) { best[k] = m[k]; bchunk[k] = t0 + c; }
+        }
+    }
+    // the winning chunk is re-scanned from the source points for the first index that attains the minimum
+#pragma unroll
+    for (int k = 0; k < kNnQ; ++k) {
+        int qi = q0 + tid + k * kNnThreads;
+        if (qi >= n_x) continue;
+        int bi = bchunk[k];
+        for (int j = 0; j < kNnChunk; ++j) {
+            int i = bchunk[k] + j;
+            if (i >= n_y) break;
+            float px, py, pz;
+            nn_rotate(R, rot != nullptr, yb + (size_t)i * 3, px, py, pz);
+            if (nn_d2(qx[k], qy[k], qz[k], px, py, pz) == best[k]) { bi = i; break; }
+        }
+        float v = sqrtf(best[k]);
+        if (scale) v = __fadd_rn(__fmul_rn(v, scale[qi]), shift[qi]);
+        dist[(size_t)b * dist_stride + qi] = v;
+        if (idx) idx[(size_t)b * n_x + qi] = bi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------ fp32 linear
+constexpr int kLinBM = 32, kLinBN = 64, kLinBK = 16, kLinThreads = 128;
+
+__global__ void __launch_bounds__(kLinThreads)
+linear_f32_kernel(int M, int N, int K, const float* __restrict__ x, long long ldx, const float* __restrict__ W,
+                  long long ldw, const float* __restrict__ bias, const float* res, long long ldr, int act, float slope,
+                  float* y, long long ldy) {
+    __shared__ __align__(16) float As[kLinBK][kLinBM];
+    __shared__ __align__(16) float Bs[kLinBK][kLinBN];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // 16 x 8 threads, 4 x 4 outputs each
+    const int m0 = blockIdx.y * kLinBM, n0 = blockIdx.x * kLinBN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    // loaders: one row per thread, a contiguous run of k per thread, so the transposed shared-memory writes are
+    // conflict-free (consecutive threads -> consecutive rows)
+    const int ar = tid & 31, ak = (tid >> 5) * 4;   // A: 32 rows x 16 k, 4 k per thread
+    const int br = tid & 63, bk = (tid >> 6) * 8;   // B: 64 rows x 16 k, 8 k per thread
+    const bool a_ok = m0 + ar < M, b_ok = n0 + br < N;
+    const float* ap = x + (size_t)(a_ok ? m0 + ar : 0) * ldx;
+    const float* bp = W + (size_t)(b_ok ? n0 + br : 0) * ldw;
+    for (int k0 = 0; k0 < K; k0 += kLinBK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int k = k0 + ak + i;
+            As[ak + i][ar] = (a_ok && k < K) ? ap[k] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int k = k0 + bk + i;
+            Bs[bk + i][br] = (b_ok && k < K) ? bp[k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kLinBK; ++kk) {
+            float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            float4 w = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (bias) v += bias[n];
+            if (res) v += res[(size_t)m * ldr + n];
+            if (act == 1) v = v > 0.f ? v : v * slope;
+            y[(size_t)m * ldy + n] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- 6D encode / decode
+__global__ void refine_encode_kernel(int batch, const float* __restrict__ pose, const float* __restrict__ tsl,
+                                     float* __restrict__ feat, long long ld) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= batch * 16) return;
+    int b = t >> 4, k = t & 15;
+    const float* a = pose + (size_t)b * 48 + 3 * k;
+    float R[9];
+    rodrigues(a[0], a[1], a[2], R);
+    float* o = feat + (size_t)b * ld + 6 * k;  // rotmat[..., :2].reshape(bs, -1): rows x the first two columns
+    o[0] = R[0]; o[1] = R[1]; o[2] = R[3]; o[3] = R[4]; o[4] = R[6]; o[5] = R[7];
+    if (k == 0) {
+        float* tt = feat + (size_t)b * ld + 96;
+        tt[0] = tsl[(size_t)b * 3]; tt[1] = tsl[(size_t)b * 3 + 1]; tt[2] = tsl[(size_t)b * 3 + 2];
+    }
+}
+
+__global__ void refine_decode_kernel(int batch, const float* __restrict__ feat, long long ld,
+                                     const float* __restrict__ rigid, int rigid_stride, const float* __restrict__ offset,
+                                     float* __restrict__ pose_out, float* __restrict__ tsl_out,
+                                     float* __restrict__ post_rt) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= batch * 16) return;
+    int b = t >> 4, k = t & 15;
+    const float* c = feat + (size_t)b * ld + 6 * k;
+    // CRot2rotmat (refiner.py:88-98): view(-1,3,2) -> columns (c0,c2,c4) and (c1,c3,c5); F.normalize eps 1e-12
+    float a1[3] = {c[0], c[2], c[4]}, a2[3] = {c[1], c[3], c[5]};
+    float n1 = fmaxf(sqrtf(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]), 1e-12f);
+    float b1[3] = {a1[0] / n1, a1[1] / n1, a1[2] / n1};
+    float dot = b1[0] * a2[0] + b1[1] * a2[1] + b1[2] * a2[2];
+    float u[3] = {a2[0] - dot * b1[0], a2[1] - dot * b1[1], a2[2] - dot * b1[2]};
+    float n2 = fmaxf(sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]), 1e-12f);
+    float b2[3] = {u[0] / n2, u[1] / n2, u[2] / n2};
+    float b3[3] = {b1[1] * b2[2] - b1[2] * b2[1], b1[2] * b2[0] - b1[0] * b2[2], b1[0] * b2[1] - b1[1] * b2[0]};
+    float R[9] = {b1[0], b2[0], b3[0], b1[1], b2[1], b3[1], b1[2], b2[2], b3[2]};
+    float aa[3];
+    rotmat_to_aa(R, aa);
+    float* po = pose_out + (size_t)b * 48 + 3 * k;
+    po[0] = aa[0]; po[1] = aa[1]; po[2] = aa[2];
+    if (k == 0) {
+        const float* tt = feat + (size_t)b * ld + 96;
+        float tv[3] = {tt[0], tt[1], tt[2]};
+        if (tsl_out) { tsl_out[(size_t)b * 3] = tv[0]; tsl_out[(size_t)b * 3 + 1] = tv[1]; tsl_out[(size_t)b * 3 + 2] = tv[2]; }
+        if (post_rt) {
+            float* q = post_rt + (size_t)b * 12;
+            if (rigid) {  // x' = Rf (x + t + offset)   (preprocessor.py:84-88)
+                const float* F = rigid + (size_t)b * rigid_stride;
+                int rs = rigid_stride == 16 ? 4 : 3;
+                float sh[3] = {tv[0], tv[1], tv[2]};
+                if (offset) { sh[0] += offset[(size_t)b * 3]; sh[1] += offset[(size_t)b * 3 + 1]; sh[2] += offset[(size_t)b * 3 + 2]; }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    q[3 * i] = F[rs * i]; q[3 * i + 1] = F[rs * i + 1]; q[3 * i + 2] = F[rs * i + 2];
+                    q[9 + i] = F[rs * i] * sh[0] + F[rs * i + 1] * sh[1] + F[rs * i + 2] * sh[2];
+                }
+            } else {
+                q[0] = 1.f; q[1] = 0.f; q[2] = 0.f; q[3] = 0.f; q[4] = 1.f; q[5] = 0.f; q[6] = 0.f; q[7] = 0.f; q[8] = 1.f;
+                q[9] = tv[0]; q[10] = tv[1]; q[11] = tv[2];
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------- anatomical scramblers
+// manotorch AxisLayer: back / up / left axes of the 15 articulated joints in MANO chain order, expressed in each
+// joint's own frame.  21-keypoint ids of the joint and its child, chain order (index, middle, little, ring, thumb).
+__device__ __constant__ const int kAxisJoint[15] = {5, 6, 7, 9, 10, 11, 17, 18, 19, 13, 14, 15, 1, 2, 3};
+
+__device__ __forceinline__ void aa_compose(const float* a1, const float* a2, float* out) {  // axis_angle_op, scrambler.py:19-28
+    float R1[9], R2[9], Rc[9];
+    rodrigues(a1[0], a1[1], a1[2], R1);
+    rodrigues(a2[0], a2[1], a2[2], R2);
+    mat3_mul(R1, R2, Rc);
+    rotmat_to_aa(Rc, out);
+}
+
+__device__ __forceinline__ void normalize3(float* v) {
+    float n = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    v[0] /= n; v[1] /= n; v[2] /= n;
+}
+
+// one thread per sample: axes (15 small products), then 4 splay + 14 bend + 2 thumb compositions in the reference's
+// order.  bend[B,14] holds the per-joint bend angles of chain joints (1..12, 14, 15) -- for random_2 the host expands
+// its 5 per-finger draws with the interlink coefficients (scrambler.py:134-170), for random_3 they are the 14 draws.
+__global__ void scramble_axis_kernel(int batch, const float* __restrict__ pose, const float* __restrict__ joints,
+                                     const float* __restrict__ transf, const float* __restrict__ splay,
+                                     const float* __restrict__ bend, const float* __restrict__ thumb,
+                                     float* __restrict__ pose_out, float* __restrict__ axes_out) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const float* J = joints + (size_t)b * 63;
+    const float* T = transf + (size_t)b * 256;
+    float hp[48];
+#pragma unroll 1
+    for (int i = 0; i < 48; ++i) hp[i] = pose[(size_t)b * 48 + i];
+    const int splay_joint[4] = {1, 4, 7, 10};
+#pragma unroll 1
+    for (int i = 0; i < 15; ++i) {
+        int j = kAxisJoint[i];
+        float d[3] = {J[3 * j] - J[3 * j + 3], J[3 * j + 1] - J[3 * j + 4], J[3 * j + 2] - J[3 * j + 5]};
+        const float* G = T + 16 * (i + 1);  // transforms_abs[1 + i], rotation block transposed
+        float bax[3] = {G[0] * d[0] + G[4] * d[1] + G[8] * d[2], G[1] * d[0] + G[5] * d[1] + G[9] * d[2],
+                        G[2] * d[0] + G[6] * d[1] + G[10] * d[2]};
+        float up[3] = {i < 12 ? 0.f : 1.f, 1.f, i < 12 ? 0.f : 1.f};
+        float l[3] = {bax[1] * up[2] - bax[2] * up[1], bax[2] * up[0] - bax[0] * up[2], bax[0] * up[1] - bax[1] * up[0]};
+        float u[3] = {l[1] * bax[2] - l[2] * bax[1], l[2] * bax[0] - l[0] * bax[2], l[0] * bax[1] - l[1] * bax[0]};
+        normalize3(bax); normalize3(u); normalize3(l);
+        if (axes_out) {
+            float* ao = axes_out + ((size_t)b * 15 + i) * 9;
+            ao[0] = bax[0]; ao[1] = bax[1]; ao[2] = bax[2]; ao[3] = u[0]; ao[4] = u[1]; ao[5] = u[2];
+            ao[6] = l[0]; ao[7] = l[1]; ao[8] = l[2];
+        }
+        const int jc = i + 1;  // chain joint this axis belongs to
+        float* h = hp + 3 * jc;
+        if (jc == 13) {  // thumb base: bend about l, then splay about u, both pre-multiplied (scrambler.py:172-181)
+            float t0 = thumb[(size_t)b * 2], t1 = thumb[(size_t)b * 2 + 1];
+            float ab_[3] = {l[0] * t0, l[1] * t0, l[2] * t0}, as_[3] = {u[0] * t1, u[1] * t1, u[2] * t1}, tmp[3];
+            aa_compose(ab_, h, tmp);
+            aa_compose(as_, tmp, h);
+            continue;
+        }
+        if (jc == splay_joint[0] || jc == splay_joint[1] || jc == splay_joint[2] || jc == splay_joint[3]) {
+            float s = splay[(size_t)b * 4 + (jc - 1) / 3];  // post-multiplied: R(pose) R(splay)  (scrambler.py:124-128)
+            float as_[3] = {u[0] * s, u[1] * s, u[2] * s}, tmp[3];
+            aa_compose(h, as_, tmp);
+            h[0] = tmp[0]; h[1] = tmp[1]; h[2] = tmp[2];
+        }
+        float g = bend[(size_t)b * 14 + (jc < 13 ? jc - 1 : jc - 2)];  // pre-multiplied: R(bend) R(pose)
+        float ab_[3] = {l[0] * g, l[1] * g, l[2] * g}, tmp[3];
+        aa_compose(ab_, h, tmp);
+        h[0] = tmp[0]; h[1] = tmp[1]; h[2] = tmp[2];
+    }
+#pragma unroll 1
+    for (int i = 0; i < 48; ++i) pose_out[(size_t)b * 48 + i] = hp[i];
+}
+
+}  // namespace ab
+
+// ------------------------------------------------------------------------------------------------------- C ABI
+extern "C" int ab_chamfer_nn(int batch, int n_x, const float* x, int n_y, const float* y_points, const int32_t* obj_id,
+                             const float* rot, int rot_stride, const float* scale, const float* shift, float* dist,
+                             int64_t dist_stride, int32_t* idx, void* stream) {
+    AB_REQUIRE(batch >= 0 && n_x >= 0 && n_y >= 0, "negative size");
+    if (batch == 0 || n_x == 0) return AB_OK;
+    AB_REQUIRE(n_y > 0, "empty target cloud: the nearest neighbour is undefined");
+    AB_REQUIRE(batch <= 65535, "batch > 65535: split the call");
+    AB_REQUIRE(x && y_points && dist, "null pointer");
+    AB_REQUIRE(rot == nullptr || rot_stride == 9 || rot_stride == 16, "rot_stride must be 9 (3x3) or 16 (4x4 pose)");
+    AB_REQUIRE((scale == nullptr) == (shift == nullptr), "scale and shift go together");
+    AB_REQUIRE(dist_stride >= n_x, "dist_stride < n_x");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(ab::cdiv(n_x, ab::kNnThreads * ab::kNnQ), batch);
+    {
+        ab::StageTimer tm(AB_STAGE_CHAMFER, st);
+        ab::chamfer_nn_kernel<<<grid, ab::kNnThreads, 0, st>>>(n_x, x, n_y, y_points, obj_id, rot, rot_stride, scale,
+                                                              shift, dist, (long long)dist_stride, idx);
+    }
+    ab::count_launch();
+    return ab::check_launch("chamfer_nn_kernel");
+}
+
+extern "C" int ab_linear_f32(int M, int N, int K, const float* x, int64_t ldx, const float* W, int64_t ldw,
+                             const float* bias, const float* residual, int64_t ldr, int act, float slope, float* y,
+                             int64_t ldy, void* stream) {
+    AB_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative size");
+    if (M == 0 || N == 0) return AB_OK;
+    AB_REQUIRE(x && W && y, "null pointer");
+    AB_REQUIRE(ldx >= K && ldw >= K && ldy >= N && (!residual || ldr >= N), "leading dimension too small");
+    AB_REQUIRE(act == 0 || act == 1, "act: 0 none, 1 leaky relu");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(ab::cdiv(N, ab::kLinBN), ab::cdiv(M, ab::kLinBM));
+    AB_REQUIRE(grid.y <= 65535, "M too large: split the call");
+    {
+        ab::StageTimer tm(AB_STAGE_LINEAR_F32, st);
+        ab::linear_f32_kernel<<<grid, ab::kLinThreads, 0, st>>>(M, N, K, x, (long long)ldx, W, (long long)ldw, bias,
+                                                               residual, (long long)ldr, act, slope, y, (long long)ldy);
+    }
+    ab::count_launch();
+    return ab::check_launch("linear_f32_kernel");
+}
+
+extern "C" int ab_refine_encode(int batch, const float* pose, const float* tsl, float* feat, int64_t ld, void* stream) {
+    AB_REQUIRE(batch >= 0, "negative batch");
+    if (batch == 0) return AB_OK;
+    AB_REQUIRE(pose && tsl && feat && ld >= 99, "null pointer / ld < 99");
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        ab::StageTimer tm(AB_STAGE_REFINE_MISC, st);
+        ab::refine_encode_kernel<<<ab::cdiv(batch * 16, 128), 128, 0, st>>>(batch, pose, tsl, feat, (long long)ld);
+    }
+    ab::count_launch();
+    return ab::check_launch("refine_encode_kernel");
+}
+
+extern "C" int ab_refine_decode(int batch, const float* feat, int64_t ld, const float* rigid, int rigid_stride,
+                                const float* offset, float* pose_out, float* tsl_out, float* post_rt, void* stream) {
+    AB_REQUIRE(batch >= 0, "negative batch");
+    if (batch == 0) return AB_OK;
+    AB_REQUIRE(feat && pose_out && ld >= 99, "null pointer / ld < 99");
+    AB_REQUIRE(rigid == nullptr || rigid_stride == 9 || rigid_stride == 16, "rigid_stride must be 9 or 16");
+    AB_REQUIRE(rigid != nullptr || offset == nullptr, "offset without rigid");
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        ab::StageTimer tm(AB_STAGE_REFINE_MISC, st);
+        ab::refine_decode_kernel<<<ab::cdiv(batch * 16, 128), 128, 0, st>>>(batch, feat, (long long)ld, rigid, rigid_stride,
+                                                                          offset, pose_out, tsl_out, post_rt);
+    }
+    ab::count_launch();
+    return ab::check_launch("refine_decode_kernel");
+}
+
+extern "C" int ab_scramble_anatomical(int batch, const float* pose, const float* joints, const float* transforms_abs,
+                                      const float* splay, const float* bend, const float* thumb, float* pose_out,
+                                      float* axes_out, void* stream) {
+    AB_REQUIRE(batch >= 0, "negative batch");
+    if (batch == 0) return AB_OK;
+    AB_REQUIRE(pose && joints && transforms_abs && splay && bend && thumb && pose_out, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        ab::StageTimer tm(AB_STAGE_REFINE_MISC, st);
+        ab::scramble_axis_kernel<<<ab::cdiv(batch, 64), 64, 0, st>>>(batch, pose, joints, transforms_abs, splay, bend,
+                                                                    thumb, pose_out, axes_out);
+    }
+    ab::count_launch();
+    return ab::check_launch("scramble_axis_kernel");
+}

@@ -66,6 +66,15 @@ EXPORTS = {
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_pose_generate_workspace_bytes": (C.c_uint64, [C.c_int]),
     "ab_pose_generate": (C.c_int, [C.POINTER(ManoModelStruct), C.c_int] + [C.c_void_p] * 13),
+    "ab_pose_prelude": (C.c_int, [C.POINTER(ManoModelStruct), C.c_int] + [C.c_void_p] * 14),
+    "ab_chamfer_nn": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ab_linear_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ab_refine_encode": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ab_refine_decode": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_scramble_anatomical": (C.c_int, [C.c_int] + [C.c_void_p] * 9),
     "ab_render_workspace_bytes": (C.c_uint64, [C.POINTER(SceneStruct), C.POINTER(CameraStruct), C.c_int]),
     "ab_render_batch": (C.c_int, [C.POINTER(SceneStruct), C.POINTER(CameraStruct), C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_void_p, c_i32_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -163,7 +172,8 @@ def launch_count() -> int:
 STAGES = {0: "raster_vertex_kernel", 1: "raster_triangle_kernel", 2: "raster_resolve_kernel", 3: "mano_lbs_kernel",
           4: "posegen_prelude_kernel", 5: "ccv_cdf+draw_kernels", 6: "view_kernel", 7: "gemm_bf16_tn_kernel",
           8: "im2col_kernel", 9: "elementwise_kernels", 10: "head_decode_kernel", 11: "gemm_bf16_tn_kernel<im2col TMA>", 12: "wgrad_bf16_kernel", 13: "train_elementwise_kernels", 14: "optimizer_kernels", 15: "bn_apply_kernel", 16: "bn_bwd_reduce_kernel",
-          17: "bn_bwd_apply_kernel", 18: "bn_finalize_kernel", 19: "augment_kernels"}
+          17: "bn_bwd_apply_kernel", 18: "bn_finalize_kernel", 19: "augment_kernels",
+          20: "chamfer_nn_kernel", 21: "linear_f32_kernel", 22: "refine_misc_kernels"}
 
 
 def profile_enable(on: bool) -> None:

@@ -76,6 +76,18 @@ class ManoLayer(nn.Module):
         return jt[None] + betas.to(jt.dtype) @ self.k_j_shapedirs[:3].T
 
     @torch.no_grad()
+    def lbs_into(self, pose: torch.Tensor, betas: Optional[torch.Tensor], post_rt: Optional[torch.Tensor],
+                 verts: torch.Tensor, joints: torch.Tensor, transf: Optional[torch.Tensor] = None) -> None:
+        """One ab_mano_forward launch into caller-owned buffers; post_rt [B,12] = rigid map fused into the store
+        (x' = R x + t).  Used by the refiner, whose MANO forwards are each followed by a translation / rigid map."""
+        B, dev = pose.shape[0], pose.device
+        m = self.model_struct()
+        with torch.cuda.device(dev):
+            rc = lib.load().ab_mano_forward(C.byref(m), B, lib.ptr(pose), lib.ptr(betas), lib.ptr(post_rt), -1,
+                                            lib.ptr(verts), lib.ptr(joints), lib.ptr(transf), lib.stream_ptr(dev))
+        lib.check(rc, "ab_mano_forward")
+
+    @torch.no_grad()
     def forward(self, pose_coeffs: torch.Tensor, betas: Optional[torch.Tensor] = None, **kwargs) -> MANOOutput:
         lib.require_cuda(pose_coeffs, "pose_coeffs")
         if pose_coeffs.dim() != 2 or pose_coeffs.shape[1] != 48:

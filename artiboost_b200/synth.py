@@ -12,8 +12,8 @@ import numpy as np
 import torch
 
 from . import assets
-from .artiboost import (GraspEngine, NullRefine, ObjEngine, OVGSet, PreProcessorPoseGenerator, RandomScrambler,
-                        Renderer, ViewEngine, make_mesh)
+from .artiboost import (GraspEngine, HORefiner, NullRefine, ObjEngine, OVGSet, PreProcessorPoseGenerator, Renderer,
+                        Scrambler, ViewEngine, make_mesh)
 from .artiboost.renderer import PYRENDER_EXTRINSIC, PointLight
 
 # config/ho3dv2_clasbased_jlol_artiboost2.yaml:6-20,42-45 (HO3D CCV space), render camera rescaled to 256^2 (same FoV
@@ -22,6 +22,10 @@ DEFAULT_CFG = {
     "VIEW": {"PERSP_U_BINS": 12, "PERSP_THETA_BINS": 24, "CAMERA_Z_RANGE": [0.45, 0.55]},
     "GRASP_NUM": 50,
     "SCRAMBLER": {"TYPE": "random", "HAND_TSL_SIGMA": 0.01, "HAND_POSE_SIGMA": 0.1},
+    # the shipped config's refiner is "hand_obj" (yaml:47-50); its GrabNet weights are a licensed asset, so the synthetic
+    # default stays "null".  {"TYPE": "hand_obj", "PRETRAINED": path or None, "ITERS": 3} builds HORefiner (randomly
+    # initialised when PRETRAINED is None -- same arithmetic, meaningless refinement).
+    "REFINER": {"TYPE": "null"},
     "RENDER_SIZE": [256, 256],
     "CAM_PARAM": {"FX": 217.5, "FY": 217.5, "CX": 128.0, "CY": 128.0},
 }
@@ -50,8 +54,16 @@ class SynthPipeline:
         self.occurence_map = torch.zeros(shape, dtype=torch.bool, device=dev)
         self.ovg_set = OVGSet(self.obj_engine, self.grasp_engine, self.view_engine, 0, 0, self.grasp_engine.n_grasp,
                               torch.zeros(shape, dtype=torch.bool), device=dev, generator=self.generator)
-        self.refiner = NullRefine(mano_model=self.mano_model).to(dev)
-        self.scrambler = RandomScrambler(cfg["SCRAMBLER"])
+        rcfg = cfg.get("REFINER", {"TYPE": "null"})
+        if rcfg["TYPE"] == "hand_obj":
+            torch.manual_seed(seed)
+            self.refiner = HORefiner(rcfg, mano_model=self.mano_model)
+            np.random.seed(seed)  # resample_obj draws from np.random (refiner.py:180)
+            self.refiner.setup(self.obj_engine.obj_trimeshes_mapping)
+            self.refiner = self.refiner.to(dev)
+        else:
+            self.refiner = NullRefine(mano_model=self.mano_model).to(dev)
+        self.scrambler = Scrambler.build(cfg["SCRAMBLER"]["TYPE"], cfg["SCRAMBLER"])
         self.pose_generator = PreProcessorPoseGenerator(self.refiner, self.scrambler, self.refiner.refine_net.mano_layer,
                                                         self.refiner.refine_net.mano_layer).to(dev)
         self.pose_generator.generator = self.generator

@@ -66,6 +66,9 @@ AB_API uint64_t ab_launch_count(void);
 #define AB_STAGE_BN_BWD_APPLY 17
 #define AB_STAGE_BN_FINALIZE 18
 #define AB_STAGE_AUGMENT 19
+#define AB_STAGE_CHAMFER 20
+#define AB_STAGE_LINEAR_F32 21
+#define AB_STAGE_REFINE_MISC 22
 #define AB_STAGE_COUNT 24
 AB_API int ab_profile_enable(int on);
 AB_API int ab_profile_collect(double* ms_per_stage, int64_t* launches_per_stage, int n_stages);
@@ -117,6 +120,55 @@ AB_API int ab_pose_generate(const ab_mano_model* model, int batch, const float* 
                      const float* hand_tsl, const float* persp_rotmat, const float* camera_free_transf,
                      const float* z_offset, const float* noise_tsl, const float* noise_angle, float* final_obj_pose,
                      float* final_hand_verts, float* final_joints, void* ws, void* stream);
+
+/* The per-sample prelude of the pose generator on its own (preprocessor.py:20-74: object pose, view-frame hand pose,
+ * translation fix-up, optional `random` scrambling), for the refiners / scramblers that are not fused into
+ * ab_pose_generate.  Outputs final_obj_pose [B,16], pose_out [B,48] (scrambler_res["hand_pose"]), tsl_out [B,3]
+ * (scrambler_res["hand_tsl"]), cam_sys_offset [B,3] (preprocessor.py:38) and post_rt [B,12], the rigid map
+ * x' = Rf (x + tsl + cam_sys_offset) of preprocessor.py:84-88 in ab_mano_forward's post_rt layout.             */
+AB_API int ab_pose_prelude(const ab_mano_model* model, int batch, const float* hand_pose, const float* hand_shape,
+                    const float* hand_tsl, const float* persp_rotmat, const float* camera_free_transf,
+                    const float* z_offset, const float* noise_tsl, const float* noise_angle, float* final_obj_pose,
+                    float* pose_out, float* tsl_out, float* cam_sys_offset, float* post_rt, void* stream);
+
+/* ---------------------------------------------------------------------------- hand-object refiner (REFINER hand_obj)
+ * Replaces point2point_signed (anakin/artiboost/refiner.py:21-85) as HORefiner / _RefineNet call it (:193,:264):
+ * for every x[b,i] the nearest point of the sample's object cloud and the Euclidean distance to it (the third-party
+ * chamfer_distance kernel + gather + norm of the reference; first minimum wins).  The cloud of sample b is
+ * y_points[obj_id[b]] (obj_id NULL: y_points[b]), [*, n_y, 3]; rot (NULL or [B,rot_stride], rot_stride 9 = 3x3,
+ * 16 = the rotation block of a 4x4 pose) rotates it first: y = R o, the `verts_object` of refiner.py:190-191, never
+ * materialised.  Output dist[b*dist_stride + i] = |x - y_nn| (x scale[i] + shift[i] when given: the eval-mode
+ * BatchNorm1d(778) of refiner.py:266 folded in), idx [B,n_x] (may be NULL) = index of the nearest point.          */
+AB_API int ab_chamfer_nn(int batch, int n_x, const float* x, int n_y, const float* y_points, const int32_t* obj_id,
+                  const float* rot, int rot_stride, const float* scale, const float* shift, float* dist,
+                  int64_t dist_stride, int32_t* idx, void* stream);
+
+/* fp32 linear layer of the RefineNet MLP (nn.Linear + folded BatchNorm1d + LeakyReLU + ResBlock skip,
+ * refiner.py:288-319): y[M,N] = act(x[M,K] W[N,K]^T + bias[N] (+ residual[M,N])), act 0 none / 1 leaky relu(slope).
+ * Leading dimensions in elements; y may alias residual.                                                          */
+AB_API int ab_linear_f32(int M, int N, int K, const float* x, int64_t ldx, const float* W, int64_t ldw, const float* bias,
+                  const float* residual, int64_t ldr, int act, float slope, float* y, int64_t ldy, void* stream);
+
+/* refiner.py:253-257: feat[b, 0:96] = first two columns of the 16 joint rotation matrices of pose [B,48] (row-major
+ * 3x2 per joint), feat[b, 96:99] = tsl [B,3].  ld = row stride of feat in floats.                                 */
+AB_API int ab_refine_encode(int batch, const float* pose, const float* tsl, float* feat, int64_t ld, void* stream);
+
+/* parms_decode (refiner.py:88-107): CRot2rotmat + rotmat_to_aa of feat[b, 0:96] -> pose_out [B,48]; feat[b, 96:99] ->
+ * tsl_out [B,3] (may be NULL); post_rt [B,12] (may be NULL) = the rigid map of the LBS launch that follows:
+ * x' = x + t when rigid is NULL, x' = R (x + t + offset) otherwise (rigid [B,rigid_stride], 9 or 16; offset [B,3]
+ * or NULL) -- preprocessor.py:84-88 fused into the refiner's last MANO forward.                                   */
+AB_API int ab_refine_decode(int batch, const float* feat, int64_t ld, const float* rigid, int rigid_stride,
+                     const float* offset, float* pose_out, float* tsl_out, float* post_rt, void* stream);
+
+/* RandomScrambler2 / RandomScrambler3 (anakin/artiboost/scrambler.py:84-260) over manotorch's AxisLayer: per-joint
+ * back / up / left axes from joints [B,21,3] and transforms_abs [B,16,4,4] (MANO chain order), then
+ * pose[j] <- aa(R(pose[j]) R(u * splay)) for the four knuckles, pose[j] <- aa(R(l * bend) R(pose[j])) for the 14
+ * bending joints, and the thumb base about l then u.  splay [B,4], bend [B,14] (chain joints 1..12, 14, 15; the host
+ * expands random_2's five per-finger draws with the interlink coefficients 1 / 1.1 / 0.9), thumb [B,2], all
+ * pre-scaled N(0, sigma) draws.  pose_out [B,48]; axes_out [B,15,3,3] (b,u,l rows) or NULL.                       */
+AB_API int ab_scramble_anatomical(int batch, const float* pose, const float* joints, const float* transforms_abs,
+                           const float* splay, const float* bend, const float* thumb, float* pose_out, float* axes_out,
+                           void* stream);
 
 /* --------------------------------------------------------------------------------------------------- rasteriser
  * Replaces Renderer.__call__ (anakin/utils/renderer.py:101-123) over pyrender's OffscreenRenderer

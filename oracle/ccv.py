@@ -95,8 +95,12 @@ def random_scrambler(hand_pose, hand_tsl, n_tsl, n_angle):
 
 
 def pose_generator(mano_model, hand_pose, hand_shape, hand_tsl, persp_rotmat, camera_free_transf, z_offset,
-                   n_tsl=None, n_angle=None):
-    """-> dict(final_obj_pose [B,4,4], final_hand_verts [B,778,3], final_joints [B,21,3], hand_pose, hand_tsl)."""
+                   n_tsl=None, n_angle=None, scrambler=None, refiner=None):
+    """-> dict(final_obj_pose [B,4,4], final_hand_verts [B,778,3], final_joints [B,21,3], hand_pose, hand_tsl).
+
+    scrambler: optional callable(feed dict of preprocessor.py:66-73) -> (hand_pose, hand_tsl), used instead of the
+    `random` scrambler (anatomical scramblers, oracle/refine.py); refiner: optional callable(hand_pose, hand_tsl,
+    obj_rot) -> dict(hand_verts, joints) used instead of NullRefine (preprocessor.py:76-82)."""
     f32 = np.float32
     hand_pose, hand_shape, hand_tsl = (np.asarray(x, f32) for x in (hand_pose, hand_shape, hand_tsl))
     Rv = np.asarray(persp_rotmat, f32)
@@ -122,11 +126,23 @@ def pose_generator(mano_model, hand_pose, hand_shape, hand_tsl, persp_rotmat, ca
     off0 = c - np.einsum("bij,bj->bi", R0, c)
     off1 = c - np.einsum("bij,bj->bi", R1, c)
     new_tsl = np.einsum("bij,bj->bi", Rv_inv, off0 + hand_tsl) - off1
-    if n_tsl is not None:
+    if scrambler is not None:
+        out2 = layer(new_pose, hand_shape)  # MANO forward #2, for hand_transf (preprocessor.py:62-63)
+        feed = {"hand_pose": new_pose, "hand_tsl": new_tsl, "hand_transf": out2.transforms_abs,
+                "joints": np.einsum("bij,bvj->bvi", Rv_inv, joints).astype(f32),
+                "hand_verts": np.einsum("bij,bvj->bvi", Rv_inv, out.verts + hand_tsl[:, None]).astype(f32)}
+        new_pose, new_tsl = scrambler(feed)
+    elif n_tsl is not None:
         new_pose, new_tsl = random_scrambler(new_pose, new_tsl, n_tsl, n_angle)
-    ref = layer(new_pose)  # NullRefine: betas=None (refiner.py:138)
-    verts = ref.verts + new_tsl[:, None] + cam_sys_offset[:, None]
-    jts = ref.joints + new_tsl[:, None] + cam_sys_offset[:, None]
+    if refiner is not None:
+        r = refiner(new_pose, new_tsl, obj_pose[:, :3, :3])
+        verts = r["hand_verts"] + cam_sys_offset[:, None]
+        jts = r["joints"] + cam_sys_offset[:, None]
+        new_pose, new_tsl = r["hand_pose"], r["hand_tsl"]
+    else:
+        ref = layer(new_pose)  # NullRefine: betas=None (refiner.py:138)
+        verts = ref.verts + new_tsl[:, None] + cam_sys_offset[:, None]
+        jts = ref.joints + new_tsl[:, None] + cam_sys_offset[:, None]
     Rf = free[:, :3, :3]
     return {
         "final_obj_pose": obj_pose.astype(f32),

@@ -18,8 +18,10 @@ shim) on the synthetic MANO pickle: see tests/golden/make_golden.py.
 API surface mirrors what the hot path reads from manotorch's MANOOutput (grasp_engine.py:137-145):
 verts, joints, center_idx, center_joint, full_poses, betas, transforms_abs.  `transforms_abs` ordering and
 `get_rotation_center` are [recalled] from manotorch (not verifiable here): transforms are returned in the
-MANO chain order 0..15 re-indexed to the 21-joint order without tips
-[0,13,14,15,1,2,3,4,5,6,10,11,12,7,8,9]; rotation centre = root joint of the shaped template.
+MANO chain order 0..15 (wrist, index, middle, little, ring, thumb) -- the order its consumers in the reference
+require: manotorch's AxisLayer pairs transforms_abs[:, 1:] with the chain-ordered keypoint list
+[5,6,7, 9,10,11, 17,18,19, 13,14,15, 1,2,3] and anakin/artiboost/scrambler.py:124-181 indexes the resulting axes with
+chain-order pose indices; rotation centre = root joint of the shaped template.
 """
 from collections import namedtuple
 
@@ -28,7 +30,7 @@ import numpy as np
 PARENTS = [-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14]
 TIP_VERTS = [745, 317, 444, 556, 673]
 JOINT_REORDER = [0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20]
-TRANSF_REORDER = [0, 13, 14, 15, 1, 2, 3, 4, 5, 6, 10, 11, 12, 7, 8, 9]
+TRANSF_REORDER = list(range(16))
 
 MANOOutput = namedtuple("MANOOutput", ["verts", "joints", "center_idx", "center_joint", "full_poses", "betas",
                                        "transforms_abs"])
