@@ -19,6 +19,17 @@ class ObjEngine:
         self.corners_can = torch.from_numpy(
             np.stack([np.asarray(objects[k]["corners_can"], np.float32) for k in self._obj_names])).to(device)
 
+    @staticmethod
+    def build(dataset_type: str, query_obj: List[str], device="cuda", **paths):
+        """object_engine.py:21-27 on the real assets (artiboost_b200/assets_real.py); `paths` override the reference's
+        hard-coded locations (obj_root=..., corner_file=...)."""
+        from .. import assets_real
+        if dataset_type == "HO3D":
+            return ObjEngine(assets_real.load_ho3d_objects(query_obj, **paths), query_obj, device=device)
+        elif dataset_type == "DexYCB":
+            return ObjEngine(assets_real.load_dexycb_objects(query_obj, **paths), query_obj, device=device)
+        raise NotImplementedError(dataset_type)
+
     @property
     def obj_names(self):
         return self._obj_names

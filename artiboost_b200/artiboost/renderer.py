@@ -106,14 +106,16 @@ class Renderer:
                 xs = (np.arange(bw) * a.shape[1]) // bw
                 bgs.append(a[ys][:, xs])
             self.backgrounds = up(np.stack(bgs))
+            # the kernel reads an RGBX copy: one aligned 32-bit load per background pixel instead of three byte loads
+            self._bgs4 = torch.cat([self.backgrounds, torch.zeros_like(self.backgrounds[..., :1])], -1).contiguous()
         self.scene = lib.SceneStruct(
             len(self.obj_names), self.obj_verts.data_ptr(), self.obj_faces.data_ptr(), self.obj_colors.data_ptr(),
             C.cast(self._voff, lib.c_i32_p), C.cast(self._foff, lib.c_i32_p), n_hv, hf.shape[0], self.n_hand_tex,
             self.hand_faces.data_ptr(), self.hand_colors.data_ptr(),
-            None if self.backgrounds is None else self.backgrounds.data_ptr(),
+            None if self.backgrounds is None else self._bgs4.data_ptr(),
             0 if self.backgrounds is None else self.backgrounds.shape[0],
             0 if self.backgrounds is None else self.backgrounds.shape[1],
-            0 if self.backgrounds is None else self.backgrounds.shape[2])
+            0 if self.backgrounds is None else self.backgrounds.shape[2], 4)
         self.camera = lib.CameraStruct(self.width, self.height, float(cam_intr[0, 0]), float(cam_intr[1, 1]),
                                        float(cam_intr[0, 2]), float(cam_intr[1, 2]), float(znear), int(cull_backface),
                                        0.8, float(diffuse), 128, 128, 128)  # ambient 0.8, bg 0.5 (renderer.py:77)

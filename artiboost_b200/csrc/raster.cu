@@ -19,12 +19,28 @@
 //                              restores the key buffer to "empty" where it was hit.
 // HBM traffic per view is the output (9 B / pixel) plus the 9.4 KB of per-view inputs; scratch never needs to
 // leave L2 when `chunk` is sized so (chunk * (8*W*H + 16*verts)) stays well under the 126 MB L2.
+#include <stdlib.h>
+
+#include <mutex>
+
 #include "common.cuh"
 
 namespace ab {
 
 constexpr int kMaxObjects = 64;
 constexpr unsigned long long kEmptyKey = ~0ull;
+
+// floor(n / d) for n < 2^30 as (n * m) >> s with m = ceil(2^s / d), s = 31 + ceil(log2 d): m < 2^32, and with
+// e = m d - 2^s in [0, d) the quotient is exact because n e < 2^30 2^ceil(log2 d) <= 2^s.
+static void make_fastdiv(unsigned d, unsigned* m, int* s) {
+    int L = 0;
+    while ((1ull << L) < d) ++L;
+    *s = 31 + L;
+    *m = (unsigned)(((1ull << *s) + d - 1) / d);
+}
+__device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned m, int s) {
+    return (unsigned)(((unsigned long long)n * m) >> s);
+}
 
 struct RasterParams {
     // scene
@@ -34,7 +50,9 @@ struct RasterParams {
     const int4* hand_faces;
     const uchar4* hand_colors;
     const uint8_t* bgs;
-    int n_obj, n_hv, n_hf, n_tex, n_bg, bg_h, bg_w;
+    int n_obj, n_hv, n_hf, n_tex, n_bg, bg_h, bg_w, bg_ch;
+    unsigned div_w_m, div_2w_m, div_2h_m;  // exact division by W, 2W, 2H as multiply + shift (FastDiv below)
+    int div_w_s, div_2w_s, div_2h_s;
     int max_ov, max_of;  // launch sizing
     // camera
     int W, H;
@@ -375,72 +393,98 @@ __device__ __forceinline__ PixelOut shade_pixel(const RasterParams& P, int view,
 // appended to a CTA-local list.  Phase 2: the CTA's covered pixels are dealt one per thread, so the long shading path runs
 // on fully populated warps instead of on the few lanes of each row segment that touch the hand or the object
 // (~9 % of the frame); their outputs overwrite the placeholders of phase 1 after the barrier.
-template <int PX>
+template <int PX, int G>
 __global__ void __launch_bounds__(256)
 raster_resolve_kernel(const __grid_constant__ RasterParams P) {
-    __shared__ unsigned hit_prim[256 * PX];
-    __shared__ unsigned short hit_px[256 * PX];
+    __shared__ unsigned hit_prim[256 * PX * G];
+    __shared__ unsigned short hit_px[256 * PX * G];
     __shared__ int n_hit;
     const int view = blockIdx.y;
-    const int cta_p0 = blockIdx.x * 256 * PX;
-    const int p0 = cta_p0 + threadIdx.x * PX;
+    const int cta_p0 = blockIdx.x * 256 * PX * G;
     const int npx = P.W * P.H;
     if (threadIdx.x == 0) n_hit = 0;
     __syncthreads();
     unsigned long long* kbase = P.keys + (size_t)view * npx;
     const size_t obase = (size_t)view * npx;
-    if (p0 < npx) {
-        unsigned long long k[PX];
-        if constexpr (PX == 4) {
-            const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(kbase + p0), k23 = *reinterpret_cast<const ulonglong2*>(kbase + p0 + 2);
-            k[0] = k01.x; k[1] = k01.y; k[2] = k23.x; k[3] = k23.y;
-        } else {
-            k[0] = kbase[p0];
+    {
+        // G independent groups of PX pixels per thread (group g of a warp = 32 * PX consecutive pixels): all key loads
+        // first, then all background fetches, then the stores -- G * (PX / 2 + PX) loads in flight per thread
+        unsigned long long k[G][PX];
+        uchar4 c[G][PX];
+        int p0[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            p0[g] = cta_p0 + (g * 256 + threadIdx.x) * PX;
+#pragma unroll
+            for (int j = 0; j < PX; ++j) k[g][j] = kEmptyKey;
+            if (p0[g] < npx) {
+                if constexpr (PX == 4) {
+                    const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(kbase + p0[g]),
+                                     k23 = *reinterpret_cast<const ulonglong2*>(kbase + p0[g] + 2);
+                    k[g][0] = k01.x; k[g][1] = k01.y; k[g][2] = k23.x; k[g][3] = k23.y;
+                } else {
+                    k[g][0] = kbase[p0[g]];
+                }
+            }
         }
-        const int py = p0 / P.W, px0 = p0 - py * P.W;
         const int32_t* sel = P.bg_sel ? P.bg_sel + 5 * (size_t)view : nullptr;
         const bool has_bg = sel && P.bgs && sel[0] >= 0;
-        const uint8_t* bg_row = nullptr;
-        unsigned bg_x0 = 0, bg_cw = 0;
-        if (has_bg) {
-            const unsigned sy = (unsigned)sel[2] + ((unsigned)(2 * py + 1) * (unsigned)sel[4]) / (unsigned)(2 * P.H);
-            bg_row = P.bgs + 3 * (((size_t)sel[0] * P.bg_h + sy) * P.bg_w);
-            bg_x0 = (unsigned)sel[1];
-            bg_cw = (unsigned)sel[3];
-        }
-        uchar4 c[PX];
+        // background texels are fetched for every pixel, covered or not (phase 2 overwrites the covered ones): the fetch
+        // does not wait for the key loads, so the L2 round trips of a thread overlap instead of chaining
 #pragma unroll
-        for (int j = 0; j < PX; ++j) {
-            c[j] = make_uchar4((uint8_t)P.bg_r, (uint8_t)P.bg_g, (uint8_t)P.bg_b, 0);
-            if (k[j] == kEmptyKey) {
-                if (has_bg) {
-                    const unsigned sx = bg_x0 + ((unsigned)(2 * (px0 + j) + 1) * bg_cw) / (unsigned)(2 * P.W);
-                    const uint8_t* src = bg_row + 3 * (size_t)sx;
-                    c[j] = make_uchar4(src[0], src[1], src[2], 0);
+        for (int g = 0; g < G; ++g) {
+#pragma unroll
+            for (int j = 0; j < PX; ++j) c[g][j] = make_uchar4((uint8_t)P.bg_r, (uint8_t)P.bg_g, (uint8_t)P.bg_b, 0);
+            if (has_bg && p0[g] < npx) {
+                const int py = (int)fastdiv((unsigned)p0[g], P.div_w_m, P.div_w_s), px0 = p0[g] - py * P.W;
+                const unsigned sy = (unsigned)sel[2] + fastdiv((unsigned)(2 * py + 1) * (unsigned)sel[4], P.div_2h_m, P.div_2h_s);
+                const uint8_t* bg_row = P.bgs + (size_t)P.bg_ch * (((size_t)sel[0] * P.bg_h + sy) * P.bg_w);
+                const unsigned bg_x0 = (unsigned)sel[1], bg_cw = (unsigned)sel[3];
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
+                    const unsigned sx = bg_x0 + fastdiv((unsigned)(2 * (px0 + j) + 1) * bg_cw, P.div_2w_m, P.div_2w_s);
+                    if (P.bg_ch == 4) {
+                        c[g][j] = __ldg(reinterpret_cast<const uchar4*>(bg_row) + sx);
+                        c[g][j].w = 0;
+                    } else {
+                        const uint8_t* src = bg_row + 3 * (size_t)sx;
+                        c[g][j] = make_uchar4(src[0], src[1], src[2], 0);
+                    }
                 }
-            } else {
-                const int slot = atomicAdd(&n_hit, 1);
-                hit_px[slot] = (unsigned short)(threadIdx.x * PX + j);
-                hit_prim[slot] = (unsigned)(k[j] & 0xffffffffull);
             }
         }
-        const size_t o = obase + p0;
-        if constexpr (PX == 4) {
-            if (P.rgba) {
-                uint4 v;
-                v.x = *reinterpret_cast<unsigned*>(&c[0]); v.y = *reinterpret_cast<unsigned*>(&c[1]);
-                v.z = *reinterpret_cast<unsigned*>(&c[2]); v.w = *reinterpret_cast<unsigned*>(&c[3]);
-                *reinterpret_cast<uint4*>(P.rgba + 4 * o) = v;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (p0[g] >= npx) continue;
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                if (k[g][j] != kEmptyKey) {
+                    const int slot = atomicAdd(&n_hit, 1);
+                    hit_px[slot] = (unsigned short)((g * 256 + threadIdx.x) * PX + j);
+                    hit_prim[slot] = (unsigned)(k[g][j] & 0xffffffffull);
+                }
             }
-            if (P.depth) *reinterpret_cast<float4*>(P.depth + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (P.seg) *reinterpret_cast<unsigned*>(P.seg + o) = 0u;
-        } else {
-            if (P.rgba) reinterpret_cast<uchar4*>(P.rgba)[o] = c[0];
-            if (P.depth) P.depth[o] = 0.0f;
-            if (P.seg) P.seg[o] = 0;
+            const size_t o = obase + p0[g];
+            if constexpr (PX == 4) {
+                if (P.rgba) {
+                    uint4 v;
+                    v.x = *reinterpret_cast<unsigned*>(&c[g][0]); v.y = *reinterpret_cast<unsigned*>(&c[g][1]);
+                    v.z = *reinterpret_cast<unsigned*>(&c[g][2]); v.w = *reinterpret_cast<unsigned*>(&c[g][3]);
+                    *reinterpret_cast<uint4*>(P.rgba + 4 * o) = v;
+                }
+                if (P.depth) *reinterpret_cast<float4*>(P.depth + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (P.seg) *reinterpret_cast<unsigned*>(P.seg + o) = 0u;
+            } else {
+                if (P.rgba) reinterpret_cast<uchar4*>(P.rgba)[o] = c[g][0];
+                if (P.depth) P.depth[o] = 0.0f;
+                if (P.seg) P.seg[o] = 0;
+            }
         }
     }
     __syncthreads();
+    // Phase 2: the CTA's covered pixels, one per thread, so the long shading path runs on fully populated warps; it
+    // overlaps with the streaming phase 1 of the other CTAs resident on the SM (measured: a separate grid-wide shading
+    // kernel over a compacted list is slower in total, 19 + 18 us against 30 us per 64 views).
     const int total = n_hit;
     if (total == 0) return;
     const int oid = P.obj_id[view];
@@ -451,7 +495,7 @@ raster_resolve_kernel(const __grid_constant__ RasterParams P) {
     }
     for (int i = threadIdx.x; i < total; i += 256) {
         const int p = cta_p0 + hit_px[i];
-        const int py = p / P.W, px = p - py * P.W;
+        const int py = (int)fastdiv((unsigned)p, P.div_w_m, P.div_w_s), px = p - py * P.W;
         const PixelOut r = shade_pixel(P, view, oid, n_ov, n_of, px, py, hit_prim[i]);
         kbase[p] = kEmptyKey;  // leave the key buffer empty for the next chunk
         const size_t o = obase + p;
@@ -469,14 +513,39 @@ static int max_hand_obj_verts(const ab_scene* s) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Chunks alternate between the caller's stream and one library-owned auxiliary stream per device (each with its own
+// scratch set), so the set-up-bound triangle pass of one chunk shares the SMs with the write-bound resolve pass of the
+// other and the tails of the kernels overlap.  Fork / join is by events, so the call stays asynchronous and ordered on
+// the caller's stream (and capturable into a CUDA graph).
+constexpr int kMaxDevices = 16;
+constexpr int kMaxSets = 8;
+struct AuxStreams {
+    std::mutex mu;
+    cudaStream_t aux[kMaxDevices][kMaxSets] = {};
+    cudaEvent_t fork[kMaxDevices] = {}, join[kMaxDevices][kMaxSets] = {};
+};
+static AuxStreams g_aux;
+
+static int raster_sets() {  // chunks in flight (AB_RASTER_STREAMS overrides; 1 = everything on the caller's stream)
+    static const int n = [] {
+        const char* e = getenv("AB_RASTER_STREAMS");
+        const int v = e ? atoi(e) : 4;
+        return v < 1 ? 1 : (v > kMaxSets ? kMaxSets : v);
+    }();
+    return n;
+}
+
+static size_t scratch_set_bytes(int chunk, int npx, int pv_stride) {
+    return align_up((size_t)chunk * npx * 8, 256) + align_up((size_t)chunk * pv_stride * 16, 256);
+}
+
 }  // namespace ab
 
 extern "C" uint64_t ab_render_workspace_bytes(const ab_scene* scene, const ab_camera* cam, int chunk) {
     if (!scene || !cam || chunk <= 0 || cam->width <= 0 || cam->height <= 0) return 0;
     if (scene->n_obj > 0 && !scene->obj_vert_off_host) return 0;
-    const size_t keys = ab::align_up((size_t)chunk * cam->width * cam->height * 8, 256);
-    const size_t pv = (size_t)chunk * ab::align_up((size_t)ab::max_hand_obj_verts(scene) + scene->n_hand_verts, 8) * 16;
-    return keys + pv;
+    const int pv_stride = (int)ab::align_up((size_t)ab::max_hand_obj_verts(scene) + scene->n_hand_verts, 8);
+    return (size_t)ab::raster_sets() * ab::scratch_set_bytes(chunk, cam->width * cam->height, pv_stride);
 }
 
 extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int batch, int chunk,
@@ -510,6 +579,12 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
     P.bgs = scene->bgs;
     P.n_obj = scene->n_obj; P.n_hv = scene->n_hand_verts; P.n_hf = scene->n_hand_faces; P.n_tex = scene->n_hand_tex;
     P.n_bg = scene->n_bg; P.bg_h = scene->bg_h; P.bg_w = scene->bg_w;
+    P.bg_ch = scene->bg_channels == 4 ? 4 : 3;
+    AB_REQUIRE(scene->bg_channels == 0 || scene->bg_channels == 3 || scene->bg_channels == 4, "bg_channels must be 3 or 4");
+    AB_REQUIRE(P.bg_ch == 3 || ((uintptr_t)scene->bgs & 3) == 0, "RGBX backgrounds must be 4-byte aligned");
+    make_fastdiv((unsigned)cam->width, &P.div_w_m, &P.div_w_s);
+    make_fastdiv(2u * (unsigned)cam->width, &P.div_2w_m, &P.div_2w_s);
+    make_fastdiv(2u * (unsigned)cam->height, &P.div_2h_m, &P.div_2h_s);
     P.W = cam->width; P.H = cam->height;
     P.fx = cam->fx; P.fy = cam->fy; P.cx = cam->cx; P.cy = cam->cy; P.znear = cam->znear;
     P.ambient = cam->ambient; P.diffuse = cam->diffuse; P.cull = cam->cull_backface;
@@ -526,12 +601,38 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
     }
     const int npx = P.W * P.H;
     P.pv_stride = (int)align_up((size_t)scene_max_ov + P.n_hv, 8);
-    P.keys = (unsigned long long*)ws;
-    P.pv = (int4*)((char*)ws + align_up((size_t)chunk * npx * 8, 256));
-    AB_CUDA(cudaMemsetAsync(P.keys, 0xFF, (size_t)min(chunk, batch) * npx * 8, st));
-
-    for (int v0 = 0; v0 < batch; v0 += chunk) {
+    const size_t set_bytes = scratch_set_bytes(chunk, npx, P.pv_stride);
+    const size_t keys_bytes = align_up((size_t)chunk * npx * 8, 256);
+    const int n_chunks = cdiv(batch, chunk);
+    const int sets = min(raster_sets(), n_chunks);
+    const bool dual = sets > 1;
+    int dev = 0;
+    std::unique_lock<std::mutex> lock(g_aux.mu, std::defer_lock);
+    if (dual) {
+        AB_CUDA(cudaGetDevice(&dev));
+        AB_REQUIRE(dev < kMaxDevices, "device index out of range");
+        lock.lock();  // the per-device events are reused by every call
+        if (!g_aux.fork[dev]) AB_CUDA(cudaEventCreateWithFlags(&g_aux.fork[dev], cudaEventDisableTiming));
+        for (int i = 1; i < sets; ++i) {
+            if (!g_aux.aux[dev][i]) {
+                AB_CUDA(cudaStreamCreateWithFlags(&g_aux.aux[dev][i], cudaStreamNonBlocking));
+                AB_CUDA(cudaEventCreateWithFlags(&g_aux.join[dev][i], cudaEventDisableTiming));
+            }
+        }
+    }
+    for (int i = 0; i < sets; ++i) AB_CUDA(cudaMemsetAsync((char*)ws + i * set_bytes, 0xFF, keys_bytes, st));
+    if (dual) {
+        AB_CUDA(cudaEventRecord(g_aux.fork[dev], st));
+        for (int i = 1; i < sets; ++i) AB_CUDA(cudaStreamWaitEvent(g_aux.aux[dev][i], g_aux.fork[dev], 0));
+    }
+    const cudaStream_t caller = st;
+    int chunk_idx = 0;
+    for (int v0 = 0; v0 < batch; v0 += chunk, ++chunk_idx) {
         const int n = min(chunk, batch - v0);
+        const int set = chunk_idx % sets;
+        st = set ? g_aux.aux[dev][set] : caller;
+        P.keys = (unsigned long long*)((char*)ws + set * set_bytes);
+        P.pv = (int4*)((char*)ws + set * set_bytes + keys_bytes);
         int max_ov = scene_max_ov, max_of = scene_max_of;
         if (obj_id_host) {
             max_ov = max_of = 0;
@@ -568,12 +669,17 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
             // 4 pixels per thread needs 16-byte aligned output rows: W % 4 == 0 and 16 / 16 / 4-byte aligned bases
             const bool vec = (P.W % 4 == 0) && (((uintptr_t)P.rgba & 15) == 0) && (((uintptr_t)P.depth & 15) == 0) &&
                              (((uintptr_t)P.seg & 3) == 0);
-            if (vec) raster_resolve_kernel<4><<<dim3(cdiv(npx, 1024), n), 256, 0, st>>>(P);
-            else raster_resolve_kernel<1><<<dim3(cdiv(npx, 256), n), 256, 0, st>>>(P);
+            if (vec) raster_resolve_kernel<4, 1><<<dim3(cdiv(npx, 1024), n), 256, 0, st>>>(P);
+            else raster_resolve_kernel<1, 1><<<dim3(cdiv(npx, 256), n), 256, 0, st>>>(P);
+
         }
         count_launch(3);
         int rc = check_launch("ab_render_batch");
         if (rc) return rc;
+    }
+    for (int i = 1; i < sets; ++i) {
+        AB_CUDA(cudaEventRecord(g_aux.join[dev][i], g_aux.aux[dev][i]));
+        AB_CUDA(cudaStreamWaitEvent(caller, g_aux.join[dev][i], 0));
     }
     return AB_OK;
 }

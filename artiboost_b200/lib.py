@@ -25,7 +25,7 @@ class SceneStruct(C.Structure):
                 ("obj_vert_off_host", c_i32_p), ("obj_face_off_host", c_i32_p),
                 ("n_hand_verts", C.c_int32), ("n_hand_faces", C.c_int32), ("n_hand_tex", C.c_int32),
                 ("hand_faces", C.c_void_p), ("hand_colors", C.c_void_p), ("bgs", C.c_void_p),
-                ("n_bg", C.c_int32), ("bg_h", C.c_int32), ("bg_w", C.c_int32)]
+                ("n_bg", C.c_int32), ("bg_h", C.c_int32), ("bg_w", C.c_int32), ("bg_channels", C.c_int32)]
 
 
 class CameraStruct(C.Structure):

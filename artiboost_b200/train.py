@@ -72,6 +72,44 @@ class FusedAdam:
     def grad_norm(self) -> torch.Tensor:
         return self.sumsq.sqrt()
 
+    # -- torch.optim.Adam checkpoint format, so that `train_param.pth.tar` files move between the reference's loop
+    # (anakin/utils/io_utils.py:34,74-84: optimizer.state_dict() / load_state_dict()) and this one
+    def state_dict(self) -> dict:
+        step = float(self.state[0].item())
+        state, off = {}, 0
+        for i, p in enumerate(self.fp.params):
+            k = p.numel()
+            if step > 0:
+                state[i] = {"step": torch.tensor(step), "exp_avg": self.m[off:off + k].view_as(p).clone(),
+                            "exp_avg_sq": self.v[off:off + k].view_as(p).clone()}
+            off += k
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd, "amsgrad": False,
+                 "maximize": False, "params": list(range(len(self.fp.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        ids = [i for g in sd["param_groups"] for i in g["params"]]
+        if len(ids) != len(self.fp.params):
+            raise ValueError(f"loaded state dict has {len(ids)} parameters, the optimizer has {len(self.fp.params)}")
+        g0 = sd["param_groups"][0]
+        self.lr, self.betas, self.eps = float(g0["lr"]), tuple(g0["betas"]), float(g0["eps"])
+        self.wd = float(g0.get("weight_decay", 0.0))
+        self.m.zero_()
+        self.v.zero_()
+        step, off = 0.0, 0
+        for pid, p in zip(ids, self.fp.params):
+            k = p.numel()
+            st = sd["state"].get(pid)
+            if st is not None:
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer state {pid} has shape {tuple(st['exp_avg'].shape)}, parameter {tuple(p.shape)}")
+                self.m[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                self.v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                step = max(step, float(st["step"]))
+            off += k
+        b1, b2 = self.betas
+        self.state.copy_(torch.tensor([step, 1.0 - b1 ** step, 1.0 - b2 ** step]))
+
 
 class CCVFeedback:
     """Per-(object, view, grasp) error capture during training and the weight update of `update_method_1`

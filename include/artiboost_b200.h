@@ -184,8 +184,9 @@ typedef struct {
     int32_t n_hand_verts, n_hand_faces, n_hand_tex;
     const int32_t* hand_faces;  /* [n_hand_faces,4]                                                     */
     const uint8_t* hand_colors; /* [n_hand_tex, n_hand_verts, 4]                                        */
-    const uint8_t* bgs;         /* [n_bg, bg_h, bg_w, 3] or NULL                                        */
+    const uint8_t* bgs;         /* [n_bg, bg_h, bg_w, bg_channels] or NULL                              */
     int32_t n_bg, bg_h, bg_w;
+    int32_t bg_channels;        /* 3 (RGB; 0 means 3) or 4 (RGBX, 4-byte aligned: one 32-bit load per pixel) */
 } ab_scene;
 
 typedef struct {

@@ -135,7 +135,8 @@ def test_refine_encode_decode(lib_built):
     pose[0, 3:6] = 0
     tsl = rng.normal(0, 0.1, (B, 3)).astype(np.float32)
     feat = torch.zeros((B, 120), device=DEV)
-    rc = lib.load().ab_refine_encode(B, lib.ptr(t(pose)), lib.ptr(t(tsl)), feat[:, 10:].data_ptr(), 120, None)
+    pose_d, tsl_d = t(pose), t(tsl)  # keep the device copies alive across the asynchronous launch
+    rc = lib.load().ab_refine_encode(B, lib.ptr(pose_d), lib.ptr(tsl_d), feat[:, 10:].data_ptr(), 120, None)
     lib.check(rc, "ab_refine_encode")
     torch.cuda.synchronize()
     R = rot.aa_to_rotmat(pose.reshape(B, 16, 3).astype(np.float64))
