@@ -53,10 +53,12 @@ def chamfer_nn(x: torch.Tensor, y_points: torch.Tensor, obj_id: Optional[torch.T
         rs = 16 if rot.shape[-1] == 4 else 9
     if obj_id is not None:
         obj_id = obj_id.to(torch.int32).contiguous()
+    L = lib.load()
+    ws = torch.empty(max(int(L.ab_chamfer_nn_workspace_bytes(B, P1)), 8) // 8, dtype=torch.int64, device=x.device)
     with torch.cuda.device(x.device):
-        rc = lib.load().ab_chamfer_nn(B, P1, lib.ptr(x), y_points.shape[1], lib.ptr(y_points), lib.ptr(obj_id),
-                                      lib.ptr(rot), rs, lib.ptr(scale), lib.ptr(shift), out.data_ptr(),
-                                      out.stride(0) if B > 0 else P1, lib.ptr(idx), lib.stream_ptr(x.device))
+        rc = L.ab_chamfer_nn(B, P1, lib.ptr(x), y_points.shape[1], lib.ptr(y_points), lib.ptr(obj_id),
+                             lib.ptr(rot), rs, lib.ptr(scale), lib.ptr(shift), out.data_ptr(),
+                             out.stride(0) if B > 0 else P1, lib.ptr(idx), lib.ptr(ws), lib.stream_ptr(x.device))
     lib.check(rc, "ab_chamfer_nn")
     return out, idx
 
@@ -161,19 +163,22 @@ class _RefineNet(nn.Module):
                 rb = getattr(self, name)
                 s1, t1 = _bn_affine(rb.bn1)
                 s2, t2 = _bn_affine(rb.bn2)
-                f[name] = dict(W1=(rb.fc1.weight.float() * s1[:, None]).contiguous(), b1=(rb.fc1.bias.float() * s1 + t1).contiguous(),
+                # fc1 (+ bn1) and fc3 read the same input and both end in the LeakyReLU: one GEMM with N = 256 + Fout
+                f[name] = dict(W13=torch.cat([rb.fc1.weight.float() * s1[:, None], rb.fc3.weight.float()], 0).contiguous(),
+                               b13=torch.cat([rb.fc1.bias.float() * s1 + t1, rb.fc3.bias.float()], 0).contiguous(),
                                W2=(rb.fc2.weight.float() * s2[:, None]).contiguous(), b2=(rb.fc2.bias.float() * s2 + t2).contiguous(),
-                               W3=rb.fc3.weight.detach().float().contiguous(), b3=rb.fc3.bias.detach().float().contiguous())
+                               n1=rb.fc1.weight.shape[0])
             f["Wo"] = torch.cat([self.out_p.weight, self.out_t.weight], 0).detach().float().contiguous()
             f["bo"] = torch.cat([self.out_p.bias, self.out_t.bias], 0).detach().float().contiguous()
         self._folded = (key, f)
         return f
 
-    def _resblock(self, w, x, out, h, xin):
-        """ResBlock.forward (refiner.py:306-319): out = ll(ll(fc3 x) + bn2(fc2(ll(bn1(fc1 x)))))."""
-        linear_f32(x, w["W1"], w["b1"], h, leaky=0.2)
-        linear_f32(x, w["W3"], w["b3"], xin, leaky=0.2)
-        linear_f32(h, w["W2"], w["b2"], out, residual=xin, leaky=0.2)
+    def _resblock(self, w, x, out, hx):
+        """ResBlock.forward (refiner.py:306-319): out = ll(ll(fc3 x) + bn2(fc2(ll(bn1(fc1 x))))).  hx [B, 256 + Fout]
+        holds ll(bn1(fc1 x)) | ll(fc3 x)."""
+        n1 = w["n1"]
+        linear_f32(x, w["W13"], w["b13"], hx, leaky=0.2)
+        linear_f32(hx[:, :n1], w["W2"], w["b2"], out, residual=hx[:, n1:], leaky=0.2)
 
     @torch.no_grad()
     def _iterate(self, feat, hand_pose, hand_tsl, cloud, h2o_first=None, rigid=None, offset=None):
@@ -193,8 +198,7 @@ class _RefineNet(nn.Module):
         pose = torch.empty((B, 48), device=dev, dtype=torch.float32)
         tsl = torch.empty((B, 3), device=dev, dtype=torch.float32)
         post = torch.empty((B, 12), device=dev, dtype=torch.float32)
-        h = torch.empty((B, 256), device=dev, dtype=torch.float32)
-        xin = torch.empty((B, hs), device=dev, dtype=torch.float32)
+        hx = torch.empty((B, 256 + hs), device=dev, dtype=torch.float32)
         st = lib.stream_ptr(dev)
 
         def decode(rg=None, off=None):
@@ -215,9 +219,9 @@ class _RefineNet(nn.Module):
                 chamfer_nn(verts, scale=f["bn_s"], shift=f["bn_t"], out=h2o, return_idx=False, **cloud)
             else:
                 h2o.copy_(h2o_first * f["bn_s"] + f["bn_t"])
-            self._resblock(f["rb1"], X0, X, h, xin)
-            self._resblock(f["rb2"], feat, X, h, xin)
-            self._resblock(f["rb3"], feat, X, h, xin)
+            self._resblock(f["rb1"], X0, X, hx)
+            self._resblock(f["rb2"], feat, X, hx)
+            self._resblock(f["rb3"], feat, X, hx)
             linear_f32(X, f["Wo"], f["bo"], f6d, residual=f6d)   # init_pose += out_p(X); init_trans += out_t(X)
         decode(rigid, offset)
         self.mano_layer.lbs_into(pose, None, post, verts, joints)

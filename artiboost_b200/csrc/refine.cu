@@ -73,8 +73,7 @@ __device__ __forceinline__ void nn_rotate(const float* R, bool rot, const float*
 __global__ void __launch_bounds__(kNnThreads)
 chamfer_nn_kernel(int n_x, const float* __restrict__ x, int n_y, const float* __restrict__ y_points,
                   const int32_t* __restrict__ obj_id, const float* __restrict__ rot, int rot_stride,
-                  const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ dist,
-                  long long dist_stride, int32_t* __restrict__ idx) {
+                  unsigned long long* __restrict__ keys) {
     __shared__ __align__(16) float sx[kNnTile], sy[kNnTile], sz[kNnTile];  // SoA: one LDS.128 = 4 points of one axis
     const int b = blockIdx.y, tid = threadIdx.x;
     const int q0 = blockIdx.x * (kNnThreads * kNnQ);
@@ -99,7 +98,8 @@ chamfer_nn_kernel(int n_x, const float* __restrict__ x, int n_y, const float* __
         best[k] = __int_as_float(0x7f800000);
         bchunk[k] = 0;
     }
-    for (int t0 = 0; t0 < n_y; t0 += kNnTile) {
+    {   // one tile of the cloud per CTA (blockIdx.z): the tiles of a sample meet again in the atomicMin below
+        const int t0 = blockIdx.z * kNnTile;
         const int tn = min(kNnTile, n_y - t0);
         const int tn_pad = (tn + kNnChunk - 1) / kNnChunk * kNnChunk;
         __syncthreads();
@@ -151,23 +151,42 @@ chamfer_nn_kernel(int n_x, const float* __restrict__ x, int n_y, const float* __
             nn_rotate(R, rot != nullptr, yb + (size_t)i * 3, px, py, pz);
             if (nn_d2(qx[k], qy[k], qz[k], px, py, pz) == best[k]) { bi = i; break; }
         }
-        float v = sqrtf(best[k]);
-        if (scale) v = __fadd_rn(__fmul_rn(v, scale[qi]), shift[qi]);
-        dist[(size_t)b * dist_stride + qi] = v;
-        if (idx) idx[(size_t)b * n_x + qi] = bi;
+        // d >= 0, so the float bits order like the values; the index in the low word makes the smallest index win ties
+        atomicMin(keys + (size_t)b * n_x + qi, ((unsigned long long)__float_as_uint(best[k]) << 32) | (unsigned)bi);
     }
 }
 
+__global__ void chamfer_finalize_kernel(int total, int n_x, unsigned long long* __restrict__ keys,
+                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                        float* __restrict__ dist, long long dist_stride, int32_t* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int b = i / n_x, qi = i - b * n_x;
+    const unsigned long long k = keys[i];
+    float v = sqrtf(__uint_as_float((unsigned)(k >> 32)));
+    if (scale) v = __fadd_rn(__fmul_rn(v, scale[qi]), shift[qi]);
+    dist[(size_t)b * dist_stride + qi] = v;
+    if (idx) idx[i] = (int32_t)(k & 0xffffffffull);
+}
+
 // ------------------------------------------------------------------------------------------------------ fp32 linear
-constexpr int kLinBM = 32, kLinBN = 64, kLinBK = 16, kLinThreads = 128;
+// 32 x 64 output tile per CTA, 4 x 4 outputs per thread; the K loop is shared out over kLinKG groups of 128 threads
+// (k-tiles g, g + KG, ...), whose partial tiles are added in a fixed order through shared memory: the MLP's GEMMs are
+// small (M = batch, N <= 768), so the K split is what puts >= 16 warps on every SM, and the fixed order keeps the
+// result bit-reproducible.
+constexpr int kLinBM = 32, kLinBN = 64, kLinBK = 16, kLinKG = 4, kLinThreads = 128 * kLinKG;
 
 __global__ void __launch_bounds__(kLinThreads)
 linear_f32_kernel(int M, int N, int K, const float* __restrict__ x, long long ldx, const float* __restrict__ W,
                   long long ldw, const float* __restrict__ bias, const float* res, long long ldr, int act, float slope,
                   float* y, long long ldy) {
-    __shared__ __align__(16) float As[kLinBK][kLinBM];
-    __shared__ __align__(16) float Bs[kLinBK][kLinBN];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // 16 x 8 threads, 4 x 4 outputs each
+    // operand tiles; after the K loop the same storage carries the partial tiles of groups 1.. ([group][element][thread])
+    __shared__ __align__(16) float smem[kLinKG * kLinBK * (kLinBM + kLinBN)];
+    static_assert((kLinKG - 1) * 16 * 128 <= kLinKG * kLinBK * (kLinBM + kLinBN), "partial tiles must fit the operand storage");
+    float (*As)[kLinBK][kLinBM] = reinterpret_cast<float (*)[kLinBK][kLinBM]>(smem);
+    float (*Bs)[kLinBK][kLinBN] = reinterpret_cast<float (*)[kLinBK][kLinBN]>(smem + kLinKG * kLinBK * kLinBM);
+    float (*red)[16][128] = reinterpret_cast<float (*)[16][128]>(smem);
+    const int kg = threadIdx.x >> 7, tid = threadIdx.x & 127, tx = tid & 15, ty = tid >> 4;  // 16 x 8 threads per group
     const int m0 = blockIdx.y * kLinBM, n0 = blockIdx.x * kLinBN;
     float acc[4][4];
 #pragma unroll
@@ -181,22 +200,25 @@ linear_f32_kernel(int M, int N, int K, const float* __restrict__ x, long long ld
     const bool a_ok = m0 + ar < M, b_ok = n0 + br < N;
     const float* ap = x + (size_t)(a_ok ? m0 + ar : 0) * ldx;
     const float* bp = W + (size_t)(b_ok ? n0 + br : 0) * ldw;
-    for (int k0 = 0; k0 < K; k0 += kLinBK) {
+    const int n_tiles = (K + kLinBK - 1) / kLinBK;
+    const int n_rounds = (n_tiles + kLinKG - 1) / kLinKG;  // same trip count for every group: the barriers are CTA-wide
+    for (int r = 0; r < n_rounds; ++r) {
+        const int k0 = (r * kLinKG + kg) * kLinBK;  // may lie past K for the last round: zero tiles
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             int k = k0 + ak + i;
-            As[ak + i][ar] = (a_ok && k < K) ? ap[k] : 0.f;
+            As[kg][ak + i][ar] = (a_ok && k < K) ? ap[k] : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             int k = k0 + bk + i;
-            Bs[bk + i][br] = (b_ok && k < K) ? bp[k] : 0.f;
+            Bs[kg][bk + i][br] = (b_ok && k < K) ? bp[k] : 0.f;
         }
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < kLinBK; ++kk) {
-            float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-            float4 w = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            float4 a = *reinterpret_cast<const float4*>(&As[kg][kk][ty * 4]);
+            float4 w = *reinterpret_cast<const float4*>(&Bs[kg][kk][tx * 4]);
             float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -205,6 +227,20 @@ linear_f32_kernel(int M, int N, int K, const float* __restrict__ x, long long ld
         }
         __syncthreads();
     }
+    if (kg > 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[kg - 1][4 * i + j][tid] = acc[i][j];
+    }
+    __syncthreads();
+    if (kg > 0) return;
+#pragma unroll
+    for (int g = 0; g < kLinKG - 1; ++g)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += red[g][4 * i + j][tid];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int m = m0 + ty * 4 + i;
@@ -361,25 +397,39 @@ __global__ void scramble_axis_kernel(int batch, const float* __restrict__ pose, 
 }  // namespace ab
 
 // ------------------------------------------------------------------------------------------------------- C ABI
+extern "C" uint64_t ab_chamfer_nn_workspace_bytes(int batch, int n_x) {
+    return batch > 0 && n_x > 0 ? (uint64_t)batch * n_x * 8 : 0;
+}
+
 extern "C" int ab_chamfer_nn(int batch, int n_x, const float* x, int n_y, const float* y_points, const int32_t* obj_id,
                              const float* rot, int rot_stride, const float* scale, const float* shift, float* dist,
-                             int64_t dist_stride, int32_t* idx, void* stream) {
+                             int64_t dist_stride, int32_t* idx, void* ws, void* stream) {
     AB_REQUIRE(batch >= 0 && n_x >= 0 && n_y >= 0, "negative size");
     if (batch == 0 || n_x == 0) return AB_OK;
     AB_REQUIRE(n_y > 0, "empty target cloud: the nearest neighbour is undefined");
     AB_REQUIRE(batch <= 65535, "batch > 65535: split the call");
-    AB_REQUIRE(x && y_points && dist, "null pointer");
+    AB_REQUIRE(x && y_points && dist && ws, "null pointer");
+    AB_REQUIRE(((uintptr_t)ws & 7) == 0, "workspace must be 8-byte aligned");
     AB_REQUIRE(rot == nullptr || rot_stride == 9 || rot_stride == 16, "rot_stride must be 9 (3x3) or 16 (4x4 pose)");
     AB_REQUIRE((scale == nullptr) == (shift == nullptr), "scale and shift go together");
     AB_REQUIRE(dist_stride >= n_x, "dist_stride < n_x");
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(ab::cdiv(n_x, ab::kNnThreads * ab::kNnQ), batch);
+    const int splits = ab::cdiv(n_y, ab::kNnTile);
+    AB_REQUIRE(splits <= 65535, "n_y too large");
+    dim3 grid(ab::cdiv(n_x, ab::kNnThreads * ab::kNnQ), batch, splits);
+    unsigned long long* keys = (unsigned long long*)ws;
+    AB_CUDA(cudaMemsetAsync(keys, 0xFF, (size_t)batch * n_x * 8, st));
     {
         ab::StageTimer tm(AB_STAGE_CHAMFER, st);
-        ab::chamfer_nn_kernel<<<grid, ab::kNnThreads, 0, st>>>(n_x, x, n_y, y_points, obj_id, rot, rot_stride, scale,
-                                                              shift, dist, (long long)dist_stride, idx);
+        ab::chamfer_nn_kernel<<<grid, ab::kNnThreads, 0, st>>>(n_x, x, n_y, y_points, obj_id, rot, rot_stride, keys);
     }
-    ab::count_launch();
+    {
+        ab::StageTimer tm(AB_STAGE_REFINE_MISC, st);
+        const int total = batch * n_x;
+        ab::chamfer_finalize_kernel<<<ab::cdiv(total, 256), 256, 0, st>>>(total, n_x, keys, scale, shift, dist,
+                                                                         (long long)dist_stride, idx);
+    }
+    ab::count_launch(2);
     return ab::check_launch("chamfer_nn_kernel");
 }
 

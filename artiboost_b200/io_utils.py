@@ -143,13 +143,13 @@ class Recorder:
         path = os.path.join(self.dump_path, "artiboost", "sample_weight")
         os.makedirs(path, exist_ok=True)
         with open(os.path.join(path, f"{epoch:0>3}_{'train' if is_train else 'val'}.pkl"), "wb") as f:
-            pickle.dump(np.array(weight_map.detach().cpu()), f)
+            pickle.dump(weight_map.detach().cpu().numpy().copy(), f)
 
     def record_sample_occurence(self, occurence_map: torch.Tensor, epoch: int, is_train: bool = True):
         path = os.path.join(self.dump_path, "artiboost", "occurence_map")
         os.makedirs(path, exist_ok=True)
         with open(os.path.join(path, f"{epoch:0>3}.pkl"), "wb") as f:
-            pickle.dump(np.array(occurence_map.detach().cpu()), f)
+            pickle.dump(occurence_map.detach().cpu().numpy().copy(), f)
 
     def resume_artiboost_loader(self, loader, resume_epoch: int, resume_path: str):
         epoch = resume_epoch - 1

@@ -67,8 +67,9 @@ EXPORTS = {
     "ab_pose_generate_workspace_bytes": (C.c_uint64, [C.c_int]),
     "ab_pose_generate": (C.c_int, [C.POINTER(ManoModelStruct), C.c_int] + [C.c_void_p] * 13),
     "ab_pose_prelude": (C.c_int, [C.POINTER(ManoModelStruct), C.c_int] + [C.c_void_p] * 14),
+    "ab_chamfer_nn_workspace_bytes": (C.c_uint64, [C.c_int, C.c_int]),
     "ab_chamfer_nn": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
-                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_linear_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                 C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
     "ab_refine_encode": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -138,10 +138,13 @@ AB_API int ab_pose_prelude(const ab_mano_model* model, int batch, const float* h
  * y_points[obj_id[b]] (obj_id NULL: y_points[b]), [*, n_y, 3]; rot (NULL or [B,rot_stride], rot_stride 9 = 3x3,
  * 16 = the rotation block of a 4x4 pose) rotates it first: y = R o, the `verts_object` of refiner.py:190-191, never
  * materialised.  Output dist[b*dist_stride + i] = |x - y_nn| (x scale[i] + shift[i] when given: the eval-mode
- * BatchNorm1d(778) of refiner.py:266 folded in), idx [B,n_x] (may be NULL) = index of the nearest point.          */
+ * BatchNorm1d(778) of refiner.py:266 folded in), idx [B,n_x] (may be NULL) = index of the nearest point.
+ * ws: ab_chamfer_nn_workspace_bytes(batch, n_x) bytes, 8-byte aligned (per-vertex 64-bit keys through which the CTAs that
+ * scan different tiles of one cloud combine their minima).                                                        */
+AB_API uint64_t ab_chamfer_nn_workspace_bytes(int batch, int n_x);
 AB_API int ab_chamfer_nn(int batch, int n_x, const float* x, int n_y, const float* y_points, const int32_t* obj_id,
                   const float* rot, int rot_stride, const float* scale, const float* shift, float* dist,
-                  int64_t dist_stride, int32_t* idx, void* stream);
+                  int64_t dist_stride, int32_t* idx, void* ws, void* stream);
 
 /* fp32 linear layer of the RefineNet MLP (nn.Linear + folded BatchNorm1d + LeakyReLU + ResBlock skip,
  * refiner.py:288-319): y[M,N] = act(x[M,K] W[N,K]^T + bias[N] (+ residual[M,N])), act 0 none / 1 leaky relu(slope).
