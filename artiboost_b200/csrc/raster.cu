@@ -21,6 +21,7 @@
 // leave L2 when `chunk` is sized so (chunk * (8*W*H + 16*verts)) stays well under the 126 MB L2.
 #include <stdlib.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -519,7 +520,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // other and the tails of the kernels overlap.  Fork / join is by events, so the call stays asynchronous and ordered on
 // the caller's stream (and capturable into a CUDA graph).
 constexpr int kMaxDevices = 16;
-constexpr int kMaxSets = 8;
+constexpr int kMaxSets = 4;
 struct AuxStreams {
     std::mutex mu;
     cudaStream_t aux[kMaxDevices][kMaxSets] = {};
@@ -527,12 +528,16 @@ struct AuxStreams {
 };
 static AuxStreams g_aux;
 
-static int raster_sets() {  // chunks in flight (AB_RASTER_STREAMS overrides; 1 = everything on the caller's stream)
-    static const int n = [] {
+constexpr int kWsSets = 4;  // scratch sets every workspace is sized for
+static std::atomic<int> g_sets{0};
+static int raster_sets() {  // chunks in flight: 4 by default, AB_RASTER_STREAMS / ab_set_raster_streams override (1..4)
+    int n = g_sets.load(std::memory_order_relaxed);
+    if (n == 0) {
         const char* e = getenv("AB_RASTER_STREAMS");
-        const int v = e ? atoi(e) : 4;
-        return v < 1 ? 1 : (v > kMaxSets ? kMaxSets : v);
-    }();
+        n = e ? atoi(e) : kWsSets;
+        n = n < 1 ? 1 : (n > kWsSets ? kWsSets : n);
+        g_sets.store(n, std::memory_order_relaxed);
+    }
     return n;
 }
 
@@ -542,11 +547,17 @@ static size_t scratch_set_bytes(int chunk, int npx, int pv_stride) {
 
 }  // namespace ab
 
+extern "C" int ab_set_raster_streams(int n) {
+    AB_REQUIRE(n >= 1 && n <= ab::kWsSets, "n must be in 1..4");
+    ab::g_sets.store(n, std::memory_order_relaxed);
+    return AB_OK;
+}
+
 extern "C" uint64_t ab_render_workspace_bytes(const ab_scene* scene, const ab_camera* cam, int chunk) {
     if (!scene || !cam || chunk <= 0 || cam->width <= 0 || cam->height <= 0) return 0;
     if (scene->n_obj > 0 && !scene->obj_vert_off_host) return 0;
     const int pv_stride = (int)ab::align_up((size_t)ab::max_hand_obj_verts(scene) + scene->n_hand_verts, 8);
-    return (size_t)ab::raster_sets() * ab::scratch_set_bytes(chunk, cam->width * cam->height, pv_stride);
+    return (size_t)ab::kWsSets * ab::scratch_set_bytes(chunk, cam->width * cam->height, pv_stride);
 }
 
 extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int batch, int chunk,

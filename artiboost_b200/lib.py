@@ -76,6 +76,7 @@ EXPORTS = {
     "ab_refine_decode": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_scramble_anatomical": (C.c_int, [C.c_int] + [C.c_void_p] * 9),
+    "ab_set_raster_streams": (C.c_int, [C.c_int]),
     "ab_render_workspace_bytes": (C.c_uint64, [C.POINTER(SceneStruct), C.POINTER(CameraStruct), C.c_int]),
     "ab_render_batch": (C.c_int, [C.POINTER(SceneStruct), C.POINTER(CameraStruct), C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_void_p, c_i32_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

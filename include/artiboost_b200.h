@@ -208,7 +208,11 @@ typedef struct {
  * when NULL they are sized to the largest object in the scene (no host sync either way).
  * Outputs: rgba u8[B,H,W,4], depth f32[B,H,W] (0 = background), seg u8[B,H,W] (0 bg, 1 hand, 2 object); any may
  * be NULL.  ws: workspace of ab_render_workspace_bytes() bytes; views are processed in chunks of `chunk`
- * views so the scratch stays L2-resident.                                                                 */
+ * views so the scratch stays L2-resident.  Up to four chunks are in flight at a time, on the caller's stream and on
+ * library-owned auxiliary streams (fork / join by events: the call stays ordered on `stream`); the workspace holds four
+ * scratch sets.  ab_set_raster_streams(n), n in 1..4, sets the number in flight (1 = everything on `stream`; default 4
+ * or the AB_RASTER_STREAMS environment variable).                                                          */
+AB_API int ab_set_raster_streams(int n);
 AB_API uint64_t ab_render_workspace_bytes(const ab_scene* scene, const ab_camera* cam, int chunk);
 AB_API int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int batch, int chunk, const float* hand_verts,
                     const int32_t* hand_tex, const int32_t* obj_id, const int32_t* obj_id_host, const float* obj_pose,

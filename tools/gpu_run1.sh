@@ -17,3 +17,5 @@ for k in raster_triangle raster_resolve; do
 done
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:chamfer_nn -c 2 -f -o gpurun_out/${T}_chamfer_nn python -m pytest tests/test_gpu_refine.py -q -k full_batch -p no:cacheprovider > /dev/null 2>&1
 ls -la gpurun_out | tail -12
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:linear_f32 -s 3 -c 2 -f -o gpurun_out/${T}_linear_f32 python -m pytest tests/test_gpu_refine.py -q -k "synth_pipeline and hand_obj" -p no:cacheprovider > /dev/null 2>&1
+ls -la gpurun_out | tail -5
