@@ -12,6 +12,8 @@ BatchNorm / ReLU / pooling backward in the reference) runs in:
 """
 from __future__ import annotations
 
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -28,6 +30,48 @@ def _call(name, *args):
 
 def _stream(dev):
     return lib.stream_ptr(dev)
+
+
+# ------------------------------------------------------------------------------- weight gradients on a side stream
+class _AsyncWgrad:
+    """Weight-gradient kernels only feed the optimiser, so inside `async_wgrad()` they are launched on a side stream and
+    run beside the data-gradient chain of the layers below (in a captured step: a parallel branch of the CUDA graph).
+    Operands are kept alive until the join.  Off by default: plain `.backward()` callers read `.grad` right away."""
+    enabled = False
+    streams = {}
+    pending = []
+    used = set()
+
+
+@contextlib.contextmanager
+def async_wgrad():
+    _AsyncWgrad.enabled = True
+    try:
+        yield
+    finally:
+        _AsyncWgrad.enabled = False
+        for dev in list(_AsyncWgrad.used):
+            torch.cuda.current_stream(dev).wait_stream(_AsyncWgrad.streams[dev])
+        _AsyncWgrad.used.clear()
+        _AsyncWgrad.pending.clear()
+
+
+@contextlib.contextmanager
+def _wgrad_launch(dev, *keep):
+    """Stream context of one weight-gradient launch; `keep`: its operand tensors."""
+    if not _AsyncWgrad.enabled:
+        with torch.cuda.device(dev):
+            yield
+        return
+    dev = torch.device(dev)
+    side = _AsyncWgrad.streams.get(dev)
+    if side is None:
+        side = _AsyncWgrad.streams[dev] = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    _AsyncWgrad.pending.extend(k for k in keep if k is not None)
+    _AsyncWgrad.used.add(dev)
+    with torch.cuda.device(dev), torch.cuda.stream(side):
+        yield
 
 
 # --------------------------------------------------------------------------------------------- packed filters
@@ -172,7 +216,7 @@ def _conv_wgrad(x: Act, xcol, dy_mat, conv_w, kh, kw, stride, pad):
     taps = kh * kw
     dev = dy_mat.device
     dw, in_place = _grad_target(conv_w)
-    with torch.cuda.device(dev):
+    with _wgrad_launch(dev, x.data, xcol, dy_mat):
         if x.C % 64 == 0:
             _call("ab_conv_wgrad_bf16_nhwc", x.data.data_ptr(), x.B, x.H, x.W, x.C, dy_mat.data_ptr(), cout, kh, kw, stride, pad,
                   dw.data_ptr(), 1, _wgrad_ws(dy_mat.shape[0], cout, taps * x.C, dev).data_ptr(), _stream(dev))
@@ -351,7 +395,7 @@ class DeconvBNReluFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dwb, in_place = _grad_target(deconv.weight)  # rows (ky,kx,co), columns ci -> [Cin, Cout, ky, kx]
             m = lib.wgrad_map(row_div=cout, s_row_hi=1, s_row_lo=16, s_col_lo=cout * 16)
-            with torch.cuda.device(dev):
+            with _wgrad_launch(dev, dycol, x_data):
                 _call("ab_wgrad_bf16", B * H * W, 16 * cout, C, dycol.data_ptr(), 16 * cout, x_data.data_ptr(), C, dwb.data_ptr(), m,
                       _wgrad_ws(B * H * W, 16 * cout, C, dev).data_ptr(), _stream(dev))
             dw = None if in_place else dwb
@@ -419,7 +463,7 @@ class LinearFn(torch.autograd.Function):
         g = torch.zeros((dy.shape[0], npad), dtype=torch.bfloat16, device=dev)
         g[:, :n] = (dy.float() * (y.float() > 0)) if relu else dy
         dwb, in_place = _grad_target(fc.weight)
-        with torch.cuda.device(dev):
+        with _wgrad_launch(dev, g, xb):
             _call("ab_wgrad_bf16", g.shape[0], n, k, g.data_ptr(), npad, xb.data_ptr(), xb.stride(0), dwb.data_ptr(),
                   lib.wgrad_map(s_row_lo=k, s_col_lo=1), _wgrad_ws(g.shape[0], n, k, dev).data_ptr(), _stream(dev))
         dw = None if in_place else dwb

@@ -7,13 +7,14 @@ anakin/artiboost/artiboost_loader.py:279-340,503-523, on device:
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
 import torch.nn as nn
 
 from . import lib, parallel
-from .models import nhwc
+from .models import nhwc, train_ops
 from .criterions import DEFAULT_CRITERION_CFG, Criterion
 
 
@@ -168,6 +169,7 @@ class TrainStep:
         self.generator = generator
         self.world = parallel.world()[1]
         self.use_graph, self.graph_warmup = use_graph, graph_warmup
+        self.async_wgrad = os.environ.get("AB_ASYNC_WGRAD", "1") != "0"
         self._graph, self._static, self._out, self._eager_steps = None, None, None, 0
 
     def _eager(self, batch: Dict[str, torch.Tensor]):
@@ -176,7 +178,11 @@ class TrainStep:
         preds = self.arch(batch)
         preds = preds[next(iter(preds))] if "joints_3d_abs" not in preds else preds
         loss, parts = self.criterion.compute_losses(preds, batch)
-        loss.backward()
+        if self.async_wgrad:
+            with train_ops.async_wgrad():   # weight gradients on a side stream, joined before the all-reduce
+                loss.backward()
+        else:
+            loss.backward()
         parallel.allreduce_sum_(self.flat.grad)
         self.opt.step(grad_scale=1.0 / self.world)
         return loss.detach(), {k: v.detach() for k, v in preds.items()}

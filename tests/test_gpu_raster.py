@@ -110,6 +110,31 @@ def test_render_is_idempotent_and_order_independent_at_batch_512(pipe):
     check(a, oracle_views(pipe, poses, rand, idx), idx)
 
 
+def test_chunk_pipelines_do_not_change_the_result(pipe):
+    """ab_render_batch keeps up to four chunks in flight on its own streams: any number of pipelines, a ragged last
+    chunk and back-to-back calls on the shared scratch must give the same bits."""
+    from artiboost_b200 import lib
+    L = lib.load()
+    B = 300  # 18 chunks of 16 views + one of 12 at the module's chunk size
+    poses = pipe.sample_poses(B)
+    rand = pipe.draw_render_randoms(B)
+    ref = None
+    try:
+        for n in (1, 4, 2, 3, 4):
+            lib.check(L.ab_set_raster_streams(n), "ab_set_raster_streams")
+            out = {k: v.clone() for k, v in pipe.render(poses, rand).items()}
+            out2 = pipe.render(poses, rand)   # immediately again: the previous call's side streams must have joined
+            if ref is None:
+                ref = out
+            for k in ("rgba", "depth", "seg"):
+                assert torch.equal(ref[k], out[k]) and torch.equal(ref[k], out2[k]), (n, k)
+        assert L.ab_set_raster_streams(0) == -1 and L.ab_set_raster_streams(5) == -1
+    finally:
+        L.ab_set_raster_streams(4)
+    idx = [0, 15, 16, 299]
+    check(ref, oracle_views(pipe, poses, rand, idx), idx)
+
+
 def test_render_edge_cases(pipe):
     from artiboost_b200.lib import AbError
     r = pipe.renderer
