@@ -63,6 +63,67 @@ def chamfer_nn(x: torch.Tensor, y_points: torch.Tensor, obj_id: Optional[torch.T
     return out, idx
 
 
+def build_nn_groups(points: np.ndarray, group: int = 32):
+    """points [n_obj, P, 3] (static clouds) -> (sorted_points [n_obj, Pp, 3] f32, perm [n_obj, Pp] i32, boxes
+    [n_obj, 6, Pp / 32] f32) for ab_chamfer_nn_grouped: each cloud sorted along a 30-bit Morton curve over its bounding
+    box (stable, so equal codes keep their original order), padded to a multiple of 32 by repeating the last point, with
+    the axis-aligned box of every run of 32 points."""
+    points = np.asarray(points, np.float32)
+    n_obj, P, _ = points.shape
+    Pp = (P + group - 1) // group * group
+    sp = np.empty((n_obj, Pp, 3), np.float32)
+    pm = np.empty((n_obj, Pp), np.int32)
+    bx = np.empty((n_obj, 6, Pp // group), np.float32)
+
+    def spread(v):  # 10 bits -> every third bit
+        v = v.astype(np.uint64)
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+
+    for o in range(n_obj):
+        p = points[o]
+        lo, hi = p.min(0), p.max(0)
+        q = np.clip(((p - lo) / np.maximum(hi - lo, 1e-12) * 1023.0).astype(np.int64), 0, 1023)
+        code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+        order = np.argsort(code, kind="stable")
+        order = np.concatenate([order, np.full(Pp - P, order[-1])])
+        sp[o], pm[o] = p[order], order
+        g = sp[o].reshape(Pp // group, group, 3)
+        bx[o, :3], bx[o, 3:] = g.min(1).T, g.max(1).T
+    return sp, pm, bx
+
+
+def chamfer_nn_grouped(x, groups, obj_id=None, rot=None, scale=None, shift=None, out=None, return_idx=True):
+    """chamfer_nn over clouds prepared by build_nn_groups (`groups` = its three arrays as device tensors): same
+    arguments, same bits, a fraction of the pairs evaluated."""
+    lib.require_cuda(x, "x")
+    sp, pm, bx = groups
+    B, P1 = x.shape[0], x.shape[1]
+    x = x.contiguous().float()
+    if out is None:
+        out = torch.empty((B, P1), device=x.device, dtype=torch.float32)
+    assert out.stride(1) == 1 and out.dtype == torch.float32
+    idx = torch.empty((B, P1), device=x.device, dtype=torch.int32) if return_idx else None
+    rs = 0
+    if rot is not None:
+        rot = rot.contiguous().float()
+        rs = 16 if rot.shape[-1] == 4 else 9
+    if obj_id is not None:
+        obj_id = obj_id.to(torch.int32).contiguous()
+    elif sp.shape[0] != B:
+        raise ValueError("y does not have the correct shape.")
+    with torch.cuda.device(x.device):
+        rc = lib.load().ab_chamfer_nn_grouped(B, P1, lib.ptr(x), bx.shape[2], lib.ptr(sp), lib.ptr(pm), lib.ptr(bx),
+                                              lib.ptr(obj_id), lib.ptr(rot), rs, lib.ptr(scale), lib.ptr(shift),
+                                              out.data_ptr(), out.stride(0) if B > 0 else P1, lib.ptr(idx),
+                                              lib.stream_ptr(x.device))
+    lib.check(rc, "ab_chamfer_nn_grouped")
+    return out, idx
+
+
 def point2point_signed(x, y, x_normals=None, y_normals=None):
     """refiner.py:21-85 as the hot path calls it (no normals): distance from every x point to its nearest y point."""
     if x_normals is not None or y_normals is not None:
@@ -216,7 +277,11 @@ class _RefineNet(nn.Module):
                 else:
                     decode()
                     self.mano_layer.lbs_into(pose, None, post, verts, joints)
-                chamfer_nn(verts, scale=f["bn_s"], shift=f["bn_t"], out=h2o, return_idx=False, **cloud)
+                if "groups" in cloud:  # static clouds grouped at setup: same bits, ~20x fewer pairs
+                    chamfer_nn_grouped(verts, cloud["groups"], obj_id=cloud.get("obj_id"), rot=cloud.get("rot"),
+                                       scale=f["bn_s"], shift=f["bn_t"], out=h2o, return_idx=False)
+                else:
+                    chamfer_nn(verts, scale=f["bn_s"], shift=f["bn_t"], out=h2o, return_idx=False, **cloud)
             else:
                 h2o.copy_(h2o_first * f["bn_s"] + f["bn_t"])
             self._resblock(f["rb1"], X0, X, hx)
@@ -296,6 +361,7 @@ class HORefiner(nn.Module):
         self.refine_net.eval()
         self.resampled_objs = []
         self.obj_idx = {}
+        self.use_groups = True  # False: brute-force scan of the whole cloud (ab_chamfer_nn)
 
     def setup(self, obj_meshes: Dict[str, object]):
         for name, m in obj_meshes.items():
@@ -303,6 +369,12 @@ class HORefiner(nn.Module):
             self.resampled_objs.append(torch.Tensor(self.resample_obj(m)).float())
         self.resampled_objs = torch.stack(self.resampled_objs)
         self.register_buffer("resampled_objs_buffer", self.resampled_objs)
+        # the clouds are static: group them once for ab_chamfer_nn_grouped (<= 480 groups of 32 points)
+        if self.use_groups and self.resampled_objs.shape[1] <= 480 * 32:
+            sp, pm, bx = build_nn_groups(self.resampled_objs.numpy())
+            self.register_buffer("nn_sorted", torch.from_numpy(sp), persistent=False)
+            self.register_buffer("nn_perm", torch.from_numpy(pm), persistent=False)
+            self.register_buffer("nn_boxes", torch.from_numpy(bx), persistent=False)
 
     @staticmethod
     def resample_obj(obj_mesh, n_sample_verts: int = 10000):
@@ -334,6 +406,8 @@ class HORefiner(nn.Module):
                                              lib.stream_ptr(dev))
         lib.check(rc, "ab_refine_encode")
         cloud = dict(y_points=self.resampled_objs_buffer, obj_id=obj_id, rot=obj_rot)
+        if self.use_groups and hasattr(self, "nn_sorted"):
+            cloud["groups"] = (self.nn_sorted, self.nn_perm, self.nn_boxes)
         return net._iterate(feat, hand_pose, hand_tsl, cloud, rigid=rigid, offset=offset)
 
     def forward(self, inp, obj_name: List[str]):

@@ -146,6 +146,18 @@ AB_API int ab_chamfer_nn(int batch, int n_x, const float* x, int n_y, const floa
                   const float* rot, int rot_stride, const float* scale, const float* shift, float* dist,
                   int64_t dist_stride, int32_t* idx, void* ws, void* stream);
 
+/* The same search over a STATIC cloud that the host has grouped once (artiboost_b200/artiboost/refiner.py
+ * build_nn_groups): sorted_points [n_obj, 32 n_groups, 3] = the cloud sorted along a Morton curve (padded by repeating
+ * its last point), perm [n_obj, 32 n_groups] = original index of every sorted point, boxes [n_obj, 6, n_groups] =
+ * per-group axis-aligned box (lo.x, lo.y, lo.z, hi.x, hi.y, hi.z rows) in the cloud's own frame.  One CTA per sample
+ * rotates the cloud into shared memory, one thread per vertex evaluates only the groups whose box can hold the nearest
+ * point; distances and indices are bit-identical to ab_chamfer_nn (same arithmetic per evaluated pair, ties to the
+ * smallest original index).  rot must be a rotation (the bounds are taken in the cloud's frame).  n_groups <= 480.  */
+AB_API int ab_chamfer_nn_grouped(int batch, int n_x, const float* x, int n_groups, const float* sorted_points,
+                          const int32_t* perm, const float* boxes, const int32_t* obj_id, const float* rot,
+                          int rot_stride, const float* scale, const float* shift, float* dist, int64_t dist_stride,
+                          int32_t* idx, void* stream);
+
 /* fp32 linear layer of the RefineNet MLP (nn.Linear + folded BatchNorm1d + LeakyReLU + ResBlock skip,
  * refiner.py:288-319): y[M,N] = act(x[M,K] W[N,K]^T + bias[N] (+ residual[M,N])), act 0 none / 1 leaky relu(slope).
  * Leading dimensions in elements; y may alias residual.                                                          */

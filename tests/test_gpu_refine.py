@@ -89,6 +89,61 @@ def test_chamfer_nn_full_batch_properties(lib_built):
     assert int(i.min()) >= 0 and int(i.max()) < 10000
 
 
+@pytest.mark.parametrize("n_x,n_y,B", [(778, 10000, 48), (5, 40, 3), (13, 33, 2), (100, 1, 2), (900, 15360, 4)])
+def test_chamfer_nn_grouped_is_bit_identical_to_the_scan(lib_built, n_x, n_y, B):
+    """ab_chamfer_nn_grouped (Morton groups + box bounds, cloud in shared memory, one thread per vertex) against ab_chamfer_nn on surface-like and
+    volumetric clouds, with rotations, exact duplicates and vertices lying on cloud points."""
+    from artiboost_b200.artiboost.refiner import build_nn_groups, chamfer_nn, chamfer_nn_grouped
+    rng = np.random.RandomState(n_x * 7 + n_y)
+    n_obj = 3
+    pts = rng.normal(0, 0.06, (n_obj, n_y, 3)).astype(np.float32)
+    d = pts[1] / np.maximum(np.linalg.norm(pts[1], axis=1, keepdims=True), 1e-6)
+    pts[1] = (d * np.array([0.08, 0.05, 0.11])).astype(np.float32)          # an ellipsoid surface, like a resampled mesh
+    if n_y > 64:
+        pts[0, 50] = pts[0, 7]                                               # duplicates far apart in index ...
+        pts[2, n_y - 1] = pts[2, 0]
+    x = rng.normal(0, 0.09, (B, n_x, 3)).astype(np.float32)
+    obj_id = rng.randint(n_obj, size=B)
+    _, _, R, _ = fx.refiner_inputs(seed=n_y, B=B)
+    R[0] = np.eye(3)
+    obj_id[0] = 0
+    x[0, 0] = pts[0, min(7, n_y - 1)]                                          # ... hit exactly: the smaller index wins
+    x[0, min(1, n_x - 1)] = pts[0, n_y // 2]
+    groups = tuple(t(a, dt) for a, dt in zip(build_nn_groups(pts), (torch.float32, torch.int32, torch.float32)))
+    oid = t(obj_id, torch.int32)
+    d0, i0 = chamfer_nn(t(x), t(pts), obj_id=oid, rot=t(R))
+    d1, i1 = chamfer_nn_grouped(t(x), groups, obj_id=oid, rot=t(R))
+    assert torch.equal(i0, i1)
+    assert torch.equal(d0.view(torch.int32), d1.view(torch.int32))
+    if n_y > 64:
+        assert int(i1[0, 0]) == 7 and float(d1[0, 0]) == 0.0
+    # folded BatchNorm, strided output, no rotation, 4x4 poses as the rotation source
+    scale, shift = t(rng.uniform(0.5, 2, n_x).astype(np.float32)), t(rng.normal(0, 1, n_x).astype(np.float32))
+    wide = torch.zeros((B, n_x + 5), device=DEV)
+    chamfer_nn_grouped(t(x), groups, obj_id=oid, scale=scale, shift=shift, out=wide[:, 2:2 + n_x], return_idx=False)
+    ref, _ = chamfer_nn(t(x), t(pts), obj_id=oid, scale=scale, shift=shift)
+    assert torch.equal(wide[:, 2:2 + n_x], ref) and float(wide[:, :2].abs().sum()) == 0
+    Pm = np.tile(np.eye(4, dtype=np.float32), (B, 1, 1))
+    Pm[:, :3, :3] = R
+    d2, i2 = chamfer_nn_grouped(t(x), groups, obj_id=oid, rot=t(Pm))
+    assert torch.equal(d2, d1) and torch.equal(i2, i1)
+
+
+def test_refiner_grouped_and_scanned_search_agree(refiner):
+    g = golden("refiner.npz")
+    names = [fx.OBJ_NAMES[i] for i in g["obj_id"]]
+    inp = {"hand_pose": t(g["pose"]), "hand_tsl": t(g["tsl"]), "obj_rot": t(g["obj_rot"])}
+    assert hasattr(refiner, "nn_sorted") and refiner.use_groups
+    a = refiner(inp, names)
+    try:
+        refiner.use_groups = False
+        b = refiner(inp, names)
+    finally:
+        refiner.use_groups = True
+    for k in ("hand_verts", "joints", "hand_pose", "hand_tsl"):
+        assert torch.equal(a[k], b[k]), k
+
+
 def test_chamfer_nn_argument_errors(lib_built):
     from artiboost_b200.artiboost.refiner import chamfer_nn, point2point_signed
     from artiboost_b200.lib import AbError
