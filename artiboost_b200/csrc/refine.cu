@@ -269,20 +269,48 @@ chamfer_nn_grouped_kernel(int n_x, const float* __restrict__ x, int n_groups, co
     }
     __syncthreads();
     // ---- phase 2
-    const int qi = blockIdx.x * kGrpThreads + tid;
+    // Vertices are dealt to threads sorted by their nearest 8-group box (a counting sort over <= 60 bins), so the threads
+    // of a warp open mostly the same groups: MANO's vertex order alone leaves a warp with a handful of useful lanes per
+    // evaluated group.
+    __shared__ int bin_cnt[64], bin_start[64];
+    __shared__ short order[kGrpThreads], order_ss[kGrpThreads];
+    if (tid < 64) bin_cnt[tid] = 0;
+    __syncthreads();
+    int key = 63;  // threads past n_x sort to the end (NS <= 60)
+    {
+        const int q0 = blockIdx.x * kGrpThreads + tid;
+        if (q0 < n_x) {
+            const float* qp0 = x + ((size_t)b * n_x + q0) * 3;
+            const float ax = qp0[0], ay = qp0[1], az = qp0[2];
+            const float ux = R[0] * ax + R[3] * ay + R[6] * az, uy = R[1] * ax + R[4] * ay + R[7] * az,
+                        uz = R[2] * ax + R[5] * ay + R[8] * az;
+            float ms0 = __int_as_float(0x7f800000);
+            key = 0;
+            for (int s = 0; s < NS; ++s) {
+                const float l = box_lb(slo[s], shi[s], ux, uy, uz);
+                if (l < ms0) { ms0 = l; key = s; }
+            }
+        }
+    }
+    const int rank = atomicAdd(&bin_cnt[key], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int k = 0; k < 64; ++k) { bin_start[k] = run; run += bin_cnt[k]; }
+    }
+    __syncthreads();
+    order[bin_start[key] + rank] = (short)tid;
+    order_ss[bin_start[key] + rank] = (short)key;
+    __syncthreads();
+    const int qi = blockIdx.x * kGrpThreads + order[tid];
     if (qi >= n_x) return;
+    const int ss = order_ss[tid];
     const float* qp = x + ((size_t)b * n_x + qi) * 3;
     const float qx = qp[0], qy = qp[1], qz = qp[2];
     const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
     // the vertex in the object frame (R^T q), for the bounds only
     const float ox = R[0] * qx + R[3] * qy + R[6] * qz, oy = R[1] * qx + R[4] * qy + R[7] * qz,
                 oz = R[2] * qx + R[5] * qy + R[8] * qz;
-    float ms = __int_as_float(0x7f800000);
-    int ss = 0;
-    for (int s = 0; s < NS; ++s) {
-        const float l = box_lb(slo[s], shi[s], ox, oy, oz);
-        if (l < ms) { ms = l; ss = s; }
-    }
     float mg = __int_as_float(0x7f800000);
     int seed = ss * kGrpSuper;
     for (int g = ss * kGrpSuper; g < min((ss + 1) * kGrpSuper, NG); ++g) {
