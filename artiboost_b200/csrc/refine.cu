@@ -388,19 +388,29 @@ linear_f32_kernel(int M, int N, int K, const float* __restrict__ x, long long ld
     const float* bp = W + (size_t)(b_ok ? n0 + br : 0) * ldw;
     const int n_tiles = (K + kLinBK - 1) / kLinBK;
     const int n_rounds = (n_tiles + kLinKG - 1) / kLinKG;  // same trip count for every group: the barriers are CTA-wide
-    for (int r = 0; r < n_rounds; ++r) {
+    // the next round's operands are fetched into registers while the current round is multiplied out of shared memory
+    float ra[4], rb[8];
+    auto fetch = [&](int r) {
         const int k0 = (r * kLinKG + kg) * kLinBK;  // may lie past K for the last round: zero tiles
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            int k = k0 + ak + i;
-            As[kg][ak + i][ar] = (a_ok && k < K) ? ap[k] : 0.f;
+            const int k = k0 + ak + i;
+            ra[i] = (a_ok && k < K) ? ap[k] : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            int k = k0 + bk + i;
-            Bs[kg][bk + i][br] = (b_ok && k < K) ? bp[k] : 0.f;
+            const int k = k0 + bk + i;
+            rb[i] = (b_ok && k < K) ? bp[k] : 0.f;
         }
+    };
+    fetch(0);
+    for (int r = 0; r < n_rounds; ++r) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) As[kg][ak + i][ar] = ra[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Bs[kg][bk + i][br] = rb[i];
         __syncthreads();
+        if (r + 1 < n_rounds) fetch(r + 1);
 #pragma unroll
         for (int kk = 0; kk < kLinBK; ++kk) {
             float4 a = *reinterpret_cast<const float4*>(&As[kg][kk][ty * 4]);
