@@ -361,7 +361,9 @@ class HORefiner(nn.Module):
         self.refine_net.eval()
         self.resampled_objs = []
         self.obj_idx = {}
-        self.use_groups = True  # False: brute-force scan of the whole cloud (ab_chamfer_nn)
+        # grouped search over the static clouds (ab_chamfer_nn_grouped): bit-identical to the scan as long as `obj_rot` is a
+        # rotation, which is what the pose generator passes (preprocessor.py:79).  False: scan the whole cloud (ab_chamfer_nn).
+        self.use_groups = True
 
     def setup(self, obj_meshes: Dict[str, object]):
         for name, m in obj_meshes.items():
