@@ -366,12 +366,12 @@ __global__ void __launch_bounds__(kLinThreads)
 linear_f32_kernel(int M, int N, int K, const float* __restrict__ x, long long ldx, const float* __restrict__ W,
                   long long ldw, const float* __restrict__ bias, const float* res, long long ldr, int act, float slope,
                   float* y, long long ldy) {
-    // operand tiles; after the K loop the same storage carries the partial tiles of groups 1.. ([group][element][thread])
-    __shared__ __align__(16) float smem[kLinKG * kLinBK * (kLinBM + kLinBN)];
-    static_assert((kLinKG - 1) * 16 * 128 <= kLinKG * kLinBK * (kLinBM + kLinBN), "partial tiles must fit the operand storage");
-    float (*As)[kLinBK][kLinBM] = reinterpret_cast<float (*)[kLinBK][kLinBM]>(smem);
-    float (*Bs)[kLinBK][kLinBN] = reinterpret_cast<float (*)[kLinBK][kLinBN]>(smem + kLinKG * kLinBK * kLinBM);
-    float (*red)[16][128] = reinterpret_cast<float (*)[16][128]>(smem);
+    // two stages of operand tiles (dynamic shared memory, 48 KB); after the K loop stage 0 carries the partial tiles of
+    // groups 1.. ([group][element][thread])
+    extern __shared__ __align__(16) float lin_smem[];
+    constexpr int kStage = kLinKG * kLinBK * (kLinBM + kLinBN);
+    static_assert((kLinKG - 1) * 16 * 128 <= kStage, "partial tiles must fit one stage of operand storage");
+    float (*red)[16][128] = reinterpret_cast<float (*)[16][128]>(lin_smem);
     const int kg = threadIdx.x >> 7, tid = threadIdx.x & 127, tx = tid & 15, ty = tid >> 4;  // 16 x 8 threads per group
     const int m0 = blockIdx.y * kLinBM, n0 = blockIdx.x * kLinBN;
     float acc[4][4];
@@ -403,14 +403,25 @@ linear_f32_kernel(int M, int N, int K, const float* __restrict__ x, long long ld
             rb[i] = (b_ok && k < K) ? bp[k] : 0.f;
         }
     };
-    fetch(0);
-    for (int r = 0; r < n_rounds; ++r) {
+    auto stage_a = [&](int st) { return reinterpret_cast<float (*)[kLinBK][kLinBM]>(lin_smem + st * kStage); };
+    auto stage_b = [&](int st) {
+        return reinterpret_cast<float (*)[kLinBK][kLinBN]>(lin_smem + st * kStage + kLinKG * kLinBK * kLinBM);
+    };
+    auto stash = [&](int st) {
+        float (*As)[kLinBK][kLinBM] = stage_a(st);
+        float (*Bs)[kLinBK][kLinBN] = stage_b(st);
 #pragma unroll
         for (int i = 0; i < 4; ++i) As[kg][ak + i][ar] = ra[i];
 #pragma unroll
         for (int i = 0; i < 8; ++i) Bs[kg][bk + i][br] = rb[i];
-        __syncthreads();
+    };
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    for (int r = 0; r < n_rounds; ++r) {   // one barrier per round: round r + 1 is staged while round r is multiplied
         if (r + 1 < n_rounds) fetch(r + 1);
+        float (*As)[kLinBK][kLinBM] = stage_a(r & 1);
+        float (*Bs)[kLinBK][kLinBN] = stage_b(r & 1);
 #pragma unroll
         for (int kk = 0; kk < kLinBK; ++kk) {
             float4 a = *reinterpret_cast<const float4*>(&As[kg][kk][ty * 4]);
@@ -421,6 +432,7 @@ linear_f32_kernel(int M, int N, int K, const float* __restrict__ x, long long ld
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
         }
+        if (r + 1 < n_rounds) stash((r + 1) & 1);
         __syncthreads();
     }
     if (kg > 0) {
@@ -644,10 +656,12 @@ extern "C" int ab_chamfer_nn_grouped(int batch, int n_x, const float* x, int n_g
     cudaStream_t st = (cudaStream_t)stream;
     const int n_super = ab::cdiv(n_groups, ab::kGrpSuper);
     const size_t smem = (size_t)3 * n_groups * ab::kGrpStride * 4 + (size_t)(n_groups + n_super) * (16 + 8);
-    static std::atomic<size_t> smem_set{0};  // opt in to > 48 KB of dynamic shared memory (once per size increase)
-    if (smem > smem_set.load(std::memory_order_relaxed)) {
+    static std::atomic<size_t> smem_set[64] = {};  // opt in to > 48 KB of dynamic shared memory (per device, once per size increase)
+    int dev = 0;
+    AB_CUDA(cudaGetDevice(&dev));
+    if (smem > smem_set[dev & 63].load(std::memory_order_relaxed)) {
         AB_CUDA(cudaFuncSetAttribute(ab::chamfer_nn_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set.store(smem, std::memory_order_relaxed);
+        smem_set[dev & 63].store(smem, std::memory_order_relaxed);
     }
     dim3 grid(ab::cdiv(n_x, ab::kGrpThreads), batch);
     {
@@ -672,8 +686,16 @@ extern "C" int ab_linear_f32(int M, int N, int K, const float* x, int64_t ldx, c
     AB_REQUIRE(grid.y <= 65535, "M too large: split the call");
     {
         ab::StageTimer tm(AB_STAGE_LINEAR_F32, st);
-        ab::linear_f32_kernel<<<grid, ab::kLinThreads, 0, st>>>(M, N, K, x, (long long)ldx, W, (long long)ldw, bias,
-                                                               residual, (long long)ldr, act, slope, y, (long long)ldy);
+        constexpr size_t smem = 2 * ab::kLinKG * ab::kLinBK * (ab::kLinBM + ab::kLinBN) * sizeof(float);  // 48 KB
+        static std::atomic<bool> opted[64] = {};  // per device: function attributes belong to the device's context
+        int dev = 0;
+        AB_CUDA(cudaGetDevice(&dev));
+        if (!opted[dev & 63].load(std::memory_order_relaxed)) {
+            AB_CUDA(cudaFuncSetAttribute(ab::linear_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            opted[dev & 63].store(true, std::memory_order_relaxed);
+        }
+        ab::linear_f32_kernel<<<grid, ab::kLinThreads, smem, st>>>(M, N, K, x, (long long)ldx, W, (long long)ldw, bias,
+                                                                  residual, (long long)ldr, act, slope, y, (long long)ldy);
     }
     ab::count_launch();
     return ab::check_launch("linear_f32_kernel");
