@@ -99,3 +99,73 @@ def test_staged_pose_generator_oracle_matches_reference(mano_model):
     np.testing.assert_allclose(out["final_obj_pose"], g["obj_pose"], rtol=0, atol=2e-6)
     np.testing.assert_allclose(out["final_hand_verts"], g["verts"], rtol=0, atol=1e-5)
     np.testing.assert_allclose(out["final_joints"], g["joints"], rtol=0, atol=1e-5)
+
+
+# ---------------------------------------------------------------------- host-side helpers of the product (no kernels)
+def test_host_subdivision_and_resampling_match_the_oracle():
+    from artiboost_b200.artiboost.refiner import HORefiner, subdivide_mesh
+    m = next(iter(fx.object_meshes().values()))
+    v, f = subdivide_mesh(m.vertices, m.faces)
+    np.testing.assert_array_equal(v, orf.subdivide(m.vertices, m.faces))
+    assert f.shape == (4 * len(m.faces), 3) and f.max() == len(v) - 1
+    # every new vertex is the midpoint of an edge of the face that produced it
+    k = len(m.faces)
+    np.testing.assert_allclose(v[f[:k, 1]], (m.vertices[m.faces[:, 0]] + m.vertices[m.faces[:, 1]]) / 2)
+    np.random.seed(5)
+    pts = np.stack([HORefiner.resample_obj(mm) for mm in fx.object_meshes().values()]).astype(np.float32)
+    np.testing.assert_array_equal(pts, resampled_objects(5))
+
+
+def test_nn_groups_cover_the_cloud():
+    from artiboost_b200.artiboost.refiner import build_nn_groups
+    pts = resampled_objects()
+    sp, pm, bx = build_nn_groups(pts)
+    n_obj, P, _ = pts.shape
+    assert sp.shape == (n_obj, 10016, 3) and pm.shape == (n_obj, 10016) and bx.shape == (n_obj, 6, 313)
+    for o in range(n_obj):
+        assert sorted(set(pm[o].tolist())) == list(range(P))              # a permutation (+ padding repeats)
+        np.testing.assert_array_equal(sp[o], pts[o][pm[o]])
+        assert (pm[o, P:] == pm[o, P - 1]).all()                           # padded with the last sorted point
+        g = sp[o].reshape(-1, 32, 3)
+        assert (g >= bx[o, :3].T[:, None]).all() and (g <= bx[o, 3:].T[:, None]).all()
+        # the groups are spatially tight: a Morton run of 32 surface samples spans a few centimetres at most
+        assert np.median((bx[o, 3:] - bx[o, :3]).max(0)) < 0.03
+
+
+def test_random_scrambler_2_bend_expansion_follows_the_reference_order():
+    """expand_bend maps the five per-finger draws onto chain joints (1..12, 14, 15) exactly like scrambler.py:134-170
+    (index, middle, RING -> joints 10-12, LITTLE -> joints 7-9, thumb with coefficients 1 / 0.9)."""
+    import torch
+    from artiboost_b200.artiboost import RandomScrambler2
+    s2 = RandomScrambler2({"HAND_TSL_SIGMA": 0.01, "HAND_POSE_SIGMA": 0.1})
+    b5 = torch.tensor([[1.0, 2.0, 3.0, 4.0, 5.0]])
+    got = s2.expand_bend(b5)[0].numpy()
+    link = np.array([1.0, 1.1, 0.9], np.float32)
+    want = np.concatenate([1 * link, 2 * link, 4 * link, 3 * link, 5 * link[[0, 2]]]).astype(np.float32)
+    np.testing.assert_array_equal(got, want)
+    # and the oracle's per-joint angles are the same numbers
+    g = golden("scrambler23.npz")
+    nz = fx.scrambler_noise()
+    _, _, l_axis = orf.axis_layer(g["joints"], g["transf"])
+    bend14 = s2.expand_bend(torch.from_numpy(nz["bend5"])).numpy()
+    p2 = orf.random_scrambler_3(orf.random_scrambler_2(g["pose"], g["joints"], g["transf"], nz["splay"], np.zeros_like(nz["bend5"]),
+                                                       np.zeros_like(nz["thumb"])),
+                                g["joints"], g["transf"], np.zeros_like(nz["splay"]), bend14, nz["thumb"])
+    np.testing.assert_allclose(p2, g["pose2"], rtol=0, atol=5e-6)
+
+
+def test_refiner_registries_and_state_dict_names():
+    from artiboost_b200.artiboost import HORefiner, NullRefine, Refiner, Scrambler
+    assert set(Refiner.build_mapping) == {"null", "hand_obj"}
+    assert {"null", "naive", "random", "random_2", "random_3"} <= set(Scrambler.build_mapping)
+    with __import__("pytest").raises(KeyError):
+        Scrambler.build("nope", {})
+    r = HORefiner({"PRETRAINED": None, "ITERS": 3}, mano_model=__import__("artiboost_b200.assets", fromlist=["x"]).make_synthetic_mano(0))
+    ours = {k for k in r.refine_net.state_dict() if not k.startswith("mano_layer.")}
+    ref = set(fx.refinenet_state()) | {k.replace("running_mean", "num_batches_tracked") for k in fx.refinenet_state()
+                                       if k.endswith("running_mean")}
+    assert ours == ref
+    missing = r.refine_net.load_state_dict({k: __import__("torch").from_numpy(v) for k, v in fx.refinenet_state().items()}, strict=False)
+    assert not missing.unexpected_keys
+    assert isinstance(Refiner.build("null", None, mano_model=r.refine_net.mano_layer and
+                                    __import__("artiboost_b200.assets", fromlist=["x"]).make_synthetic_mano(0)), NullRefine)
