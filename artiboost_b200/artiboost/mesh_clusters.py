@@ -10,12 +10,35 @@ from __future__ import annotations
 import numpy as np
 
 
-def build_clusters(vertices: np.ndarray, faces: np.ndarray, size: int = 64):
-    """-> dict(first i32[n], count i32[n], center f32[n,3], radius f32[n], axis f32[n,3], cutoff f32[n]).
+def morton_face_order(vertices: np.ndarray, faces: np.ndarray) -> np.ndarray:
+    """Permutation that sorts the faces along a 30-bit Morton curve of their centroids (stable): consecutive runs become
+    compact surface patches instead of whatever strips the modelling tool emitted.  The rasteriser would walk the faces in
+    this order but keep the ORIGINAL index as the primitive id of the z-test key, so ties still break as before."""
+    v = np.asarray(vertices, np.float64)
+    c = v[np.asarray(faces, np.int64)[:, :3]].mean(1)
+    lo, hi = c.min(0), c.max(0)
+    q = np.clip(((c - lo) / np.maximum(hi - lo, 1e-12) * 1023.0).astype(np.int64), 0, 1023).astype(np.uint64)
+
+    def spread(x):
+        x = (x | (x << np.uint64(16))) & np.uint64(0x030000FF)
+        x = (x | (x << np.uint64(8))) & np.uint64(0x0300F00F)
+        x = (x | (x << np.uint64(4))) & np.uint64(0x030C30C3)
+        x = (x | (x << np.uint64(2))) & np.uint64(0x09249249)
+        return x
+
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
+    return np.argsort(code, kind="stable")
+
+
+def build_clusters(vertices: np.ndarray, faces: np.ndarray, size: int = 64, order: np.ndarray = None):
+    """-> dict(first i32[n], count i32[n], center f32[n,3], radius f32[n], axis f32[n,3], cutoff f32[n][, order]).
     axis / cutoff: unit cone axis and min over the cluster's (non-degenerate) faces of dot(axis, face normal);
-    cutoff < 0 means the normals span more than a half-space (such a cluster is never culled)."""
+    cutoff < 0 means the normals span more than a half-space (such a cluster is never culled).
+    order: optional face permutation (morton_face_order); cluster k then holds faces order[first[k] : first[k] + count[k]]."""
     v = np.asarray(vertices, np.float64)
     f = np.asarray(faces, np.int64)[:, :3]
+    if order is not None:
+        f = f[np.asarray(order)]
     n = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
     ln = np.linalg.norm(n, axis=1)
     ok = ln > 0
@@ -37,9 +60,22 @@ def build_clusters(vertices: np.ndarray, faces: np.ndarray, size: int = 64):
             axis, cutoff = np.array([0.0, 0.0, 1.0]), 1.0
         for k, val in zip(out, (a, b - a, c, r, axis, cutoff)):
             out[k].append(val)
-    return {"first": np.asarray(out["first"], np.int32), "count": np.asarray(out["count"], np.int32),
-            "center": np.asarray(out["center"], np.float32), "radius": np.asarray(out["radius"], np.float32),
-            "axis": np.asarray(out["axis"], np.float32), "cutoff": np.asarray(out["cutoff"], np.float32)}
+    res = {"first": np.asarray(out["first"], np.int32), "count": np.asarray(out["count"], np.int32),
+           "center": np.asarray(out["center"], np.float32), "radius": np.asarray(out["radius"], np.float32),
+           "axis": np.asarray(out["axis"], np.float32), "cutoff": np.asarray(out["cutoff"], np.float32)}
+    if order is not None:
+        res["order"] = np.asarray(order, np.int64)
+    return res
+
+
+def culled_faces(clusters: dict, culled: np.ndarray) -> np.ndarray:
+    """bool per ORIGINAL face index: member of a culled cluster."""
+    per_slot = np.repeat(np.asarray(culled, bool), clusters["count"])
+    if "order" not in clusters:
+        return per_slot
+    out = np.zeros(len(per_slot), bool)
+    out[clusters["order"]] = per_slot
+    return out
 
 
 def culled_clusters(clusters: dict, pose: np.ndarray, front_sign: float, margin: float = 0.02) -> np.ndarray:

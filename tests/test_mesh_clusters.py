@@ -5,7 +5,7 @@ import numpy as np
 
 from oracle import ccv, raster
 from artiboost_b200 import assets
-from artiboost_b200.artiboost.mesh_clusters import build_clusters, culled_clusters, front_sign_of
+from artiboost_b200.artiboost.mesh_clusters import build_clusters, culled_clusters, culled_faces, front_sign_of, morton_face_order
 
 CFG = dict(width=256, height=256, fx=217.5, fy=217.5, cx=128.0, cy=128.0, znear=0.05, cull_backface=1, ambient=0.8, diffuse=0.25)
 
@@ -15,10 +15,11 @@ def test_cluster_culling_is_conservative_and_worth_it(mano_model, objects):
     hand_cols = np.full((778, 4), 200, np.uint8)
     hv = mano_model["v_template"].astype(np.float32) + np.array([0.05, 0.0, 0.5], np.float32)
     hf = np.asarray(mano_model["f"], np.int32)
-    fractions = []
+    fractions, fractions_patch = [], []
     for name, o in objects.items():
         verts, faces = o["vertices"], np.asarray(o["faces"], np.int32)[:, :3]
         cl = build_clusters(verts, faces, size=32)              # one warp of the triangle pass
+        clp = build_clusters(verts, faces, size=32, order=morton_face_order(verts, faces))   # compact patches, ids remapped
         assert cl["first"][0] == 0 and int(cl["count"].sum()) == len(faces)
         sign = front_sign_of(verts, faces)
         cols = np.concatenate([o["colors"][:, :3], np.full((len(verts), 1), 255, np.uint8)], 1) if o["colors"].shape[1] == 3 else o["colors"]
@@ -27,19 +28,21 @@ def test_cluster_culling_is_conservative_and_worth_it(mano_model, objects):
             pose = np.eye(4, dtype=np.float32)
             pose[:3, :3] = free[:3, :3] @ rot.T
             pose[:3, 3] = zoff + rng.normal(0, 0.03, 3)
-            culled = culled_clusters(cl, pose, sign)
-            keep = np.repeat(~culled, cl["count"])
-            f2 = faces.copy()
-            f2[~keep] = 0                                   # degenerate (area 0): discarded by the rules, ids preserved
             a = raster.render_view(CFG, hv, hf, hand_cols, verts, faces, cols, pose)
-            b = raster.render_view(CFG, hv, hf, hand_cols, verts, f2, cols, pose)
-            for x, y, what in zip(a, b, ("rgba", "depth", "seg", "key")):
-                assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), (name, what)
             assert (a[2] == 2).sum() > 500                   # the object is in view
-            fractions.append((~keep).mean())
+            for clusters, acc in ((cl, fractions), (clp, fractions_patch)):
+                gone = culled_faces(clusters, culled_clusters(clusters, pose, sign))
+                f2 = faces.copy()
+                f2[gone] = 0                                 # degenerate (area 0): discarded by the rules, ids preserved
+                b = raster.render_view(CFG, hv, hf, hand_cols, verts, f2, cols, pose)
+                for x, y, what in zip(a, b, ("rgba", "depth", "seg", "key")):
+                    assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), (name, what)
+                acc.append(gone.mean())
     # closed meshes seen from outside: about half of the faces are back-facing; whole clusters account for a good part
     assert np.mean(fractions) > 0.25, np.mean(fractions)
-    print("faces skipped by cluster culling: mean %.3f min %.3f max %.3f" % (np.mean(fractions), min(fractions), max(fractions)))
+    assert np.mean(fractions_patch) > np.mean(fractions)
+    print("faces skipped by cluster culling: face order mean %.3f (min %.3f max %.3f), Morton patches mean %.3f (min %.3f max %.3f)"
+          % (np.mean(fractions), min(fractions), max(fractions), np.mean(fractions_patch), min(fractions_patch), max(fractions_patch)))
 
 
 def test_front_sign_matches_the_rasteriser_rule(objects):
