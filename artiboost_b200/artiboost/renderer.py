@@ -18,6 +18,7 @@ import torch
 
 from . import DUMMY
 from .. import lib
+from .patches import PatchTable
 
 PointLight = NamedTuple("PointLight", [("color", np.ndarray), ("intensity", float), ("pose", np.ndarray)])
 DirectionalLight = NamedTuple("DirectionalLight", [("color", np.ndarray), ("intensity", float), ("pose", np.ndarray)])
@@ -48,7 +49,7 @@ def _vertex_colors(mesh, n: int) -> np.ndarray:
 
 class Renderer:
 
-    def __init__(self, width: int, height: int, gpu_id: int = 0, chunk: int = 64) -> None:
+    def __init__(self, width: int, height: int, gpu_id: int = 0, chunk: int = 512) -> None:
         if not torch.cuda.is_available():
             raise lib.AbError("Renderer needs a CUDA device: artiboost_b200 has no CPU path")
         lib.load()
@@ -108,6 +109,10 @@ class Renderer:
             self.backgrounds = up(np.stack(bgs))
             # the kernel reads an RGBX copy: one aligned 32-bit load per background pixel instead of three byte loads
             self._bgs4 = torch.cat([self.backgrounds, torch.zeros_like(self.backgrounds[..., :1])], -1).contiguous()
+        # mesh patches of the tile rasteriser (native host builder, once per scene)
+        self.obj_patches = PatchTable([(np.asarray(obj_meshes[k].vertices, np.float32), np.asarray(obj_meshes[k].faces))
+                                       for k in self.obj_names], dev)
+        self.hand_patches = PatchTable([(np.asarray(hand_meshes[0].vertices, np.float32), hf)], dev, with_pos=False)
         self.scene = lib.SceneStruct(
             len(self.obj_names), self.obj_verts.data_ptr(), self.obj_faces.data_ptr(), self.obj_colors.data_ptr(),
             C.cast(self._voff, lib.c_i32_p), C.cast(self._foff, lib.c_i32_p), n_hv, hf.shape[0], self.n_hand_tex,
@@ -115,13 +120,21 @@ class Renderer:
             None if self.backgrounds is None else self._bgs4.data_ptr(),
             0 if self.backgrounds is None else self.backgrounds.shape[0],
             0 if self.backgrounds is None else self.backgrounds.shape[1],
-            0 if self.backgrounds is None else self.backgrounds.shape[2], 4)
+            0 if self.backgrounds is None else self.backgrounds.shape[2], 4,
+            C.pointer(self.obj_patches.struct) if self.obj_names else None, C.pointer(self.hand_patches.struct))
         self.camera = lib.CameraStruct(self.width, self.height, float(cam_intr[0, 0]), float(cam_intr[1, 1]),
                                        float(cam_intr[0, 2]), float(cam_intr[1, 2]), float(znear), int(cull_backface),
                                        0.8, float(diffuse), 128, 128, 128)  # ambient 0.8, bg 0.5 (renderer.py:77)
         self.lights = lights
+        self.set_chunk(self.chunk)
+
+    def set_chunk(self, chunk: int) -> None:
+        """(Re)allocates the workspace for groups of `chunk` views (the per-tile patch lists of one group)."""
+        self.chunk = int(chunk)
         n = lib.load().ab_render_workspace_bytes(C.byref(self.scene), C.byref(self.camera), self.chunk)
-        self._ws = torch.empty(int(n) + 256, dtype=torch.uint8, device=dev)
+        if n == 0:
+            raise lib.AbError("ab_render_workspace_bytes: inconsistent scene / camera / chunk")
+        self._ws = torch.empty(int(n) + 256, dtype=torch.uint8, device=self.device)
         self._ws_off = (-self._ws.data_ptr()) % 256
 
     # ----------------------------------------------------------------------------------------------- per call

@@ -1,28 +1,31 @@
-// Batched hand+object view rasteriser (sm_100a).
+// Batched hand+object view rasteriser (sm_100a): tile-binned, z-buffer in shared memory.
 //
 // Replaces Renderer.__call__ (anakin/utils/renderer.py:101-123) over pyrender's OffscreenRenderer
 // (anakin/utils/frender_utils.py:179-205): B views per call instead of one GL draw + two glReadPixels per call.
 // The rule set (fixed-point snapping, top-left fill rule, 1/z depth, z-test key, shading) is the one stated at the
-// top of oracle/raster.c; every fp32 operation below is individually rounded in the same order (this file is
+// top of oracle/raster.c; every fp32 operation of the rules is individually rounded in the same order (this file is
 // compiled with -fmad=false and uses explicit __fmaf_rn where the rules say "fma").
 //
-// Views are processed in chunks; per chunk three kernels run back to back on the caller's stream:
-//   1. raster_vertex_kernel    one thread per (view, vertex): object model matrix, pinhole projection, snapping
-//                              to 24.8 fixed point.  16 B per projected vertex, coalesced, into an L2-resident scratch.
-//   2. raster_triangle_kernel  one thread per (view, triangle): integer set-up, cull, pixel bbox, coverage with
-//                              exact integer edge functions (32-bit when the bbox is < 128 px, else 64-bit),
-//                              z-test by RED.MIN.U64 on key = depth_bits << 32 | prim_id into the chunk's key
-//                              buffer (8 B / pixel, L2-resident).  At 256^2 most triangles cover 0-2 pixel centres,
-//                              so the pass is set-up bound, not fill bound.
-//   3. raster_resolve_kernel   one thread per 4 consecutive pixels: winner triangle re-set-up, exact depth,
-//                              shading, background compositing; 16-byte RGBA / depth stores, 4-byte seg stores;
-//                              restores the key buffer to "empty" where it was hit.
-// HBM traffic per view is the output (9 B / pixel) plus the 9.4 KB of per-view inputs; scratch never needs to
-// leave L2 when `chunk` is sized so (chunk * (8*W*H + 16*verts)) stays well under the 126 MB L2.
+// Meshes are walked as patches (patches.cu: <= 32 faces over <= 32 vertices, bounding sphere + normal cone).
+// Two kernels per group of views:
+//   1. raster_bin_kernel   object patches, one thread each: sphere centre + cone axis into camera space, conservative
+//                          back-face test of the whole patch (margin derived from the 24.8 snapping error and the
+//                          patch's worst perimeter / area ratio), conservative screen box of the sphere -> appended to
+//                          the list of every 64x64 tile it may touch.  Hand patches (vertices change per view), one
+//                          warp each: exact box of the projected vertices by warp reductions.
+//   2. raster_tile_kernel  one CTA per (view, tile).  The tile's z-buffer (64-bit key = depth bits << 32 | primitive
+//                          id per pixel, 32 KB) lives in SHARED memory.  Warps pull patches from the tile's list; per
+//                          patch a lane per vertex (model matrix, projection, snapping -> 16 B in a per-warp slab),
+//                          then a lane per face (integer set-up, cull, bbox clipped to the tile; exact integer edge
+//                          functions; small boxes walked by the lane itself, large ones by the whole warp), z-test by
+//                          a shared-memory 64-bit atomic min.  Then the CTA streams the tile out: background crop /
+//                          flat colour, zero depth and seg with 16-byte stores, covered pixels compacted into a list
+//                          and shaded on full warps (winner re-set-up, flat normal, point light).
+// Nothing but the per-view inputs, the tile lists (a few KB per view) and the output image (9 B / pixel) touches HBM or
+// L2: no projected-vertex scratch, no key buffer, no memset of either.  Tiles without geometry (most of the frame) skip
+// the z-buffer altogether and are pure write streams that overlap with the set-up work of the busy tiles on the same SM.
+#include <limits.h>
 #include <stdlib.h>
-
-#include <atomic>
-#include <mutex>
 
 #include "common.cuh"
 
@@ -30,6 +33,14 @@ namespace ab {
 
 constexpr int kMaxObjects = 64;
 constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr int kTile = 64;                 // tile edge in pixels
+constexpr int kTilePx = kTile * kTile;
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kOwnMax = 16;               // a lane walks its own triangle when its clipped bbox has at most this many pixels
+constexpr unsigned kHandBit = 0x8000u;    // list entries: patch index (relative to its mesh) | kHandBit for hand patches
+constexpr unsigned kFull = 0xffffffffu;
+constexpr float kSnapEps = 0.0032f;       // bound on the displacement (pixels) of a projected vertex by fp32 evaluation + 24.8 snapping
 
 // floor(n / d) for n < 2^30 as (n * m) >> s with m = ceil(2^s / d), s = 31 + ceil(log2 d): m < 2^32, and with
 // e = m d - 2^s in [0, d) the quotient is exact because n e < 2^30 2^ceil(log2 d) <= 2^s.
@@ -51,33 +62,43 @@ struct RasterParams {
     const int4* hand_faces;
     const uchar4* hand_colors;
     const uint8_t* bgs;
+    // patches
+    const float4* op_pos;     // [P][32]
+    const uint32_t* op_face;  // [P][32]
+    const int32_t* op_prim;   // [P][32]
+    const float4* op_bound;   // [P][3]
+    const int32_t* hp_vid;
+    const uint32_t* hp_face;
+    const int32_t* hp_prim;
+    int n_hp;                 // hand patches
+    int obj_bin_blocks;       // blocks of the binning grid that serve object patches
     int n_obj, n_hv, n_hf, n_tex, n_bg, bg_h, bg_w, bg_ch;
-    unsigned div_w_m, div_2w_m, div_2h_m;  // exact division by W, 2W, 2H as multiply + shift (FastDiv below)
+    unsigned div_w_m, div_2w_m, div_2h_m;  // exact division by W, 2W, 2H as multiply + shift
     int div_w_s, div_2w_s, div_2h_s;
-    int max_ov, max_of;  // launch sizing
     // camera
     int W, H;
     float fx, fy, cx, cy, znear, ambient, diffuse;
     int cull;
     int bg_r, bg_g, bg_b;
-    // per-view inputs (already offset to the chunk's first view)
+    // tiles
+    int tiles_x, tiles_y, n_tiles, list_cap;
+    int* bin_count;             // [views][n_tiles]
+    unsigned short* bin_list;   // [views][n_tiles][list_cap]
+    // per-view inputs (already offset to the group's first view)
     const float* hand_verts;
     const int32_t* hand_tex;
     const int32_t* obj_id;
     const float* obj_pose;
     const float* light;
     const int32_t* bg_sel;
-    // outputs (offset to the chunk)
+    // outputs (offset to the group)
     uint8_t* rgba;
     float* depth;
     uint8_t* seg;
-    // scratch
-    unsigned long long* keys;  // [chunk][H][W]
-    int4* pv;                  // [chunk][pv_stride]  {x, y, iz bits, ok}
-    int pv_stride;
     int n_views;
     int vert_off[kMaxObjects + 1];
     int face_off[kMaxObjects + 1];
+    int patch_off[kMaxObjects + 1];
 };
 
 // ---- rule: vertex ------------------------------------------------------------------------------------------
@@ -104,62 +125,105 @@ __device__ __forceinline__ void xform(const float* __restrict__ M, float x, floa
     o[2] = __fmaf_rn(M[10], z, __fmaf_rn(M[9], y, __fmaf_rn(M[8], x, M[11])));
 }
 
-__global__ void __launch_bounds__(256)
-raster_vertex_kernel(const __grid_constant__ RasterParams P) {
+__device__ __forceinline__ int floordiv256(int v) { return v >> 8; }
+
+// ---- binning -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bin_append(const RasterParams& P, int view, int px_lo, int px_hi, int py_lo, int py_hi,
+                                           unsigned entry) {
+    const int tx_lo = px_lo / kTile, tx_hi = px_hi / kTile, ty_lo = py_lo / kTile, ty_hi = py_hi / kTile;
+    for (int ty = ty_lo; ty <= ty_hi; ++ty)
+        for (int tx = tx_lo; tx <= tx_hi; ++tx) {
+            const int bin = view * P.n_tiles + ty * P.tiles_x + tx;
+            const int slot = atomicAdd(P.bin_count + bin, 1);
+            P.bin_list[(size_t)bin * P.list_cap + slot] = (unsigned short)entry;
+        }
+}
+
+// Object patch: everything happens on the patch's bounding sphere (centre s, radius r, camera space) and its normal
+// cone (unit axis a, every face normal n within acos(c) of it).
+//  * Back-face test.  With p0, p1, p2 the camera-space corners of a face and n = (p1-p0) x (p2-p0) = 2 A n^ its winding
+//    normal, the projected signed area is exactly  area2 = fx fy (p0 . n) / (z0 z1 z2)  pixels^2, and the rule culls
+//    area2 > 0.  For p in the sphere and n^ in the cone,  n^ . p >= |s| cos(phi + theta) - r =: Bnd  (phi = angle(a, s),
+//    theta = acos c; needs phi + theta <= pi, hence c > 0 and cos phi > 0).  Snapping (and fp32 evaluation) moves each
+//    projected corner by at most eps pixels, which changes area2 by at most 2 eps (projected perimeter) + 4 eps^2, and a
+//    world-space segment of length L projects to at most L g pixels, g = max(fx, fy) (1 + T) / zmin, T = the largest
+//    |(x, y)| / z over the sphere.  So every face of the patch is certainly culled when
+//        Bnd > 1.5 zmax^3 / (fx fy) (eps q g + 4 eps^2 ia) + 2e-5,    q = max perimeter / area, ia = max 1 / (2 area).
+//  * Screen box.  x / z over the box [sx - r, sx + r] x [zmin, zmax] is extremal at its corners; 0.05 px of slack covers
+//    snapping and fp32.  Pixels whose CENTRE lies in the box are the only ones a face of the patch can cover.
+__global__ void __launch_bounds__(kThreads)
+raster_bin_kernel(const __grid_constant__ RasterParams P) {
     const int view = blockIdx.y;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int oid = P.obj_id[view];
-    const int n_ov = oid >= 0 ? P.vert_off[oid + 1] - P.vert_off[oid] : 0;
-    if (t >= n_ov + P.n_hv) return;
-    float c[3];
-    if (t < n_ov) {
-        const float* v = P.obj_verts + 3 * (size_t)(P.vert_off[oid] + t);
-        xform(P.obj_pose + 16 * (size_t)view, v[0], v[1], v[2], c);
+    if ((int)blockIdx.x < P.obj_bin_blocks) {
+        if (oid < 0) return;
+        const int i = blockIdx.x * kThreads + threadIdx.x;
+        if (i >= P.patch_off[oid + 1] - P.patch_off[oid]) return;
+        const float4* bp = P.op_bound + 3 * (size_t)(P.patch_off[oid] + i);
+        const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2);
+        const float* M = P.obj_pose + 16 * (size_t)view;
+        float s[3];
+        xform(M, b0.x, b0.y, b0.z, s);
+        const float r = b0.w;
+        const float zmin = s[2] - r, zmax = s[2] + r;
+        if (P.cull && b1.w > 0.0f && zmin > 1e-4f) {
+            const float ax = M[0] * b1.x + M[1] * b1.y + M[2] * b1.z;
+            const float ay = M[4] * b1.x + M[5] * b1.y + M[6] * b1.z;
+            const float az = M[8] * b1.x + M[9] * b1.y + M[10] * b1.z;
+            const float ls = sqrtf(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+            const float la = sqrtf(ax * ax + ay * ay + az * az);  // 1 for a rigid pose; a scaled pose keeps the test valid
+            const float cos_phi = (ax * s[0] + ay * s[1] + az * s[2]) / (ls * la);
+            if (cos_phi > 0.0f) {
+                const float c = b1.w;
+                const float sin_phi = sqrtf(fmaxf(0.0f, 1.0f - cos_phi * cos_phi));
+                const float sin_th = sqrtf(fmaxf(0.0f, 1.0f - c * c));
+                const float bnd = ls * (cos_phi * c - sin_phi * sin_th) - r;
+                const float T = (sqrtf(s[0] * s[0] + s[1] * s[1]) + r) / zmin;
+                const float g = fmaxf(P.fx, P.fy) * (1.0f + T) / zmin;
+                const float need = 1.5f * zmax * zmax * zmax / (P.fx * P.fy) * (kSnapEps * b2.x * g + 4.0f * kSnapEps * kSnapEps * b2.y) + 2e-5f;
+                if (bnd > need) return;  // inf / NaN in `need` (degenerate faces) compares false: not culled
+            }
+        }
+        int px_lo = 0, px_hi = P.W - 1, py_lo = 0, py_hi = P.H - 1;
+        if (zmin > 1e-4f) {
+            const float ilo = 1.0f / zmin, ihi = 1.0f / zmax;
+            const float xl = s[0] - r, xh = s[0] + r, yl = s[1] - r, yh = s[1] + r;
+            float umin = P.fx * fminf(xl * ilo, xl * ihi) + P.cx, umax = P.fx * fmaxf(xh * ilo, xh * ihi) + P.cx;
+            float vmin = P.fy * fminf(yl * ilo, yl * ihi) + P.cy, vmax = P.fy * fmaxf(yh * ilo, yh * ihi) + P.cy;
+            umin = fminf(fmaxf(ceilf(umin - 0.55f), -1.0e6f), 1.0e6f); umax = fminf(fmaxf(floorf(umax - 0.45f), -1.0e6f), 1.0e6f);
+            vmin = fminf(fmaxf(ceilf(vmin - 0.55f), -1.0e6f), 1.0e6f); vmax = fminf(fmaxf(floorf(vmax - 0.45f), -1.0e6f), 1.0e6f);
+            px_lo = max((int)umin, 0); px_hi = min((int)umax, P.W - 1);
+            py_lo = max((int)vmin, 0); py_hi = min((int)vmax, P.H - 1);
+            if (px_lo > px_hi || py_lo > py_hi) return;
+        }
+        bin_append(P, view, px_lo, px_hi, py_lo, py_hi, (unsigned)i);
     } else {
-        const float* v = P.hand_verts + 3 * ((size_t)view * P.n_hv + (t - n_ov));
-        c[0] = v[0]; c[1] = v[1]; c[2] = v[2];
+        const int w = ((int)blockIdx.x - P.obj_bin_blocks) * kWarps + (threadIdx.x >> 5);
+        if (w >= P.n_hp) return;
+        const int lane = threadIdx.x & 31;
+        const int v = __ldg(P.hp_vid + w * 32 + lane);
+        int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+        if (v >= 0) {
+            const float* hv = P.hand_verts + 3 * ((size_t)view * P.n_hv + v);
+            const int4 p = project(P, hv[0], hv[1], hv[2]);
+            if (p.w) { mnx = mxx = p.x; mny = mxy = p.y; }  // faces with an invalid corner are never drawn
+        }
+        mnx = __reduce_min_sync(kFull, mnx); mxx = __reduce_max_sync(kFull, mxx);
+        mny = __reduce_min_sync(kFull, mny); mxy = __reduce_max_sync(kFull, mxy);
+        if (lane != 0 || mnx > mxx) return;
+        const int px_lo = max(floordiv256(mnx + 127), 0), px_hi = min(floordiv256(mxx - 128), P.W - 1);
+        const int py_lo = max(floordiv256(mny + 127), 0), py_hi = min(floordiv256(mxy - 128), P.H - 1);
+        if (px_lo > px_hi || py_lo > py_hi) return;
+        bin_append(P, view, px_lo, px_hi, py_lo, py_hi, (unsigned)w | kHandBit);
     }
-    P.pv[(size_t)view * P.pv_stride + t] = project(P, c[0], c[1], c[2]);
 }
 
 // ---- rule: triangle ----------------------------------------------------------------------------------------
-// Triangles whose snapped bbox is under 64 px in both axes (all of them in valid ArtiBoost views) take the "small"
+// Triangles whose snapped bbox is under 64 px in both axes (all of them in valid ArtiBoost views) take the int32
 // path: every factor of the edge functions is below 2^14 + 2^8 in magnitude, so products and their differences are
 // exact in int32.  Larger ones take the int64 path.  Both produce the same integers, hence the same floats.
 constexpr int kSmallExtent = 16384;  // 64 px in 24.8 fixed point
-constexpr int kTriThreads = 256;
 
-struct TriRec {            // one per surviving triangle of a CTA (shared memory); 27 words: odd stride, no bank pattern
-    int x0, y0, w;         // pixel bbox origin, width
-    int f;                 // primitive id
-    int e[3];              // small path: edge values at the centre of pixel (x0, y0)
-    int ex[3], ey[3];      // small path: edge steps per pixel in x / y
-    float iz[3];
-    float sarea;           // (float)|area2|
-    int nbias;             // bit i set <=> edge i is not a top/left edge (E_i == 0 is outside)
-    int big;               // 1 -> int64 path from vx, vy, s
-    int vx[3], vy[3], s;
-    int pad;
-};
-
-__device__ __forceinline__ float depth_from(const float* iz, float sarea, float f0, float f1, float f2, float* num_out,
-                                            float* a) {
-    a[0] = __fmul_rn(f0, iz[0]);
-    a[1] = __fmul_rn(f1, iz[1]);
-    a[2] = __fmul_rn(f2, iz[2]);
-    const float num = __fmaf_rn(f2, iz[2], __fmaf_rn(f1, iz[1], a[0]));
-    *num_out = num;
-    return __fdiv_rn(sarea, num);
-}
-
-__device__ __forceinline__ int floordiv256(int v) { return v >> 8; }
-
-__device__ __forceinline__ void emit(unsigned long long* __restrict__ keys, int idx, float z, int f) {
-    const unsigned long long k = ((unsigned long long)__float_as_uint(z) << 32) | (unsigned)f;
-    atomicMin(keys + idx, k);  // result unused -> RED.E.MIN.64
-}
-
-// signed 2*area with the sign convention of the rule set; `small` selects the exact-in-int32 evaluation
 __device__ __forceinline__ long long area2_of(const int4& a, const int4& b, const int4& d, bool small) {
     if (small) return (long long)((b.x - a.x) * (d.y - a.y) - (d.x - a.x) * (b.y - a.y));
     return (long long)(b.x - a.x) * (long long)(d.y - a.y) - (long long)(d.x - a.x) * (long long)(b.y - a.y);
@@ -171,146 +235,54 @@ __device__ __forceinline__ long long edge64(const int* x, const int* y, int s, i
     return (long long)s * (dx * (py - y[i1]) - dy * (px - x[i1]));
 }
 
-// Phase A: one thread per triangle -- gather, pixel bbox (most sub-pixel triangles stop here), area / cull, edge
-// set-up into shared memory.  Phase B: the CTA's surviving bbox ROWS are dealt out evenly to all 256 threads (block
-// scan + binary search), so lanes stay busy although triangles differ in size by two orders of magnitude.
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kTriThreads, kMinBlocks)
-raster_triangle_kernel(const __grid_constant__ RasterParams P) {
-    __shared__ TriRec recs[kTriThreads];
-    __shared__ int prefix[kTriThreads + 1];
-    __shared__ int warp_tot[kTriThreads / 32];
-    const int view = blockIdx.y;
-    const int t = threadIdx.x;
-    const int f = blockIdx.x * kTriThreads + t;
-    const int oid = P.obj_id[view];
-    int n_of = 0, n_ov = 0;
-    if (oid >= 0) {
-        n_of = P.face_off[oid + 1] - P.face_off[oid];
-        n_ov = P.vert_off[oid + 1] - P.vert_off[oid];
-    }
-    if (blockIdx.x * kTriThreads >= n_of + P.n_hf) return;  // whole CTA past the end (launch sized for the largest object)
-    int rows = 0;
-    if (f < n_of + P.n_hf) {
-        int4 idx;
-        int off;
-        if (f < n_of) { idx = __ldg(P.obj_faces + P.face_off[oid] + f); off = 0; }
-        else { idx = __ldg(P.hand_faces + (f - n_of)); off = n_ov; }
-        const int4* pv = P.pv + (size_t)view * P.pv_stride + off;
-        const int4 a = pv[idx.x], b = pv[idx.y], d = pv[idx.z];
-        if (a.w & b.w & d.w) {
-            const int minx = min(a.x, min(b.x, d.x)), maxx = max(a.x, max(b.x, d.x));
-            const int miny = min(a.y, min(b.y, d.y)), maxy = max(a.y, max(b.y, d.y));
-            const int x0 = max(floordiv256(minx - 128 + 255), 0), x1 = min(floordiv256(maxx - 128), P.W - 1);
-            const int y0 = max(floordiv256(miny - 128 + 255), 0), y1 = min(floordiv256(maxy - 128), P.H - 1);
-            if (x0 <= x1 && y0 <= y1) {
-                const bool small = (maxx - minx < kSmallExtent) && (maxy - miny < kSmallExtent);
-                const long long area2 = area2_of(a, b, d, small);
-                if (area2 != 0 && !(area2 > 0 && P.cull)) {
-                    TriRec& r = recs[t];
-                    const int s = area2 > 0 ? 1 : -1;
-                    const int vx[3] = {a.x, b.x, d.x}, vy[3] = {a.y, b.y, d.y};
-                    r.x0 = x0; r.y0 = y0; r.w = x1 - x0 + 1; r.f = f;
-                    r.iz[0] = __int_as_float(a.z); r.iz[1] = __int_as_float(b.z); r.iz[2] = __int_as_float(d.z);
-                    r.sarea = __ll2float_rn(area2 > 0 ? area2 : -area2);
-                    r.big = small ? 0 : 1;
-                    r.s = s;
-                    int nbias = 0;
-                    const int cx0 = 256 * x0 + 128, cy0 = 256 * y0 + 128;
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {  // edge i runs v[i+1] -> v[i+2], opposite vertex i
-                        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-                        const int dx = s * (vx[i2] - vx[i1]), dy = s * (vy[i2] - vy[i1]);  // |.| <= 2^23: no overflow
-                        if (!((dy < 0) || (dy == 0 && dx > 0))) nbias |= 1 << i;
-                        r.vx[i] = vx[i]; r.vy[i] = vy[i];
-                        if (small) {
-                            r.e[i] = dx * (cy0 - vy[i1]) - dy * (cx0 - vx[i1]);
-                            r.ex[i] = -256 * dy;
-                            r.ey[i] = 256 * dx;
-                        }
-                    }
-                    r.nbias = nbias;
-                    rows = y1 - y0 + 1;
-                }
-            }
-        }
-    }
-    // ---- exclusive block scan of the row counts
-    const int lane = t & 31, wid = t >> 5;
-    int incl = rows;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_tot[wid] = incl;
-    __syncthreads();
-    int base = 0;
-#pragma unroll
-    for (int w = 0; w < kTriThreads / 32; ++w) base += (w < wid) ? warp_tot[w] : 0;
-    prefix[t] = base + incl - rows;
-    if (t == kTriThreads - 1) prefix[kTriThreads] = base + incl;
-    __syncthreads();
-    const int total = prefix[kTriThreads];
-    unsigned long long* keys = P.keys + (size_t)view * P.W * P.H;
-    // ---- phase B: one bbox row per thread per iteration
-    for (int c = t; c < total; c += kTriThreads) {
-        int lo = 1, hi = kTriThreads;  // first index with prefix[idx] > c; prefix[0] = 0 <= c, 256 candidates -> 8 halvings
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int mid = (lo + hi) >> 1;
-            if (prefix[mid] > c) hi = mid; else lo = mid + 1;
-        }
-        const TriRec& r = recs[lo - 1];
-        const int row = c - prefix[lo - 1];
-        const int py = r.y0 + row;
-        const int b0 = -(r.nbias & 1), b1 = -((r.nbias >> 1) & 1), b2 = -((r.nbias >> 2) & 1);
-        const float iz[3] = {r.iz[0], r.iz[1], r.iz[2]};
-        const float sarea = r.sarea;
-        const int fid = r.f, w = r.w, kbase = py * P.W + r.x0;
-        if (!r.big) {
-            int e0 = r.e[0] + row * r.ey[0], e1 = r.e[1] + row * r.ey[1], e2 = r.e[2] + row * r.ey[2];
-            const int ex0 = r.ex[0], ex1 = r.ex[1], ex2 = r.ex[2];
-            for (int i = 0; i < w; ++i) {
-                if (((e0 + b0) | (e1 + b1) | (e2 + b2)) >= 0) {
-                    float num, aa[3];
-                    const float z = depth_from(iz, sarea, __int2float_rn(e0), __int2float_rn(e1), __int2float_rn(e2), &num, aa);
-                    emit(keys, kbase + i, z, fid);
-                }
-                e0 += ex0; e1 += ex1; e2 += ex2;
-            }
-        } else {
-            const int vx[3] = {r.vx[0], r.vx[1], r.vx[2]}, vy[3] = {r.vy[0], r.vy[1], r.vy[2]};
-            const int s = r.s;
-            const long long cy = 256ll * py + 128;
-            for (int i = 0; i < w; ++i) {
-                const long long cx = 256ll * (r.x0 + i) + 128;
-                const long long e0 = edge64(vx, vy, s, 0, cx, cy), e1 = edge64(vx, vy, s, 1, cx, cy),
-                                e2 = edge64(vx, vy, s, 2, cx, cy);
-                if (((e0 + b0) | (e1 + b1) | (e2 + b2)) >= 0) {
-                    float num, aa[3];
-                    const float z = depth_from(iz, sarea, __ll2float_rn(e0), __ll2float_rn(e1), __ll2float_rn(e2), &num, aa);
-                    emit(keys, kbase + i, z, fid);
-                }
-            }
-        }
+// z-test: key = depth bits << 32 | primitive id, minimum wins (nearest; ties to the lower id)
+__device__ __forceinline__ void emit(unsigned long long* zbuf, int idx, float f0, float f1, float f2, float iz0, float iz1,
+                                     float iz2, float sarea, unsigned prim) {
+    const float num = __fmaf_rn(f2, iz2, __fmaf_rn(f1, iz1, __fmul_rn(f0, iz0)));
+    const float z = __fdiv_rn(sarea, num);
+    const unsigned long long k = ((unsigned long long)__float_as_uint(z) << 32) | prim;
+    // shared memory has no native 64-bit min: compare-and-swap, entered only when the fragment is in front
+    unsigned long long old = zbuf[idx];
+    while (k < old) {
+        const unsigned long long prev = atomicCAS(zbuf + idx, old, k);
+        if (prev == old) break;
+        old = prev;
     }
 }
 
-// ---- rule: shading + resolve -------------------------------------------------------------------------------
+// ---- rule: shading -------------------------------------------------------------------------------------------
 struct PixelOut { uchar4 rgba; float depth; uint8_t seg; };
 
-__device__ __forceinline__ PixelOut shade_pixel(const RasterParams& P, int view, int oid, int n_ov, int n_of, int px,
-                                                int py, unsigned f) {
+// The winner passed set-up in the patch loop: recompute its edge values at this pixel the same way.  `z` is the
+// depth of the z-test key (the bits the patch loop computed).
+__device__ __forceinline__ PixelOut shade_pixel(const RasterParams& P, const float* __restrict__ M, int view, int oid,
+                                                int n_of, int px, int py, unsigned f, float z) {
     int4 idx;
-    int off;
     const bool is_obj = (int)f < n_of;
-    if (is_obj) { idx = __ldg(P.obj_faces + P.face_off[oid] + f); off = 0; }
-    else { idx = __ldg(P.hand_faces + (f - n_of)); off = n_ov; }
-    const int4* pv = P.pv + (size_t)view * P.pv_stride + off;
+    if (is_obj) idx = __ldg(P.obj_faces + P.face_off[oid] + f);
+    else idx = __ldg(P.hand_faces + (f - n_of));
     const int vi[3] = {idx.x, idx.y, idx.z};
-    const int4 a4 = pv[vi[0]], b4 = pv[vi[1]], d4 = pv[vi[2]];
-    // the winner passed set-up in the triangle pass: recompute its edge values at this pixel the same way
+    float p[3][3];
+    uchar4 col[3];
+    if (is_obj) {
+        const int vo = P.vert_off[oid];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float* v = P.obj_verts + 3 * (size_t)(vo + vi[j]);
+            xform(M, v[0], v[1], v[2], p[j]);
+            col[j] = __ldg(P.obj_colors + vo + vi[j]);
+        }
+    } else {
+        const float* hv = P.hand_verts + 3 * (size_t)view * P.n_hv;
+        const uchar4* hc = P.hand_colors + (size_t)P.hand_tex[view] * P.n_hv;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            p[j][0] = hv[3 * vi[j]]; p[j][1] = hv[3 * vi[j] + 1]; p[j][2] = hv[3 * vi[j] + 2];
+            col[j] = __ldg(hc + vi[j]);
+        }
+    }
+    const int4 a4 = project(P, p[0][0], p[0][1], p[0][2]), b4 = project(P, p[1][0], p[1][1], p[1][2]),
+               d4 = project(P, p[2][0], p[2][1], p[2][2]);
     const int vx[3] = {a4.x, b4.x, d4.x}, vy[3] = {a4.y, b4.y, d4.y};
     const float iz[3] = {__int_as_float(a4.z), __int_as_float(b4.z), __int_as_float(d4.z)};
     const int minx = min(vx[0], min(vx[1], vx[2])), maxx = max(vx[0], max(vx[1], vx[2]));
@@ -332,30 +304,10 @@ __device__ __forceinline__ PixelOut shade_pixel(const RasterParams& P, int view,
 #pragma unroll
         for (int i = 0; i < 3; ++i) fe[i] = __ll2float_rn(edge64(vx, vy, s, i, cx, cy));
     }
-    float num, a[3];
-    const float z = depth_from(iz, __ll2float_rn(area2 > 0 ? area2 : -area2), fe[0], fe[1], fe[2], &num, a);
-    float p[3][3];
-    uchar4 col[3];
-    if (is_obj) {
-        const float* M = P.obj_pose + 16 * (size_t)view;
-        const int vo = P.vert_off[oid];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const float* v = P.obj_verts + 3 * (size_t)(vo + vi[j]);
-            xform(M, v[0], v[1], v[2], p[j]);
-            col[j] = __ldg(P.obj_colors + vo + vi[j]);
-        }
-    } else {
-        const float* hv = P.hand_verts + 3 * (size_t)view * P.n_hv;
-        const uchar4* hc = P.hand_colors + (size_t)P.hand_tex[view] * P.n_hv;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            p[j][0] = hv[3 * vi[j]]; p[j][1] = hv[3 * vi[j] + 1]; p[j][2] = hv[3 * vi[j] + 2];
-            col[j] = __ldg(hc + vi[j]);
-        }
-    }
+    const float a0 = __fmul_rn(fe[0], iz[0]), a1 = __fmul_rn(fe[1], iz[1]), a2 = __fmul_rn(fe[2], iz[2]);
+    const float num = __fmaf_rn(fe[2], iz[2], __fmaf_rn(fe[1], iz[1], a0));
     const float inv = __fdiv_rn(1.0f, num);
-    const float w0 = __fmul_rn(a[0], inv), w1 = __fmul_rn(a[1], inv), w2 = __fmul_rn(a[2], inv);
+    const float w0 = __fmul_rn(a0, inv), w1 = __fmul_rn(a1, inv), w2 = __fmul_rn(a2, inv);
     const float e1x = __fsub_rn(p[1][0], p[0][0]), e1y = __fsub_rn(p[1][1], p[0][1]), e1z = __fsub_rn(p[1][2], p[0][2]);
     const float e2x = __fsub_rn(p[2][0], p[0][0]), e2y = __fsub_rn(p[2][1], p[0][1]), e2z = __fsub_rn(p[2][2], p[0][2]);
     const float nx = __fmaf_rn(e1y, e2z, -__fmul_rn(e1z, e2y));
@@ -389,175 +341,296 @@ __device__ __forceinline__ PixelOut shade_pixel(const RasterParams& P, int view,
     return r;
 }
 
-// Phase 1, one thread per PX consecutive pixels of a row (PX = 4 when W % 4 == 0, else 1): 32-byte key loads; background
-// pixels are finished here -- crop fetch with 32-bit divisions (operands < 2^30), one 16-byte RGBA store, one 16-byte
-// depth store and one 4-byte seg store per thread, i.e. 512 + 512 + 128 contiguous bytes per warp; covered pixels are
-// appended to a CTA-local list.  Phase 2: the CTA's covered pixels are dealt one per thread, so the long shading path runs
-// on fully populated warps instead of on the few lanes of each row segment that touch the hand or the object
-// (~9 % of the frame); their outputs overwrite the placeholders of phase 1 after the barrier.
-template <int PX, int G>
-__global__ void __launch_bounds__(256)
-raster_resolve_kernel(const __grid_constant__ RasterParams P) {
-    __shared__ unsigned hit_prim[256 * PX * G];
-    __shared__ unsigned short hit_px[256 * PX * G];
-    __shared__ int n_hit;
-    const int view = blockIdx.y;
-    const int cta_p0 = blockIdx.x * 256 * PX * G;
-    const int npx = P.W * P.H;
-    if (threadIdx.x == 0) n_hit = 0;
-    __syncthreads();
-    unsigned long long* kbase = P.keys + (size_t)view * npx;
-    const size_t obase = (size_t)view * npx;
-    {
-        // G independent groups of PX pixels per thread (group g of a warp = 32 * PX consecutive pixels): all key loads
-        // first, then all background fetches, then the stores -- G * (PX / 2 + PX) loads in flight per thread
-        unsigned long long k[G][PX];
-        uchar4 c[G][PX];
-        int p0[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            p0[g] = cta_p0 + (g * 256 + threadIdx.x) * PX;
-#pragma unroll
-            for (int j = 0; j < PX; ++j) k[g][j] = kEmptyKey;
-            if (p0[g] < npx) {
-                if constexpr (PX == 4) {
-                    const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(kbase + p0[g]),
-                                     k23 = *reinterpret_cast<const ulonglong2*>(kbase + p0[g] + 2);
-                    k[g][0] = k01.x; k[g][1] = k01.y; k[g][2] = k23.x; k[g][3] = k23.y;
-                } else {
-                    k[g][0] = kbase[p0[g]];
+// ---- the tile kernel -----------------------------------------------------------------------------------------
+// PX = pixels per thread in the output stream: 4 when W % 4 == 0 and the output rows are 16-byte aligned, else 1.
+template <int PX>
+__global__ void __launch_bounds__(kThreads, 4)
+raster_tile_kernel(const __grid_constant__ RasterParams P) {
+    __shared__ __align__(16) unsigned long long zbuf[kTilePx];  // 32 KB
+    __shared__ __align__(16) int4 slab[kWarps][32];             // projected vertices of the patch a warp is on
+    __shared__ unsigned short hit_px[kTilePx];                  // covered pixels of the tile (tile-local index)
+    __shared__ __align__(16) float Msh[12];
+    __shared__ int next_patch, n_hit;
+
+    const int view = blockIdx.y, tile = blockIdx.x;
+    const int tx0 = (tile % P.tiles_x) * kTile, ty0 = (tile / P.tiles_x) * kTile;
+    const int tx1 = min(tx0 + kTile, P.W) - 1, ty1 = min(ty0 + kTile, P.H) - 1;  // inclusive
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int bin = view * P.n_tiles + tile;
+    const int count = P.bin_count[bin];
+    const int oid = P.obj_id[view];
+    const int n_of = oid >= 0 ? P.face_off[oid + 1] - P.face_off[oid] : 0;
+
+    if (count > 0) {
+        if (t == 0) { next_patch = 0; n_hit = 0; }
+        if (t < 12) Msh[t] = oid >= 0 ? P.obj_pose[16 * (size_t)view + t] : 0.0f;
+        ulonglong2* z2 = reinterpret_cast<ulonglong2*>(zbuf);
+        for (int i = t; i < kTilePx / 2; i += kThreads) z2[i] = make_ulonglong2(kEmptyKey, kEmptyKey);
+        __syncthreads();
+        const unsigned short* list = P.bin_list + (size_t)bin * P.list_cap;
+        const int poff = oid >= 0 ? P.patch_off[oid] : 0;
+        int4* my_slab = slab[wid];
+        for (;;) {
+            int li = 0;
+            if (lane == 0) li = atomicAdd(&next_patch, 1);
+            li = __shfl_sync(kFull, li, 0);
+            if (li >= count) break;
+            const unsigned entry = list[li];
+            const bool hand = (entry & kHandBit) != 0;
+            const size_t prow = ((size_t)(hand ? 0 : poff) + (entry & 0x7fffu)) * 32 + lane;
+            // ---- a lane per vertex
+            float c[3] = {0.0f, 0.0f, 0.0f};
+            bool on;
+            if (!hand) {
+                const float4 q = __ldg(P.op_pos + prow);
+                on = q.w != 0.0f;
+                xform(Msh, q.x, q.y, q.z, c);
+            } else {
+                const int v = __ldg(P.hp_vid + prow);
+                on = v >= 0;
+                if (on) {
+                    const float* hv = P.hand_verts + 3 * ((size_t)view * P.n_hv + v);
+                    c[0] = hv[0]; c[1] = hv[1]; c[2] = hv[2];
                 }
             }
-        }
-        const int32_t* sel = P.bg_sel ? P.bg_sel + 5 * (size_t)view : nullptr;
-        const bool has_bg = sel && P.bgs && sel[0] >= 0;
-        // background texels are fetched for every pixel, covered or not (phase 2 overwrites the covered ones): the fetch
-        // does not wait for the key loads, so the L2 round trips of a thread overlap instead of chaining
+            int4 pvv = project(P, c[0], c[1], c[2]);
+            if (!on) pvv.w = 0;
+            my_slab[lane] = pvv;
+            const int mnx = __reduce_min_sync(kFull, on ? pvv.x : INT_MAX), mxx = __reduce_max_sync(kFull, on ? pvv.x : INT_MIN);
+            const int mny = __reduce_min_sync(kFull, on ? pvv.y : INT_MAX), mxy = __reduce_max_sync(kFull, on ? pvv.y : INT_MIN);
+            const bool overlap = floordiv256(mnx + 127) <= tx1 && floordiv256(mxx - 128) >= tx0 &&
+                                 floordiv256(mny + 127) <= ty1 && floordiv256(mxy - 128) >= ty0;
+            __syncwarp();
+            if (overlap) {
+                // ---- a lane per face
+                const unsigned fw = __ldg((hand ? P.hp_face : P.op_face) + prow);
+                int n = 0, x0 = 0, y0 = 0, w = 0;
+                bool small = false;
+                long long area2 = 0;
+                int4 a, b, d;
+                a = b = d = make_int4(0, 0, 0, 0);
+                if (fw != 0xFFFFFFFFu) {
+                    a = my_slab[fw & 31]; b = my_slab[(fw >> 8) & 31]; d = my_slab[(fw >> 16) & 31];
+                    if (a.w & b.w & d.w) {
+                        const int minx = min(a.x, min(b.x, d.x)), maxx = max(a.x, max(b.x, d.x));
+                        const int miny = min(a.y, min(b.y, d.y)), maxy = max(a.y, max(b.y, d.y));
+                        x0 = max(floordiv256(minx + 127), tx0);
+                        y0 = max(floordiv256(miny + 127), ty0);
+                        const int x1 = min(floordiv256(maxx - 128), tx1), y1 = min(floordiv256(maxy - 128), ty1);
+                        if (x0 <= x1 && y0 <= y1) {
+                            small = (maxx - minx < kSmallExtent) && (maxy - miny < kSmallExtent);
+                            area2 = area2_of(a, b, d, small);
+                            if (area2 != 0 && !(area2 > 0 && P.cull)) { w = x1 - x0 + 1; n = w * (y1 - y0 + 1); }
+                        }
+                    }
+                }
+                unsigned prim = 0;
+                if (n > 0) prim = (unsigned)(__ldg((hand ? P.hp_prim : P.op_prim) + prow) + (hand ? n_of : 0));
+                const bool own = n > 0 && small && n <= kOwnMax;
+                if (own) {
+                    const int s = area2 > 0 ? 1 : -1;
+                    const int vx[3] = {a.x, b.x, d.x}, vy[3] = {a.y, b.y, d.y};
+                    const float iz0 = __int_as_float(a.z), iz1 = __int_as_float(b.z), iz2 = __int_as_float(d.z);
+                    const float sarea = __ll2float_rn(area2 > 0 ? area2 : -area2);
+                    const int cx0 = 256 * x0 + 128, cy0 = 256 * y0 + 128;
+                    int e[3], ex[3], ey[3], nb = 0;  // e: biased so that "inside" is e >= 0 on all three
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
+                    for (int i = 0; i < 3; ++i) {  // edge i runs v[i+1] -> v[i+2], opposite vertex i
+                        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+                        const int dx = s * (vx[i2] - vx[i1]), dy = s * (vy[i2] - vy[i1]);
+                        const int bias = ((dy < 0) || (dy == 0 && dx > 0)) ? 0 : 1;  // 1: not a top/left edge, E == 0 is outside
+                        nb |= bias << i;
+                        e[i] = dx * (cy0 - vy[i1]) - dy * (cx0 - vx[i1]) - bias;
+                        ex[i] = -256 * dy;
+                        ey[i] = 256 * dx - w * ex[i];  // to the first pixel of the next row
+                    }
+                    int idx = (y0 - ty0) * kTile + (x0 - tx0), x = 0;
+                    for (int k = 0; k < n; ++k) {
+                        if ((e[0] | e[1] | e[2]) >= 0)
+                            emit(zbuf, idx, __int2float_rn(e[0] + (nb & 1)), __int2float_rn(e[1] + ((nb >> 1) & 1)),
+                                 __int2float_rn(e[2] + ((nb >> 2) & 1)), iz0, iz1, iz2, sarea, prim);
+                        e[0] += ex[0]; e[1] += ex[1]; e[2] += ex[2];
+                        ++idx;
+                        if (++x == w) { x = 0; idx += kTile - w; e[0] += ey[0]; e[1] += ey[1]; e[2] += ey[2]; }
+                    }
+                }
+                // ---- large boxes: the whole warp walks one triangle at a time
+                unsigned coop = __ballot_sync(kFull, n > 0 && !own);
+                while (coop) {
+                    const int src = __ffs(coop) - 1;
+                    coop &= coop - 1;
+                    const unsigned cfw = __shfl_sync(kFull, fw, src);
+                    const int cx0 = __shfl_sync(kFull, x0, src), cy0 = __shfl_sync(kFull, y0, src);
+                    const int cw = __shfl_sync(kFull, w, src), cn = __shfl_sync(kFull, n, src);
+                    const unsigned cprim = __shfl_sync(kFull, prim, src);
+                    const int4 ca = my_slab[cfw & 31], cb = my_slab[(cfw >> 8) & 31], cd = my_slab[(cfw >> 16) & 31];
+                    const int vx[3] = {ca.x, cb.x, cd.x}, vy[3] = {ca.y, cb.y, cd.y};
+                    const float iz0 = __int_as_float(ca.z), iz1 = __int_as_float(cb.z), iz2 = __int_as_float(cd.z);
+                    const int minx = min(vx[0], min(vx[1], vx[2])), maxx = max(vx[0], max(vx[1], vx[2]));
+                    const int miny = min(vy[0], min(vy[1], vy[2])), maxy = max(vy[0], max(vy[1], vy[2]));
+                    const bool csmall = (maxx - minx < kSmallExtent) && (maxy - miny < kSmallExtent);
+                    const long long carea2 = area2_of(ca, cb, cd, csmall);
+                    const int s = carea2 > 0 ? 1 : -1;
+                    const float sarea = __ll2float_rn(carea2 > 0 ? carea2 : -carea2);
+                    int bias[3];
 #pragma unroll
-            for (int j = 0; j < PX; ++j) c[g][j] = make_uchar4((uint8_t)P.bg_r, (uint8_t)P.bg_g, (uint8_t)P.bg_b, 0);
-            if (has_bg && p0[g] < npx) {
-                const int py = (int)fastdiv((unsigned)p0[g], P.div_w_m, P.div_w_s), px0 = p0[g] - py * P.W;
-                const unsigned sy = (unsigned)sel[2] + fastdiv((unsigned)(2 * py + 1) * (unsigned)sel[4], P.div_2h_m, P.div_2h_s);
-                const uint8_t* bg_row = P.bgs + (size_t)P.bg_ch * (((size_t)sel[0] * P.bg_h + sy) * P.bg_w);
-                const unsigned bg_x0 = (unsigned)sel[1], bg_cw = (unsigned)sel[3];
+                    for (int i = 0; i < 3; ++i) {
+                        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+                        const int dx = s * (vx[i2] - vx[i1]), dy = s * (vy[i2] - vy[i1]);  // |.| <= 2^23: no overflow
+                        bias[i] = ((dy < 0) || (dy == 0 && dx > 0)) ? 0 : 1;
+                    }
+                    const float inv_w = 1.0f / (float)cw;
+                    for (int k = lane; k < cn; k += 32) {
+                        const int ry = (int)(((float)k + 0.5f) * inv_w), rx = k - ry * cw;  // exact: k < 4096, cw <= 64
+                        const int px = cx0 + rx, py = cy0 + ry;
+                        const int idx = (py - ty0) * kTile + (px - tx0);
+                        if (csmall) {
+                            const int ccx = 256 * px + 128, ccy = 256 * py + 128;
+                            int e[3];
 #pragma unroll
-                for (int j = 0; j < PX; ++j) {
-                    const unsigned sx = bg_x0 + fastdiv((unsigned)(2 * (px0 + j) + 1) * bg_cw, P.div_2w_m, P.div_2w_s);
-                    if (P.bg_ch == 4) {
-                        c[g][j] = __ldg(reinterpret_cast<const uchar4*>(bg_row) + sx);
-                        c[g][j].w = 0;
-                    } else {
-                        const uint8_t* src = bg_row + 3 * (size_t)sx;
-                        c[g][j] = make_uchar4(src[0], src[1], src[2], 0);
+                            for (int i = 0; i < 3; ++i) {
+                                const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+                                const int dx = s * (vx[i2] - vx[i1]), dy = s * (vy[i2] - vy[i1]);
+                                e[i] = dx * (ccy - vy[i1]) - dy * (ccx - vx[i1]);
+                            }
+                            if (((e[0] - bias[0]) | (e[1] - bias[1]) | (e[2] - bias[2])) >= 0)
+                                emit(zbuf, idx, __int2float_rn(e[0]), __int2float_rn(e[1]), __int2float_rn(e[2]), iz0, iz1, iz2,
+                                     sarea, cprim);
+                        } else {
+                            const long long ccx = 256ll * px + 128, ccy = 256ll * py + 128;
+                            const long long e0 = edge64(vx, vy, s, 0, ccx, ccy), e1 = edge64(vx, vy, s, 1, ccx, ccy),
+                                            e2 = edge64(vx, vy, s, 2, ccx, ccy);
+                            if (((e0 - bias[0]) | (e1 - bias[1]) | (e2 - bias[2])) >= 0)
+                                emit(zbuf, idx, __ll2float_rn(e0), __ll2float_rn(e1), __ll2float_rn(e2), iz0, iz1, iz2, sarea,
+                                     cprim);
+                        }
                     }
                 }
             }
+            __syncwarp();  // the slab is rewritten by the next patch
         }
+        __syncthreads();
+    }
+
+    // ---- stream the tile out: background everywhere, covered pixels collected for the shading pass
+    constexpr int TPR = kTile / PX;        // threads per tile row
+    constexpr int RPP = kThreads / TPR;    // rows per pass
+    const int32_t* sel = P.bg_sel ? P.bg_sel + 5 * (size_t)view : nullptr;
+    const bool has_bg = sel && P.bgs && sel[0] >= 0;
+    const size_t obase = (size_t)view * P.W * P.H;
+#pragma unroll 2
+    for (int pass = 0; pass < kTile / RPP; ++pass) {
+        const int row = pass * RPP + t / TPR, col = (t % TPR) * PX;
+        const int px0 = tx0 + col, py = ty0 + row;
+        const bool in = px0 <= tx1 && py <= ty1;  // PX == 4 only when W % 4 == 0: a group is entirely in or out
+        unsigned long long k[PX];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            if (p0[g] >= npx) continue;
+        for (int j = 0; j < PX; ++j) k[j] = kEmptyKey;
+        if (count > 0 && in) {
+            if constexpr (PX == 4) {
+                const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(zbuf + row * kTile + col),
+                                 k23 = *reinterpret_cast<const ulonglong2*>(zbuf + row * kTile + col + 2);
+                k[0] = k01.x; k[1] = k01.y; k[2] = k23.x; k[3] = k23.y;
+            } else {
+                k[0] = zbuf[row * kTile + col];
+            }
+        }
+        uchar4 c[PX];
+#pragma unroll
+        for (int j = 0; j < PX; ++j) c[j] = make_uchar4((uint8_t)P.bg_r, (uint8_t)P.bg_g, (uint8_t)P.bg_b, 0);
+        if (has_bg && in) {
+            const unsigned sy = (unsigned)sel[2] + fastdiv((unsigned)(2 * py + 1) * (unsigned)sel[4], P.div_2h_m, P.div_2h_s);
+            const uint8_t* bg_row = P.bgs + (size_t)P.bg_ch * (((size_t)sel[0] * P.bg_h + sy) * P.bg_w);
+            const unsigned bg_x0 = (unsigned)sel[1], bg_cw = (unsigned)sel[3];
 #pragma unroll
             for (int j = 0; j < PX; ++j) {
-                if (k[g][j] != kEmptyKey) {
-                    const int slot = atomicAdd(&n_hit, 1);
-                    hit_px[slot] = (unsigned short)((g * 256 + threadIdx.x) * PX + j);
-                    hit_prim[slot] = (unsigned)(k[g][j] & 0xffffffffull);
+                const unsigned sx = bg_x0 + fastdiv((unsigned)(2 * (px0 + j) + 1) * bg_cw, P.div_2w_m, P.div_2w_s);
+                if (P.bg_ch == 4) {
+                    c[j] = __ldg(reinterpret_cast<const uchar4*>(bg_row) + sx);
+                    c[j].w = 0;
+                } else {
+                    const uint8_t* src = bg_row + 3 * (size_t)sx;
+                    c[j] = make_uchar4(src[0], src[1], src[2], 0);
                 }
             }
-            const size_t o = obase + p0[g];
+        }
+        if (count > 0) {  // CTA-uniform
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                const bool hit = k[j] != kEmptyKey;
+                const unsigned m = __ballot_sync(kFull, hit);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&n_hit, __popc(m));
+                    base = __shfl_sync(kFull, base, 0);
+                    if (hit) hit_px[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)(row * kTile + col + j);
+                }
+            }
+        }
+        if (in) {
+            const size_t o = obase + (size_t)py * P.W + px0;
             if constexpr (PX == 4) {
                 if (P.rgba) {
                     uint4 v;
-                    v.x = *reinterpret_cast<unsigned*>(&c[g][0]); v.y = *reinterpret_cast<unsigned*>(&c[g][1]);
-                    v.z = *reinterpret_cast<unsigned*>(&c[g][2]); v.w = *reinterpret_cast<unsigned*>(&c[g][3]);
+                    v.x = *reinterpret_cast<unsigned*>(&c[0]); v.y = *reinterpret_cast<unsigned*>(&c[1]);
+                    v.z = *reinterpret_cast<unsigned*>(&c[2]); v.w = *reinterpret_cast<unsigned*>(&c[3]);
                     *reinterpret_cast<uint4*>(P.rgba + 4 * o) = v;
                 }
                 if (P.depth) *reinterpret_cast<float4*>(P.depth + o) = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (P.seg) *reinterpret_cast<unsigned*>(P.seg + o) = 0u;
             } else {
-                if (P.rgba) reinterpret_cast<uchar4*>(P.rgba)[o] = c[g][0];
+                if (P.rgba) reinterpret_cast<uchar4*>(P.rgba)[o] = c[0];
                 if (P.depth) P.depth[o] = 0.0f;
                 if (P.seg) P.seg[o] = 0;
             }
         }
     }
+    if (count == 0) return;
     __syncthreads();
-    // Phase 2: the CTA's covered pixels, one per thread, so the long shading path runs on fully populated warps; it
-    // overlaps with the streaming phase 1 of the other CTAs resident on the SM (measured: a separate grid-wide shading
-    // kernel over a compacted list is slower in total, 19 + 18 us against 30 us per 64 views).
+    // ---- shade the covered pixels, one per thread, on fully populated warps; their outputs overwrite the placeholders
     const int total = n_hit;
-    if (total == 0) return;
-    const int oid = P.obj_id[view];
-    int n_of = 0, n_ov = 0;
-    if (oid >= 0) {
-        n_of = P.face_off[oid + 1] - P.face_off[oid];
-        n_ov = P.vert_off[oid + 1] - P.vert_off[oid];
-    }
-    for (int i = threadIdx.x; i < total; i += 256) {
-        const int p = cta_p0 + hit_px[i];
-        const int py = (int)fastdiv((unsigned)p, P.div_w_m, P.div_w_s), px = p - py * P.W;
-        const PixelOut r = shade_pixel(P, view, oid, n_ov, n_of, px, py, hit_prim[i]);
-        kbase[p] = kEmptyKey;  // leave the key buffer empty for the next chunk
-        const size_t o = obase + p;
+    for (int i = t; i < total; i += kThreads) {
+        const int idx = hit_px[i];
+        const unsigned long long key = zbuf[idx];
+        const int px = tx0 + (idx & (kTile - 1)), py = ty0 + (idx >> 6);
+        const PixelOut r = shade_pixel(P, Msh, view, oid, n_of, px, py, (unsigned)(key & 0xffffffffull),
+                                       __uint_as_float((unsigned)(key >> 32)));
+        const size_t o = obase + (size_t)py * P.W + px;
         if (P.rgba) reinterpret_cast<uchar4*>(P.rgba)[o] = r.rgba;
         if (P.depth) P.depth[o] = r.depth;
         if (P.seg) P.seg[o] = r.seg;
     }
 }
 
-static int max_hand_obj_verts(const ab_scene* s) {
-    int m = 0;
-    for (int i = 0; i < s->n_obj; ++i) m = max(m, s->obj_vert_off_host[i + 1] - s->obj_vert_off_host[i]);
-    return m;
-}
-
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Chunks alternate between the caller's stream and one library-owned auxiliary stream per device (each with its own
-// scratch set), so the set-up-bound triangle pass of one chunk shares the SMs with the write-bound resolve pass of the
-// other and the tails of the kernels overlap.  Fork / join is by events, so the call stays asynchronous and ordered on
-// the caller's stream (and capturable into a CUDA graph).
-constexpr int kMaxDevices = 16;
-constexpr int kMaxSets = 4;
-struct AuxStreams {
-    std::mutex mu;
-    cudaStream_t aux[kMaxDevices][kMaxSets] = {};
-    cudaEvent_t fork[kMaxDevices] = {}, join[kMaxDevices][kMaxSets] = {};
+struct Geometry {  // what the workspace layout depends on
+    int tiles_x, tiles_y, n_tiles, list_cap, max_op;
 };
-static AuxStreams g_aux;
 
-constexpr int kWsSets = 4;  // scratch sets every workspace is sized for
-static std::atomic<int> g_sets{0};
-static int raster_sets() {  // chunks in flight: 4 by default, AB_RASTER_STREAMS / ab_set_raster_streams override (1..4)
-    int n = g_sets.load(std::memory_order_relaxed);
-    if (n == 0) {
-        const char* e = getenv("AB_RASTER_STREAMS");
-        n = e ? atoi(e) : kWsSets;
-        n = n < 1 ? 1 : (n > kWsSets ? kWsSets : n);
-        g_sets.store(n, std::memory_order_relaxed);
-    }
-    return n;
-}
-
-static size_t scratch_set_bytes(int chunk, int npx, int pv_stride) {
-    return align_up((size_t)chunk * npx * 8, 256) + align_up((size_t)chunk * pv_stride * 16, 256);
+static int geometry_of(const ab_scene* s, const ab_camera* cam, Geometry* g) {
+    if (!s || !cam || cam->width <= 0 || cam->height <= 0) return -1;
+    if (!s->hand_patches || !s->hand_patches->patch_off_host || s->hand_patches->n_mesh != 1) return -1;
+    if (s->n_obj > 0 && (!s->obj_patches || !s->obj_patches->patch_off_host || s->obj_patches->n_mesh != s->n_obj)) return -1;
+    g->tiles_x = cdiv(cam->width, kTile);
+    g->tiles_y = cdiv(cam->height, kTile);
+    g->n_tiles = g->tiles_x * g->tiles_y;
+    g->max_op = 0;
+    for (int i = 0; i < s->n_obj; ++i)
+        g->max_op = max(g->max_op, s->obj_patches->patch_off_host[i + 1] - s->obj_patches->patch_off_host[i]);
+    const int n_hp = s->hand_patches->patch_off_host[1] - s->hand_patches->patch_off_host[0];
+    if (g->max_op > 0x7fff || n_hp > 0x7fff || n_hp <= 0) return -1;
+    g->list_cap = (int)align_up((size_t)g->max_op + n_hp, 8);
+    return 0;
 }
 
 }  // namespace ab
 
-extern "C" int ab_set_raster_streams(int n) {
-    AB_REQUIRE(n >= 1 && n <= ab::kWsSets, "n must be in 1..4");
-    ab::g_sets.store(n, std::memory_order_relaxed);
-    return AB_OK;
-}
-
 extern "C" uint64_t ab_render_workspace_bytes(const ab_scene* scene, const ab_camera* cam, int chunk) {
-    if (!scene || !cam || chunk <= 0 || cam->width <= 0 || cam->height <= 0) return 0;
-    if (scene->n_obj > 0 && !scene->obj_vert_off_host) return 0;
-    const int pv_stride = (int)ab::align_up((size_t)ab::max_hand_obj_verts(scene) + scene->n_hand_verts, 8);
-    return (size_t)ab::kWsSets * ab::scratch_set_bytes(chunk, cam->width * cam->height, pv_stride);
+    ab::Geometry g;
+    if (chunk <= 0 || ab::geometry_of(scene, cam, &g)) return 0;
+    return ab::align_up((size_t)chunk * g.n_tiles * sizeof(int), 256) +
+           ab::align_up((size_t)chunk * g.n_tiles * g.list_cap * sizeof(unsigned short), 256);
 }
 
 extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int batch, int chunk,
@@ -567,14 +640,21 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
                                void* stream) {
     using namespace ab;
     AB_REQUIRE(scene && cam, "null scene / camera");
-    AB_REQUIRE(batch >= 0 && chunk > 0, "bad batch / chunk");
+    AB_REQUIRE(batch >= 0 && chunk > 0 && chunk <= 65535, "bad batch / chunk");
     AB_REQUIRE(cam->width > 0 && cam->height > 0 && cam->width <= 4096 && cam->height <= 4096, "bad image size");
+    AB_REQUIRE(cam->fx > 0.0f && cam->fy > 0.0f, "focal lengths must be positive");
     AB_REQUIRE(scene->n_obj >= 0 && scene->n_obj <= kMaxObjects, "n_obj out of range (max 64)");
     AB_REQUIRE(scene->n_obj == 0 || (scene->obj_verts && scene->obj_faces && scene->obj_colors &&
                                      scene->obj_vert_off_host && scene->obj_face_off_host), "null object arrays");
     AB_REQUIRE(!scene->bgs || (scene->bg_w > 0 && scene->bg_h > 0 && scene->bg_w <= 65535 && scene->bg_h <= 65535), "bad background size");
     AB_REQUIRE(scene->n_hand_verts > 0 && scene->n_hand_faces > 0 && scene->n_hand_tex > 0 && scene->hand_faces &&
                    scene->hand_colors, "bad hand mesh");
+    Geometry g;
+    AB_REQUIRE(geometry_of(scene, cam, &g) == 0, "missing / inconsistent patch tables (ab_build_patches_host; at most 32767 patches per mesh)");
+    const ab_patch_table* hp = scene->hand_patches;
+    const ab_patch_table* op = scene->obj_patches;
+    AB_REQUIRE(hp->vid && hp->face && hp->prim, "null hand patch arrays");
+    AB_REQUIRE(scene->n_obj == 0 || (op->pos && op->face && op->prim && op->bound), "null object patch arrays");
     if (batch == 0) return AB_OK;
     AB_REQUIRE(hand_verts && hand_tex && obj_id && obj_pose && light && ws, "null per-view input / workspace");
     AB_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
@@ -589,6 +669,13 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
     P.hand_faces = reinterpret_cast<const int4*>(scene->hand_faces);
     P.hand_colors = reinterpret_cast<const uchar4*>(scene->hand_colors);
     P.bgs = scene->bgs;
+    P.op_pos = scene->n_obj ? reinterpret_cast<const float4*>(op->pos) : nullptr;
+    P.op_face = scene->n_obj ? op->face : nullptr;
+    P.op_prim = scene->n_obj ? op->prim : nullptr;
+    P.op_bound = scene->n_obj ? reinterpret_cast<const float4*>(op->bound) : nullptr;
+    AB_REQUIRE(((uintptr_t)P.op_pos & 15) == 0 && ((uintptr_t)P.op_bound & 15) == 0, "patch pos / bound must be 16-byte aligned");
+    P.hp_vid = hp->vid; P.hp_face = hp->face; P.hp_prim = hp->prim;
+    P.n_hp = hp->patch_off_host[1] - hp->patch_off_host[0];
     P.n_obj = scene->n_obj; P.n_hv = scene->n_hand_verts; P.n_hf = scene->n_hand_faces; P.n_tex = scene->n_hand_tex;
     P.n_bg = scene->n_bg; P.bg_h = scene->bg_h; P.bg_w = scene->bg_w;
     P.bg_ch = scene->bg_channels == 4 ? 4 : 3;
@@ -601,63 +688,32 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
     P.fx = cam->fx; P.fy = cam->fy; P.cx = cam->cx; P.cy = cam->cy; P.znear = cam->znear;
     P.ambient = cam->ambient; P.diffuse = cam->diffuse; P.cull = cam->cull_backface;
     P.bg_r = cam->bg_r; P.bg_g = cam->bg_g; P.bg_b = cam->bg_b;
-    int scene_max_ov = 0, scene_max_of = 0;
     for (int i = 0; i <= scene->n_obj; ++i) {
         P.vert_off[i] = scene->n_obj ? scene->obj_vert_off_host[i] : 0;
         P.face_off[i] = scene->n_obj ? scene->obj_face_off_host[i] : 0;
-        if (i > 0) {
-            AB_REQUIRE(P.vert_off[i] >= P.vert_off[i - 1] && P.face_off[i] >= P.face_off[i - 1], "offsets not sorted");
-            scene_max_ov = max(scene_max_ov, P.vert_off[i] - P.vert_off[i - 1]);
-            scene_max_of = max(scene_max_of, P.face_off[i] - P.face_off[i - 1]);
-        }
+        P.patch_off[i] = scene->n_obj ? op->patch_off_host[i] : 0;
+        if (i > 0)
+            AB_REQUIRE(P.vert_off[i] >= P.vert_off[i - 1] && P.face_off[i] >= P.face_off[i - 1] &&
+                           P.patch_off[i] >= P.patch_off[i - 1], "offsets not sorted");
     }
+    P.tiles_x = g.tiles_x; P.tiles_y = g.tiles_y; P.n_tiles = g.n_tiles; P.list_cap = g.list_cap;
+    const size_t count_bytes = align_up((size_t)chunk * g.n_tiles * sizeof(int), 256);
+    P.bin_count = (int*)ws;
+    P.bin_list = (unsigned short*)((char*)ws + count_bytes);
     const int npx = P.W * P.H;
-    P.pv_stride = (int)align_up((size_t)scene_max_ov + P.n_hv, 8);
-    const size_t set_bytes = scratch_set_bytes(chunk, npx, P.pv_stride);
-    const size_t keys_bytes = align_up((size_t)chunk * npx * 8, 256);
-    const int n_chunks = cdiv(batch, chunk);
-    const int sets = min(raster_sets(), n_chunks);
-    const bool dual = sets > 1;
-    int dev = 0;
-    std::unique_lock<std::mutex> lock(g_aux.mu, std::defer_lock);
-    if (dual) {
-        AB_CUDA(cudaGetDevice(&dev));
-        AB_REQUIRE(dev < kMaxDevices, "device index out of range");
-        lock.lock();  // the per-device events are reused by every call
-        if (!g_aux.fork[dev]) AB_CUDA(cudaEventCreateWithFlags(&g_aux.fork[dev], cudaEventDisableTiming));
-        for (int i = 1; i < sets; ++i) {
-            if (!g_aux.aux[dev][i]) {
-                AB_CUDA(cudaStreamCreateWithFlags(&g_aux.aux[dev][i], cudaStreamNonBlocking));
-                AB_CUDA(cudaEventCreateWithFlags(&g_aux.join[dev][i], cudaEventDisableTiming));
-            }
-        }
-    }
-    for (int i = 0; i < sets; ++i) AB_CUDA(cudaMemsetAsync((char*)ws + i * set_bytes, 0xFF, keys_bytes, st));
-    if (dual) {
-        AB_CUDA(cudaEventRecord(g_aux.fork[dev], st));
-        for (int i = 1; i < sets; ++i) AB_CUDA(cudaStreamWaitEvent(g_aux.aux[dev][i], g_aux.fork[dev], 0));
-    }
-    const cudaStream_t caller = st;
-    int chunk_idx = 0;
-    for (int v0 = 0; v0 < batch; v0 += chunk, ++chunk_idx) {
+    const int hand_blocks = cdiv(P.n_hp, kWarps);
+    for (int v0 = 0; v0 < batch; v0 += chunk) {
         const int n = min(chunk, batch - v0);
-        const int set = chunk_idx % sets;
-        st = set ? g_aux.aux[dev][set] : caller;
-        P.keys = (unsigned long long*)((char*)ws + set * set_bytes);
-        P.pv = (int4*)((char*)ws + set * set_bytes + keys_bytes);
-        int max_ov = scene_max_ov, max_of = scene_max_of;
+        int max_op = g.max_op;
         if (obj_id_host) {
-            max_ov = max_of = 0;
+            max_op = 0;
             for (int i = 0; i < n; ++i) {
                 const int o = obj_id_host[v0 + i];
                 AB_REQUIRE(o < scene->n_obj, "obj_id out of range");
-                if (o >= 0) {
-                    max_ov = max(max_ov, P.vert_off[o + 1] - P.vert_off[o]);
-                    max_of = max(max_of, P.face_off[o + 1] - P.face_off[o]);
-                }
+                if (o >= 0) max_op = max(max_op, P.patch_off[o + 1] - P.patch_off[o]);
             }
         }
-        P.max_ov = max_ov; P.max_of = max_of;
+        P.obj_bin_blocks = cdiv(max_op, kThreads);
         P.n_views = n;
         P.hand_verts = hand_verts + (size_t)v0 * P.n_hv * 3;
         P.hand_tex = hand_tex + v0;
@@ -668,36 +724,22 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
         P.rgba = rgba ? rgba + (size_t)v0 * npx * 4 : nullptr;
         P.depth = depth ? depth + (size_t)v0 * npx : nullptr;
         P.seg = seg ? seg + (size_t)v0 * npx : nullptr;
+        AB_CUDA(cudaMemsetAsync(P.bin_count, 0, (size_t)n * g.n_tiles * sizeof(int), st));
         {
-            StageTimer tm(AB_STAGE_RASTER_VERTEX, st);
-            raster_vertex_kernel<<<dim3(cdiv(max_ov + P.n_hv, 256), n), 256, 0, st>>>(P);
+            StageTimer tm(AB_STAGE_RASTER_BIN, st);
+            raster_bin_kernel<<<dim3(P.obj_bin_blocks + hand_blocks, n), kThreads, 0, st>>>(P);
         }
         {
-            StageTimer tm(AB_STAGE_RASTER_TRIANGLE, st);
-            // 6 resident CTAs per SM (40 registers, a few spilled words): with several chunks in flight the pass is
-            // latency-bound, and occupancy buys more than the spills cost (measured 1.15 -> 1.24 M views/s against 4 CTAs)
-            static const int minb = getenv("AB_TRI_MINB") ? atoi(getenv("AB_TRI_MINB")) : 6;
-            const dim3 grid(cdiv(max_of + P.n_hf, kTriThreads), n);
-            if (minb == 4) raster_triangle_kernel<4><<<grid, kTriThreads, 0, st>>>(P);
-            else if (minb == 8) raster_triangle_kernel<8><<<grid, kTriThreads, 0, st>>>(P);
-            else raster_triangle_kernel<6><<<grid, kTriThreads, 0, st>>>(P);
-        }
-        {
-            StageTimer tm(AB_STAGE_RASTER_RESOLVE, st);
+            StageTimer tm(AB_STAGE_RASTER_TILE, st);
             // 4 pixels per thread needs 16-byte aligned output rows: W % 4 == 0 and 16 / 16 / 4-byte aligned bases
             const bool vec = (P.W % 4 == 0) && (((uintptr_t)P.rgba & 15) == 0) && (((uintptr_t)P.depth & 15) == 0) &&
                              (((uintptr_t)P.seg & 3) == 0);
-            if (vec) raster_resolve_kernel<4, 1><<<dim3(cdiv(npx, 1024), n), 256, 0, st>>>(P);
-            else raster_resolve_kernel<1, 1><<<dim3(cdiv(npx, 256), n), 256, 0, st>>>(P);
-
+            if (vec) raster_tile_kernel<4><<<dim3(g.n_tiles, n), kThreads, 0, st>>>(P);
+            else raster_tile_kernel<1><<<dim3(g.n_tiles, n), kThreads, 0, st>>>(P);
         }
-        count_launch(3);
+        count_launch(2);
         int rc = check_launch("ab_render_batch");
         if (rc) return rc;
-    }
-    for (int i = 1; i < sets; ++i) {
-        AB_CUDA(cudaEventRecord(g_aux.join[dev][i], g_aux.aux[dev][i]));
-        AB_CUDA(cudaStreamWaitEvent(caller, g_aux.join[dev][i], 0));
     }
     return AB_OK;
 }

@@ -20,12 +20,18 @@ class ManoModelStruct(C.Structure):
                                           "weights")]
 
 
+class PatchTableStruct(C.Structure):
+    _fields_ = [("n_mesh", C.c_int32), ("patch_off_host", c_i32_p), ("pos", C.c_void_p), ("vid", C.c_void_p),
+                ("face", C.c_void_p), ("prim", C.c_void_p), ("bound", C.c_void_p)]
+
+
 class SceneStruct(C.Structure):
     _fields_ = [("n_obj", C.c_int32), ("obj_verts", C.c_void_p), ("obj_faces", C.c_void_p), ("obj_colors", C.c_void_p),
                 ("obj_vert_off_host", c_i32_p), ("obj_face_off_host", c_i32_p),
                 ("n_hand_verts", C.c_int32), ("n_hand_faces", C.c_int32), ("n_hand_tex", C.c_int32),
                 ("hand_faces", C.c_void_p), ("hand_colors", C.c_void_p), ("bgs", C.c_void_p),
-                ("n_bg", C.c_int32), ("bg_h", C.c_int32), ("bg_w", C.c_int32), ("bg_channels", C.c_int32)]
+                ("n_bg", C.c_int32), ("bg_h", C.c_int32), ("bg_w", C.c_int32), ("bg_channels", C.c_int32),
+                ("obj_patches", C.POINTER(PatchTableStruct)), ("hand_patches", C.POINTER(PatchTableStruct))]
 
 
 class CameraStruct(C.Structure):
@@ -79,7 +85,9 @@ EXPORTS = {
     "ab_refine_decode": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_scramble_anatomical": (C.c_int, [C.c_int] + [C.c_void_p] * 9),
-    "ab_set_raster_streams": (C.c_int, [C.c_int]),
+    "ab_patch_capacity": (C.c_int, [C.c_int]),
+    "ab_build_patches_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "ab_render_workspace_bytes": (C.c_uint64, [C.POINTER(SceneStruct), C.POINTER(CameraStruct), C.c_int]),
     "ab_render_batch": (C.c_int, [C.POINTER(SceneStruct), C.POINTER(CameraStruct), C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_void_p, c_i32_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -174,7 +182,7 @@ def launch_count() -> int:
     return int(load().ab_launch_count())
 
 
-STAGES = {0: "raster_vertex_kernel", 1: "raster_triangle_kernel", 2: "raster_resolve_kernel", 3: "mano_lbs_kernel",
+STAGES = {0: "raster_bin_kernel", 1: "raster_tile_kernel", 3: "mano_lbs_kernel",
           4: "posegen_prelude_kernel", 5: "ccv_cdf+draw_kernels", 6: "view_kernel", 7: "gemm_bf16_tn_kernel",
           8: "im2col_kernel", 9: "elementwise_kernels", 10: "head_decode_kernel", 11: "gemm_bf16_tn_kernel<im2col TMA>", 12: "wgrad_bf16_kernel", 13: "train_elementwise_kernels", 14: "optimizer_kernels", 15: "bn_apply_kernel", 16: "bn_bwd_reduce_kernel",
           17: "bn_bwd_apply_kernel", 18: "bn_finalize_kernel", 19: "augment_kernels",

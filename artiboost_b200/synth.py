@@ -34,7 +34,7 @@ DEFAULT_CFG = {
 class SynthPipeline:
 
     def __init__(self, obj_names: Optional[List[str]] = None, device="cuda", seed: int = 0, cfg: Optional[dict] = None,
-                 n_hand_tex: int = 51, n_bg: int = 8, chunk: int = 64, mano_model: Optional[Dict] = None,
+                 n_hand_tex: int = 51, n_bg: int = 8, chunk: int = 512, mano_model: Optional[Dict] = None,
                  objects: Optional[Dict[str, dict]] = None, grasps: Optional[Dict[str, list]] = None):
         self.cfg = cfg = dict(DEFAULT_CFG if cfg is None else cfg)
         self.device = dev = torch.device(device)

@@ -46,9 +46,9 @@ AB_API uint64_t ab_launch_count(void);
 /* Per-stage device timing for bench.py's roofline line: when enabled, every kernel launch of this library is
  * bracketed by CUDA events on the launching stream; ab_profile_collect waits for them and returns the summed
  * milliseconds and launch counts per stage id (AB_STAGE_*).  Off by default.                                  */
-#define AB_STAGE_RASTER_VERTEX 0
-#define AB_STAGE_RASTER_TRIANGLE 1
-#define AB_STAGE_RASTER_RESOLVE 2
+#define AB_STAGE_RASTER_BIN 0
+#define AB_STAGE_RASTER_TILE 1
+#define AB_STAGE_RESERVED_2 2
 #define AB_STAGE_MANO_LBS 3
 #define AB_STAGE_POSEGEN_PRELUDE 4
 #define AB_STAGE_CCV 5
@@ -188,7 +188,36 @@ AB_API int ab_scramble_anatomical(int batch, const float* pose, const float* joi
 /* --------------------------------------------------------------------------------------------------- rasteriser
  * Replaces Renderer.__call__ (anakin/utils/renderer.py:101-123) over pyrender's OffscreenRenderer
  * (anakin/utils/frender_utils.py:179-205), batched: one call renders `batch` hand+object views.
- * Rule set (pixel-exact on seg/coverage/depth-bits against oracle/raster.c): see DESIGN.md "Raster rules".   */
+ * Rule set (pixel-exact on seg/coverage/depth-bits against oracle/raster.c): see DESIGN.md "Raster rules".
+ *
+ * Mesh patches.  The rasteriser walks a mesh as patches of <= 32 faces over <= 32 vertices (one warp per patch: a lane
+ * per vertex, then a lane per face), each with a bounding sphere and a normal cone so that back-facing patches are
+ * dropped and the others are placed into 64x64 pixel tiles before any of their vertices is fetched.  This replaces
+ * the per-object VBO + GL culling / clipping of pyrender (renderer.py:79-93).  ab_build_patches_host is HOST code
+ * (no device needed): it fills caller-owned HOST arrays of `capacity` = ab_patch_capacity(n_faces) patches for ONE
+ * mesh; the caller concatenates the first *n_patches rows of every mesh, uploads them and fills ab_patch_table.
+ *   pos   f32 [capacity][32][4]  xyz of the lane's vertex + 1.0 (0.0: lane unused); may be NULL for a mesh whose
+ *                                 vertices change per view (the hand: the kernel gathers hand_verts through `vid`)
+ *   vid   i32 [capacity][32]     mesh-local vertex index of the lane, -1 unused
+ *   face  u32 [capacity][32]     patch-local corner lanes a | b << 8 | c << 16, 0xFFFFFFFF unused
+ *   prim  i32 [capacity][32]     ORIGINAL mesh-local face index (the z-test tie-break id), -1 unused
+ *   bound f32 [capacity][12]     sphere centre xyz, radius | cone axis xyz, min cos to the axis | max perimeter / area,
+ *                                 max 1 / (2 area) over the faces (for the snapping margin of the cone test) | #verts, #faces
+ * faces: [n_faces][face_stride] i32, the first three entries of a row are used.                              */
+typedef struct {
+    int32_t n_mesh;
+    const int32_t* patch_off_host; /* HOST [n_mesh+1] prefix offsets (in patches) of every mesh                 */
+    const float* pos;              /* device [P][32][4] or NULL                                                  */
+    const int32_t* vid;            /* device [P][32]                                                             */
+    const uint32_t* face;          /* device [P][32]                                                             */
+    const int32_t* prim;           /* device [P][32]                                                             */
+    const float* bound;            /* device [P][12]                                                             */
+} ab_patch_table;
+AB_API int ab_patch_capacity(int n_faces);
+AB_API int ab_build_patches_host(const float* verts, int n_verts, const int32_t* faces, int n_faces, int face_stride,
+                          int capacity, float* pos, int32_t* vid, uint32_t* face, int32_t* prim, float* bound,
+                          int32_t* n_patches);
+
 typedef struct {
     int32_t n_obj;              /* number of object meshes                                              */
     const float* obj_verts;     /* [sum V,3] canonical (bbox-centred) vertices, all objects concatenated  */
@@ -202,6 +231,8 @@ typedef struct {
     const uint8_t* bgs;         /* [n_bg, bg_h, bg_w, bg_channels] or NULL                              */
     int32_t n_bg, bg_h, bg_w;
     int32_t bg_channels;        /* 3 (RGB; 0 means 3) or 4 (RGBX, 4-byte aligned: one 32-bit load per pixel) */
+    const ab_patch_table* obj_patches;  /* n_mesh = n_obj, with `pos` (NULL allowed when n_obj == 0)     */
+    const ab_patch_table* hand_patches; /* n_mesh = 1, `pos` unused                                      */
 } ab_scene;
 
 typedef struct {
@@ -216,15 +247,14 @@ typedef struct {
 /* Per-view inputs: hand_verts [B,778,3] camera space, hand_tex [B] texture id (renderer.py:102), obj_id [B]
  * (<0 = CONST.DUMMY: hand only), obj_pose [B,16], light [B] point-light intensity (renderer.py:103-104),
  * bg_sel [B,5] = {bg id (<0 none), x0, y0, crop_w, crop_h} or NULL.
- * obj_id_host: HOST copy of obj_id or NULL.  When given, launches are sized to the largest selected object;
- * when NULL they are sized to the largest object in the scene (no host sync either way).
+ * obj_id_host: HOST copy of obj_id or NULL.  When given, the binning launch is sized to the largest selected object;
+ * when NULL to the largest object in the scene (no host sync either way).
  * Outputs: rgba u8[B,H,W,4], depth f32[B,H,W] (0 = background), seg u8[B,H,W] (0 bg, 1 hand, 2 object); any may
- * be NULL.  ws: workspace of ab_render_workspace_bytes() bytes; views are processed in chunks of `chunk`
- * views so the scratch stays L2-resident.  Up to four chunks are in flight at a time, on the caller's stream and on
- * library-owned auxiliary streams (fork / join by events: the call stays ordered on `stream`); the workspace holds four
- * scratch sets.  ab_set_raster_streams(n), n in 1..4, sets the number in flight (1 = everything on `stream`; default 4
- * or the AB_RASTER_STREAMS environment variable).                                                          */
-AB_API int ab_set_raster_streams(int n);
+ * be NULL.  ws: workspace of ab_render_workspace_bytes() bytes (per-tile patch lists for `chunk` views); a batch
+ * larger than `chunk` is rendered as consecutive groups of `chunk` views on `stream`.  Two kernels per group:
+ * raster_bin_kernel (cone cull + tile placement of every patch) and raster_tile_kernel (one CTA per 64x64 tile:
+ * z-buffer in shared memory, vertex transform + exact integer coverage per patch, shading and background fill; the
+ * only HBM traffic is the per-view inputs, the patch lists and the output image).                           */
 AB_API uint64_t ab_render_workspace_bytes(const ab_scene* scene, const ab_camera* cam, int chunk);
 AB_API int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int batch, int chunk, const float* hand_verts,
                     const int32_t* hand_tex, const int32_t* obj_id, const int32_t* obj_id_host, const float* obj_pose,

@@ -110,29 +110,78 @@ def test_render_is_idempotent_and_order_independent_at_batch_512(pipe):
     check(a, oracle_views(pipe, poses, rand, idx), idx)
 
 
-def test_chunk_pipelines_do_not_change_the_result(pipe):
-    """ab_render_batch keeps up to four chunks in flight on its own streams: any number of pipelines, a ragged last
-    chunk and back-to-back calls on the shared scratch must give the same bits."""
-    from artiboost_b200 import lib
-    L = lib.load()
-    B = 300  # 18 chunks of 16 views + one of 12 at the module's chunk size
+def test_view_groups_do_not_change_the_result(pipe):
+    """A batch larger than the workspace's `chunk` is rendered as consecutive groups of views: any group size, a ragged
+    last group and back-to-back calls on the shared workspace must give the same bits."""
+    B = 300  # 18 groups of 16 views + one of 12 at the module's chunk size
     poses = pipe.sample_poses(B)
     rand = pipe.draw_render_randoms(B)
     ref = None
     try:
-        for n in (1, 4, 2, 3, 4):
-            lib.check(L.ab_set_raster_streams(n), "ab_set_raster_streams")
+        for n in (16, 300, 7, 512, 64):
+            pipe.renderer.set_chunk(n)
             out = {k: v.clone() for k, v in pipe.render(poses, rand).items()}
-            out2 = pipe.render(poses, rand)   # immediately again: the previous call's side streams must have joined
+            out2 = pipe.render(poses, rand)   # immediately again on the same workspace
             if ref is None:
                 ref = out
             for k in ("rgba", "depth", "seg"):
                 assert torch.equal(ref[k], out[k]) and torch.equal(ref[k], out2[k]), (n, k)
-        assert L.ab_set_raster_streams(0) == -1 and L.ab_set_raster_streams(5) == -1
     finally:
-        L.ab_set_raster_streams(4)
+        pipe.renderer.set_chunk(16)
     idx = [0, 15, 16, 299]
     check(ref, oracle_views(pipe, poses, rand, idx), idx)
+
+
+def test_bench_configuration_matches_oracle_on_64_views(lib_built):
+    """The exact configuration bench.py times (SynthPipeline(seed=1): 51 hand textures, 8 backgrounds, batch 512 in one
+    group): 64 views spread over the batch, bit for bit against oracle/raster.c."""
+    from artiboost_b200.synth import SynthPipeline
+    bp = SynthPipeline(device=DEV, seed=1)
+    B = 512
+    poses = bp.sample_poses(B)
+    rand = bp.draw_render_randoms(B)
+    views = bp.render(poses, rand)
+    idx = list(range(0, B, 8))
+    assert len(idx) == 64
+    check(views, oracle_views(bp, poses, rand, idx), idx)
+
+
+def _pipe_with_camera(size, f, c, **kw):
+    from artiboost_b200.synth import DEFAULT_CFG, SynthPipeline
+    cfg = dict(DEFAULT_CFG, RENDER_SIZE=list(size), CAM_PARAM={"FX": f[0], "FY": f[1], "CX": c[0], "CY": c[1]})
+    return SynthPipeline(device=DEV, seed=4, cfg=cfg, n_hand_tex=3, n_bg=2, **kw)
+
+
+@pytest.mark.parametrize("size,f,c", [((250, 190), (217.5, 230.0), (125.0, 95.0)),     # ragged tiles, scalar output path
+                                      ((512, 512), (435.0, 435.0), (256.0, 256.0)),    # the reference's render size (yaml:52-61)
+                                      ((100, 60), (90.0, 90.0), (50.0, 30.0))])        # smaller than one tile row
+def test_other_image_sizes_match_oracle(lib_built, size, f, c):
+    p = _pipe_with_camera(size, f, c)
+    B = 6
+    poses = p.sample_poses(B)
+    rand = p.draw_render_randoms(B)
+    views = p.render(poses, rand)
+    assert views["seg"].shape == (B, size[1], size[0])
+    check(views, oracle_views(p, poses, rand, range(B)), range(B))
+    assert int((views["seg"] > 0).sum()) > 100
+
+
+def test_close_up_views_match_oracle(lib_built):
+    """Geometry right in front of the camera: triangles tens of pixels across (the warp-cooperative path), extents beyond
+    64 px (the int64 edge functions), patches that straddle the near plane and every tile of the frame."""
+    p = _pipe_with_camera((256, 256), (217.5, 217.5), (128.0, 128.0))
+    B = 8
+    poses = p.sample_poses(B)
+    rand = p.draw_render_randoms(B)
+    z = torch.tensor([0.40, 0.38, 0.36, 0.34, 0.32, 0.30, 0.42, 0.41], device=DEV)
+    poses["final_obj_pose"] = poses["final_obj_pose"].clone()
+    poses["final_obj_pose"][:, 2, 3] -= z
+    poses["final_hand_verts"] = poses["final_hand_verts"] - torch.stack([torch.zeros_like(z), torch.zeros_like(z), z], 1)[:, None]
+    for cull in (1, 0):
+        p.renderer.camera.cull_backface = cull
+        views = p.render(poses, rand)
+        check(views, oracle_views(p, poses, rand, range(B), cull=cull), range(B))
+    assert float((views["seg"] > 0).float().mean()) > 0.2
 
 
 def test_render_edge_cases(pipe):
