@@ -37,8 +37,9 @@ constexpr int kTile = 64;                 // tile edge in pixels
 constexpr int kTilePx = kTile * kTile;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kOwnMax = 16;               // a lane walks its own triangle when its clipped bbox has at most this many pixels
 constexpr unsigned kHandBit = 0x8000u;    // list entries: patch index (relative to its mesh) | kHandBit for hand patches
+constexpr unsigned kMultiBit = 0x4000u;   //               | kMultiBit when the binning box spans several tiles (the tile kernel then
+constexpr unsigned kIndexMask = 0x3fffu;  //               tests the exact box of the projected vertices before the face phase)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr float kSnapEps = 0.0032f;       // bound on the displacement (pixels) of a projected vertex by fp32 evaluation + 24.8 snapping
 
@@ -112,7 +113,7 @@ __device__ __forceinline__ int snap(float u) {
 __device__ __forceinline__ int4 project(const RasterParams& P, float X, float Y, float Z) {
     int4 r;
     r.w = (Z >= P.znear) ? 1 : 0;
-    float iz = __fdiv_rn(1.0f, Z);
+    float iz = __frcp_rn(Z);  // correctly rounded, i.e. the rule's 1.0f / Z
     r.z = __float_as_int(iz);
     r.x = snap(__fmaf_rn(P.fx, __fmul_rn(X, iz), P.cx));
     r.y = snap(__fmaf_rn(P.fy, __fmul_rn(Y, iz), P.cy));
@@ -131,6 +132,7 @@ __device__ __forceinline__ int floordiv256(int v) { return v >> 8; }
 __device__ __forceinline__ void bin_append(const RasterParams& P, int view, int px_lo, int px_hi, int py_lo, int py_hi,
                                            unsigned entry) {
     const int tx_lo = px_lo / kTile, tx_hi = px_hi / kTile, ty_lo = py_lo / kTile, ty_hi = py_hi / kTile;
+    if (tx_lo != tx_hi || ty_lo != ty_hi) entry |= kMultiBit;
     for (int ty = ty_lo; ty <= ty_hi; ++ty)
         for (int tx = tx_lo; tx <= tx_hi; ++tx) {
             const int bin = view * P.n_tiles + ty * P.tiles_x + tx;
@@ -343,13 +345,16 @@ __device__ __forceinline__ PixelOut shade_pixel(const RasterParams& P, const flo
 
 // ---- the tile kernel -----------------------------------------------------------------------------------------
 // PX = pixels per thread in the output stream: 4 when W % 4 == 0 and the output rows are 16-byte aligned, else 1.
-template <int PX>
+// BG4: backgrounds are RGBX (one aligned 32-bit load per pixel) instead of packed RGB.
+template <int PX, bool BG4>
 __global__ void __launch_bounds__(kThreads, 4)
 raster_tile_kernel(const __grid_constant__ RasterParams P) {
     __shared__ __align__(16) unsigned long long zbuf[kTilePx];  // 32 KB
     __shared__ __align__(16) int4 slab[kWarps][32];             // projected vertices of the patch a warp is on
     __shared__ unsigned short hit_px[kTilePx];                  // covered pixels of the tile (tile-local index)
     __shared__ __align__(16) float Msh[12];
+    __shared__ unsigned char rank_lane[kWarps][32];             // per warp: lane of the k-th box that has rows
+    __shared__ __align__(16) int colmap[kTile];                 // background source column of every tile column
     __shared__ int next_patch, n_hit;
 
     const int view = blockIdx.y, tile = blockIdx.x;
@@ -358,11 +363,15 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int bin = view * P.n_tiles + tile;
     const int count = P.bin_count[bin];
-    const int oid = P.obj_id[view];
-    const int n_of = oid >= 0 ? P.face_off[oid + 1] - P.face_off[oid] : 0;
+    const int32_t* sel = P.bg_sel ? P.bg_sel + 5 * (size_t)view : nullptr;
+    const bool has_bg = sel && P.bgs && sel[0] >= 0;
+    if (has_bg && t < kTile)  // nearest-neighbour source column of every tile column, once per CTA (exact multiply-shift division)
+        colmap[t] = sel[1] + (int)fastdiv((unsigned)(2 * min(tx0 + t, P.W - 1) + 1) * (unsigned)sel[3], P.div_2w_m, P.div_2w_s);
 
     if (count > 0) {
-        if (t == 0) { next_patch = 0; n_hit = 0; }
+        const int oid = P.obj_id[view];
+        const int n_of = oid >= 0 ? P.face_off[oid + 1] - P.face_off[oid] : 0;
+        if (t == 0) { next_patch = kWarps; n_hit = 0; }  // the first kWarps list entries go to the warps by index
         if (t < 12) Msh[t] = oid >= 0 ? P.obj_pose[16 * (size_t)view + t] : 0.0f;
         ulonglong2* z2 = reinterpret_cast<ulonglong2*>(zbuf);
         for (int i = t; i < kTilePx / 2; i += kThreads) z2[i] = make_ulonglong2(kEmptyKey, kEmptyKey);
@@ -370,14 +379,18 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
         const unsigned short* list = P.bin_list + (size_t)bin * P.list_cap;
         const int poff = oid >= 0 ? P.patch_off[oid] : 0;
         int4* my_slab = slab[wid];
-        for (;;) {
-            int li = 0;
-            if (lane == 0) li = atomicAdd(&next_patch, 1);
-            li = __shfl_sync(kFull, li, 0);
-            if (li >= count) break;
-            const unsigned entry = list[li];
+        unsigned char* my_rank = rank_lane[wid];
+        const unsigned lt_mask = (1u << lane) - 1u;
+        int li = wid;
+        unsigned entry = li < count ? list[li] : 0u;
+        while (li < count) {
             const bool hand = (entry & kHandBit) != 0;
-            const size_t prow = ((size_t)(hand ? 0 : poff) + (entry & 0x7fffu)) * 32 + lane;
+            const size_t prow = ((size_t)(hand ? 0 : poff) + (entry & kIndexMask)) * 32 + lane;
+            const bool multi = (entry & kMultiBit) != 0;
+            // the patch's face words and primitive ids do not depend on the vertex phase: issue their loads first, and claim
+            // + fetch the next list entry, so that one round of memory latency per patch is exposed instead of four
+            const unsigned fw = __ldg((hand ? P.hp_face : P.op_face) + prow);
+            const int prim_local = __ldg((hand ? P.hp_prim : P.op_prim) + prow);
             // ---- a lane per vertex
             float c[3] = {0.0f, 0.0f, 0.0f};
             bool on;
@@ -393,18 +406,26 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
                     c[0] = hv[0]; c[1] = hv[1]; c[2] = hv[2];
                 }
             }
+            {
+                int nli = 0;
+                if (lane == 0) nli = atomicAdd(&next_patch, 1);
+                li = __shfl_sync(kFull, nli, 0);
+                entry = li < count ? list[li] : 0u;
+            }
             int4 pvv = project(P, c[0], c[1], c[2]);
             if (!on) pvv.w = 0;
             my_slab[lane] = pvv;
-            const int mnx = __reduce_min_sync(kFull, on ? pvv.x : INT_MAX), mxx = __reduce_max_sync(kFull, on ? pvv.x : INT_MIN);
-            const int mny = __reduce_min_sync(kFull, on ? pvv.y : INT_MAX), mxy = __reduce_max_sync(kFull, on ? pvv.y : INT_MIN);
-            const bool overlap = floordiv256(mnx + 127) <= tx1 && floordiv256(mxx - 128) >= tx0 &&
-                                 floordiv256(mny + 127) <= ty1 && floordiv256(mxy - 128) >= ty0;
+            bool overlap = true;
+            if (multi) {  // warp-uniform
+                const int mnx = __reduce_min_sync(kFull, on ? pvv.x : INT_MAX), mxx = __reduce_max_sync(kFull, on ? pvv.x : INT_MIN);
+                const int mny = __reduce_min_sync(kFull, on ? pvv.y : INT_MAX), mxy = __reduce_max_sync(kFull, on ? pvv.y : INT_MIN);
+                overlap = floordiv256(mnx + 127) <= tx1 && floordiv256(mxx - 128) >= tx0 &&
+                          floordiv256(mny + 127) <= ty1 && floordiv256(mxy - 128) >= ty0;
+            }
             __syncwarp();
             if (overlap) {
                 // ---- a lane per face
-                const unsigned fw = __ldg((hand ? P.hp_face : P.op_face) + prow);
-                int n = 0, x0 = 0, y0 = 0, w = 0;
+                int n = 0, x0 = 0, y0 = 0, w = 0, h = 0;
                 bool small = false;
                 long long area2 = 0;
                 int4 a, b, d;
@@ -420,58 +441,110 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
                         if (x0 <= x1 && y0 <= y1) {
                             small = (maxx - minx < kSmallExtent) && (maxy - miny < kSmallExtent);
                             area2 = area2_of(a, b, d, small);
-                            if (area2 != 0 && !(area2 > 0 && P.cull)) { w = x1 - x0 + 1; n = w * (y1 - y0 + 1); }
+                            if (area2 != 0 && !(area2 > 0 && P.cull)) { w = x1 - x0 + 1; h = y1 - y0 + 1; n = w * h; }
                         }
                     }
                 }
-                unsigned prim = 0;
-                if (n > 0) prim = (unsigned)(__ldg((hand ? P.hp_prim : P.op_prim) + prow) + (hand ? n_of : 0));
-                const bool own = n > 0 && small && n <= kOwnMax;
-                if (own) {
+                const unsigned prim = (unsigned)(prim_local + (hand ? n_of : 0));
+                // int32 set-up of every surviving lane: edge values at the centre of pixel (x0, y0), biased so that "inside"
+                // is e >= 0 on all three; the steps per pixel are -256 dy (x) and 256 dx (y), kept as (dx, dy) in 16 + 16 bits
+                int e[3] = {0, 0, 0}, dd[3] = {0, 0, 0}, nb = 0;
+                float iz0 = 0.f, iz1 = 0.f, iz2 = 0.f, sarea = 0.f;
+                if (n > 0 && small) {
                     const int s = area2 > 0 ? 1 : -1;
                     const int vx[3] = {a.x, b.x, d.x}, vy[3] = {a.y, b.y, d.y};
-                    const float iz0 = __int_as_float(a.z), iz1 = __int_as_float(b.z), iz2 = __int_as_float(d.z);
-                    const float sarea = __ll2float_rn(area2 > 0 ? area2 : -area2);
+                    iz0 = __int_as_float(a.z); iz1 = __int_as_float(b.z); iz2 = __int_as_float(d.z);
+                    sarea = __int2float_rn(abs((int)area2));
                     const int cx0 = 256 * x0 + 128, cy0 = 256 * y0 + 128;
-                    int e[3], ex[3], ey[3], nb = 0;  // e: biased so that "inside" is e >= 0 on all three
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {  // edge i runs v[i+1] -> v[i+2], opposite vertex i
                         const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-                        const int dx = s * (vx[i2] - vx[i1]), dy = s * (vy[i2] - vy[i1]);
+                        const int dx = s * (vx[i2] - vx[i1]), dy = s * (vy[i2] - vy[i1]);  // |.| < 2^14
                         const int bias = ((dy < 0) || (dy == 0 && dx > 0)) ? 0 : 1;  // 1: not a top/left edge, E == 0 is outside
                         nb |= bias << i;
                         e[i] = dx * (cy0 - vy[i1]) - dy * (cx0 - vx[i1]) - bias;
-                        ex[i] = -256 * dy;
-                        ey[i] = 256 * dx - w * ex[i];  // to the first pixel of the next row
-                    }
-                    int idx = (y0 - ty0) * kTile + (x0 - tx0), x = 0;
-                    for (int k = 0; k < n; ++k) {
-                        if ((e[0] | e[1] | e[2]) >= 0)
-                            emit(zbuf, idx, __int2float_rn(e[0] + (nb & 1)), __int2float_rn(e[1] + ((nb >> 1) & 1)),
-                                 __int2float_rn(e[2] + ((nb >> 2) & 1)), iz0, iz1, iz2, sarea, prim);
-                        e[0] += ex[0]; e[1] += ex[1]; e[2] += ex[2];
-                        ++idx;
-                        if (++x == w) { x = 0; idx += kTile - w; e[0] += ey[0]; e[1] += ey[1]; e[2] += ey[2]; }
+                        dd[i] = (dx & 0xffff) | (dy << 16);
                     }
                 }
-                // ---- large boxes: the whole warp walks one triangle at a time
-                unsigned coop = __ballot_sync(kFull, n > 0 && !own);
-                while (coop) {
-                    const int src = __ffs(coop) - 1;
-                    coop &= coop - 1;
+                // ---- coverage: the ROWS of all surviving boxes of the patch are dealt to the lanes.  Warp scan of the row
+                // counts; the owner of row j of a chunk of 32 rows is found from a bit mask of the positions where a box starts
+                // (one warp reduction) and a rank -> lane table; its set-up comes by indexed shuffles.  A row's candidate span
+                // follows from the edge functions: e_i + x ex_i >= 0 bounds x from below (ex_i > 0) or from above (ex_i < 0); the
+                // fp32 guess is at most one pixel wide of the truth on either side (rows of up to 4 pixels skip the guess), and
+                // every candidate is then tested with the exact integers.
+                const int rows = (n > 0 && small) ? h : 0;
+                int incl = rows;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int total = __shfl_sync(kFull, incl, 31);
+                if (total > 0) {  // warp-uniform
+                    const int pre = incl - rows;
+                    const unsigned owners = __ballot_sync(kFull, rows > 0);
+                    if (rows > 0) my_rank[__popc(owners & lt_mask)] = (unsigned char)lane;
+                    __syncwarp();
+                    const int last_rank = __popc(owners) - 1;
+                    const int pack = (x0 - tx0) | ((y0 - ty0) << 6) | (w << 12) | (nb << 19);
+                    for (int j0 = 0; j0 < total; j0 += 32) {
+                        const int rel = pre - j0;
+                        const unsigned starts = __reduce_or_sync(kFull, (rows > 0 && rel >= 0 && rel < 32) ? (1u << rel) : 0u);
+                        const int before = __popc(__ballot_sync(kFull, rows > 0 && rel < 0));
+                        const int rank = before + __popc(starts & (0xffffffffu >> (31 - lane))) - 1;
+                        const int own = my_rank[min(max(rank, 0), last_rank)];
+                        const int j = j0 + lane;
+                        const int ry = j - __shfl_sync(kFull, pre, own);
+                        const int ce0 = __shfl_sync(kFull, e[0], own), ce1 = __shfl_sync(kFull, e[1], own), ce2 = __shfl_sync(kFull, e[2], own);
+                        const int cd0 = __shfl_sync(kFull, dd[0], own), cd1 = __shfl_sync(kFull, dd[1], own), cd2 = __shfl_sync(kFull, dd[2], own);
+                        const float ciz0 = __shfl_sync(kFull, iz0, own), ciz1 = __shfl_sync(kFull, iz1, own), ciz2 = __shfl_sync(kFull, iz2, own);
+                        const float csarea = __shfl_sync(kFull, sarea, own);
+                        const unsigned cprim = __shfl_sync(kFull, prim, own);
+                        const int cpack = __shfl_sync(kFull, pack, own);
+                        const int cw = (cpack >> 12) & 127, cnb = cpack >> 19;
+                        const bool act = j < total;
+                        const int cex0 = -256 * (cd0 >> 16), cex1 = -256 * (cd1 >> 16), cex2 = -256 * (cd2 >> 16);
+                        const int r0 = ce0 + ry * (256 * (int)(short)cd0), r1 = ce1 + ry * (256 * (int)(short)cd1),
+                                  r2 = ce2 + ry * (256 * (int)(short)cd2);  // biased edge values at x = 0 of the row
+                        int lo = 0, hi = act ? cw - 1 : -1;
+                        if (__any_sync(kFull, act && cw > 4)) {
+                            if (cex0 != 0) {
+                                const int fl = min(__float2int_rd(__fdividef(-(float)r0, (float)cex0)), 1 << 20);
+                                if (cex0 > 0) lo = max(lo, fl); else hi = min(hi, fl + 1);
+                            }
+                            if (cex1 != 0) {
+                                const int fl = min(__float2int_rd(__fdividef(-(float)r1, (float)cex1)), 1 << 20);
+                                if (cex1 > 0) lo = max(lo, fl); else hi = min(hi, fl + 1);
+                            }
+                            if (cex2 != 0) {
+                                const int fl = min(__float2int_rd(__fdividef(-(float)r2, (float)cex2)), 1 << 20);
+                                if (cex2 > 0) lo = max(lo, fl); else hi = min(hi, fl + 1);
+                            }
+                        }
+                        const int base = (((cpack >> 6) & 63) + ry) * kTile + (cpack & 63);
+                        for (int x = lo; x <= hi; ++x) {
+                            const int f0 = r0 + x * cex0, f1 = r1 + x * cex1, f2 = r2 + x * cex2;
+                            if ((f0 | f1 | f2) >= 0)
+                                emit(zbuf, base + x, __int2float_rn(f0 + (cnb & 1)), __int2float_rn(f1 + ((cnb >> 1) & 1)),
+                                     __int2float_rn(f2 + ((cnb >> 2) & 1)), ciz0, ciz1, ciz2, csarea, cprim);
+                        }
+                    }
+                }
+                // ---- extents of 64 px and more (close-ups): int64 edge functions, the warp walks the box pixel by pixel
+                unsigned big = __ballot_sync(kFull, n > 0 && !small);
+                while (big) {
+                    const int src = __ffs(big) - 1;
+                    big &= big - 1;
                     const unsigned cfw = __shfl_sync(kFull, fw, src);
                     const int cx0 = __shfl_sync(kFull, x0, src), cy0 = __shfl_sync(kFull, y0, src);
                     const int cw = __shfl_sync(kFull, w, src), cn = __shfl_sync(kFull, n, src);
                     const unsigned cprim = __shfl_sync(kFull, prim, src);
                     const int4 ca = my_slab[cfw & 31], cb = my_slab[(cfw >> 8) & 31], cd = my_slab[(cfw >> 16) & 31];
                     const int vx[3] = {ca.x, cb.x, cd.x}, vy[3] = {ca.y, cb.y, cd.y};
-                    const float iz0 = __int_as_float(ca.z), iz1 = __int_as_float(cb.z), iz2 = __int_as_float(cd.z);
-                    const int minx = min(vx[0], min(vx[1], vx[2])), maxx = max(vx[0], max(vx[1], vx[2]));
-                    const int miny = min(vy[0], min(vy[1], vy[2])), maxy = max(vy[0], max(vy[1], vy[2]));
-                    const bool csmall = (maxx - minx < kSmallExtent) && (maxy - miny < kSmallExtent);
-                    const long long carea2 = area2_of(ca, cb, cd, csmall);
+                    const float jz0 = __int_as_float(ca.z), jz1 = __int_as_float(cb.z), jz2 = __int_as_float(cd.z);
+                    const long long carea2 = area2_of(ca, cb, cd, false);
                     const int s = carea2 > 0 ? 1 : -1;
-                    const float sarea = __ll2float_rn(carea2 > 0 ? carea2 : -carea2);
+                    const float jarea = __ll2float_rn(carea2 > 0 ? carea2 : -carea2);
                     int bias[3];
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
@@ -483,91 +556,60 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
                     for (int k = lane; k < cn; k += 32) {
                         const int ry = (int)(((float)k + 0.5f) * inv_w), rx = k - ry * cw;  // exact: k < 4096, cw <= 64
                         const int px = cx0 + rx, py = cy0 + ry;
-                        const int idx = (py - ty0) * kTile + (px - tx0);
-                        if (csmall) {
-                            const int ccx = 256 * px + 128, ccy = 256 * py + 128;
-                            int e[3];
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-                                const int dx = s * (vx[i2] - vx[i1]), dy = s * (vy[i2] - vy[i1]);
-                                e[i] = dx * (ccy - vy[i1]) - dy * (ccx - vx[i1]);
-                            }
-                            if (((e[0] - bias[0]) | (e[1] - bias[1]) | (e[2] - bias[2])) >= 0)
-                                emit(zbuf, idx, __int2float_rn(e[0]), __int2float_rn(e[1]), __int2float_rn(e[2]), iz0, iz1, iz2,
-                                     sarea, cprim);
-                        } else {
-                            const long long ccx = 256ll * px + 128, ccy = 256ll * py + 128;
-                            const long long e0 = edge64(vx, vy, s, 0, ccx, ccy), e1 = edge64(vx, vy, s, 1, ccx, ccy),
-                                            e2 = edge64(vx, vy, s, 2, ccx, ccy);
-                            if (((e0 - bias[0]) | (e1 - bias[1]) | (e2 - bias[2])) >= 0)
-                                emit(zbuf, idx, __ll2float_rn(e0), __ll2float_rn(e1), __ll2float_rn(e2), iz0, iz1, iz2, sarea,
-                                     cprim);
-                        }
+                        const long long ccx = 256ll * px + 128, ccy = 256ll * py + 128;
+                        const long long e0 = edge64(vx, vy, s, 0, ccx, ccy), e1 = edge64(vx, vy, s, 1, ccx, ccy),
+                                        e2 = edge64(vx, vy, s, 2, ccx, ccy);
+                        if (((e0 - bias[0]) | (e1 - bias[1]) | (e2 - bias[2])) >= 0)
+                            emit(zbuf, (py - ty0) * kTile + (px - tx0), __ll2float_rn(e0), __ll2float_rn(e1), __ll2float_rn(e2), jz0,
+                                 jz1, jz2, jarea, cprim);
                     }
                 }
             }
-            __syncwarp();  // the slab is rewritten by the next patch
+            __syncwarp();  // the slab and the rank table are rewritten by the next patch
         }
-        __syncthreads();
+    } else {
+        __syncthreads();  // colmap
     }
 
-    // ---- stream the tile out: background everywhere, covered pixels collected for the shading pass
+    // ---- stream the background out: flat colour or the nearest-neighbour crop, zero depth and seg.  This does not depend on
+    // the z-buffer (covered pixels are overwritten by the shading pass below, after a barrier), so a warp that runs out of
+    // patches starts it at once instead of waiting for the others.
     constexpr int TPR = kTile / PX;        // threads per tile row
     constexpr int RPP = kThreads / TPR;    // rows per pass
-    const int32_t* sel = P.bg_sel ? P.bg_sel + 5 * (size_t)view : nullptr;
-    const bool has_bg = sel && P.bgs && sel[0] >= 0;
     const size_t obase = (size_t)view * P.W * P.H;
-#pragma unroll 2
-    for (int pass = 0; pass < kTile / RPP; ++pass) {
-        const int row = pass * RPP + t / TPR, col = (t % TPR) * PX;
-        const int px0 = tx0 + col, py = ty0 + row;
-        const bool in = px0 <= tx1 && py <= ty1;  // PX == 4 only when W % 4 == 0: a group is entirely in or out
-        unsigned long long k[PX];
-#pragma unroll
-        for (int j = 0; j < PX; ++j) k[j] = kEmptyKey;
-        if (count > 0 && in) {
+    const uchar4 flat = make_uchar4((uint8_t)P.bg_r, (uint8_t)P.bg_g, (uint8_t)P.bg_b, 0);
+    const int col = (t % TPR) * PX, px0 = tx0 + col;
+    if (px0 <= tx1) {  // PX == 4 only when W % 4 == 0: a group of 4 pixels is entirely in or out
+        int sx[PX];
+        if (has_bg) {
             if constexpr (PX == 4) {
-                const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(zbuf + row * kTile + col),
-                                 k23 = *reinterpret_cast<const ulonglong2*>(zbuf + row * kTile + col + 2);
-                k[0] = k01.x; k[1] = k01.y; k[2] = k23.x; k[3] = k23.y;
+                const int4 q = *reinterpret_cast<const int4*>(colmap + col);
+                sx[0] = q.x; sx[1] = q.y; sx[2] = q.z; sx[3] = q.w;
             } else {
-                k[0] = zbuf[row * kTile + col];
+                sx[0] = colmap[col];
             }
         }
-        uchar4 c[PX];
 #pragma unroll
-        for (int j = 0; j < PX; ++j) c[j] = make_uchar4((uint8_t)P.bg_r, (uint8_t)P.bg_g, (uint8_t)P.bg_b, 0);
-        if (has_bg && in) {
-            const unsigned sy = (unsigned)sel[2] + fastdiv((unsigned)(2 * py + 1) * (unsigned)sel[4], P.div_2h_m, P.div_2h_s);
-            const uint8_t* bg_row = P.bgs + (size_t)P.bg_ch * (((size_t)sel[0] * P.bg_h + sy) * P.bg_w);
-            const unsigned bg_x0 = (unsigned)sel[1], bg_cw = (unsigned)sel[3];
+        for (int pass = 0; pass < kTile / RPP; ++pass) {
+            const int py = ty0 + pass * RPP + t / TPR;
+            if (py > ty1) continue;
+            uchar4 c[PX];
 #pragma unroll
-            for (int j = 0; j < PX; ++j) {
-                const unsigned sx = bg_x0 + fastdiv((unsigned)(2 * (px0 + j) + 1) * bg_cw, P.div_2w_m, P.div_2w_s);
-                if (P.bg_ch == 4) {
-                    c[j] = __ldg(reinterpret_cast<const uchar4*>(bg_row) + sx);
-                    c[j].w = 0;
-                } else {
-                    const uint8_t* src = bg_row + 3 * (size_t)sx;
-                    c[j] = make_uchar4(src[0], src[1], src[2], 0);
+            for (int j = 0; j < PX; ++j) c[j] = flat;
+            if (has_bg) {
+                const unsigned sy = (unsigned)sel[2] + fastdiv((unsigned)(2 * py + 1) * (unsigned)sel[4], P.div_2h_m, P.div_2h_s);
+                const uint8_t* bg_row = P.bgs + (BG4 ? 4 : 3) * (((size_t)sel[0] * P.bg_h + sy) * P.bg_w);
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
+                    if constexpr (BG4) {
+                        c[j] = __ldg(reinterpret_cast<const uchar4*>(bg_row) + sx[j]);
+                        c[j].w = 0;
+                    } else {
+                        const uint8_t* src = bg_row + 3 * (size_t)sx[j];
+                        c[j] = make_uchar4(src[0], src[1], src[2], 0);
+                    }
                 }
             }
-        }
-        if (count > 0) {  // CTA-uniform
-#pragma unroll
-            for (int j = 0; j < PX; ++j) {
-                const bool hit = k[j] != kEmptyKey;
-                const unsigned m = __ballot_sync(kFull, hit);
-                if (m) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&n_hit, __popc(m));
-                    base = __shfl_sync(kFull, base, 0);
-                    if (hit) hit_px[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)(row * kTile + col + j);
-                }
-            }
-        }
-        if (in) {
             const size_t o = obase + (size_t)py * P.W + px0;
             if constexpr (PX == 4) {
                 if (P.rgba) {
@@ -586,8 +628,25 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
         }
     }
     if (count == 0) return;
+    __syncthreads();  // every warp's fragments are in the z-buffer, every placeholder store has been issued
+    // ---- collect the covered pixels of the tile ...
+    for (int i = t; i < kTilePx / 2; i += kThreads) {
+        const ulonglong2 k = reinterpret_cast<const ulonglong2*>(zbuf)[i];
+        const bool h0 = k.x != kEmptyKey, h1 = k.y != kEmptyKey;
+        const unsigned m0 = __ballot_sync(kFull, h0), m1 = __ballot_sync(kFull, h1);
+        if (m0 | m1) {  // warp-uniform
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&n_hit, __popc(m0) + __popc(m1));
+            base = __shfl_sync(kFull, base, 0);
+            const unsigned lt = (1u << lane) - 1u;
+            if (h0) hit_px[base + __popc(m0 & lt)] = (unsigned short)(2 * i);
+            if (h1) hit_px[base + __popc(m0) + __popc(m1 & lt)] = (unsigned short)(2 * i + 1);
+        }
+    }
     __syncthreads();
-    // ---- shade the covered pixels, one per thread, on fully populated warps; their outputs overwrite the placeholders
+    // ---- ... and shade them, one per thread, on fully populated warps; their outputs overwrite the placeholders
+    const int oid = P.obj_id[view];
+    const int n_of = oid >= 0 ? P.face_off[oid + 1] - P.face_off[oid] : 0;
     const int total = n_hit;
     for (int i = t; i < total; i += kThreads) {
         const int idx = hit_px[i];
@@ -619,7 +678,7 @@ static int geometry_of(const ab_scene* s, const ab_camera* cam, Geometry* g) {
     for (int i = 0; i < s->n_obj; ++i)
         g->max_op = max(g->max_op, s->obj_patches->patch_off_host[i + 1] - s->obj_patches->patch_off_host[i]);
     const int n_hp = s->hand_patches->patch_off_host[1] - s->hand_patches->patch_off_host[0];
-    if (g->max_op > 0x7fff || n_hp > 0x7fff || n_hp <= 0) return -1;
+    if (g->max_op > (int)kIndexMask || n_hp > (int)kIndexMask || n_hp <= 0) return -1;
     g->list_cap = (int)align_up((size_t)g->max_op + n_hp, 8);
     return 0;
 }
@@ -650,7 +709,7 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
     AB_REQUIRE(scene->n_hand_verts > 0 && scene->n_hand_faces > 0 && scene->n_hand_tex > 0 && scene->hand_faces &&
                    scene->hand_colors, "bad hand mesh");
     Geometry g;
-    AB_REQUIRE(geometry_of(scene, cam, &g) == 0, "missing / inconsistent patch tables (ab_build_patches_host; at most 32767 patches per mesh)");
+    AB_REQUIRE(geometry_of(scene, cam, &g) == 0, "missing / inconsistent patch tables (ab_build_patches_host; at most 16383 patches per mesh)");
     const ab_patch_table* hp = scene->hand_patches;
     const ab_patch_table* op = scene->obj_patches;
     AB_REQUIRE(hp->vid && hp->face && hp->prim, "null hand patch arrays");
@@ -734,8 +793,11 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
             // 4 pixels per thread needs 16-byte aligned output rows: W % 4 == 0 and 16 / 16 / 4-byte aligned bases
             const bool vec = (P.W % 4 == 0) && (((uintptr_t)P.rgba & 15) == 0) && (((uintptr_t)P.depth & 15) == 0) &&
                              (((uintptr_t)P.seg & 3) == 0);
-            if (vec) raster_tile_kernel<4><<<dim3(g.n_tiles, n), kThreads, 0, st>>>(P);
-            else raster_tile_kernel<1><<<dim3(g.n_tiles, n), kThreads, 0, st>>>(P);
+            const dim3 grid(g.n_tiles, n);
+            if (vec && P.bg_ch == 4) raster_tile_kernel<4, true><<<grid, kThreads, 0, st>>>(P);
+            else if (vec) raster_tile_kernel<4, false><<<grid, kThreads, 0, st>>>(P);
+            else if (P.bg_ch == 4) raster_tile_kernel<1, true><<<grid, kThreads, 0, st>>>(P);
+            else raster_tile_kernel<1, false><<<grid, kThreads, 0, st>>>(P);
         }
         count_launch(2);
         int rc = check_launch("ab_render_batch");
