@@ -27,6 +27,10 @@
 #include <limits.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 
 namespace ab {
@@ -55,6 +59,8 @@ __device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned m, int s) {
     return (unsigned)(((unsigned long long)n * m) >> s);
 }
 
+constexpr int kMaxOrder = 256;  // frames of up to 1024 x 1024 pixels get the ranked tile order (below)
+
 struct RasterParams {
     // scene
     const float* obj_verts;
@@ -72,7 +78,6 @@ struct RasterParams {
     const uint32_t* hp_face;
     const int32_t* hp_prim;
     int n_hp;                 // hand patches
-    int obj_bin_blocks;       // blocks of the binning grid that serve object patches
     int n_obj, n_hv, n_hf, n_tex, n_bg, bg_h, bg_w, bg_ch;
     unsigned div_w_m, div_2w_m, div_2h_m;  // exact division by W, 2W, 2H as multiply + shift
     int div_w_s, div_2w_s, div_2h_s;
@@ -83,6 +88,11 @@ struct RasterParams {
     int bg_r, bg_g, bg_b;
     // tiles
     int tiles_x, tiles_y, n_tiles, list_cap;
+    int near_tiles;             // tiles of a view rendered in the first pass over the views (see raster_tile_kernel)
+    unsigned div_n1_m, div_n2_m, div_tx_m;  // exact division by near_tiles, n_tiles - near_tiles, tiles_x
+    int div_n1_s, div_n2_s, div_tx_s;
+    int use_order;              // 0: more than kMaxOrder tiles, natural order
+    unsigned short tile_order[kMaxOrder];  // tiles by distance from the principal point
     int* bin_count;             // [views][n_tiles]
     unsigned short* bin_list;   // [views][n_tiles][list_cap]
     // per-view inputs (already offset to the group's first view)
@@ -129,15 +139,17 @@ __device__ __forceinline__ void xform(const float* __restrict__ M, float x, floa
 __device__ __forceinline__ int floordiv256(int v) { return v >> 8; }
 
 // ---- binning -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bin_append(const RasterParams& P, int view, int px_lo, int px_hi, int py_lo, int py_hi,
-                                           unsigned entry) {
+constexpr int kMaxTiles = 4096;  // 4096 x 4096 pixels
+
+__device__ __forceinline__ void bin_append(const RasterParams& P, int* cnt, int view, int px_lo, int px_hi, int py_lo,
+                                           int py_hi, unsigned entry) {
     const int tx_lo = px_lo / kTile, tx_hi = px_hi / kTile, ty_lo = py_lo / kTile, ty_hi = py_hi / kTile;
     if (tx_lo != tx_hi || ty_lo != ty_hi) entry |= kMultiBit;
     for (int ty = ty_lo; ty <= ty_hi; ++ty)
         for (int tx = tx_lo; tx <= tx_hi; ++tx) {
-            const int bin = view * P.n_tiles + ty * P.tiles_x + tx;
-            const int slot = atomicAdd(P.bin_count + bin, 1);
-            P.bin_list[(size_t)bin * P.list_cap + slot] = (unsigned short)entry;
+            const int tile = ty * P.tiles_x + tx;
+            const int slot = atomicAdd(cnt + tile, 1);  // shared memory: this CTA owns every list of the view
+            P.bin_list[((size_t)view * P.n_tiles + tile) * P.list_cap + slot] = (unsigned short)entry;
         }
 }
 
@@ -153,17 +165,24 @@ __device__ __forceinline__ void bin_append(const RasterParams& P, int view, int 
 //        Bnd > 1.5 zmax^3 / (fx fy) (eps q g + 4 eps^2 ia) + 2e-5,    q = max perimeter / area, ia = max 1 / (2 area).
 //  * Screen box.  x / z over the box [sx - r, sx + r] x [zmin, zmax] is extremal at its corners; 0.05 px of slack covers
 //    snapping and fp32.  Pixels whose CENTRE lies in the box are the only ones a face of the patch can cover.
+// One CTA per view: its threads take the object patches, its warps the hand patches (four at a time, all loads of the
+// four issued before any is used: the vertex id -> position gathers are two dependent round trips); the per-tile counters
+// live in shared memory (no global atomics, and no clearing between calls: every count is written).
 __global__ void __launch_bounds__(kThreads)
 raster_bin_kernel(const __grid_constant__ RasterParams P) {
-    const int view = blockIdx.y;
+    __shared__ int cnt[kMaxTiles];
+    const int view = blockIdx.x;
     const int oid = P.obj_id[view];
-    if ((int)blockIdx.x < P.obj_bin_blocks) {
-        if (oid < 0) return;
-        const int i = blockIdx.x * kThreads + threadIdx.x;
-        if (i >= P.patch_off[oid + 1] - P.patch_off[oid]) return;
-        const float4* bp = P.op_bound + 3 * (size_t)(P.patch_off[oid] + i);
-        const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2);
-        const float* M = P.obj_pose + 16 * (size_t)view;
+    for (int i = threadIdx.x; i < P.n_tiles; i += kThreads) cnt[i] = 0;
+    float M[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) M[i] = P.obj_pose[16 * (size_t)view + i];
+    __syncthreads();
+    const int n_op = oid >= 0 ? P.patch_off[oid + 1] - P.patch_off[oid] : 0;
+    const float4* bounds = P.op_bound + 3 * (size_t)(oid >= 0 ? P.patch_off[oid] : 0);
+#pragma unroll 2
+    for (int i = threadIdx.x; i < n_op; i += kThreads) {
+        const float4 b0 = __ldg(bounds + 3 * i), b1 = __ldg(bounds + 3 * i + 1), b2 = __ldg(bounds + 3 * i + 2);
         float s[3];
         xform(M, b0.x, b0.y, b0.z, s);
         const float r = b0.w;
@@ -183,7 +202,7 @@ raster_bin_kernel(const __grid_constant__ RasterParams P) {
                 const float T = (sqrtf(s[0] * s[0] + s[1] * s[1]) + r) / zmin;
                 const float g = fmaxf(P.fx, P.fy) * (1.0f + T) / zmin;
                 const float need = 1.5f * zmax * zmax * zmax / (P.fx * P.fy) * (kSnapEps * b2.x * g + 4.0f * kSnapEps * kSnapEps * b2.y) + 2e-5f;
-                if (bnd > need) return;  // inf / NaN in `need` (degenerate faces) compares false: not culled
+                if (bnd > need) continue;  // inf / NaN in `need` (degenerate faces) compares false: not culled
             }
         }
         int px_lo = 0, px_hi = P.W - 1, py_lo = 0, py_hi = P.H - 1;
@@ -196,28 +215,45 @@ raster_bin_kernel(const __grid_constant__ RasterParams P) {
             vmin = fminf(fmaxf(ceilf(vmin - 0.55f), -1.0e6f), 1.0e6f); vmax = fminf(fmaxf(floorf(vmax - 0.45f), -1.0e6f), 1.0e6f);
             px_lo = max((int)umin, 0); px_hi = min((int)umax, P.W - 1);
             py_lo = max((int)vmin, 0); py_hi = min((int)vmax, P.H - 1);
-            if (px_lo > px_hi || py_lo > py_hi) return;
+            if (px_lo > px_hi || py_lo > py_hi) continue;
         }
-        bin_append(P, view, px_lo, px_hi, py_lo, py_hi, (unsigned)i);
-    } else {
-        const int w = ((int)blockIdx.x - P.obj_bin_blocks) * kWarps + (threadIdx.x >> 5);
-        if (w >= P.n_hp) return;
-        const int lane = threadIdx.x & 31;
-        const int v = __ldg(P.hp_vid + w * 32 + lane);
-        int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
-        if (v >= 0) {
-            const float* hv = P.hand_verts + 3 * ((size_t)view * P.n_hv + v);
-            const int4 p = project(P, hv[0], hv[1], hv[2]);
-            if (p.w) { mnx = mxx = p.x; mny = mxy = p.y; }  // faces with an invalid corner are never drawn
-        }
-        mnx = __reduce_min_sync(kFull, mnx); mxx = __reduce_max_sync(kFull, mxx);
-        mny = __reduce_min_sync(kFull, mny); mxy = __reduce_max_sync(kFull, mxy);
-        if (lane != 0 || mnx > mxx) return;
-        const int px_lo = max(floordiv256(mnx + 127), 0), px_hi = min(floordiv256(mxx - 128), P.W - 1);
-        const int py_lo = max(floordiv256(mny + 127), 0), py_hi = min(floordiv256(mxy - 128), P.H - 1);
-        if (px_lo > px_hi || py_lo > py_hi) return;
-        bin_append(P, view, px_lo, px_hi, py_lo, py_hi, (unsigned)w | kHandBit);
+        bin_append(P, cnt, view, px_lo, px_hi, py_lo, py_hi, (unsigned)i);
     }
+    const int lane = threadIdx.x & 31;
+    const float* hverts = P.hand_verts + 3 * (size_t)view * P.n_hv;
+    constexpr int kAhead = 4;
+    for (int w0 = threadIdx.x >> 5; w0 < P.n_hp; w0 += kAhead * kWarps) {
+        int v[kAhead];
+        float X[kAhead], Y[kAhead], Z[kAhead];
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k) {
+            const int w = w0 + k * kWarps;
+            v[k] = w < P.n_hp ? __ldg(P.hp_vid + w * 32 + lane) : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k) {
+            X[k] = Y[k] = Z[k] = 0.0f;
+            if (v[k] >= 0) { X[k] = hverts[3 * v[k]]; Y[k] = hverts[3 * v[k] + 1]; Z[k] = hverts[3 * v[k] + 2]; }
+        }
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k) {
+            const int w = w0 + k * kWarps;
+            int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+            if (v[k] >= 0) {
+                const int4 p = project(P, X[k], Y[k], Z[k]);
+                if (p.w) { mnx = mxx = p.x; mny = mxy = p.y; }  // faces with an invalid corner are never drawn
+            }
+            mnx = __reduce_min_sync(kFull, mnx); mxx = __reduce_max_sync(kFull, mxx);
+            mny = __reduce_min_sync(kFull, mny); mxy = __reduce_max_sync(kFull, mxy);
+            if (lane != 0 || w >= P.n_hp || mnx > mxx) continue;
+            const int px_lo = max(floordiv256(mnx + 127), 0), px_hi = min(floordiv256(mxx - 128), P.W - 1);
+            const int py_lo = max(floordiv256(mny + 127), 0), py_hi = min(floordiv256(mxy - 128), P.H - 1);
+            if (px_lo > px_hi || py_lo > py_hi) continue;
+            bin_append(P, cnt, view, px_lo, px_hi, py_lo, py_hi, (unsigned)w | kHandBit);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.n_tiles; i += kThreads) P.bin_count[(size_t)view * P.n_tiles + i] = cnt[i];
 }
 
 // ---- rule: triangle ----------------------------------------------------------------------------------------
@@ -355,10 +391,28 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
     __shared__ __align__(16) float Msh[12];
     __shared__ unsigned char rank_lane[kWarps][32];             // per warp: lane of the k-th box that has rows
     __shared__ __align__(16) int colmap[kTile];                 // background source column of every tile column
-    __shared__ int next_patch, n_hit;
+    __shared__ int n_hit, next_pair;
 
-    const int view = blockIdx.y, tile = blockIdx.x;
-    const int tx0 = (tile % P.tiles_x) * kTile, ty0 = (tile / P.tiles_x) * kTile;
+    // CTAs are handed out in launch order, so the order of the work decides how the grid ends.  The tiles of a view are
+    // ranked by their distance from the principal point (ArtiBoost places the object there, yaml:13-20 CAMERA_Z_RANGE on the
+    // optical axis): the first `near_tiles` of every view come first, view by view, so that set-up bound and write bound
+    // CTAs share every SM; the outermost tiles of all views -- almost always pure background, short CTAs -- come last and
+    // fill the SMs while the last busy tiles finish.
+    int view, tile;
+    {
+        const unsigned b = blockIdx.x, n1 = (unsigned)P.near_tiles, total1 = (unsigned)P.n_views * n1;
+        if (b < total1) {
+            view = (int)fastdiv(b, P.div_n1_m, P.div_n1_s);
+            tile = (int)(b - (unsigned)view * n1);
+        } else {
+            const unsigned r = b - total1, n2 = (unsigned)P.n_tiles - n1;
+            view = (int)fastdiv(r, P.div_n2_m, P.div_n2_s);
+            tile = (int)(n1 + (r - (unsigned)view * n2));
+        }
+        if (P.use_order) tile = P.tile_order[tile];
+    }
+    const int tile_y = (int)fastdiv((unsigned)tile, P.div_tx_m, P.div_tx_s), tile_x = tile - tile_y * P.tiles_x;
+    const int tx0 = tile_x * kTile, ty0 = tile_y * kTile;
     const int tx1 = min(tx0 + kTile, P.W) - 1, ty1 = min(ty0 + kTile, P.H) - 1;  // inclusive
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int bin = view * P.n_tiles + tile;
@@ -371,46 +425,59 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
     if (count > 0) {
         const int oid = P.obj_id[view];
         const int n_of = oid >= 0 ? P.face_off[oid + 1] - P.face_off[oid] : 0;
-        if (t == 0) { next_patch = kWarps; n_hit = 0; }  // the first kWarps list entries go to the warps by index
+        if (t == 0) { n_hit = 0; next_pair = 2 * kWarps; }
         if (t < 12) Msh[t] = oid >= 0 ? P.obj_pose[16 * (size_t)view + t] : 0.0f;
         ulonglong2* z2 = reinterpret_cast<ulonglong2*>(zbuf);
         for (int i = t; i < kTilePx / 2; i += kThreads) z2[i] = make_ulonglong2(kEmptyKey, kEmptyKey);
         __syncthreads();
         const unsigned short* list = P.bin_list + (size_t)bin * P.list_cap;
         const int poff = oid >= 0 ? P.patch_off[oid] : 0;
+        // per-lane base pointers: a patch is a 32-bit element offset from them
+        const float4* op_pos = P.op_pos + (size_t)poff * 32 + lane;
+        const uint32_t* op_face = P.op_face + (size_t)poff * 32 + lane;
+        const int32_t* op_prim = P.op_prim + (size_t)poff * 32 + lane;
+        const int32_t* hp_vid = P.hp_vid + lane;
+        const uint32_t* hp_face = P.hp_face + lane;
+        const int32_t* hp_prim = P.hp_prim + lane;
+        const float* hverts = P.hand_verts + 3 * (size_t)view * P.n_hv;
         int4* my_slab = slab[wid];
         unsigned char* my_rank = rank_lane[wid];
         const unsigned lt_mask = (1u << lane) - 1u;
-        int li = wid;
+        // warps claim list entries two at a time from a shared counter (the first pair by warp index); the second entry of a
+        // pair and the next pair are fetched one patch ahead.  A warp that runs out goes on to the background below instead
+        // of waiting for the others.
+        int li = 2 * wid;
         unsigned entry = li < count ? list[li] : 0u;
         while (li < count) {
             const bool hand = (entry & kHandBit) != 0;
-            const size_t prow = ((size_t)(hand ? 0 : poff) + (entry & kIndexMask)) * 32 + lane;
+            const unsigned poffs = (entry & kIndexMask) * 32u;
             const bool multi = (entry & kMultiBit) != 0;
-            // the patch's face words and primitive ids do not depend on the vertex phase: issue their loads first, and claim
-            // + fetch the next list entry, so that one round of memory latency per patch is exposed instead of four
-            const unsigned fw = __ldg((hand ? P.hp_face : P.op_face) + prow);
-            const int prim_local = __ldg((hand ? P.hp_prim : P.op_prim) + prow);
+            // the patch's face words and primitive ids do not depend on the vertex phase: issue their loads first, so that
+            // one round of memory latency per patch is exposed instead of three
+            const unsigned fw = __ldg((hand ? hp_face : op_face) + poffs);
+            const int prim_local = __ldg((hand ? hp_prim : op_prim) + poffs);
+            if (li & 1) {  // second of a pair: claim the next pair (warp-uniform)
+                int nli = 0;
+                if (lane == 0) nli = atomicAdd(&next_pair, 2);
+                li = __shfl_sync(kFull, nli, 0);
+            } else {
+                ++li;
+            }
+            entry = li < count ? list[li] : 0u;
             // ---- a lane per vertex
             float c[3] = {0.0f, 0.0f, 0.0f};
             bool on;
             if (!hand) {
-                const float4 q = __ldg(P.op_pos + prow);
+                const float4 q = __ldg(op_pos + poffs);
                 on = q.w != 0.0f;
                 xform(Msh, q.x, q.y, q.z, c);
             } else {
-                const int v = __ldg(P.hp_vid + prow);
+                const int v = __ldg(hp_vid + poffs);
                 on = v >= 0;
                 if (on) {
-                    const float* hv = P.hand_verts + 3 * ((size_t)view * P.n_hv + v);
+                    const float* hv = hverts + 3 * v;
                     c[0] = hv[0]; c[1] = hv[1]; c[2] = hv[2];
                 }
-            }
-            {
-                int nli = 0;
-                if (lane == 0) nli = atomicAdd(&next_patch, 1);
-                li = __shfl_sync(kFull, nli, 0);
-                entry = li < count ? list[li] : 0u;
             }
             int4 pvv = project(P, c[0], c[1], c[2]);
             if (!on) pvv.w = 0;
@@ -425,9 +492,8 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
             __syncwarp();
             if (overlap) {
                 // ---- a lane per face
-                int n = 0, x0 = 0, y0 = 0, w = 0, h = 0;
+                int n = 0, x0 = 0, y0 = 0, w = 0, h = 0, area = 0;  // area: the int32 value when `small`, else only its sign
                 bool small = false;
-                long long area2 = 0;
                 int4 a, b, d;
                 a = b = d = make_int4(0, 0, 0, 0);
                 if (fw != 0xFFFFFFFFu) {
@@ -440,8 +506,13 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
                         const int x1 = min(floordiv256(maxx - 128), tx1), y1 = min(floordiv256(maxy - 128), ty1);
                         if (x0 <= x1 && y0 <= y1) {
                             small = (maxx - minx < kSmallExtent) && (maxy - miny < kSmallExtent);
-                            area2 = area2_of(a, b, d, small);
-                            if (area2 != 0 && !(area2 > 0 && P.cull)) { w = x1 - x0 + 1; h = y1 - y0 + 1; n = w * h; }
+                            if (small) {
+                                area = (b.x - a.x) * (d.y - a.y) - (d.x - a.x) * (b.y - a.y);
+                            } else {
+                                const long long a2 = area2_of(a, b, d, false);
+                                area = a2 > 0 ? 1 : (a2 < 0 ? -1 : 0);
+                            }
+                            if (area != 0 && !(area > 0 && P.cull)) { w = x1 - x0 + 1; h = y1 - y0 + 1; n = w * h; }
                         }
                     }
                 }
@@ -451,10 +522,10 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
                 int e[3] = {0, 0, 0}, dd[3] = {0, 0, 0}, nb = 0;
                 float iz0 = 0.f, iz1 = 0.f, iz2 = 0.f, sarea = 0.f;
                 if (n > 0 && small) {
-                    const int s = area2 > 0 ? 1 : -1;
+                    const int s = area > 0 ? 1 : -1;
                     const int vx[3] = {a.x, b.x, d.x}, vy[3] = {a.y, b.y, d.y};
                     iz0 = __int_as_float(a.z); iz1 = __int_as_float(b.z); iz2 = __int_as_float(d.z);
-                    sarea = __int2float_rn(abs((int)area2));
+                    sarea = __int2float_rn(abs(area));
                     const int cx0 = 256 * x0 + 128, cy0 = 256 * y0 + 128;
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {  // edge i runs v[i+1] -> v[i+2], opposite vertex i
@@ -577,10 +648,12 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
     constexpr int TPR = kTile / PX;        // threads per tile row
     constexpr int RPP = kThreads / TPR;    // rows per pass
     const size_t obase = (size_t)view * P.W * P.H;
-    const uchar4 flat = make_uchar4((uint8_t)P.bg_r, (uint8_t)P.bg_g, (uint8_t)P.bg_b, 0);
+    const unsigned flat = (unsigned)(P.bg_r & 255) | ((unsigned)(P.bg_g & 255) << 8) | ((unsigned)(P.bg_b & 255) << 16);
     const int col = (t % TPR) * PX, px0 = tx0 + col;
     if (px0 <= tx1) {  // PX == 4 only when W % 4 == 0: a group of 4 pixels is entirely in or out
         int sx[PX];
+        unsigned bg_y0 = 0, bg_ch_ = 0;
+        const uint8_t* bg_img = nullptr;
         if (has_bg) {
             if constexpr (PX == 4) {
                 const int4 q = *reinterpret_cast<const int4*>(colmap + col);
@@ -588,40 +661,35 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
             } else {
                 sx[0] = colmap[col];
             }
+            bg_y0 = (unsigned)sel[2]; bg_ch_ = (unsigned)sel[4];
+            bg_img = P.bgs + (size_t)(BG4 ? 4 : 3) * ((size_t)sel[0] * P.bg_h * P.bg_w);
         }
+        size_t o = obase + (size_t)(ty0 + t / TPR) * P.W + px0;
 #pragma unroll
-        for (int pass = 0; pass < kTile / RPP; ++pass) {
+        for (int pass = 0; pass < kTile / RPP; ++pass, o += (size_t)RPP * P.W) {
             const int py = ty0 + pass * RPP + t / TPR;
-            if (py > ty1) continue;
-            uchar4 c[PX];
+            if (py > ty1) break;
+            unsigned c[PX];
 #pragma unroll
             for (int j = 0; j < PX; ++j) c[j] = flat;
             if (has_bg) {
-                const unsigned sy = (unsigned)sel[2] + fastdiv((unsigned)(2 * py + 1) * (unsigned)sel[4], P.div_2h_m, P.div_2h_s);
-                const uint8_t* bg_row = P.bgs + (BG4 ? 4 : 3) * (((size_t)sel[0] * P.bg_h + sy) * P.bg_w);
+                const unsigned sy = bg_y0 + fastdiv((unsigned)(2 * py + 1) * bg_ch_, P.div_2h_m, P.div_2h_s);
 #pragma unroll
                 for (int j = 0; j < PX; ++j) {
                     if constexpr (BG4) {
-                        c[j] = __ldg(reinterpret_cast<const uchar4*>(bg_row) + sx[j]);
-                        c[j].w = 0;
+                        c[j] = __ldg(reinterpret_cast<const unsigned*>(bg_img) + sy * (unsigned)P.bg_w + (unsigned)sx[j]) & 0x00ffffffu;
                     } else {
-                        const uint8_t* src = bg_row + 3 * (size_t)sx[j];
-                        c[j] = make_uchar4(src[0], src[1], src[2], 0);
+                        const uint8_t* src = bg_img + 3 * (size_t)(sy * (unsigned)P.bg_w + (unsigned)sx[j]);
+                        c[j] = (unsigned)src[0] | ((unsigned)src[1] << 8) | ((unsigned)src[2] << 16);
                     }
                 }
             }
-            const size_t o = obase + (size_t)py * P.W + px0;
             if constexpr (PX == 4) {
-                if (P.rgba) {
-                    uint4 v;
-                    v.x = *reinterpret_cast<unsigned*>(&c[0]); v.y = *reinterpret_cast<unsigned*>(&c[1]);
-                    v.z = *reinterpret_cast<unsigned*>(&c[2]); v.w = *reinterpret_cast<unsigned*>(&c[3]);
-                    *reinterpret_cast<uint4*>(P.rgba + 4 * o) = v;
-                }
+                if (P.rgba) *reinterpret_cast<uint4*>(P.rgba + 4 * o) = make_uint4(c[0], c[1], c[2], c[3]);
                 if (P.depth) *reinterpret_cast<float4*>(P.depth + o) = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (P.seg) *reinterpret_cast<unsigned*>(P.seg + o) = 0u;
             } else {
-                if (P.rgba) reinterpret_cast<uchar4*>(P.rgba)[o] = c[0];
+                if (P.rgba) reinterpret_cast<unsigned*>(P.rgba)[o] = c[0];
                 if (P.depth) P.depth[o] = 0.0f;
                 if (P.seg) P.seg[o] = 0;
             }
@@ -699,7 +767,7 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
                                void* stream) {
     using namespace ab;
     AB_REQUIRE(scene && cam, "null scene / camera");
-    AB_REQUIRE(batch >= 0 && chunk > 0 && chunk <= 65535, "bad batch / chunk");
+    AB_REQUIRE(batch >= 0 && chunk > 0 && chunk <= 65535, "bad batch / chunk (at most 65535 views per group)");
     AB_REQUIRE(cam->width > 0 && cam->height > 0 && cam->width <= 4096 && cam->height <= 4096, "bad image size");
     AB_REQUIRE(cam->fx > 0.0f && cam->fy > 0.0f, "focal lengths must be positive");
     AB_REQUIRE(scene->n_obj >= 0 && scene->n_obj <= kMaxObjects, "n_obj out of range (max 64)");
@@ -759,20 +827,31 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
     const size_t count_bytes = align_up((size_t)chunk * g.n_tiles * sizeof(int), 256);
     P.bin_count = (int*)ws;
     P.bin_list = (unsigned short*)((char*)ws + count_bytes);
+    // tiles by distance of their centre from the principal point; the outer `defer` of them go last
+    {
+        P.use_order = g.n_tiles <= kMaxOrder;
+        int defer = 0;
+        if (P.use_order) {
+            std::vector<std::pair<float, unsigned short>> rank((size_t)g.n_tiles);
+            for (int i = 0; i < g.n_tiles; ++i) {
+                const float dx = ((i % g.tiles_x) + 0.5f) * kTile - cam->cx, dy = ((i / g.tiles_x) + 0.5f) * kTile - cam->cy;
+                rank[i] = {dx * dx + dy * dy, (unsigned short)i};
+            }
+            std::stable_sort(rank.begin(), rank.end());
+            for (int i = 0; i < g.n_tiles; ++i) P.tile_order[i] = rank[i].second;
+            static const int defer_pct = getenv("AB_RASTER_DEFER_PCT") ? atoi(getenv("AB_RASTER_DEFER_PCT")) : 50;
+            defer = max(0, min(g.n_tiles * defer_pct / 100, g.n_tiles - 1));
+        }
+        P.near_tiles = g.n_tiles - defer;
+        make_fastdiv((unsigned)P.near_tiles, &P.div_n1_m, &P.div_n1_s);
+        make_fastdiv((unsigned)max(defer, 1), &P.div_n2_m, &P.div_n2_s);
+        make_fastdiv((unsigned)g.tiles_x, &P.div_tx_m, &P.div_tx_s);
+    }
     const int npx = P.W * P.H;
-    const int hand_blocks = cdiv(P.n_hp, kWarps);
     for (int v0 = 0; v0 < batch; v0 += chunk) {
         const int n = min(chunk, batch - v0);
-        int max_op = g.max_op;
-        if (obj_id_host) {
-            max_op = 0;
-            for (int i = 0; i < n; ++i) {
-                const int o = obj_id_host[v0 + i];
-                AB_REQUIRE(o < scene->n_obj, "obj_id out of range");
-                if (o >= 0) max_op = max(max_op, P.patch_off[o + 1] - P.patch_off[o]);
-            }
-        }
-        P.obj_bin_blocks = cdiv(max_op, kThreads);
+        if (obj_id_host)
+            for (int i = 0; i < n; ++i) AB_REQUIRE(obj_id_host[v0 + i] < scene->n_obj, "obj_id out of range");
         P.n_views = n;
         P.hand_verts = hand_verts + (size_t)v0 * P.n_hv * 3;
         P.hand_tex = hand_tex + v0;
@@ -783,17 +862,16 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
         P.rgba = rgba ? rgba + (size_t)v0 * npx * 4 : nullptr;
         P.depth = depth ? depth + (size_t)v0 * npx : nullptr;
         P.seg = seg ? seg + (size_t)v0 * npx : nullptr;
-        AB_CUDA(cudaMemsetAsync(P.bin_count, 0, (size_t)n * g.n_tiles * sizeof(int), st));
         {
             StageTimer tm(AB_STAGE_RASTER_BIN, st);
-            raster_bin_kernel<<<dim3(P.obj_bin_blocks + hand_blocks, n), kThreads, 0, st>>>(P);
+            raster_bin_kernel<<<n, kThreads, 0, st>>>(P);
         }
         {
             StageTimer tm(AB_STAGE_RASTER_TILE, st);
             // 4 pixels per thread needs 16-byte aligned output rows: W % 4 == 0 and 16 / 16 / 4-byte aligned bases
             const bool vec = (P.W % 4 == 0) && (((uintptr_t)P.rgba & 15) == 0) && (((uintptr_t)P.depth & 15) == 0) &&
                              (((uintptr_t)P.seg & 3) == 0);
-            const dim3 grid(g.n_tiles, n);
+            const dim3 grid(g.n_tiles * n);
             if (vec && P.bg_ch == 4) raster_tile_kernel<4, true><<<grid, kThreads, 0, st>>>(P);
             else if (vec) raster_tile_kernel<4, false><<<grid, kThreads, 0, st>>>(P);
             else if (P.bg_ch == 4) raster_tile_kernel<1, true><<<grid, kThreads, 0, st>>>(P);
