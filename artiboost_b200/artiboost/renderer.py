@@ -226,19 +226,20 @@ class Renderer:
                  "seg": torch.empty((sub_batch, H, W), dtype=torch.uint8, device=dev),
                  "free": torch.cuda.Event()} for _ in range(2)]
         bufs = self._host_bufs[key]
+        keys = [k for k in ("rgba", "depth", "seg") if k in out]   # only what the caller asked for is rendered and copied
         for j, v0 in enumerate(range(0, B, sub_batch)):
             n = min(sub_batch, B - v0)
             buf = bufs[j & 1]
             main.wait_event(buf["free"])  # the copy that last read this staging set has finished
             sl = slice(v0, v0 + n)
-            stage = {k: buf[k][:n] for k in ("rgba", "depth", "seg")}
+            stage = {k: buf[k][:n] for k in keys}
             self.render_batch(d_in[0][sl], d_in[1][sl], d_in[2][sl], d_in[3][sl], d_in[4][sl],
-                              None if d_in[5] is None else d_in[5][sl], out=stage)
+                              None if d_in[5] is None else d_in[5][sl], out=stage, want=keys)
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(done)
-                for k in ("rgba", "depth", "seg"):
+                for k in keys:
                     out[k][sl].copy_(stage[k], non_blocking=True)
                 buf["free"].record(self._copy_stream)
         main.wait_stream(self._copy_stream)

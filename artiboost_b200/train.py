@@ -208,6 +208,14 @@ class TrainStep:
             self._out = self._eager(self._static)
         self._graph = graph
 
+    def close(self):
+        """Destroys the captured graph (it holds the NCCL all-reduce of the step): call before
+        torch.distributed.destroy_process_group(), which otherwise waits on work the graph still references."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.flat.flat.device)
+            self._graph.reset()
+        self._graph, self._static, self._out = None, None, None
+
     def __call__(self, batch: Dict[str, torch.Tensor]):
         self._check_grads()
         if not self.use_graph:
@@ -347,6 +355,13 @@ class ArtiBoostLoop:
                 done.record(self._side)
             self._prefetched = (nxt, done)
         return loss
+
+    def close(self):
+        """Joins the prefetch stream and destroys the captured training graph (see TrainStep.close)."""
+        self._prefetched = None
+        if self._side is not None:
+            torch.cuda.current_stream(self.pipe.device).wait_stream(self._side)
+        self.train_step.close()
 
     def end_epoch(self):
         self._prefetched = None  # it was drawn with the old weights

@@ -20,6 +20,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the host-side legs of this file (CPU baseline, asset generation, the
+# torch reference models' initialisation) then crawl on one core.  Give every rank its share of the cores instead --
+# before numpy / torch load their OpenMP runtimes.
+if os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+
 BATCH = 512
 SIZE = 256
 BYTES_PER_VIEW_OUT = SIZE * SIZE * 9                # RGBA8 + depth f32 + seg u8
@@ -106,13 +112,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 256
+    sample = BATCH   # the same 512 views per step as our arm
     vps, ms, threads = cpu_reference(args.steps, args.warmup, sample)
     line = {
-        "impl": "reference", "metric": "synthesised views/sec (rasteriser, RGBA+depth+seg 256x256)", "value": vps,
+        "impl": "reference", "metric": METRIC, "value": vps,
         "unit": "views/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, sample_views_per_step=sample),
+        "config": workload_config(args.gpus),
         "cpu_baseline": {"value": vps, "unit": "views/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} views/step x {args.steps} steps of the batch-512 workload, oracle/raster.c "
                                    f"with OpenMP over views on {threads} host threads (pyrender/EGL cannot run here)"},
@@ -122,13 +128,45 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+METRIC = "synthesised views/sec (rasteriser, RGBA+depth+seg 256x256)"
+
+
 def workload_config(n_gpus, **extra):
     cfg = {"workload": "BASELINE.json configs[1]: batch-512 hand+object rasteriser only (RGBA8+depth f32+seg u8, 256x256)",
            "views_per_step_per_gpu": BATCH, "image": [SIZE, SIZE], "ccv_space": [4, 288, 50],
            "hand_mesh": [778, 1538], "object_mesh": [8192, 16380], "parallelism": f"views sharded over {n_gpus} rank(s), no collective",
-           "l2": "each step writes 302 MB of views (> 126 MB L2); meshes (1.2 MB) are shared by the batch and L2-resident by design"}
+           "l2": "each step writes 302 MB of views (> 126 MB L2); meshes and patch tables (3 MB) are shared by the batch and L2-resident by design"}
     cfg.update(extra)
     return cfg
+
+
+def oracle_check(pipe, poses, rand, out, idx):
+    """A few views of the timed batch against oracle/raster.c, bit for bit (outside every timed region)."""
+    import numpy as np
+    from oracle import raster
+    r = pipe.renderer
+    K = pipe.cam_intr
+    cfg = dict(width=r.width, height=r.height, fx=float(K[0, 0]), fy=float(K[1, 1]), cx=float(K[0, 2]), cy=float(K[1, 2]),
+               znear=0.05, cull_backface=1, ambient=0.8, diffuse=0.25)
+    hf = r.hand_faces.cpu().numpy()[:, :3]
+    hcols = r.hand_colors.cpu().numpy()
+    bgs = r.backgrounds.cpu().numpy()
+    ocols = r.obj_colors.cpu().numpy()
+    ok = 0
+    for i in idx:
+        oid = int(poses["obj_id"][i])
+        o = pipe.objects[pipe.obj_names[oid]]
+        sel = rand["bg_sel"][i].cpu().numpy()
+        rgba, depth, seg, _ = raster.render_view(
+            cfg, poses["final_hand_verts"][i].cpu().numpy(), hf, hcols[int(rand["hand_tex"][i])], o["vertices"], o["faces"],
+            ocols[r._voff[oid]:r._voff[oid + 1]], poses["final_obj_pose"][i].cpu().numpy(), light=float(rand["light"][i]),
+            bg=bgs[sel[0]], bg_sel=sel[1:])
+        same = (np.array_equal(out["seg"][i].cpu().numpy(), seg) and np.array_equal(out["rgba"][i].cpu().numpy(), rgba)
+                and np.array_equal(out["depth"][i].cpu().numpy().view(np.uint32), depth.view(np.uint32)))
+        if not same:
+            raise SystemExit(f"bench: view {i} of the timed batch differs from oracle/raster.c")
+        ok += 1
+    return ok
 
 
 # ------------------------------------------------------------------------------------------------------ our arm
@@ -154,8 +192,9 @@ def run_ours(args):
     if not os.path.exists(lib.LIB_PATH):
         build.build()
     lib.load()
+    wall = {"start": time.perf_counter()}
 
-    pipe = SynthPipeline(device=dev, seed=1 + rank, chunk=args.chunk)
+    pipe = SynthPipeline(device=dev, seed=1 + rank, chunk=BATCH)
     poses = pipe.sample_poses(BATCH)            # CCV draw -> view -> grasp -> pose generator (device)
     rand = pipe.draw_render_randoms(BATCH)
     out = {"rgba": torch.empty((BATCH, SIZE, SIZE, 4), dtype=torch.uint8, device=dev),
@@ -167,48 +206,81 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step():
+    def eager_step():
         pipe.render(poses, rand, out=out)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+    # one step = ab_render_batch over the resident batch, replayed from a CUDA graph so that the 1 -> 8 GPU curve does not
+    # depend on the host (the call is two kernel launches; it is capture-safe by construction)
+    l0 = lib.launch_count()
+    eager_step()
+    torch.cuda.synchronize(dev)
+    launches_per_step = lib.launch_count() - l0
+    side = torch.cuda.Stream(dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        eager_step()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(graph, stream=side):
+            eager_step()
+    torch.cuda.synchronize(dev)
+    step = graph.replay
+
     vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
     ids = [v for v in vis.split(",") if v.strip().isdigit()]
-    sampler = ClockSampler(int(ids[local]) if len(ids) > local else local)
+    sampler = ClockSampler(int(ids[local]) if len(ids) > local else local, period=0.05)
     sampler.start()
-    lib.profile_enable(True)
-    l0 = lib.launch_count()
+    # warm-up: the requested number of steps, then the same step for another 0.4 s -- the clock record then holds samples
+    # taken under this very load although the timed region itself is only milliseconds long
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize(dev)
+    t_end = time.perf_counter() + 0.4
+    while time.perf_counter() < t_end:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize(dev)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = lib.launch_count() - l0
-    lib.profile_enable(False)
-    stages_live = lib.profile_collect()   # per-launch spans while four chunk pipelines share the GPU
+    ms_total_local = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    # per-kernel durations with ONE chunk in flight (each kernel alone on the GPU, as an ncu launch list sees them): the
-    # denominators of the dominant kernel's roofline entry
-    lib.check(lib.load().ab_set_raster_streams(1), "ab_set_raster_streams")
-    for _ in range(3):
+    per_rank = torch.zeros(world, dtype=torch.float64, device=dev)
+    per_rank[rank] = ms_total_local / args.steps
+    if world > 1:
+        dist.all_reduce(per_rank)
+    per_rank_ms = [float(x) for x in per_rank.tolist()]
+    ms_total = max(per_rank_ms) * args.steps
+    value = world * BATCH * args.steps / (ms_total * 1e-3)
+    launches = launches_per_step * args.steps
+
+    # distribution of single steps (events around every replay), outside the headline region
+    n_dist = max(50, min(args.steps, 200))
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_dist + 1)]
+    evs[0].record()
+    for i in range(n_dist):
         step()
+        evs[i + 1].record()
+    torch.cuda.synchronize(dev)
+    per_step = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(n_dist))
+    dist_ms = {"p10": per_step[n_dist // 10], "p50": per_step[n_dist // 2], "p90": per_step[(9 * n_dist) // 10], "n": n_dist}
+
+    # per-kernel device time (events on the launching stream around every launch, eager submission)
+    for _ in range(3):
+        eager_step()
     torch.cuda.synchronize(dev)
     lib.profile_enable(True)
     iso_steps = max(5, min(args.steps, 50))
     for _ in range(iso_steps):
-        step()
+        eager_step()
     torch.cuda.synchronize(dev)
     lib.profile_enable(False)
     stages = lib.profile_collect()
-    lib.check(lib.load().ab_set_raster_streams(4), "ab_set_raster_streams")
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = world * BATCH * args.steps / (ms_total * 1e-3)
+    wall["raster"] = time.perf_counter()
 
     # ---- end to end through the host-buffer API: pinned inputs H2D, views D2H, every step
     pin = lambda x: x.detach().cpu().pin_memory()  # noqa: E731
@@ -218,7 +290,7 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, 20))
 
     def e2e_step():
-        pipe.renderer.render_batch_host(*h_in, out=h_out, sub_batch=args.chunk)
+        pipe.renderer.render_batch_host(*h_in, out=h_out, sub_batch=args.sub_batch)
 
     for _ in range(2):
         e2e_step()
@@ -235,16 +307,41 @@ def run_ours(args):
     h2d = sum(x.numel() * x.element_size() for x in h_in)
     d2h = sum(x.numel() * x.element_size() for x in h_out.values())
     same = all(torch.equal(h_out[k], out[k].cpu()) for k in out)
+    # the reference's own reply is the BGR image alone (render_infra.py:57-58): the same call with that payload
+    h_rgba = {"rgba": h_out["rgba"]}
+    for _ in range(2):
+        pipe.renderer.render_batch_host(*h_in, out=h_rgba, sub_batch=args.sub_batch)
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        pipe.renderer.render_batch_host(*h_in, out=h_rgba, sub_batch=args.sub_batch)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_rgba_value = world * BATCH * e2e_steps / (float(t.item()) * 1e-3)
+    wall["e2e"] = time.perf_counter()
+
+    synth = None
+    try:
+        synth = synthesis_bench(pipe, dev, world)
+    except Exception as e:
+        if world > 1:
+            raise
+        synth = {"error": repr(e)}
+    wall["synthesis"] = time.perf_counter()
 
     train = None
     if not args.no_train:
-        del h_out, h_in
+        del h_out, h_in, h_rgba
         try:
             train = train_bench(dev, world, rank)
         except Exception as e:  # the secondary workload must never cost the headline line
             if world > 1:
                 raise
             train = {"error": repr(e)}
+    wall["train"] = time.perf_counter()
 
     if rank != 0:
         finish(world, dev)
@@ -263,11 +360,9 @@ def run_ours(args):
                 "kernel_share_of_step": dom_ms / sum(v[0] for v in stages.values()),
                 "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak},
                 "stage_ms_per_step": {k: v[0] / iso_steps for k, v in stages.items()},
-                "stage_ms_per_step_4_chunks_in_flight": {k: v[0] / args.steps for k, v in stages_live.items()},
-                "note": "set-up bound, not HBM bound: ~17.9k mostly sub-pixel triangles per view (SURVEY.md 8d). `achieved` and "
-                        "stage_ms_per_step are per-kernel durations with one chunk in flight (kernel alone on the GPU, "
-                        "events on its stream); the timed region (`value`, whole_step) runs four chunk pipelines "
-                        "concurrently, which is why the step is shorter than the sum of its kernels"}
+                "note": "instruction-issue bound, not HBM bound: ~17.9k mostly sub-pixel triangles per view (SURVEY.md 8d); "
+                        "the tile kernel writes the output exactly once (traffic / algorithmic = 1.0) and keeps z-buffer, "
+                        "projected vertices and coverage work in shared memory and registers"}
     traffic_file = os.path.join(ROOT, "profiles", "raster_traffic.json")
     if os.path.exists(traffic_file):
         try:
@@ -276,25 +371,34 @@ def run_ours(args):
             pass
 
     cpu = None
+    checked = 0
     if world == 1 and not args.no_cpu_baseline:
-        vps, _, threads = cpu_reference(steps=40, warmup=2, sample_views=256)
+        vps, _, threads = cpu_reference(steps=20, warmup=2, sample_views=BATCH)
         cpu = {"value": vps, "unit": "views/s", "cores": threads, "kind": "port",
-               "sample": f"256 views x 40 passes of the same workload, oracle/raster.c, OpenMP over views on {threads} host threads"}
+               "sample": f"{BATCH} views x 20 passes of the same workload, oracle/raster.c, OpenMP over views on {threads} host threads"}
+        eager_step()
+        checked = oracle_check(pipe, poses, rand, out, list(range(0, BATCH, BATCH // 8)))
+    wall["cpu"] = time.perf_counter()
 
     line = {
-        "metric": "synthesised views/sec (rasteriser, RGBA+depth+seg 256x256)", "value": value, "unit": "views/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "metric": METRIC, "value": value, "unit": "views/s",
+        "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(world, chunk=args.chunk),
+        "config": workload_config(world, views_per_launch=BATCH, submission="CUDA graph replay of ab_render_batch"),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "matches_device_path": bool(same),
-                "api": "Renderer.render_batch_host: pinned host inputs -> ab_render_batch -> pinned host RGBA+depth+seg"},
+                "steps": e2e_steps, "matches_device_path": bool(same), "sub_batch": args.sub_batch,
+                "api": "Renderer.render_batch_host: pinned host inputs -> ab_render_batch -> pinned host RGBA+depth+seg",
+                "rgba_only_views_per_s": e2e_rgba_value,
+                "rgba_only_note": "same call returning the colour image alone, the payload of the reference's reply (render_infra.py:57-58)"},
         "gpu_launches": int(launches),
+        "gpu_launches_note": f"{launches_per_step} kernels of this library per step (raster_bin_kernel, raster_tile_kernel), replayed from a CUDA graph",
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "oracle_checked": checked,
+        "step_ms_distribution": dist_ms,
     }
-    line["extras"] = {}
+    line["extras"] = {"synthesis_configs1": synth}
     if train is not None:
         line["extras"]["train_loop_configs3"] = train
     if world == 1 and not args.no_network:
@@ -302,13 +406,72 @@ def run_ours(args):
             line["extras"]["network_forward_configs2"] = network_forward_bench(dev)
         except Exception as e:  # the secondary workload must never cost the headline line
             line["extras"]["network_forward_configs2"] = {"error": repr(e)}
-    if world == 1 and not args.no_network:
+        wall["network"] = time.perf_counter()
         try:
             line["extras"]["hand_obj_refiner_8f3"] = refiner_bench(dev)
         except Exception as e:
             line["extras"]["hand_obj_refiner_8f3"] = {"error": repr(e)}
+        wall["refiner"] = time.perf_counter()
+    keys = list(wall)
+    line["wall_s"] = {keys[i + 1]: round(wall[keys[i + 1]] - wall[keys[i]], 2) for i in range(len(keys) - 1)}
+    # the driver keeps the tail of stdout: the numbers of the secondary metrics go last, at the top level
+    if isinstance(synth, dict):
+        line["synthesised_views_per_s_sample_to_raster"] = synth.get("views_per_s")
+    if isinstance(train, dict):
+        for k_out, k_in in (("train_images_per_s", "images_per_s"), ("train_vs_torch_bf16", "vs_torch_bf16_autocast"),
+                            ("train_vs_torch_fp32", "vs_torch_fp32"), ("mpcpe_after_train_mm", "mpcpe_after_train_mm")):
+            line[k_out] = train.get(k_in)
+    line["per_rank_ms"] = per_rank_ms
     print(json.dumps(line), flush=True)
     finish(world, dev)
+
+
+def synthesis_bench(pipe, dev, world, batch=BATCH, steps=20, warmup=3):
+    """views/s of the whole synthesis path -- CCV draw -> view -> grasp lookup -> pose generator (MANO LBS)
+    -> rasterise -- for a batch of 512 (REFINER null, scrambler random), eager submission."""
+    import torch
+    import torch.distributed as dist
+
+    from artiboost_b200 import lib
+    out = {"rgba": torch.empty((batch, SIZE, SIZE, 4), dtype=torch.uint8, device=dev),
+           "depth": torch.empty((batch, SIZE, SIZE), dtype=torch.float32, device=dev),
+           "seg": torch.empty((batch, SIZE, SIZE), dtype=torch.uint8, device=dev)}
+    for _ in range(warmup):
+        pipe.synthesise(batch, out=out)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    l0 = lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        pipe.synthesise(batch, out=out)
+    e1.record()
+    host_ms = (time.perf_counter() - t0) / steps * 1e3
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    lib.profile_enable(True)
+    for _ in range(5):
+        pipe.sample_poses(batch)
+    torch.cuda.synchronize(dev)
+    lib.profile_enable(False)
+    st = lib.profile_collect()
+    res = {"batch": batch, "views_per_s": world * batch / ms * 1e3, "ms_per_batch": ms, "host_submit_ms_per_batch": host_ms,
+           "our_kernels_per_batch": (lib.launch_count() - l0) / (steps + 5),
+           "sample_poses_stage_us": {k: v[0] / v[1] * 1e3 for k, v in st.items()}}
+    lbs = st.get("mano_lbs_kernel")
+    if lbs:
+        per = lbs[0] / lbs[1] * 1e-3   # seconds per launch of `batch` samples
+        peak, _ = load_peaks()
+        res["mano_lbs"] = {"us_per_launch": per * 1e6, "samples_per_s": batch / per,
+                           "hbm_frac_algorithmic": batch / per * 10856 / (peak * 1e9),
+                           "fp32_tflops": batch / per * 1.07e6 / 1e12,
+                           "note": "10 856 B and 1.07 MFLOP per sample (BASELINE.md section 4)"}
+    return res
 
 
 def refiner_bench(dev, batch=512, steps=10, warmup=3):
@@ -381,17 +544,24 @@ def refiner_bench(dev, batch=512, steps=10, warmup=3):
 
 
 def finish(world, dev):
-    """Leave together.  With N > 1 the captured training graph still references NCCL work, and
-    destroy_process_group() can wait on it forever: synchronise, meet at a barrier, then exit without the teardown."""
+    """Leave together: every captured graph that references NCCL work has been destroyed by now (train_bench drops its
+    loop before it returns), so the process group can be torn down in order.  A watchdog ends the process if the teardown
+    still hangs, after the JSON line has been flushed."""
+    import gc
+
     import torch
     import torch.distributed as dist
     sys.stdout.flush()
     if world > 1:
+        gc.collect()
         torch.cuda.synchronize(dev)
         dist.barrier()
         torch.cuda.synchronize(dev)
-        sys.stdout.flush()
-        os._exit(0)
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        dist.destroy_process_group()
+        watchdog.cancel()
 
 
 # ------------------------------------------------------------------------ secondary workload: network forward
@@ -476,12 +646,10 @@ def network_forward_bench(dev, batch=128, steps=10, warmup=3):
             ref = torch_train_forward(model, inp)
             mpcpe = (ours["corners_3d_abs"].float() - ref["corners_3d_abs"]).norm(dim=-1).mean().item() * 1e3
             mpjpe = (ours["joints_3d_abs"].float() - ref["joints_3d_abs"]).norm(dim=-1).mean().item() * 1e3
-        gemm_ms = stages.get("gemm_bf16_tn_kernel", (0.0, 0))[0] / (steps + warmup)
         out[backbone] = {
             "batch": batch, "images_per_s": batch / ms * 1e3, "ms_per_step": ms,
             "tflops": batch * flops[backbone] / ms / 1e9, "frac_of_bf16_sustained_peak": batch * flops[backbone] / ms / 1e9 / bf16_sustained_peak(),
             "stage_ms_per_step": {k: v[0] / (steps + warmup) for k, v in stages.items()},
-            "gemm_tflops_in_kernel": batch * flops[backbone] / gemm_ms / 1e9 if gemm_ms else None,
             "torch_cudnn_fp32_images_per_s": batch / ms_fp32 * 1e3, "torch_cudnn_bf16_autocast_images_per_s": batch / ms_bf16 * 1e3,
             "mpcpe_vs_torch_fp32_mm": mpcpe, "mpjpe_vs_torch_fp32_mm": mpjpe,
         }
@@ -599,6 +767,13 @@ def train_bench(dev, world, rank, steps=8, warmup=3, batch=128, backbone="ResNet
         fixed = fixed_nchw
         out["torch_cudnn_bf16_autocast_train_images_per_s"] = batch / ms_ref16 * 1e3
         out["train_step_only_images_per_s"] = batch / ms_net * 1e3
+        out["vs_torch_fp32"] = ms_ref / ms_net          # optimisation step on the same batch, ours over the reference's path
+        out["vs_torch_bf16_autocast"] = ms_ref16 / ms_net
+    # the captured step references NCCL work: drop it before the process group is torn down
+    loop.close()
+    del loop
+    import gc
+    gc.collect()
     return out
 
 
@@ -608,7 +783,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chunk", type=int, default=64)
+    ap.add_argument("--sub-batch", type=int, default=64, help="views per device->host copy stage of the end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary full-loop train images/s measurement")
     ap.add_argument("--no-network", action="store_true", help="skip the secondary network-forward measurement")
