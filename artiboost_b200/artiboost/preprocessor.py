@@ -40,7 +40,10 @@ class PreProcessorPoseGenerator(nn.Module):
         anatomical = getattr(self.scrambler, "needs_hand_transf", False)
         if anatomical or not isinstance(self.refiner, NullRefine):
             return self._forward_staged(synth_extend, hand_pose, hand_shape, hand_tsl, persp, free, zoff, anatomical)
-        n_tsl, n_ang = self.scrambler.sample_noise(B, dev, self.generator) if self.scrambler is not None else (None, None)
+        if synth_extend.get("noise") is not None:   # drawn with the samples by the fused launch (ab_synth_draw)
+            n_tsl, n_ang = synth_extend["noise"]
+        else:
+            n_tsl, n_ang = self.scrambler.sample_noise(B, dev, self.generator) if self.scrambler is not None else (None, None)
         obj_pose = torch.empty((B, 4, 4), device=dev, dtype=torch.float32)
         verts = torch.empty((B, 778, 3), device=dev, dtype=torch.float32)
         joints = torch.empty((B, 21, 3), device=dev, dtype=torch.float32)

@@ -99,9 +99,13 @@ class RenderedDataset:
         ws = torch.empty(int(L.ab_augment_workspace_bytes(self._cfg, B)) + 256, dtype=torch.uint8, device=dev)
         ws_ptr = (ws.data_ptr() + 255) // 256 * 256
         P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        # converted copies are bound to names: a temporary would be freed (and its block handed to the next temporary)
+        # as soon as .data_ptr() returns, before the launch
+        rgba_c = rgba.contiguous()
+        joints_c = views["joints"].float().contiguous()
+        pose_c = views["obj_pose"].float().contiguous()
         with torch.cuda.device(dev):
-            rc = L.ab_crop_augment(self._cfg, B, rgba.contiguous().data_ptr(), views["joints"].float().contiguous().data_ptr(),
-                                   views["obj_pose"].float().contiguous().data_ptr(), corners_can.data_ptr(), P(draws), P(order),
+            rc = L.ab_crop_augment(self._cfg, B, lib.ptr(rgba_c), lib.ptr(joints_c), lib.ptr(pose_c), lib.ptr(corners_can), P(draws), P(order),
                                    *[out[k].data_ptr() for k in ("image", "cam_intr", "root_joint", "joints_3d", "joints_2d", "joints_vis",
                                                                  "corners_3d", "corners_2d", "corners_vis", "obj_transf")],
                                    P(aff[0]), P(aff[1]), status.data_ptr(), ws_ptr, lib.stream_ptr(dev))
@@ -109,6 +113,10 @@ class RenderedDataset:
         out["corners_can"] = corners_can
         out["obj_idx"] = self.obj_class_ids[views["obj_id"].long()]
         out["is_synth"] = torch.ones(B, device=dev)
+        # Queries.SAMPLE_IDX (rendered_dataset.py:272, hoquery.py:7): the index of the sample in the epoch's synthetic set;
+        # views drawn on the fly carry it as "sample_idx", else they are numbered from `index_base`
+        out["sample_idx"] = (views["sample_idx"].to(dev, torch.int64) if "sample_idx" in views
+                             else torch.arange(B, device=dev, dtype=torch.int64) + int(views.get("index_base", 0)))
         for k in ("obj_id", "persp_id", "grasp_id"):
             if k in views:
                 out[k] = views[k]

@@ -8,7 +8,7 @@
 // The categorical draw is an inverse-CDF search over a float64 inclusive prefix sum of the flat weight map.  Every
 // partial sum of fp32 weights in [2^-27, 2^22] is exact in fp64, so the parallel scan equals the sequential one
 // bit for bit and the draw is integer-exact against the CPU oracle for the same uniforms.
-#include "common.cuh"
+#include "view_math.cuh"
 
 namespace ab {
 
@@ -72,49 +72,12 @@ __global__ void view_kernel(const int32_t* __restrict__ persp_id, int n, int u_b
                             float* __restrict__ free_transf, float* __restrict__ z_offset) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double kPi = 3.141592653589793;
-    const int pid = persp_id[i];
-    const int u_id = pid / theta_bins, th_id = pid % theta_bins;
-    const double u_unit = 2.0 / u_bins, th_unit = (2.0 * kPi) / theta_bins;
     const float4 r = reinterpret_cast<const float4*>(rand4)[i];
-    // Precision follows the reference with a 0-dim torch tensor persp_id (ovg_set.py:138,141): bin centres, jittered
-    // u / theta, the direction vector and its normalisation are fp32 (view_engine.py:36-58); torch.rand(1) - 0.5 is
-    // an fp32 subtraction and the product with the bin size a python float; the align matrix algebra is fp64.
-    const float u_c = __fadd_rn((float)(-1.0 + u_unit / 2), __fmul_rn((float)u_id, (float)u_unit));
-    const float th_c = __fadd_rn((float)(th_unit / 2), __fmul_rn((float)th_id, (float)th_unit));
-    const float u_off = (float)((double)__fsub_rn(r.x, 0.5f) * u_unit);
-    const float th_off = (float)((double)__fsub_rn(r.y, 0.5f) * th_unit);
-    const float uf = fminf(fmaxf(__fadd_rn(u_c, u_off), -1.0f), 1.0f);
-    const float thf = fminf(fmaxf(__fadd_rn(th_c, th_off), 0.0f), (float)(2.0 * kPi));
-    const float sf = __fsqrt_rn(__fsub_rn(1.0f, __fmul_rn(uf, uf)));
-    const float xf = __fmul_rn(sf, cosf(thf)), yf = __fmul_rn(sf, sinf(thf));
-    const float nf = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(xf, xf), __fmul_rn(yf, yf)), __fmul_rn(uf, uf)));
-    const double vx = (double)__fdiv_rn(xf, nf), vy = (double)__fdiv_rn(yf, nf), vz = (double)__fdiv_rn(uf, nf);
-    double M[9];
-    if (vz == -1.0 || vz == 1.0) {
-        const double d = vz;
-        M[0] = d; M[1] = 0; M[2] = 0; M[3] = 0; M[4] = d; M[5] = 0; M[6] = 0; M[7] = 0; M[8] = d;
-    } else {
-        // k = z cross v = (-vy, vx, 0);  I + [k]x + [k]x^2 / (1 + z.v)
-        const double kx = -vy, ky = vx, inv = 1.0 / (1.0 + vz);
-        M[0] = 1.0 - ky * ky * inv; M[1] = kx * ky * inv;       M[2] = ky;
-        M[3] = kx * ky * inv;       M[4] = 1.0 - kx * kx * inv; M[5] = -kx;
-        M[6] = -ky;                 M[7] = kx;                  M[8] = 1.0 - (kx * kx + ky * ky) * inv;
-    }
-#pragma unroll
-    for (int j = 0; j < 9; ++j) persp_rotmat[(size_t)i * 9 + j] = (float)M[j];
-    const double roll = (double)r.z * (2.0 * kPi);
-    const float c = (float)cos(roll), sn = (float)sin(roll);
-    float* f = free_transf + (size_t)i * 16;
-    f[0] = c;  f[1] = -sn; f[2] = 0;  f[3] = 0;
-    f[4] = sn; f[5] = c;   f[6] = 0;  f[7] = 0;
-    f[8] = 0;  f[9] = 0;   f[10] = 1; f[11] = 0;
-    f[12] = 0; f[13] = 0;  f[14] = 0; f[15] = 1;
-    z_offset[(size_t)i * 3] = 0.0f;
-    z_offset[(size_t)i * 3 + 1] = 0.0f;
-    // torch Uniform.sample: low + rand * (high - low), three separately rounded fp32 operations
-    z_offset[(size_t)i * 3 + 2] = __fadd_rn(z_min, __fmul_rn(r.w, __fsub_rn(z_max, z_min)));
+    view_from_id(persp_id[i], u_bins, theta_bins, z_min, z_max, r.x, r.y, r.z, r.w, persp_rotmat + (size_t)i * 9,
+                 free_transf + (size_t)i * 16, z_offset + (size_t)i * 3);
 }
+
+void launch_ccv_cdf(const float* w, int n, double* cdf, cudaStream_t st) { ccv_cdf_kernel<<<1, kScanThreads, 0, st>>>(w, n, cdf); }
 
 }  // namespace ab
 

@@ -3,9 +3,10 @@
 // Replaces manotorch.ManoLayer.forward as the hot path calls it (anakin/artiboost/preprocessor.py:25,62,
 // anakin/artiboost/refiner.py:138); algorithm per anakin/postprocess/iknet/manolayer.py:182-276.
 //
-// Work split: one CTA = kS samples x one third of the vertices.  The blend-shape matrix (145 x 2334 fp32, 1.35 MB,
-// L2 resident) is streamed once per CTA with column-contiguous (coalesced) loads and applied to kS samples at a
-// time from registers; the per-sample 16-bone chain is redone by every CTA of a sample group (a few hundred
+// Work split: one CTA = kS = 8 samples x 128 of the vertices.  The CTA's slice of the blend-shape matrix (145 x 384
+// fp32 = 223 KB of the 1.35 MB, L2 resident) is streamed once per CTA with column-contiguous (coalesced) loads, 27 loads
+// in flight per thread, and applied to the 8 samples at a time from registers (round 1 ran 4 samples x a third of the
+// vertices: 173 MB of L2 reads per 512 samples; now 100 MB); the per-sample 16-bone chain is redone by every CTA of a sample group (a few hundred
 // flops) so no inter-CTA exchange is needed.  Outputs are staged in shared memory and written as contiguous
 // float runs.  The optional rigid map `post_rt` fuses the pose generator's camera transform
 // (preprocessor.py:84-88) into the store.
@@ -14,11 +15,13 @@
 namespace ab {
 
 constexpr int kV = AB_MANO_VERTS;
-constexpr int kS = 4;          // samples per CTA
-constexpr int kSplit = 3;      // vertex ranges per sample group
-constexpr int kVPer = 260;     // vertices per range (3*260 >= 778)
+constexpr int kS = 8;          // samples per CTA: every blend-shape weight fetched from L2 feeds 8 FMAs
+constexpr int kSplit = 7;      // vertex ranges per sample group
+constexpr int kVPer = 128;     // vertices per range (7*128 >= 778): 384 columns = 3 rounds of the 128 threads
+                               // (19 ranges of 42 vertices -- 1216 CTAs, 24 warps per SM -- measured the same 46 us: the launch
+                               // is bound by the dependent phases of a CTA, not by occupancy or L2 bandwidth, 2 TB/s)
 constexpr int kMaxExtra = 6;   // 5 tips + centre tip
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 constexpr int kNCoef = 10 + AB_MANO_POSE_FEAT;
 
 struct alignas(16) ManoSmem {
@@ -87,19 +90,47 @@ mano_lbs_kernel(ab_mano_model m, int batch, const float* __restrict__ pose, cons
         sm.J[s][r / 3][r % 3] = acc;
     }
     __syncthreads();
-    // ---- kinematic chain, one thread per sample; A_k = [G_R | G_t - G_R J_k]
-    if (tid < kS) {
-        const int s = tid;
-        mano_chain(&sm.R[s][0][0], &sm.J[s][0][0], &sm.G[s][0][0]);
-        for (int k = 0; k < 16; ++k) {
-            const float* g = sm.G[s][k];
-            const float* j = sm.J[s][k];
-            float* a = sm.A[s][k];
+    // ---- kinematic chain, one thread per (sample, finger): the root, then the finger's three joints; A_k = [G_R | G_t - G_R J_k]
+    if (tid < kS * 5) {
+        const int s = tid / 5, f = tid - 5 * s;
+        const float* R = &sm.R[s][0][0];
+        const float* J = &sm.J[s][0][0];
+        float g[12], a[12];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            g[4 * i] = R[3 * i]; g[4 * i + 1] = R[3 * i + 1]; g[4 * i + 2] = R[3 * i + 2];
+            g[4 * i + 3] = J[i];
+        }
+        auto emit_joint = [&](int k, const float* gk) {
+            const float* j = J + 3 * k;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                a[4 * i] = g[4 * i]; a[4 * i + 1] = g[4 * i + 1]; a[4 * i + 2] = g[4 * i + 2];
-                a[4 * i + 3] = g[4 * i + 3] - (g[4 * i] * j[0] + g[4 * i + 1] * j[1] + g[4 * i + 2] * j[2]);
+                a[4 * i] = gk[4 * i]; a[4 * i + 1] = gk[4 * i + 1]; a[4 * i + 2] = gk[4 * i + 2];
+                a[4 * i + 3] = gk[4 * i + 3] - (gk[4 * i] * j[0] + gk[4 * i + 1] * j[1] + gk[4 * i + 2] * j[2]);
             }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) { sm.G[s][k][i] = gk[i]; sm.A[s][k][i] = a[i]; }
+        };
+        if (f == 0) emit_joint(0, g);
+        int p = 0;
+#pragma unroll 1
+        for (int q = 0; q < 3; ++q) {   // joints 1 + 3f .. 3 + 3f, each the child of the previous (kManoParents)
+            const int k = 1 + 3 * f + q;
+            const float* r = R + 9 * k;
+            const float rel[3] = {J[3 * k] - J[3 * p], J[3 * k + 1] - J[3 * p + 1], J[3 * k + 2] - J[3 * p + 2]};
+            float n[12];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float x = g[4 * i], y = g[4 * i + 1], z = g[4 * i + 2];
+                n[4 * i] = x * r[0] + y * r[3] + z * r[6];
+                n[4 * i + 1] = x * r[1] + y * r[4] + z * r[7];
+                n[4 * i + 2] = x * r[2] + y * r[5] + z * r[8];
+                n[4 * i + 3] = x * rel[0] + y * rel[1] + z * rel[2] + g[4 * i + 3];
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) g[i] = n[i];
+            emit_joint(k, g);
+            p = k;
         }
     }
     // ---- blend shapes: v_posed[col] = template[col] + sum_k dirs[k][col] * coef[k], kS samples per load
@@ -113,48 +144,56 @@ mano_lbs_kernel(ab_mano_model m, int batch, const float* __restrict__ pose, cons
         float t = m.v_template[gcol];
 #pragma unroll
         for (int s = 0; s < kS; ++s) acc[s] = t;
-#pragma unroll 5
+        static_assert(kS == 8, "the blend loop reads the coefficients of 8 samples as two float4");
+#pragma unroll 10
         for (int k = 0; k < 10; ++k) {
-            float w = m.shapedirs_t[(size_t)k * (kV * 3) + gcol];
-            float4 cf = *reinterpret_cast<const float4*>(&sm.coef[k][0]);
-            acc[0] += w * cf.x; acc[1] += w * cf.y; acc[2] += w * cf.z; acc[3] += w * cf.w;
+            const float w = __ldg(m.shapedirs_t + (size_t)k * (kV * 3) + gcol);
+            const float4 c0 = *reinterpret_cast<const float4*>(&sm.coef[k][0]), c1 = *reinterpret_cast<const float4*>(&sm.coef[k][4]);
+            acc[0] += w * c0.x; acc[1] += w * c0.y; acc[2] += w * c0.z; acc[3] += w * c0.w;
+            acc[4] += w * c1.x; acc[5] += w * c1.y; acc[6] += w * c1.z; acc[7] += w * c1.w;
         }
-#pragma unroll 9
+        // 135 = 5 x 27: 27 independent L2 loads in flight per thread (the kernel runs at 12 warps / SM: latency, not issue)
+#pragma unroll 27
         for (int k = 0; k < AB_MANO_POSE_FEAT; ++k) {
-            float w = m.posedirs_t[(size_t)k * (kV * 3) + gcol];
-            float4 cf = *reinterpret_cast<const float4*>(&sm.coef[10 + k][0]);
-            acc[0] += w * cf.x; acc[1] += w * cf.y; acc[2] += w * cf.z; acc[3] += w * cf.w;
+            const float w = __ldg(m.posedirs_t + (size_t)k * (kV * 3) + gcol);
+            const float4 c0 = *reinterpret_cast<const float4*>(&sm.coef[10 + k][0]), c1 = *reinterpret_cast<const float4*>(&sm.coef[10 + k][4]);
+            acc[0] += w * c0.x; acc[1] += w * c0.y; acc[2] += w * c0.z; acc[3] += w * c0.w;
+            acc[4] += w * c1.x; acc[5] += w * c1.y; acc[6] += w * c1.z; acc[7] += w * c1.w;
         }
 #pragma unroll
         for (int s = 0; s < kS; ++s) sm.vp[s][c] = acc[s];
     }
     __syncthreads();
-    // ---- skinning: x = (sum_k w_vk A_k) [v_posed; 1], in place
-    for (int i = tid; i < nv * kS; i += kThreads) {
-        int s = i / nv, lv = i - s * nv;
-        int gv = lv < nv_own ? v0 + lv : sm.extra[lv - nv_own];
-        float T[12];
-#pragma unroll
-        for (int j = 0; j < 12; ++j) T[j] = 0.0f;
+    // ---- skinning: x = (sum_k w_vk A_k) [v_posed; 1], in place; a thread per vertex, its 16 weights loaded once for
+    // the kS samples
+    for (int lv = tid; lv < nv; lv += kThreads) {
+        const int gv = lv < nv_own ? v0 + lv : sm.extra[lv - nv_own];
         const float4* wp = reinterpret_cast<const float4*>(m.weights + (size_t)gv * 16);
+        float w[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            float4 w4 = wp[q];
-            float w[4] = {w4.x, w4.y, w4.z, w4.w};
+            const float4 w4 = __ldg(wp + q);
+            w[4 * q] = w4.x; w[4 * q + 1] = w4.y; w[4 * q + 2] = w4.z; w[4 * q + 3] = w4.w;
+        }
+#pragma unroll 1
+        for (int s = 0; s < kS; ++s) {
+            float T[12];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int j = 0; j < 12; ++j) T[j] = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
                 if (w[r] != 0.0f) {
-                    const float* a = sm.A[s][4 * q + r];
+                    const float* a = sm.A[s][r];
 #pragma unroll
                     for (int j = 0; j < 12; ++j) T[j] += w[r] * a[j];
                 }
             }
+            float* p = &sm.vp[s][3 * lv];
+            const float x = p[0], y = p[1], z = p[2];
+            p[0] = T[0] * x + T[1] * y + T[2] * z + T[3];
+            p[1] = T[4] * x + T[5] * y + T[6] * z + T[7];
+            p[2] = T[8] * x + T[9] * y + T[10] * z + T[11];
         }
-        float* p = &sm.vp[s][3 * lv];
-        float x = p[0], y = p[1], z = p[2];
-        p[0] = T[0] * x + T[1] * y + T[2] * z + T[3];
-        p[1] = T[4] * x + T[5] * y + T[6] * z + T[7];
-        p[2] = T[8] * x + T[9] * y + T[10] * z + T[11];
     }
     __syncthreads();
     if (tid < kS * 3) {

@@ -458,6 +458,8 @@ head_decode_bwd_kernel(const float* __restrict__ logits, const float* __restrict
 }
 
 // ---- optimiser: sum of squares of the flat gradient (for clip_grad_norm_) and the fused Adam update
+// Two passes in a fixed order (no atomics: the clip coefficient, and with it the whole step, is bit-reproducible):
+// CTA b leaves its partial in out[1 + b], sumsq_finish_kernel adds the partials up into out[0].
 __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* out) {
     __shared__ float red[32];
     float s = 0.0f;
@@ -470,7 +472,22 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* ou
         s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (threadIdx.x == 0) atomicAdd(out, s);
+        if (threadIdx.x == 0) out[1 + blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) sumsq_finish_kernel(float* out, int n_part) {
+    __shared__ float red[8];
+    float s = 0.0f;
+    for (int i = threadIdx.x; i < n_part; i += 256) s += out[1 + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        out[0] = t;
     }
 }
 
@@ -672,7 +689,10 @@ extern "C" int ab_sumsq(const float* g, int64_t n, float* out, void* stream) {
     AB_REQUIRE(g && out, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_OPTIMIZER, st);
-    sumsq_kernel<<<(unsigned)min((long long)148 * 8, (long long)nblk(n, 256)), 256, 0, st>>>(g, n, out);
+    const unsigned parts = (unsigned)min((long long)AB_SUMSQ_PARTS, (long long)nblk(n, 256));
+    sumsq_kernel<<<parts, 256, 0, st>>>(g, n, out);
+    sumsq_finish_kernel<<<1, 256, 0, st>>>(out, (int)parts);
+    count_launch(1);
     AB_LAUNCH_END("sumsq_kernel");
 }
 

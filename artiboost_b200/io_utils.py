@@ -20,6 +20,46 @@ import torch
 RandomState = namedtuple("RandomState", ["torch_rng_state", "torch_cuda_rng_state", "torch_cuda_rng_state_all",
                                          "numpy_rng_state", "random_rng_state"])  # anakin/utils/misc.py:11-21
 RandomState.__new__.__defaults__ = (None,) * len(RandomState._fields)
+# The reference pickles and unpickles this tuple as `anakin.utils.misc.RandomState` (io_utils.py:33-36,54-57): a file
+# written under any other module path makes its load_random_state fail (swallowed: the run resumes with a fresh RNG).
+# So the class claims the reference's path, dumps go through _dump_random_state (which makes that path resolvable while
+# pickle checks it) and loads go through _RefUnpickler (which resolves it without `anakin` being importable).
+REF_MODULE = "anakin.utils.misc"
+RandomState.__module__ = REF_MODULE
+
+
+class _RefUnpickler(pickle.Unpickler):
+
+    def find_class(self, module, name):
+        if name == "RandomState" and module in (REF_MODULE, __name__):
+            return RandomState
+        return super().find_class(module, name)
+
+
+def _dump_random_state(rs: "RandomState", f) -> None:
+    import sys
+    import types
+    added = []
+    try:
+        parts = REF_MODULE.split(".")
+        for i in range(1, len(parts) + 1):   # stub packages only where the real ones are not importable
+            name = ".".join(parts[:i])
+            if name not in sys.modules:
+                try:
+                    __import__(name)
+                except Exception:  # noqa: BLE001
+                    sys.modules[name] = types.ModuleType(name)
+                    added.append(name)
+        mod = sys.modules[REF_MODULE]
+        had = getattr(mod, "RandomState", None)
+        if had is None or had is not RandomState:
+            rs = RandomState(*rs) if had is None else had(*rs)   # the real class when the reference is importable
+            if had is None:
+                mod.RandomState = RandomState
+        pickle.dump(rs, f)
+    finally:
+        for name in reversed(added):
+            sys.modules.pop(name, None)
 
 
 def _model_list(model):
@@ -38,7 +78,7 @@ def save_states(state: dict, is_best: bool, checkpoint="checkpoint", foldname="c
         sd = {k: v.detach().clone().cpu() for k, v in inner.state_dict().items()}
         torch.save(sd, os.path.join(foldname, f"{type(model).__name__}.pth.tar"))
     with open(os.path.join(foldname, "random_state.pkl"), "wb") as f:
-        pickle.dump(state.pop("random_state"), f)
+        _dump_random_state(state.pop("random_state"), f)
     torch.save(state, os.path.join(foldname, "train_param.pth.tar"))
     if snapshot and state["epoch"] % snapshot == 0:
         shutil.copytree(foldname, os.path.join(checkpoint, "checkpoint_{}".format(state["epoch"])))
@@ -59,7 +99,7 @@ def load_random_state(resume_path: str) -> bool:
     """io_utils.py:56-72: best effort, like the reference (a failure is reported, not raised)."""
     try:
         with open(resume_path, "rb") as f:
-            rs = pickle.load(f)
+            rs = _RefUnpickler(f).load()
         random.setstate(rs.random_rng_state)
         np.random.set_state(rs.numpy_rng_state)
         torch.set_rng_state(rs.torch_rng_state)
@@ -84,9 +124,12 @@ def load_train_param(optimizer, scheduler, resume_path: str, map_location=None) 
         raise ValueError(f"Couldn't resume from {resume_path}: {e!r}") from e
 
 
-def load_arch(model, resume_path: str, startswith=None, strict=True, as_parallel=False, map_location=None):
+def load_arch(model, resume_path: str, startswith=None, strict=True, as_parallel=False, map_location=None, rank=None):
     """io_utils.py:99-124: one `<ModelClass>.pth.tar` per entry of `model.model_list`; handles the `module.` prefix of
-    DataParallel checkpoints and the `startswith` sub-module filter."""
+    DataParallel checkpoints and the `startswith` sub-module filter.  map_location defaults like the reference's: "cuda"
+    when `rank` is None, else that rank's device (:101-104)."""
+    if map_location is None and torch.cuda.is_available():
+        map_location = "cuda" if rank is None else f"cuda:{rank}"
     try:
         for m in _model_list(model):
             ckpt = torch.load(os.path.join(resume_path, f"{type(m).__name__}.pth.tar"), map_location=map_location)

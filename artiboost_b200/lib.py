@@ -34,6 +34,14 @@ class SceneStruct(C.Structure):
                 ("obj_patches", C.POINTER(PatchTableStruct)), ("hand_patches", C.POINTER(PatchTableStruct))]
 
 
+class SynthSpaceStruct(C.Structure):
+    _fields_ = [("n_obj", C.c_int32), ("n_persp", C.c_int32), ("n_grasp", C.c_int32), ("u_bins", C.c_int32),
+                ("theta_bins", C.c_int32), ("z_min", C.c_float), ("z_max", C.c_float), ("grasp_table", C.c_void_p),
+                ("tsl_sigma", C.c_float), ("pose_sigma", C.c_float), ("n_hand_tex", C.c_int32), ("light_lo", C.c_float),
+                ("light_hi", C.c_float), ("n_bg", C.c_int32), ("bg_h", C.c_int32), ("bg_w", C.c_int32), ("width", C.c_int32),
+                ("height", C.c_int32)]
+
+
 class CameraStruct(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
                 ("cy", C.c_float), ("znear", C.c_float), ("cull_backface", C.c_int32), ("ambient", C.c_float),
@@ -70,6 +78,9 @@ EXPORTS = {
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_view_from_id": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_ccv_cdf": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ab_synth_draw": (C.c_int, [C.POINTER(SynthSpaceStruct), C.c_void_p, C.c_int, C.c_uint64, C.c_uint64] + [C.c_void_p] * 18),
+    "ab_ccv_blacklist": (C.c_int, [C.POINTER(SynthSpaceStruct), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_pose_generate_workspace_bytes": (C.c_uint64, [C.c_int]),
     "ab_pose_generate": (C.c_int, [C.POINTER(ManoModelStruct), C.c_int] + [C.c_void_p] * 13),
     "ab_pose_prelude": (C.c_int, [C.POINTER(ManoModelStruct), C.c_int] + [C.c_void_p] * 14),
@@ -133,6 +144,8 @@ EXPORTS = {
                                                                                   C.c_void_p]),
 }
 
+SYNTH_UNIFORMS = 32  # AB_SYNTH_UNIFORMS
+SUMSQ_PARTS = 1184  # AB_SUMSQ_PARTS: ab_sumsq writes out[0] and up to this many partials behind it
 STAT_PARTS = 1184  # AB_STAT_PARTS: rows of the column-reduction workspace (2 * STAT_PARTS * C floats)
 _lib = None
 
@@ -182,7 +195,7 @@ def launch_count() -> int:
     return int(load().ab_launch_count())
 
 
-STAGES = {0: "raster_bin_kernel", 1: "raster_tile_kernel", 3: "mano_lbs_kernel",
+STAGES = {0: "raster_bin_kernel", 1: "raster_tile_kernel", 2: "synth_draw_kernel", 3: "mano_lbs_kernel",
           4: "posegen_prelude_kernel", 5: "ccv_cdf+draw_kernels", 6: "view_kernel", 7: "gemm_bf16_tn_kernel",
           8: "im2col_kernel", 9: "elementwise_kernels", 10: "head_decode_kernel", 11: "gemm_bf16_tn_kernel<im2col TMA>", 12: "wgrad_bf16_kernel", 13: "train_elementwise_kernels", 14: "optimizer_kernels", 15: "bn_apply_kernel", 16: "bn_bwd_reduce_kernel",
           17: "bn_bwd_apply_kernel", 18: "bn_finalize_kernel", 19: "augment_kernels",

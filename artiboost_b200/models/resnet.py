@@ -121,8 +121,30 @@ class ResNet(nn.Module):
             layers.append(block(self.inplanes, planes))
         return nn.Sequential(*layers)
 
-    def load_pretrained(self):
-        raise RuntimeError("ImageNet weights cannot be downloaded here (no network): load a state_dict instead")
+    # file names of the torchvision ImageNet checkpoints the reference fetches (anakin/models/resnet.py:14-20)
+    PRETRAINED_FILES = {"ResNet18": "resnet18-5c106cde.pth", "ResNet34": "resnet34-333f7ec4.pth",
+                        "ResNet50": "resnet50-19c8e357.pth", "ResNet101": "resnet101-5d3b4d8f.pth",
+                        "ResNet152": "resnet152-b121ed2d.pth"}
+
+    def load_pretrained(self, source=True):
+        """PRETRAINED: true / "<path>" (anakin/models/resnet.py:194-197).  The reference downloads the torchvision
+        checkpoint through model_zoo; this build has no network, so `true` looks where model_zoo would have cached the
+        file ($ARTIBOOST_PRETRAINED_DIR, then $TORCH_HOME/hub/checkpoints) and a string is taken as the path of a
+        state_dict file.  Missing files raise: silently training from scratch would not be the configured run."""
+        import os
+        if isinstance(source, (str, os.PathLike)):
+            path = os.fspath(source)
+        else:
+            name = self.PRETRAINED_FILES[type(self).__name__]
+            dirs = [os.environ.get("ARTIBOOST_PRETRAINED_DIR"), os.path.join(torch.hub.get_dir(), "checkpoints")]
+            path = next((os.path.join(d, name) for d in dirs if d and os.path.exists(os.path.join(d, name))), None)
+            if path is None:
+                raise FileNotFoundError(f"PRETRAINED: true needs {name} in $ARTIBOOST_PRETRAINED_DIR or "
+                                        f"{dirs[1]} (no network to download it); or set PRETRAINED to a state_dict path")
+        state = torch.load(path, map_location="cpu")
+        state = state.get("state_dict", state) if isinstance(state, dict) else state
+        self.load_state_dict(state)
+        nhwc.bump_params()  # packed bf16 filter copies are stale
 
     def forward_acts(self, image: torch.Tensor) -> Dict[str, object]:
         """NHWC bf16 feature maps (what the head consumes without a layout round trip)."""
@@ -163,7 +185,7 @@ class ResNet18(ResNet):
     def __init__(self, **cfg):
         super().__init__(BasicBlock, [2, 2, 2, 2], **cfg)
         if cfg["PRETRAINED"]:
-            self.load_pretrained()
+            self.load_pretrained(cfg["PRETRAINED"])
 
 
 @BACKBONE.register_module
@@ -173,7 +195,7 @@ class ResNet34(ResNet):
     def __init__(self, **cfg):
         super().__init__(BasicBlock, [3, 4, 6, 3], **cfg)
         if cfg["PRETRAINED"]:
-            self.load_pretrained()
+            self.load_pretrained(cfg["PRETRAINED"])
 
 
 @BACKBONE.register_module
@@ -183,7 +205,7 @@ class ResNet50(ResNet):
     def __init__(self, **cfg):
         super().__init__(Bottleneck, [3, 4, 6, 3], **cfg)
         if cfg["PRETRAINED"]:
-            self.load_pretrained()
+            self.load_pretrained(cfg["PRETRAINED"])
 
 
 @BACKBONE.register_module
@@ -193,7 +215,7 @@ class ResNet101(ResNet):
     def __init__(self, **cfg):
         super().__init__(Bottleneck, [3, 4, 23, 3], **cfg)
         if cfg["PRETRAINED"]:
-            self.load_pretrained()
+            self.load_pretrained(cfg["PRETRAINED"])
 
 
 @BACKBONE.register_module
@@ -203,4 +225,4 @@ class ResNet152(ResNet):
     def __init__(self, **cfg):
         super().__init__(Bottleneck, [3, 8, 36, 3], **cfg)
         if cfg["PRETRAINED"]:
-            self.load_pretrained()
+            self.load_pretrained(cfg["PRETRAINED"])

@@ -57,9 +57,11 @@ def async_wgrad():
 
 
 @contextlib.contextmanager
-def _wgrad_launch(dev, *keep):
-    """Stream context of one weight-gradient launch; `keep`: its operand tensors."""
-    if not _AsyncWgrad.enabled:
+def _wgrad_launch(dev, *keep, in_place=True):
+    """Stream context of one weight-gradient launch; `keep`: its operand tensors.  A gradient that is RETURNED to autograd
+    (`in_place` false: the parameter owns no dense fp32 .grad to accumulate into) is consumed on the caller's stream right
+    after the Function returns, so it is never produced on the side stream."""
+    if not _AsyncWgrad.enabled or not in_place:
         with torch.cuda.device(dev):
             yield
         return
@@ -216,7 +218,7 @@ def _conv_wgrad(x: Act, xcol, dy_mat, conv_w, kh, kw, stride, pad):
     taps = kh * kw
     dev = dy_mat.device
     dw, in_place = _grad_target(conv_w)
-    with _wgrad_launch(dev, x.data, xcol, dy_mat):
+    with _wgrad_launch(dev, x.data, xcol, dy_mat, in_place=in_place):
         if x.C % 64 == 0:
             _call("ab_conv_wgrad_bf16_nhwc", x.data.data_ptr(), x.B, x.H, x.W, x.C, dy_mat.data_ptr(), cout, kh, kw, stride, pad,
                   dw.data_ptr(), 1, _wgrad_ws(dy_mat.shape[0], cout, taps * x.C, dev).data_ptr(), _stream(dev))
@@ -395,7 +397,7 @@ class DeconvBNReluFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dwb, in_place = _grad_target(deconv.weight)  # rows (ky,kx,co), columns ci -> [Cin, Cout, ky, kx]
             m = lib.wgrad_map(row_div=cout, s_row_hi=1, s_row_lo=16, s_col_lo=cout * 16)
-            with _wgrad_launch(dev, dycol, x_data):
+            with _wgrad_launch(dev, dycol, x_data, in_place=in_place):
                 _call("ab_wgrad_bf16", B * H * W, 16 * cout, C, dycol.data_ptr(), 16 * cout, x_data.data_ptr(), C, dwb.data_ptr(), m,
                       _wgrad_ws(B * H * W, 16 * cout, C, dev).data_ptr(), _stream(dev))
             dw = None if in_place else dwb
@@ -463,7 +465,7 @@ class LinearFn(torch.autograd.Function):
         g = torch.zeros((dy.shape[0], npad), dtype=torch.bfloat16, device=dev)
         g[:, :n] = (dy.float() * (y.float() > 0)) if relu else dy
         dwb, in_place = _grad_target(fc.weight)
-        with _wgrad_launch(dev, g, xb):
+        with _wgrad_launch(dev, g, xb, in_place=in_place):
             _call("ab_wgrad_bf16", g.shape[0], n, k, g.data_ptr(), npad, xb.data_ptr(), xb.stride(0), dwb.data_ptr(),
                   lib.wgrad_map(s_row_lo=k, s_col_lo=1), _wgrad_ws(g.shape[0], n, k, dev).data_ptr(), _stream(dev))
         dw = None if in_place else dwb

@@ -8,10 +8,12 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional
 
+import ctypes as C
+
 import numpy as np
 import torch
 
-from . import assets
+from . import assets, lib
 from .artiboost import (GraspEngine, HORefiner, NullRefine, ObjEngine, OVGSet, PreProcessorPoseGenerator, Renderer,
                         Scrambler, ViewEngine, make_mesh)
 from .artiboost.renderer import PYRENDER_EXTRINSIC, PointLight
@@ -35,7 +37,8 @@ class SynthPipeline:
 
     def __init__(self, obj_names: Optional[List[str]] = None, device="cuda", seed: int = 0, cfg: Optional[dict] = None,
                  n_hand_tex: int = 51, n_bg: int = 8, chunk: int = 512, mano_model: Optional[Dict] = None,
-                 objects: Optional[Dict[str, dict]] = None, grasps: Optional[Dict[str, list]] = None):
+                 objects: Optional[Dict[str, dict]] = None, grasps: Optional[Dict[str, list]] = None,
+                 filter_back: bool = True, fused_draw: bool = True):
         self.cfg = cfg = dict(DEFAULT_CFG if cfg is None else cfg)
         self.device = dev = torch.device(device)
         if dev.type != "cuda":
@@ -50,10 +53,19 @@ class SynthPipeline:
         self.generator = torch.Generator(device=dev)
         self.generator.manual_seed(seed)
         shape = (len(self.obj_names), self.view_engine.n_persp_center, self.grasp_engine.n_grasp)
+        self._seed, self._offset = int(seed), 0       # the Philox stream of the fused draw: (seed, per-call offset)
+        self._space = None                            # ab_synth_space; completed once the renderer exists (texture / bg counts)
+        self._cdf, self._cdf_key = None, None
+        self._occ_map = torch.zeros(shape, dtype=torch.bool, device=dev)
+        self._occ_count = torch.zeros(shape, dtype=torch.int32, device=dev)
+        self._render_rand = None
         self.sample_weight_map = torch.ones(shape, device=dev)
-        self.occurence_map = torch.zeros(shape, dtype=torch.bool, device=dev)
+        # artiboost_loader.py:125-130: back-of-hand cells are blacklisted and never drawn
+        self.blacklist_map = (self.construct_blacklist_map() if filter_back
+                              else torch.zeros(shape, dtype=torch.bool, device=dev))
+        self.sample_weight_map[self.blacklist_map] = 0.0
         self.ovg_set = OVGSet(self.obj_engine, self.grasp_engine, self.view_engine, 0, 0, self.grasp_engine.n_grasp,
-                              torch.zeros(shape, dtype=torch.bool), device=dev, generator=self.generator)
+                              self.blacklist_map, device=dev, generator=self.generator)
         rcfg = cfg.get("REFINER", {"TYPE": "null"})
         if rcfg["TYPE"] == "hand_obj":
             torch.manual_seed(seed)
@@ -79,10 +91,112 @@ class SynthPipeline:
         self.renderer.setup(self.cam_intr, PYRENDER_EXTRINSIC, self.obj_engine.obj_trimeshes_mapping, self.hand_meshes,
                             self.backgrounds, [PointLight(np.array([0.9, 0.9, 0.9]), 5.0, np.eye(4))])
 
+        sc = cfg["SCRAMBLER"]
+        self.fused_draw = bool(fused_draw and rcfg["TYPE"] == "null" and sc["TYPE"] in ("random", "null"))
+        self._sigmas = ((float(sc.get("HAND_TSL_SIGMA", 0.0)), float(sc.get("HAND_POSE_SIGMA", 0.0)))
+                        if sc["TYPE"] == "random" else (0.0, 0.0))
+
+    # ------------------------------------------------------------------------------------------ CCV space on device
+    def _synth_space(self) -> "lib.SynthSpaceStruct":
+        v, r = self.view_engine, getattr(self, "renderer", None)
+        nb, bh, bw = (r.backgrounds.shape[:3] if r is not None and r.backgrounds is not None else (0, 0, 0))
+        zmin, zmax = v.camera_z_range
+        W, H = self.cfg["RENDER_SIZE"]
+        sig = getattr(self, "_sigmas", (0.0, 0.0))
+        return lib.SynthSpaceStruct(len(self.obj_names), v.n_persp_center, self.grasp_engine.n_grasp, v.persp_u_bins,
+                                    v.persp_theta_bins, float(zmin), float(zmax), self.grasp_engine.table.data_ptr(),
+                                    sig[0], sig[1], r.n_hand_tex if r is not None else 1, 1.0, 5.0, int(nb), int(bh), int(bw),
+                                    int(W), int(H))
+
+    @torch.no_grad()
+    def construct_blacklist_map(self, rand2: Optional[torch.Tensor] = None, threshold: float = -0.8, return_th: bool = False):
+        """ArtiBoostLoader._construct_blacklist_map (artiboost_loader.py:415-500) over the whole CCV space in one launch.
+        rand2 f32 [n_obj, n_persp, n_grasp, 2]: the (u, theta) jitter get_view draws per cell; drawn here when omitted, like
+        the reference's loop does."""
+        dev = self.device
+        shape = (len(self.obj_names), self.view_engine.n_persp_center, self.grasp_engine.n_grasp)
+        if rand2 is None:
+            rand2 = torch.rand(shape + (2,), device=dev, generator=self.generator)
+        rand2 = rand2.to(dev).float().contiguous()
+        out = torch.empty(shape, dtype=torch.uint8, device=dev)
+        th = torch.empty(shape, dtype=torch.float32, device=dev) if return_th else None
+        sp = self._synth_space()
+        with torch.cuda.device(dev):
+            rc = lib.load().ab_ccv_blacklist(C.byref(sp), lib.ptr(rand2), float(threshold), lib.ptr(out), lib.ptr(th),
+                                             lib.stream_ptr(dev))
+        lib.check(rc, "ab_ccv_blacklist")
+        return (out.bool(), th) if return_th else out.bool()
+
+    @property
+    def occurence_map(self) -> torch.Tensor:
+        """bool [n_obj, n_persp, n_grasp]: cells drawn so far (ovg_set.py:172-178).  The fused draw counts on the device;
+        the counts are folded into the map when it is read."""
+        self._occ_map |= self._occ_count > 0
+        self._occ_count.zero_()
+        return self._occ_map
+
+    @occurence_map.setter
+    def occurence_map(self, value: torch.Tensor):
+        self._occ_map = value.to(self.device).bool()
+        self._occ_count.zero_()
+
+    def _ccv_cdf(self) -> torch.Tensor:
+        """The fp64 CDF of the weight map, recomputed only when the map changes (once per epoch: step_eval)."""
+        w = self.sample_weight_map
+        key = (w.data_ptr(), w._version)
+        if self._cdf is None or key != self._cdf_key:
+            w = w.detach().to(self.device).float().contiguous()
+            if self._cdf is None:
+                self._cdf = torch.empty(w.numel(), dtype=torch.float64, device=self.device)
+            with torch.cuda.device(self.device):
+                lib.check(lib.load().ab_ccv_cdf(lib.ptr(w), w.numel(), lib.ptr(self._cdf), lib.stream_ptr(self.device)), "ab_ccv_cdf")
+            self._cdf_key = (self.sample_weight_map.data_ptr(), self.sample_weight_map._version)
+            self._cdf_src = w   # keeps a converted copy alive until the launch has run
+        return self._cdf
+
+    @torch.no_grad()
+    def draw(self, n: int, uniforms: Optional[torch.Tensor] = None, return_uniforms: bool = False) -> dict:
+        """One launch (ab_synth_draw): CCV cells, views, grasps, scrambler noise and the renderer's per-view draws for n
+        samples.  `uniforms` f32 [n, 32] replaces the Philox stream (tests)."""
+        dev = self.device
+        if self._space is None:
+            self._space = self._synth_space()
+        e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)  # noqa: E731
+        i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)  # noqa: E731
+        b = {"obj_id": i32(n), "persp_id": i32(n), "grasp_id": i32(n), "hand_pose": e(n, 48), "hand_shape": e(n, 10),
+             "hand_tsl": e(n, 3), "persp_rotmat": e(n, 3, 3), "camera_free_transf": e(n, 4, 4), "z_offset": e(n, 3)}
+        scr = self._sigmas != (0.0, 0.0)
+        n_tsl, n_ang = (e(n, 3), e(n, 16)) if scr else (None, None)
+        rr = {"hand_tex": i32(n), "light": e(n), "bg_sel": i32(n, 5)}
+        u_out = e(n, lib.SYNTH_UNIFORMS) if return_uniforms else None
+        if uniforms is not None:
+            uniforms = uniforms.to(dev).float().contiguous()
+        cdf = self._ccv_cdf()
+        with torch.cuda.device(dev):
+            rc = lib.load().ab_synth_draw(
+                C.byref(self._space), lib.ptr(cdf), n, self._seed, self._offset, lib.ptr(uniforms), lib.ptr(b["obj_id"]),
+                lib.ptr(b["persp_id"]), lib.ptr(b["grasp_id"]), lib.ptr(self._occ_count), lib.ptr(b["hand_pose"]),
+                lib.ptr(b["hand_shape"]), lib.ptr(b["hand_tsl"]), lib.ptr(b["persp_rotmat"]), lib.ptr(b["camera_free_transf"]),
+                lib.ptr(b["z_offset"]), lib.ptr(n_tsl), lib.ptr(n_ang), lib.ptr(rr["hand_tex"]), lib.ptr(rr["light"]),
+                lib.ptr(rr["bg_sel"]), lib.ptr(u_out), lib.stream_ptr(dev))
+        lib.check(rc, "ab_synth_draw")
+        self._offset += lib.SYNTH_UNIFORMS // 4
+        if self.renderer.backgrounds is None:
+            rr.pop("bg_sel")
+        b.update(index=None, obj_name=None, noise=(n_tsl, n_ang) if scr else None)
+        self._render_rand = (n, rr)
+        if return_uniforms:
+            b["uniforms"] = u_out
+        return b
+
     @torch.no_grad()
     def sample_poses(self, n: int) -> dict:
         """CCV draw + view + grasp + pose generator for n views -> final_obj_pose / final_hand_verts / final_joints
-        plus the (obj, persp, grasp) ids."""
+        plus the (obj, persp, grasp) ids.  With REFINER null and the `random` (or no) scrambler this is three launches: the
+        fused draw (ab_synth_draw) and the pose generator's prelude + LBS; other configurations take the staged path."""
+        if self.fused_draw:
+            return self.pose_generator(self.draw(n))
+        self._render_rand = None
         self.ovg_set.train()
         self.ovg_set.update_len(config_len_train=n)
         _, self.occurence_map = self.ovg_set.update(self.sample_weight_map, self.occurence_map)
@@ -93,6 +207,8 @@ class SynthPipeline:
         """rand: optional {"hand_tex", "light", "bg_sel"} device tensors (the per-view draws of renderer.py:102-104);
         drawn on device from the pipeline's generator when omitted."""
         B = poses["final_obj_pose"].shape[0]
+        if rand is None and self._render_rand is not None and self._render_rand[0] == B:
+            rand, self._render_rand = self._render_rand[1], None   # drawn together with these poses by the fused launch
         rand = rand or self.draw_render_randoms(B)
         return self.renderer.render_batch(poses["obj_id"], poses["final_obj_pose"], poses["final_hand_verts"],
                                           hand_tex=rand["hand_tex"], light=rand["light"], bg_sel=rand.get("bg_sel"),

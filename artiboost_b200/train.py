@@ -50,7 +50,7 @@ class FusedAdam:
         self.fp, self.lr, self.betas, self.eps, self.wd, self.max_norm = flat, lr, betas, eps, weight_decay, max_norm
         self.m = torch.zeros_like(flat.flat)
         self.v = torch.zeros_like(flat.flat)
-        self.sumsq = torch.zeros(1, device=flat.flat.device)
+        self.sumsq = torch.zeros(1 + lib.SUMSQ_PARTS, device=flat.flat.device)   # [0] = the sum, the rest per-CTA partials
         self.state = torch.zeros(3, device=flat.flat.device)  # {step count, 1 - beta1^t, 1 - beta2^t}, advanced on device
 
     @property
@@ -62,7 +62,6 @@ class FusedAdam:
         L = lib.load()
         with torch.cuda.device(dev):
             if self.max_norm > 0:
-                self.sumsq.zero_()
                 lib.check(L.ab_sumsq(fp.grad.data_ptr(), fp.numel, self.sumsq.data_ptr(), lib.stream_ptr(dev)), "ab_sumsq")
             lib.check(L.ab_adam_step(fp.flat.data_ptr(), fp.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), fp.numel,
                                      self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.state.data_ptr(),
@@ -71,7 +70,7 @@ class FusedAdam:
         nhwc.bump_params()  # the kernel rewrote the parameters in place: packed bf16 filter copies are stale
 
     def grad_norm(self) -> torch.Tensor:
-        return self.sumsq.sqrt()
+        return self.sumsq[:1].sqrt()
 
     # -- torch.optim.Adam checkpoint format, so that `train_param.pth.tar` files move between the reference's loop
     # (anakin/utils/io_utils.py:34,74-84: optimizer.state_dict() / load_state_dict()) and this one

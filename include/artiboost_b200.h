@@ -48,7 +48,7 @@ AB_API uint64_t ab_launch_count(void);
  * milliseconds and launch counts per stage id (AB_STAGE_*).  Off by default.                                  */
 #define AB_STAGE_RASTER_BIN 0
 #define AB_STAGE_RASTER_TILE 1
-#define AB_STAGE_RESERVED_2 2
+#define AB_STAGE_SYNTH_DRAW 2
 #define AB_STAGE_MANO_LBS 3
 #define AB_STAGE_POSEGEN_PRELUDE 4
 #define AB_STAGE_CCV 5
@@ -107,6 +107,41 @@ AB_API int ab_ccv_sample(const float* weight_map, int n_obj, int n_persp, int n_
  * (u jitter, theta jitter, in-plane roll, z).  Outputs persp_rotmat [n,9], camera_free_transf [n,16], z_offset [n,3]. */
 AB_API int ab_view_from_id(const int32_t* persp_id, int n, int u_bins, int theta_bins, float z_min, float z_max,
                     const float* rand4, float* persp_rotmat, float* camera_free_transf, float* z_offset, void* stream);
+
+/* ------------------------------------------------------------------------- fused synthesis draw (one launch)
+ * Everything ArtiBoostLoader.generate_render_cache + RenderedDataset.prepare_essential + Renderer.__call__ DRAW for a
+ * batch of views (anakin/artiboost/artiboost_loader.py:352-387, ovg_set.py:104-159, view_engine.py:17-86,
+ * grasp_engine.py:47-53, scrambler.py:65-81, utils/renderer.py:102-104,125-136), from one counter-based Philox stream:
+ * sample i of a call reads subsequence i of (seed, offset); a batch is reproducible from (seed, offset) alone, and
+ * successive calls pass offset += AB_SYNTH_UNIFORMS / 4.
+ *   ab_ccv_cdf: the fp64 inclusive prefix sum of weight_map[n_cells] -- once per epoch, the map only changes in step_eval.
+ *   ab_synth_draw: n samples.  `uniforms` [n, AB_SYNTH_UNIFORMS] (16-byte aligned) replaces the Philox stream when
+ *     given (tests; layout at the top of csrc/synth.cu); `uniforms_out` (optional) receives the uniforms used.
+ *     Outputs as ab_ccv_sample (+ occurrence counts, accumulated), ab_view_from_id, the grasp table rows (hand_pose [n,48],
+ *     hand_shape [n,10], hand_tsl [n,3]), noise_tsl [n,3] / noise_angle [n,16] = N(0, sigma) (optional), hand_tex [n],
+ *     light [n] = U[light_lo, light_hi), bg_sel [n,5] = {bg id, x0, y0, crop_w, crop_h} (optional).
+ *   ab_ccv_blacklist: _construct_blacklist_map (artiboost_loader.py:415-500): blacklist u8 [n_cells] = th_sgn < threshold
+ *     (reference: -0.8); rand2 [n_cells, 2] = the (u, theta) jitter of get_view for every cell, NULL = bin centres;
+ *     th_sgn f32 [n_cells] optional.                                                                                */
+#define AB_SYNTH_UNIFORMS 32
+typedef struct {
+    int32_t n_obj, n_persp, n_grasp;   /* CCV space                                                         */
+    int32_t u_bins, theta_bins;        /* VIEW_ENGINE PERSP_U_BINS / PERSP_THETA_BINS, n_persp = their product */
+    float z_min, z_max;                /* CAMERA_Z_RANGE                                                    */
+    const float* grasp_table;          /* device [n_obj, n_grasp, 61]: hand_pose 48 | hand_shape 10 | hand_tsl 3 */
+    float tsl_sigma, pose_sigma;       /* SCRAMBLER HAND_TSL_SIGMA / HAND_POSE_SIGMA (yaml:42-45)            */
+    int32_t n_hand_tex;                /* renderer.py:102                                                    */
+    float light_lo, light_hi;          /* renderer.py:103-104: U(1, 5)                                       */
+    int32_t n_bg, bg_h, bg_w, width, height; /* backgrounds and frame size for the crop rule (renderer.py:125-136) */
+} ab_synth_space;
+AB_API int ab_ccv_cdf(const float* weight_map, int n_cells, double* cdf, void* stream);
+AB_API int ab_synth_draw(const ab_synth_space* space, const double* cdf, int n, uint64_t seed, uint64_t offset,
+                  const float* uniforms, int32_t* obj_id, int32_t* persp_id, int32_t* grasp_id, int32_t* occurrence,
+                  float* hand_pose, float* hand_shape, float* hand_tsl, float* persp_rotmat, float* camera_free_transf,
+                  float* z_offset, float* noise_tsl, float* noise_angle, int32_t* hand_tex, float* light, int32_t* bg_sel,
+                  float* uniforms_out, void* stream);
+AB_API int ab_ccv_blacklist(const ab_synth_space* space, const float* rand2, float threshold, uint8_t* blacklist,
+                     float* th_sgn, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- pose generator
  * Replaces PreProcessorPoseGenerator.forward (anakin/artiboost/preprocessor.py:20-99) with the `random`
@@ -354,7 +389,10 @@ AB_API int ab_head_decode(const float* logits, int B, int ncls, int D, int H, in
  * ab_sumsq / ab_adam_step: clip_grad_norm_(max_norm) + torch.optim.Adam on one flat fp32 parameter buffer;
  *   grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).  state f32 [3] = {step count,
  *   1 - beta1^t, 1 - beta2^t} lives on the device (zero it once) and is advanced by the call itself, so a captured
- *   CUDA graph of the training step replays with the right bias corrections.  n % 4 == 0.                       */
+ *   CUDA graph of the training step replays with the right bias corrections.  n % 4 == 0.
+ *   ab_sumsq: out is f32 [1 + AB_SUMSQ_PARTS]; out[0] receives the sum (out[1..] hold the per-CTA partials of a
+ *   fixed-order two-pass reduction: no atomics, the result is bit-reproducible and needs no zeroing).            */
+#define AB_SUMSQ_PARTS 1184
 #define AB_STAT_PARTS 1184
 AB_API int ab_col_stats(const void* x, int is_f32, int M, int C, int64_t ld, float* sum, float* sumsq, float* ws, void* stream);
 AB_API int ab_bn_finalize(const float* sum_part, const float* sumsq_part, int n_part, int C, float count, const float* gamma,

@@ -163,3 +163,63 @@ def update_method_1(weight_map, cells, values, lower=0.1, upper=10.0):
     for (o, p, g), m in zip(np.asarray(cells), mult):
         w[o, p, g] *= m
     return np.clip(w, np.float32(lower), np.float32(upper))
+
+
+def blacklist_map(root_aa, u_bins, theta_bins, rand2=None, threshold=-0.8, return_th=False):
+    """ArtiBoostLoader._construct_blacklist_map (artiboost_loader.py:415-500): a cell (object, view, grasp) is blacklisted
+    when the view shows the back of the hand, th_sgn = ((Rv^T Rw back) . z) < -0.8 with Rw the wrist rotation of the grasp,
+    Rv the view alignment of the cell's (jittered) perspective and back = (1, 0.2, 0) / |.| (:482-492).
+    root_aa f[n_obj, n_grasp, 3]; rand2 f[n_obj, n_persp, n_grasp, 2] = the (u, theta) draws of get_view, None = bin centres.
+    -> bool [n_obj, n_persp, n_grasp] (and th_sgn)."""
+    root_aa = np.asarray(root_aa, np.float64)
+    n_obj, n_grasp = root_aa.shape[:2]
+    n_persp = u_bins * theta_bins
+    back = np.array([1.0, 0.2, 0.0])
+    back = back / np.linalg.norm(back)
+    out = np.zeros((n_obj, n_persp, n_grasp), bool)
+    th = np.zeros((n_obj, n_persp, n_grasp), np.float64)
+    for o in range(n_obj):
+        Rw = rot.aa_to_rotmat(root_aa[o])                # [n_grasp, 3, 3]
+        for v in range(n_persp):
+            for g in range(n_grasp):
+                ru, rth = (0.5, 0.5) if rand2 is None else rand2[o, v, g]
+                Rv, _, _ = view_from_id(v, u_bins, theta_bins, (0.45, 0.55), np.float32(ru), np.float32(rth), 0.0, np.float32(0.0))
+                arrow = Rv.astype(np.float64).T @ Rw[g] @ back
+                th[o, v, g] = arrow[2]
+                out[o, v, g] = arrow[2] < threshold
+    return (out, th) if return_th else out
+
+
+SYNTH_UNIFORMS = 32
+
+
+def synth_draw(weight_map, uniforms, u_bins, theta_bins, z_range, grasp_table, tsl_sigma, pose_sigma, n_hand_tex,
+               light_range, n_bg, bg_hw, frame_wh):
+    """What ab_synth_draw (artiboost_b200/csrc/synth.cu) derives from the uniforms of a batch -- the composition of
+    sample_ovg, view_from_id, the grasp lookup (grasp_engine.py:47-53), N(0, sigma) scrambler noise (scrambler.py:65-81,
+    Box-Muller on uniform pairs) and the renderer's per-view draws (utils/renderer.py:102-104,125-136).
+    uniforms f32 [n, 32]; layout: 0 cell | 1..4 view | 5..24 ten Box-Muller pairs | 25 texture | 26 light | 27..30 bg."""
+    u = np.asarray(uniforms, np.float32)
+    n = u.shape[0]
+    o, p, g = sample_ovg(weight_map, u[:, 0])
+    views = [view_from_id(int(p[i]), u_bins, theta_bins, z_range, u[i, 1], u[i, 2], u[i, 3], u[i, 4]) for i in range(n)]
+    rows = np.asarray(grasp_table, np.float32)[o, g]
+    u1, u2 = u[:, 5:25:2].astype(np.float64), u[:, 6:25:2].astype(np.float64)
+    r = np.sqrt(-2.0 * np.log(1.0 - u1))
+    nrm = np.stack([r * np.cos(2 * np.pi * u2), r * np.sin(2 * np.pi * u2)], -1).reshape(n, 20)
+    W, H = frame_wh
+    out = {"obj_id": o, "persp_id": p, "grasp_id": g, "hand_pose": rows[:, :48], "hand_shape": rows[:, 48:58],
+           "hand_tsl": rows[:, 58:61], "persp_rotmat": np.stack([v[0] for v in views]),
+           "camera_free_transf": np.stack([v[1] for v in views]), "z_offset": np.stack([v[2] for v in views]),
+           "noise_tsl": (nrm[:, :3] * tsl_sigma).astype(np.float32), "noise_angle": (nrm[:, 3:19] * pose_sigma).astype(np.float32),
+           "hand_tex": np.minimum((u[:, 25] * np.float32(n_hand_tex)).astype(np.int64), n_hand_tex - 1),
+           "light": (np.float32(light_range[0]) + u[:, 26] * np.float32(light_range[1] - light_range[0])).astype(np.float32)}
+    if n_bg > 0:
+        bh, bw = bg_hw
+        bid = np.minimum((u[:, 27] * np.float32(n_bg)).astype(np.int64), n_bg - 1)
+        ch = H + np.minimum((u[:, 28] * np.float32(bh - H + 1)).astype(np.int64), bh - H)
+        cw = np.minimum((ch * W) // H, bw)
+        y0 = np.minimum((u[:, 29] * (bh - ch + 1).astype(np.float32)).astype(np.int64), bh - ch)
+        x0 = np.minimum((u[:, 30] * (bw - cw + 1).astype(np.float32)).astype(np.int64), bw - cw)
+        out["bg_sel"] = np.stack([bid, x0, y0, cw, ch], 1)
+    return out

@@ -159,3 +159,103 @@ def test_pose_generator_matches_oracle_batch(mano_model, lib_built):
     np.testing.assert_allclose(out["final_obj_pose"].cpu().numpy(), ref["final_obj_pose"], rtol=1e-4, atol=2e-6)
     np.testing.assert_allclose(out["final_hand_verts"].cpu().numpy(), ref["final_hand_verts"], rtol=1e-4, atol=5e-6)
     np.testing.assert_allclose(out["final_joints"].cpu().numpy(), ref["final_joints"], rtol=1e-4, atol=5e-6)
+
+
+# ------------------------------------------------------------------------------------- fused draw / blacklist
+def _small_pipe(**kw):
+    from artiboost_b200.synth import SynthPipeline
+    return SynthPipeline(device=DEV, seed=3, n_hand_tex=7, n_bg=3, **kw)
+
+
+def test_fused_draw_matches_oracle_composition(lib_built):
+    """ab_synth_draw (one launch: CCV cell, view, grasp, scrambler noise, renderer draws) vs oracle.ccv.synth_draw on the
+    uniforms the kernel reports: ids / texture / crop integer-exact, views 1e-6, noise and light 1e-5."""
+    from oracle import ccv
+    pipe = _small_pipe()
+    rng = np.random.RandomState(1)
+    w = rng.uniform(0.1, 10, size=tuple(pipe.sample_weight_map.shape)).astype(np.float32)
+    w[1, 5, :] = 0.0
+    pipe.sample_weight_map = t(w)
+    n = 700
+    for uniforms in (None, t(rng.rand(n, 32).astype(np.float32))):
+        occ0 = pipe.occurence_map.clone()
+        b = pipe.draw(n, uniforms=uniforms, return_uniforms=True)
+        u = b["uniforms"].cpu().numpy()
+        if uniforms is not None:
+            np.testing.assert_array_equal(u, uniforms.cpu().numpy())
+        assert u.min() >= 0.0 and u.max() < 1.0
+        r = pipe.renderer
+        nb, bh, bw = r.backgrounds.shape[:3]
+        ref = ccv.synth_draw(w, u, 12, 24, (0.45, 0.55), pipe.grasp_engine.table.cpu().numpy(), 0.01, 0.1, r.n_hand_tex,
+                             (1.0, 5.0), nb, (bh, bw), (r.width, r.height))
+        for k in ("obj_id", "persp_id", "grasp_id"):
+            np.testing.assert_array_equal(b[k].cpu().numpy(), ref[k], err_msg=k)
+        for k in ("hand_pose", "hand_shape", "hand_tsl", "z_offset"):
+            np.testing.assert_array_equal(b[k].cpu().numpy(), ref[k], err_msg=k)
+        np.testing.assert_allclose(b["persp_rotmat"].cpu().numpy(), ref["persp_rotmat"], atol=3e-6)  # fp32 sincos vs numpy: a few ulp
+        np.testing.assert_allclose(b["camera_free_transf"].cpu().numpy(), ref["camera_free_transf"], atol=3e-6)
+        n_tsl, n_ang = b["noise"]
+        np.testing.assert_allclose(n_tsl.cpu().numpy(), ref["noise_tsl"], atol=1e-6, rtol=1e-4)
+        np.testing.assert_allclose(n_ang.cpu().numpy(), ref["noise_angle"], atol=1e-5, rtol=1e-4)
+        rr = pipe._render_rand[1]
+        np.testing.assert_array_equal(rr["hand_tex"].cpu().numpy(), ref["hand_tex"])
+        np.testing.assert_allclose(rr["light"].cpu().numpy(), ref["light"], rtol=1e-6)
+        np.testing.assert_array_equal(rr["bg_sel"].cpu().numpy(), ref["bg_sel"])
+        # occurrence counts are folded into the map when it is read (ovg_set.py:172-178)
+        occ = ccv.occurrence_count_map(ref["obj_id"], ref["persp_id"], ref["grasp_id"], *w.shape) > 0
+        np.testing.assert_array_equal(pipe.occurence_map.cpu().numpy(), occ0.cpu().numpy() | occ)
+        assert not pipe.occurence_map[1, 5].any()
+
+
+def test_fused_draw_stream_is_reproducible_and_well_distributed(lib_built):
+    a, b = _small_pipe(), _small_pipe()
+    ua = a.draw(4096, return_uniforms=True)["uniforms"]
+    ub = b.draw(4096, return_uniforms=True)["uniforms"]
+    assert torch.equal(ua, ub)                                  # same (seed, offset) -> same batch
+    ua2 = a.draw(4096, return_uniforms=True)["uniforms"]
+    assert not torch.equal(ua, ua2)                             # the offset advances between calls
+    u = torch.cat([ua, ua2]).double()
+    assert abs(float(u.mean()) - 0.5) < 5e-3 and abs(float(u.var()) - 1 / 12) < 2e-3
+    c = torch.corrcoef(u[:, :8].T)
+    assert float((c - torch.eye(8, device=c.device)).abs().max()) < 0.05
+    n_tsl, n_ang = a.draw(8192)["noise"]
+    assert abs(float(n_ang.mean())) < 5e-3 and abs(float(n_ang.std()) - 0.1) < 3e-3 and abs(float(n_tsl.std()) - 0.01) < 5e-4
+    # the synthesis path with the fused draw agrees with the staged path given the same inputs
+    pipe = _small_pipe()
+    batch = pipe.draw(64)
+    fused = pipe.pose_generator(batch)
+    staged = pipe.pose_generator._forward_staged(batch, batch["hand_pose"], batch["hand_shape"], batch["hand_tsl"],
+                                                 batch["persp_rotmat"], batch["camera_free_transf"], batch["z_offset"], False,
+                                                 noise=batch["noise"])
+    for k in ("final_obj_pose", "final_hand_verts", "final_joints"):
+        torch.testing.assert_close(fused[k], staged[k], rtol=1e-4, atol=2e-6)
+
+
+def test_blacklist_kernel_matches_oracle_and_reference_fixture(lib_built):
+    """ab_ccv_blacklist vs oracle.ccv.blacklist_map on the pipeline's CCV space, and vs the map the reference's own
+    _construct_blacklist_map produced (tests/golden/blacklist.npz); blacklisted cells are never drawn."""
+    from artiboost_b200 import assets
+    from artiboost_b200.synth import DEFAULT_CFG, SynthPipeline
+    from oracle import ccv
+    g = golden("blacklist.npz")
+    names = [str(x) for x in g["names"]]
+    cfg = dict(DEFAULT_CFG, VIEW={"PERSP_U_BINS": int(g["u_bins"]), "PERSP_THETA_BINS": int(g["theta_bins"]),
+                                  "CAMERA_Z_RANGE": [0.45, 0.55]}, GRASP_NUM=int(g["n_grasp"]))
+    pipe = SynthPipeline(obj_names=names, device=DEV, seed=0, cfg=cfg, n_hand_tex=2, n_bg=2)
+    np.testing.assert_array_equal(pipe.grasp_engine.table[:, :, :48].cpu().numpy(), g["hand_pose"])
+    bl, th = pipe.construct_blacklist_map(rand2=t(g["rand2"]), return_th=True)
+    np.testing.assert_array_equal(bl.cpu().numpy(), g["blacklist"])          # the reference function's output
+    # the pipeline's own (default) space against the oracle, away from the threshold
+    pipe = _small_pipe()
+    rng = np.random.RandomState(2)
+    rand2 = rng.rand(*pipe.sample_weight_map.shape, 2).astype(np.float32)
+    bl, th = pipe.construct_blacklist_map(rand2=t(rand2), return_th=True)
+    ref, ref_th = ccv.blacklist_map(pipe.grasp_engine.table[:, :, :3].cpu().numpy(), 12, 24, rand2, return_th=True)
+    np.testing.assert_allclose(th.cpu().numpy(), ref_th, atol=2e-6)
+    clear = np.abs(ref_th + 0.8) > 1e-5
+    np.testing.assert_array_equal(bl.cpu().numpy()[clear], ref[clear])
+    assert 0.02 < float(bl.float().mean()) < 0.3
+    # applied at construction (artiboost_loader.py:125-130): zero weight, never drawn
+    assert bool((pipe.sample_weight_map[pipe.blacklist_map] == 0).all()) and bool(pipe.blacklist_map.any())
+    b = pipe.draw(20000)
+    assert not bool(pipe.blacklist_map[b["obj_id"].long(), b["persp_id"].long(), b["grasp_id"].long()].any())

@@ -26,6 +26,41 @@ class _Arch(nn.Module):
         self.model_list = nn.ModuleList([HybridBaseline()])
 
 
+def test_random_state_pickle_crosses_to_the_reference_and_back(tmp_path, monkeypatch):
+    """random_state.pkl must name the class the reference imports (`anakin.utils.misc.RandomState`, io_utils.py:16,54-57):
+    a file written here loads in an interpreter that only has the reference's module, and a file the reference wrote loads
+    here without `anakin` being importable."""
+    import collections
+    import pickletools
+    import sys
+    import types
+    from artiboost_b200 import io_utils
+    np.random.seed(11)
+    path = tmp_path / "random_state.pkl"
+    with open(path, "wb") as f:
+        io_utils._dump_random_state(io_utils.capture_random_state(), f)
+    draw = np.random.rand()
+    assert "anakin" not in sys.modules                      # the stub packages used while dumping are gone again
+    names = [op[1] for op in pickletools.genops(path.read_bytes()) if isinstance(op[1], str)]
+    assert "anakin.utils.misc" in names and "artiboost_b200.io_utils" not in names
+    np.random.seed(12)
+    assert io_utils.load_random_state(str(path)) and np.random.rand() == draw      # ours -> ours, no `anakin` anywhere
+    # the reference's side: only its own module and its own namedtuple exist (anakin/utils/misc.py:11-21)
+    ref_cls = collections.namedtuple("RandomState", io_utils.RandomState._fields)
+    for name in ("anakin", "anakin.utils", "anakin.utils.misc"):
+        monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    ref_cls.__module__ = "anakin.utils.misc"
+    sys.modules["anakin.utils.misc"].RandomState = ref_cls
+    rs = pickle.loads(path.read_bytes())                    # what the reference's load_random_state does
+    assert type(rs) is ref_cls and rs.numpy_rng_state[0] == "MT19937"
+    ref_path = tmp_path / "ref_random_state.pkl"
+    ref_path.write_bytes(pickle.dumps(ref_cls(*rs)))       # what the reference's save_states writes
+    for name in ("anakin", "anakin.utils", "anakin.utils.misc"):
+        monkeypatch.delitem(sys.modules, name)
+    np.random.seed(13)
+    assert io_utils.load_random_state(str(ref_path)) and np.random.rand() == draw  # reference -> ours
+
+
 def test_checkpoint_round_trip_in_reference_layout(tmp_path):
     from artiboost_b200 import io_utils
     torch.manual_seed(0)

@@ -104,3 +104,13 @@ def test_update_method_1_matches_reference():
     np.testing.assert_allclose(w1, g["w1"], rtol=1e-6, atol=0)
     assert w1.min() >= np.float32(0.1) and w1.max() <= np.float32(10.0)
     np.testing.assert_array_equal(w1[0, 0, :5], np.float32(0.1))  # blacklisted zeros lifted by the clamp (reference quirk)
+
+
+def test_blacklist_oracle_matches_reference_function():
+    """oracle.ccv.blacklist_map vs tests/golden/blacklist.npz, recorded by running the reference's own
+    ArtiBoostLoader._construct_blacklist_map (artiboost_loader.py:415-500; make_golden_blacklist.py)."""
+    from oracle import ccv
+    g = golden("blacklist.npz")
+    bl, th = ccv.blacklist_map(g["hand_pose"][:, :, :3], int(g["u_bins"]), int(g["theta_bins"]), g["rand2"], return_th=True)
+    np.testing.assert_array_equal(bl, g["blacklist"])
+    assert 0 < bl.sum() < bl.size and np.abs(th + 0.8).min() > 1e-4   # no cell of the fixture sits on the threshold
