@@ -176,3 +176,18 @@ def test_dexycb_style_config_21_objects_sym_corner_loss(lib_built):
     assert float(seen.sum()) == 4 * loop.n_synth and int((seen > 0).sum()) >= 2   # several of the 21 objects were drawn
     w = loop.end_epoch()
     assert tuple(w.shape) == (21, 288, 50)
+
+
+def test_training_tracks_the_reference_loop(lib_built):
+    """The training-equivalence leg of bench.py at a size a test can afford: the same stream and the same initial weights
+    through this repo's step (bf16 tensor cores, fused clip + Adam, CUDA graph) and through the reference's loop arithmetic
+    (torch.nn fp32, Criterion, clip_grad_norm_, torch.optim.Adam; train/train_artiboost.py:66-96): the per-step losses stay
+    together and both networks end at the same Mean3DEPE on a fixed set of rendered samples."""
+    import bench
+    r = bench.train_equivalence(torch.device(DEV), steps=40, batch=32, eval_samples=256)
+    assert r["loss_max_rel_diff"] < 0.08, r
+    assert r["mpcpe_rel_diff"] < 0.05 and r["mpjpe_rel_diff"] < 0.10, r
+    # 40 steps at lr 5e-5 already move both networks the same way
+    assert r["loss_last_steps"]["ours"] < r["loss_first_steps"]["ours"]
+    assert r["loss_last_steps"]["reference_loop"] < r["loss_first_steps"]["reference_loop"]
+    assert abs(r["mpcpe_before_mm"]["ours"] - r["mpcpe_before_mm"]["reference_loop"]) < 3.0
