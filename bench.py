@@ -342,6 +342,15 @@ def run_ours(args):
                 raise
             train = {"error": repr(e)}
     wall["train"] = time.perf_counter()
+    dex = None
+    if not args.no_train:
+        try:
+            dex = dexycb_sym_bench(dev, world, rank)
+        except Exception as e:
+            if world > 1:
+                raise
+            dex = {"error": repr(e)}
+        wall["dexycb_sym"] = time.perf_counter()
     equiv = None
     if world == 1 and not args.no_train:
         try:
@@ -410,6 +419,8 @@ def run_ours(args):
         line["extras"]["train_loop_configs3"] = train
     if equiv is not None:
         line["extras"]["train_equivalence_configs4"] = equiv
+    if dex is not None:
+        line["extras"]["dexycb_sym_configs5"] = dex
     if world == 1 and not args.no_network:
         try:
             line["extras"]["network_forward_configs2"] = network_forward_bench(dev)
@@ -430,6 +441,8 @@ def run_ours(args):
         for k_out, k_in in (("train_images_per_s", "images_per_s"), ("train_vs_torch_bf16", "vs_torch_bf16_autocast"),
                             ("train_vs_torch_fp32", "vs_torch_fp32")):
             line[k_out] = train.get(k_in)
+    if isinstance(dex, dict):
+        line["train_images_per_s_dexycb_sym"] = dex.get("images_per_s")
     if isinstance(equiv, dict):
         line["mpcpe_after_train_mm"] = equiv.get("mpcpe_after_train_mm")
         line["mpcpe_after_train_reference_loop_mm"] = equiv.get("mpcpe_after_train_reference_loop_mm")
@@ -785,6 +798,63 @@ def train_bench(dev, world, rank, steps=8, warmup=3, batch=128, backbone="ResNet
     loop.close()
     del loop
     import gc
+    gc.collect()
+    return out
+
+
+def dexycb_sym_bench(dev, world, rank, steps=8, warmup=3, batch=128, backbone="ResNet34"):
+    """BASELINE.json configs[4]: the DexYCB clasbased_sym loop -- 21 YCB-shaped objects in the CCV space ([21, 288, 50]),
+    CENTER_IDX 9, JointsLoss (corners off) + HandOrdLoss + SymCornerLoss with a synthetic symmetry table in the
+    extend_models_info.json format (config_eval/eval_dexycb_clasbased_sym_artiboost.yaml:39,84-91), per-GPU batch 128,
+    rendered + real-shaped mix, gradient all-reduce over ranks; images/s, weak scaling."""
+    import gc
+
+    import torch
+    import torch.distributed as dist
+
+    import artiboost_b200.models as M
+    from artiboost_b200 import assets
+    from artiboost_b200.synth import SynthPipeline
+    from artiboost_b200.train import DEFAULT_PRESET, ArtiBoostLoop, make_augmenter
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import netcfg
+    arch, preset = netcfg.arch_cfg(backbone)
+    preset = dict(preset, CENTER_IDX=9)
+    arch["DATA_PRESET"] = preset
+    torch.manual_seed(1)
+    model = M.Arch({"ARCH": arch}, M.build_arch_model_list(arch, preset_cfg=preset)).to(dev)
+    pipe = SynthPipeline(obj_names=list(assets.YCB_NAMES), device=dev, seed=21 + rank)
+    info = {str(i + 1): ({"symmetries_continuous": [{"axis": [0, 0, 1], "offset": [0, 0, 0]}]} if i % 3 == 0 else
+                         {"symmetries_discrete": [[-1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]]} if i % 3 == 1 else {}) for i in range(21)}
+    crit = {"LAMBDAS": [1.0, 0.1, 1.0],
+            "CRITERION": [{"TYPE": "JointsLoss", "LAMBDA_JOINTS_3D": 1.0, "LAMBDA_CORNERS_3D": 0.0}, {"TYPE": "HandOrdLoss"},
+                          {"TYPE": "SymCornerLoss", "LAMBDA_SYM_CORNERS_3D": 1.0, "MODEL_INFO": info, "MAX_SYM_DISC_STEP": 0.05}]}
+    gen = torch.Generator(device=dev).manual_seed(200 + rank)
+    loop = ArtiBoostLoop(model, pipe, batch_size=batch, criterion_cfg=crit, generator=gen, use_graph=True)
+    loop.augmenter = make_augmenter(pipe, cfg_preset=dict(DEFAULT_PRESET, CENTER_IDX=9), generator=gen)
+    for _ in range(4 + warmup):
+        loop.step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loop.step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    seen = int((loop.feedback.err_cnt.sum(dim=(1, 2)) > 0).sum())
+    out = {"backbone": backbone, "per_gpu_batch": batch, "ccv_space": list(pipe.sample_weight_map.shape), "objects_drawn": seen,
+           "images_per_s": world * batch / ms * 1e3, "ms_per_step": ms, "losses": "JointsLoss + HandOrdLoss + SymCornerLoss",
+           "blacklisted_cells": int(pipe.blacklist_map.sum())}
+    loop.close()
+    del loop
     gc.collect()
     return out
 
