@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src, obj = os.path.join(CSRC, s), os.path.join(OBJ_DIR, s[:-3] + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
-            cmd = [nvcc, *ARCH, *COMMON, *PER_FILE.get(s, []), "-c", src, "-o", obj]
+            cmd = [nvcc, *ARCH, *COMMON, *PER_FILE.get(s, []), *os.environ.get("AB_EXTRA_NVCC_FLAGS", "").split(), "-c", src, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)

@@ -59,6 +59,7 @@ __device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned m, int s) {
     return (unsigned)(((unsigned long long)n * m) >> s);
 }
 
+constexpr int kClasses = 32;    // work classes of the tile kernel's launch order: 0 = most work ... 30, 31 = empty tiles
 constexpr int kMaxOrder = 256;  // frames of up to 1024 x 1024 pixels get the ranked tile order (below)
 
 struct RasterParams {
@@ -95,6 +96,15 @@ struct RasterParams {
     unsigned short tile_order[kMaxOrder];  // tiles by distance from the principal point
     int* bin_count;             // [views][n_tiles]
     unsigned short* bin_list;   // [views][n_tiles][list_cap]
+    // work-ordered launch (see raster_tile_kernel): the tiles of the group filed into classes by estimated work
+    int sorted;                 // 0: launch order from the ranked tile order above
+    int class_width;            // work units (list entries) per class
+    int area_shift, area_mul;   // covered-pixel estimate = summed patch area >> area_shift, worth area_mul / 64 list entries per pixel
+    int class_cap;              // entries per class list = views * n_tiles of a full group
+    int* class_total;           // [kClasses] tiles per class, cleared before the binning kernel
+    unsigned* class_list;       // [kClasses][class_cap] bin index (view * n_tiles + tile)
+    unsigned div_nt_m;          // exact division by n_tiles
+    int div_nt_s;
     // per-view inputs (already offset to the group's first view)
     const float* hand_verts;
     const int32_t* hand_tex;
@@ -141,7 +151,7 @@ __device__ __forceinline__ int floordiv256(int v) { return v >> 8; }
 // ---- binning -------------------------------------------------------------------------------------------------
 constexpr int kMaxTiles = 4096;  // 4096 x 4096 pixels
 
-__device__ __forceinline__ void bin_append(const RasterParams& P, int* cnt, int view, int px_lo, int px_hi, int py_lo,
+__device__ __forceinline__ void bin_append(const RasterParams& P, int* cnt, int* area, int view, int px_lo, int px_hi, int py_lo,
                                            int py_hi, unsigned entry) {
     const int tx_lo = px_lo / kTile, tx_hi = px_hi / kTile, ty_lo = py_lo / kTile, ty_hi = py_hi / kTile;
     if (tx_lo != tx_hi || ty_lo != ty_hi) entry |= kMultiBit;
@@ -149,6 +159,9 @@ __device__ __forceinline__ void bin_append(const RasterParams& P, int* cnt, int 
         for (int tx = tx_lo; tx <= tx_hi; ++tx) {
             const int tile = ty * P.tiles_x + tx;
             const int slot = atomicAdd(cnt + tile, 1);  // shared memory: this CTA owns every list of the view
+            if (P.sorted)  // screen area of the patch inside the tile: with the list length, the tile's work estimate
+                atomicAdd(area + tile, (min(px_hi, tx * kTile + kTile - 1) - max(px_lo, tx * kTile) + 1) *
+                                           (min(py_hi, ty * kTile + kTile - 1) - max(py_lo, ty * kTile) + 1));
             P.bin_list[((size_t)view * P.n_tiles + tile) * P.list_cap + slot] = (unsigned short)entry;
         }
 }
@@ -171,9 +184,10 @@ __device__ __forceinline__ void bin_append(const RasterParams& P, int* cnt, int 
 __global__ void __launch_bounds__(kThreads)
 raster_bin_kernel(const __grid_constant__ RasterParams P) {
     __shared__ int cnt[kMaxTiles];
+    __shared__ int area[kMaxTiles];
     const int view = blockIdx.x;
     const int oid = P.obj_id[view];
-    for (int i = threadIdx.x; i < P.n_tiles; i += kThreads) cnt[i] = 0;
+    for (int i = threadIdx.x; i < P.n_tiles; i += kThreads) { cnt[i] = 0; area[i] = 0; }
     float M[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) M[i] = P.obj_pose[16 * (size_t)view + i];
@@ -217,7 +231,7 @@ raster_bin_kernel(const __grid_constant__ RasterParams P) {
             py_lo = max((int)vmin, 0); py_hi = min((int)vmax, P.H - 1);
             if (px_lo > px_hi || py_lo > py_hi) continue;
         }
-        bin_append(P, cnt, view, px_lo, px_hi, py_lo, py_hi, (unsigned)i);
+        bin_append(P, cnt, area, view, px_lo, px_hi, py_lo, py_hi, (unsigned)i);
     }
     const int lane = threadIdx.x & 31;
     const float* hverts = P.hand_verts + 3 * (size_t)view * P.n_hv;
@@ -249,11 +263,24 @@ raster_bin_kernel(const __grid_constant__ RasterParams P) {
             const int px_lo = max(floordiv256(mnx + 127), 0), px_hi = min(floordiv256(mxx - 128), P.W - 1);
             const int py_lo = max(floordiv256(mny + 127), 0), py_hi = min(floordiv256(mxy - 128), P.H - 1);
             if (px_lo > px_hi || py_lo > py_hi) continue;
-            bin_append(P, cnt, view, px_lo, px_hi, py_lo, py_hi, (unsigned)w | kHandBit);
+            bin_append(P, cnt, area, view, px_lo, px_hi, py_lo, py_hi, (unsigned)w | kHandBit);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < P.n_tiles; i += kThreads) P.bin_count[(size_t)view * P.n_tiles + i] = cnt[i];
+    for (int i = threadIdx.x; i < P.n_tiles; i += kThreads) {
+        const int c = cnt[i];
+        P.bin_count[(size_t)view * P.n_tiles + i] = c;
+        if (P.sorted) {
+            // File the tile under its work class (most work in class 0, empty tiles in the last class).  Work in list
+            // entries: measured on B200 (tools/trace_raster.py), a tile CTA takes ~0.25 us per entry in the patch loop and
+            // ~0.02 us per covered pixel in the shading pass; the covered pixels are estimated from the summed screen
+            // boxes of the tile's patches.
+            const int est = c + ((min(area[i] >> P.area_shift, kTilePx) * P.area_mul) >> 6);
+            const int cls = c == 0 ? kClasses - 1 : kClasses - 2 - min(kClasses - 2, (est - 1) / P.class_width);
+            const int pos = atomicAdd(P.class_total + cls, 1);
+            P.class_list[(size_t)cls * P.class_cap + pos] = (unsigned)(view * P.n_tiles + i);
+        }
+    }
 }
 
 // ---- rule: triangle ----------------------------------------------------------------------------------------
@@ -379,6 +406,13 @@ __device__ __forceinline__ PixelOut shade_pixel(const RasterParams& P, const flo
     return r;
 }
 
+#ifdef AB_RASTER_TRACE
+// Debug build only (tools/trace_raster.py): start / end time, SM, list length and covered pixels of every tile CTA.
+__device__ unsigned long long g_trace[6 * 32768];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#endif
+
 // ---- the tile kernel -----------------------------------------------------------------------------------------
 // PX = pixels per thread in the output stream: 4 when W % 4 == 0 and the output rows are 16-byte aligned, else 1.
 // BG4: backgrounds are RGBX (one aligned 32-bit load per pixel) instead of packed RGB.
@@ -391,15 +425,39 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
     __shared__ __align__(16) float Msh[12];
     __shared__ unsigned char rank_lane[kWarps][32];             // per warp: lane of the k-th box that has rows
     __shared__ __align__(16) int colmap[kTile];                 // background source column of every tile column
-    __shared__ int n_hit, next_pair;
+    __shared__ int n_hit, next_entry;
 
-    // CTAs are handed out in launch order, so the order of the work decides how the grid ends.  The tiles of a view are
-    // ranked by their distance from the principal point (ArtiBoost places the object there, yaml:13-20 CAMERA_Z_RANGE on the
-    // optical axis): the first `near_tiles` of every view come first, view by view, so that set-up bound and write bound
-    // CTAs share every SM; the outermost tiles of all views -- almost always pure background, short CTAs -- come last and
-    // fill the SMs while the last busy tiles finish.
+    // CTAs are handed out in launch order, so the order of the work decides how the grid ends.  Groups too large for the
+    // work-ordered launch fall back to a static order: the tiles of a view ranked by their distance from the principal point
+    // (ArtiBoost places the object there, yaml:13-20 CAMERA_Z_RANGE on the optical axis), the first `near_tiles` of every
+    // view first, view by view, the outermost tiles of all views -- almost always pure background -- last.
     int view, tile;
-    {
+    if (P.sorted) {
+        // Work-ordered launch.  The binning kernel filed every tile of the group under a class by its estimated work.
+        // Busy tiles are handed out most work first, so that the CTAs still running when the grid drains are the short
+        // ones (a busy tile runs 10-50x longer than an empty one; in launch order by view the long tiles of the last views
+        // were the tail of the kernel: per-CTA timeline in profiles/); the empty tiles -- pure write streams -- follow and
+        // fill the SMs while the last busy tiles finish.
+        const unsigned b = blockIdx.x, n0 = (unsigned)P.class_total[kClasses - 1], nb = gridDim.x - n0;
+        unsigned bin_id;
+        if (b >= nb) {
+            bin_id = P.class_list[(size_t)(kClasses - 1) * P.class_cap + (b - nb)];
+        } else {
+            const int l = threadIdx.x & 31;
+            const int tot = l < kClasses - 1 ? P.class_total[l] : 0;
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(kFull, incl, o);
+                if (l >= o) incl += v;
+            }
+            const int cls = __popc(__ballot_sync(kFull, incl <= (int)b));   // first class whose inclusive count exceeds b
+            const int excl = __shfl_sync(kFull, incl - tot, cls);
+            bin_id = P.class_list[(size_t)cls * P.class_cap + ((int)b - excl)];
+        }
+        view = (int)fastdiv(bin_id, P.div_nt_m, P.div_nt_s);
+        tile = (int)(bin_id - (unsigned)view * (unsigned)P.n_tiles);
+    } else {
         const unsigned b = blockIdx.x, n1 = (unsigned)P.near_tiles, total1 = (unsigned)P.n_views * n1;
         if (b < total1) {
             view = (int)fastdiv(b, P.div_n1_m, P.div_n1_s);
@@ -417,6 +475,9 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int bin = view * P.n_tiles + tile;
     const int count = P.bin_count[bin];
+#ifdef AB_RASTER_TRACE
+    unsigned long long t_start = gtime(), t_patch = 0;
+#endif
     const int32_t* sel = P.bg_sel ? P.bg_sel + 5 * (size_t)view : nullptr;
     const bool has_bg = sel && P.bgs && sel[0] >= 0;
     if (has_bg && t < kTile)  // nearest-neighbour source column of every tile column, once per CTA (exact multiply-shift division)
@@ -425,7 +486,7 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
     if (count > 0) {
         const int oid = P.obj_id[view];
         const int n_of = oid >= 0 ? P.face_off[oid + 1] - P.face_off[oid] : 0;
-        if (t == 0) { n_hit = 0; next_pair = 2 * kWarps; }
+        if (t == 0) { n_hit = 0; next_entry = kWarps; }
         if (t < 12) Msh[t] = oid >= 0 ? P.obj_pose[16 * (size_t)view + t] : 0.0f;
         ulonglong2* z2 = reinterpret_cast<ulonglong2*>(zbuf);
         for (int i = t; i < kTilePx / 2; i += kThreads) z2[i] = make_ulonglong2(kEmptyKey, kEmptyKey);
@@ -443,10 +504,10 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
         int4* my_slab = slab[wid];
         unsigned char* my_rank = rank_lane[wid];
         const unsigned lt_mask = (1u << lane) - 1u;
-        // warps claim list entries two at a time from a shared counter (the first pair by warp index); the second entry of a
-        // pair and the next pair are fetched one patch ahead.  A warp that runs out goes on to the background below instead
-        // of waiting for the others.
-        int li = 2 * wid;
+        // warps claim list entries one at a time from a shared counter (the first by warp index; claiming pairs left the
+        // warps of a CTA further apart at the barrier below); the next entry is fetched one patch ahead.  A warp that runs out
+        // goes on to the background below instead of waiting for the others.
+        int li = wid;
         unsigned entry = li < count ? list[li] : 0u;
         while (li < count) {
             const bool hand = (entry & kHandBit) != 0;
@@ -456,12 +517,10 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
             // one round of memory latency per patch is exposed instead of three
             const unsigned fw = __ldg((hand ? hp_face : op_face) + poffs);
             const int prim_local = __ldg((hand ? hp_prim : op_prim) + poffs);
-            if (li & 1) {  // second of a pair: claim the next pair (warp-uniform)
+            {
                 int nli = 0;
-                if (lane == 0) nli = atomicAdd(&next_pair, 2);
+                if (lane == 0) nli = atomicAdd(&next_entry, 1);
                 li = __shfl_sync(kFull, nli, 0);
-            } else {
-                ++li;
             }
             entry = li < count ? list[li] : 0u;
             // ---- a lane per vertex
@@ -695,8 +754,17 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
             }
         }
     }
+#ifdef AB_RASTER_TRACE
+    if (count == 0 && threadIdx.x == 0 && blockIdx.x < 32768) {
+        unsigned long long* q = g_trace + 6 * blockIdx.x;
+        q[0] = t_start; q[1] = gtime(); q[2] = smid(); q[3] = 0; q[4] = 0; q[5] = q[1];
+    }
+#endif
     if (count == 0) return;
     __syncthreads();  // every warp's fragments are in the z-buffer, every placeholder store has been issued
+#ifdef AB_RASTER_TRACE
+    t_patch = gtime();
+#endif
     // ---- collect the covered pixels of the tile ...
     for (int i = t; i < kTilePx / 2; i += kThreads) {
         const ulonglong2 k = reinterpret_cast<const ulonglong2*>(zbuf)[i];
@@ -727,6 +795,13 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
         if (P.depth) P.depth[o] = r.depth;
         if (P.seg) P.seg[o] = r.seg;
     }
+#ifdef AB_RASTER_TRACE
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x < 32768) {
+        unsigned long long* q = g_trace + 6 * blockIdx.x;
+        q[0] = t_start; q[1] = gtime(); q[2] = smid(); q[3] = count; q[4] = total; q[5] = t_patch;
+    }
+#endif
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -751,13 +826,27 @@ static int geometry_of(const ab_scene* s, const ab_camera* cam, Geometry* g) {
     return 0;
 }
 
+// The work-ordered launch keeps its class lists in the workspace; groups of more than 32767 tiles use the static order.
+static bool sorted_ok(int chunk, int n_tiles) { return (size_t)chunk * n_tiles <= 32767; }
+static size_t sorted_bytes(int chunk, int n_tiles) {
+    if (!sorted_ok(chunk, n_tiles)) return 0;
+    return 256 + align_up((size_t)kClasses * chunk * n_tiles * sizeof(unsigned), 256);
+}
+
 }  // namespace ab
+
+#ifdef AB_RASTER_TRACE
+extern "C" __attribute__((visibility("default"))) int ab_debug_raster_trace(unsigned long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, ab::g_trace, sizeof(unsigned long long) * 6 * (size_t)n);
+}
+#endif
 
 extern "C" uint64_t ab_render_workspace_bytes(const ab_scene* scene, const ab_camera* cam, int chunk) {
     ab::Geometry g;
     if (chunk <= 0 || ab::geometry_of(scene, cam, &g)) return 0;
     return ab::align_up((size_t)chunk * g.n_tiles * sizeof(int), 256) +
-           ab::align_up((size_t)chunk * g.n_tiles * g.list_cap * sizeof(unsigned short), 256);
+           ab::align_up((size_t)chunk * g.n_tiles * g.list_cap * sizeof(unsigned short), 256) +
+           ab::sorted_bytes(chunk, g.n_tiles);
 }
 
 extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int batch, int chunk,
@@ -827,6 +916,17 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
     const size_t count_bytes = align_up((size_t)chunk * g.n_tiles * sizeof(int), 256);
     P.bin_count = (int*)ws;
     P.bin_list = (unsigned short*)((char*)ws + count_bytes);
+    {
+        static const int want_sorted = getenv("AB_RASTER_SORTED") ? atoi(getenv("AB_RASTER_SORTED")) : 1;
+        const size_t list_bytes = align_up((size_t)chunk * g.n_tiles * g.list_cap * sizeof(unsigned short), 256);
+        P.sorted = sorted_ok(chunk, g.n_tiles) ? (want_sorted != 0) : 0;
+        P.class_total = (int*)((char*)ws + count_bytes + list_bytes);
+        P.class_list = (unsigned*)((char*)P.class_total + 256);
+        P.class_cap = chunk * g.n_tiles;
+        P.area_shift = 1; P.area_mul = 5;  // half the summed boxes ~ covered pixels; 5 / 64 entries per pixel (0.02 us / 0.25 us)
+        P.class_width = max(1, (g.list_cap / 2 + ((kTilePx * P.area_mul) >> 6) + kClasses - 2) / (kClasses - 1));
+        make_fastdiv((unsigned)g.n_tiles, &P.div_nt_m, &P.div_nt_s);
+    }
     // tiles by distance of their centre from the principal point; the outer `defer` of them go last
     {
         P.use_order = g.n_tiles <= kMaxOrder;
@@ -862,6 +962,7 @@ extern "C" int ab_render_batch(const ab_scene* scene, const ab_camera* cam, int 
         P.rgba = rgba ? rgba + (size_t)v0 * npx * 4 : nullptr;
         P.depth = depth ? depth + (size_t)v0 * npx : nullptr;
         P.seg = seg ? seg + (size_t)v0 * npx : nullptr;
+        if (P.sorted) AB_CUDA(cudaMemsetAsync(P.class_total, 0, kClasses * sizeof(int), st));
         {
             StageTimer tm(AB_STAGE_RASTER_BIN, st);
             raster_bin_kernel<<<n, kThreads, 0, st>>>(P);
