@@ -112,14 +112,24 @@ class FusedAdam:
 
 
 class CCVFeedback:
-    """Per-(object, view, grasp) error capture during training and the weight update of `update_method_1`
-    (val_metric.py:76-135 ValMetricMean3DEPE2 + artiboost_loader.py:292-340,503-523), kept on the device."""
+    """Per-(object, view, grasp) error capture during training and the mining strategies `update_method_1..4`
+    (val_metric.py:76-135 ValMetricMean3DEPE2 + artiboost_loader.py:240-265,292-340,503-598), kept on the device.
 
-    def __init__(self, shape, device, lower=0.1, upper=10.0):
+    method: the reference's `UPDATE_METHOD` key ("method_1" percentile, "method_2" incremental, "method_3" lower-bound
+    deactivation, "method_4" = method_1 for the first 75 % of the epochs, then method_3); lower / upper =
+    `WEIGHT_UPDATE.LOWER/UPPER`; dist_lower / dist_upper = `DIST_THRESHOLD.LOWER/UPPER` (millimetres)."""
+
+    METHODS = ("method_1", "method_2", "method_3", "method_4")
+
+    def __init__(self, shape, device, lower=0.1, upper=10.0, method="method_1", dist_lower=8.0, dist_upper=16.0, n_epochs=1):
+        if method not in self.METHODS:
+            raise KeyError(method)  # the reference's update_method_mapping lookup fails the same way
         self.shape = tuple(shape)
         self.err_sum = torch.zeros(self.shape, device=device)
         self.err_cnt = torch.zeros(self.shape, device=device)
         self.lower, self.upper = lower, upper
+        self.method, self.dist_lower, self.dist_upper, self.n_epochs = method, dist_lower, dist_upper, n_epochs
+        self.dist_lower_ratio = -1.0  # as reported by method_3 / method_4 (-1: not evaluated)
 
     @torch.no_grad()
     def feed(self, pred_corners_abs, targ_corners_abs, obj_id, persp_id, grasp_id, is_synth=None):
@@ -131,18 +141,41 @@ class CCVFeedback:
         self.err_sum.view(-1).index_add_(0, flat, err.float() * w)
         self.err_cnt.view(-1).index_add_(0, flat, w.float())
 
+    def _confidence(self, val):
+        vmax, vmin = val.max(), val.min()
+        return (vmax - val) / (vmax - vmin + 1e-8)
+
+    def _method_1(self, new, seen, val):   # artiboost_loader.py:503-523
+        new[seen] = new[seen] * (1.0 / (self._confidence(val) + 0.5))
+        return torch.clamp(new, self.lower, self.upper)  # also lifts blacklisted zeros to `lower`, like the reference
+
+    def _method_2(self, new, seen, val):   # :526-545
+        step = torch.where(self._confidence(val) > 0.5, -0.1, 0.1).to(new.dtype)
+        new[seen] = new[seen] + step
+        return torch.clamp(new, self.lower, self.upper)
+
+    def _method_3(self, new, seen, val):   # :548-569 (no clamp: deactivated cells stay at 0)
+        low, high = val < self.dist_lower, val > self.dist_upper
+        cur = new[seen]
+        new[seen] = torch.where(low, torch.zeros_like(cur), torch.where(high, torch.ones_like(cur), cur * 0.5))
+        self.dist_lower_ratio = float(low.float().mean())
+        return new
+
     @torch.no_grad()
-    def step_eval(self, weight_map: torch.Tensor) -> torch.Tensor:
-        """All-reduce the cell statistics over ranks, apply update_method_1, reset.  -> new weight map."""
+    def step_eval(self, weight_map: torch.Tensor, epoch_idx: int = 0) -> torch.Tensor:
+        """All-reduce the cell statistics over ranks, apply the configured update method, reset.  -> new weight map."""
         parallel.allreduce_cell_errors_(self.err_sum, self.err_cnt)
         seen = self.err_cnt > 0
         new = weight_map.clone()
+        self.dist_lower_ratio = -1.0
         if bool(seen.any()):
             val = self.err_sum[seen] / self.err_cnt[seen]
-            vmax, vmin = val.max(), val.min()
-            conf = (vmax - val) / (vmax - vmin + 1e-8)
-            new[seen] = new[seen] * (1.0 / (conf + 0.5))
-        new = torch.clamp(new, self.lower, self.upper)  # also lifts blacklisted zeros to `lower`, like the reference
+            method = self.method
+            if method == "method_4":   # :572-598
+                method = "method_1" if float(epoch_idx) / self.n_epochs < 0.75 else "method_3"
+            new = {"method_1": self._method_1, "method_2": self._method_2, "method_3": self._method_3}[method](new, seen, val)
+        elif self.method in ("method_1", "method_2") or (self.method == "method_4" and float(epoch_idx) / self.n_epochs < 0.75):
+            new = torch.clamp(new, self.lower, self.upper)
         self.err_sum.zero_()
         self.err_cnt.zero_()
         return new
@@ -305,7 +338,9 @@ class ArtiBoostLoop:
 
     def __init__(self, arch: nn.Module, pipe, batch_size: int = 128, synth_factor: float = 0.6, real_source=None,
                  criterion_cfg: Optional[dict] = None, lr=5e-5, grad_clip=1e-3, generator=None, use_graph: bool = False,
-                 augment: bool = True, prefetch: bool = True):
+                 augment: bool = True, prefetch: bool = True, artiboost_cfg: Optional[dict] = None):
+        """artiboost_cfg: the reference's ARTIBOOST node; read here: UPDATE_METHOD, WEIGHT_UPDATE.LOWER/UPPER,
+        DIST_THRESHOLD.LOWER/UPPER, EPOCH (artiboost_loader.py:81,240-265)."""
         self.pipe, self.batch_size = pipe, batch_size
         self.prefetch, self._prefetched, self._side = prefetch, None, None
         self.augmenter = make_augmenter(pipe, generator=generator) if augment else None
@@ -314,7 +349,12 @@ class ArtiBoostLoop:
         self.generator = generator
         self.real_source = real_source or (lambda n: real_shaped_batch(n, pipe.device, self.generator, pipe.renderer.width))
         self.train_step = TrainStep(arch, criterion_cfg, lr=lr, grad_clip=grad_clip, generator=generator, use_graph=use_graph)
-        self.feedback = CCVFeedback(pipe.sample_weight_map.shape, pipe.device)
+        ab = artiboost_cfg or {}
+        wu, dt = ab.get("WEIGHT_UPDATE", {}), ab.get("DIST_THRESHOLD", {})
+        self.feedback = CCVFeedback(pipe.sample_weight_map.shape, pipe.device, lower=wu.get("LOWER", 0.1), upper=wu.get("UPPER", 10.0),
+                                    method=ab.get("UPDATE_METHOD", "method_1"), dist_lower=dt.get("LOWER", 8.0),
+                                    dist_upper=dt.get("UPPER", 16.0), n_epochs=ab.get("EPOCH", 1))
+        self.epoch_idx = 0
 
     def make_batch(self) -> Dict[str, torch.Tensor]:
         synth = synth_to_batch(self.pipe.synthesise(self.n_synth), self.pipe, augmenter=self.augmenter)
@@ -366,5 +406,6 @@ class ArtiBoostLoop:
         self._prefetched = None  # it was drawn with the old weights
         if self._side is not None:
             torch.cuda.current_stream(self.pipe.device).wait_stream(self._side)
-        self.pipe.sample_weight_map = self.feedback.step_eval(self.pipe.sample_weight_map)
+        self.pipe.sample_weight_map = self.feedback.step_eval(self.pipe.sample_weight_map, epoch_idx=self.epoch_idx)
+        self.epoch_idx += 1
         return self.pipe.sample_weight_map

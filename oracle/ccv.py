@@ -7,7 +7,7 @@ CPU restatement of the CCV-space sampler, the view engine and the pose generator
   view_from_id        anakin/artiboost/view_engine.py:17-86
   random_scrambler    anakin/artiboost/scrambler.py:65-81
   pose_generator      anakin/artiboost/preprocessor.py:20-99 with NullRefine (refiner.py:131-147)
-  update_method_1     anakin/artiboost/artiboost_loader.py:503-523
+  update_method_1..4  anakin/artiboost/artiboost_loader.py:503-598
 
 Random draws are explicit inputs (the reference mixes np.random / torch.rand / torch.distributions across
 processes, so stream parity is impossible; SURVEY.md section 7 "RNG parity").  Pinned by tests/golden/*.npz made by
@@ -163,6 +163,37 @@ def update_method_1(weight_map, cells, values, lower=0.1, upper=10.0):
     for (o, p, g), m in zip(np.asarray(cells), mult):
         w[o, p, g] *= m
     return np.clip(w, np.float32(lower), np.float32(upper))
+
+
+def _confidence(values):
+    v = np.asarray(values, np.float64)
+    return (v.max() - v) / (v.max() - v.min() + 1e-8)
+
+
+def update_method_2(weight_map, cells, values, lower=0.1, upper=10.0):
+    """Incremental mining, artiboost_loader.py:526-545: -0.1 where the confidence exceeds 0.5, +0.1 elsewhere, clamp."""
+    w = np.array(weight_map, np.float32, copy=True)
+    for (o, p, g), dec in zip(np.asarray(cells), _confidence(values) > 0.5):
+        w[o, p, g] += np.float32(-0.1 if dec else 0.1)
+    return np.clip(w, np.float32(lower), np.float32(upper))
+
+
+def update_method_3(weight_map, cells, values, dist_lower=8.0, dist_upper=16.0):
+    """Lower-bound deactivation, artiboost_loader.py:548-569: 0 below dist_lower, 1 above dist_upper, halved between;
+    no clamp.  -> (weights, dist_lower_ratio)."""
+    w = np.array(weight_map, np.float32, copy=True)
+    v = np.asarray(values, np.float64)
+    low, high = v < dist_lower, v > dist_upper
+    for (o, p, g), lo_, hi_ in zip(np.asarray(cells), low, high):
+        w[o, p, g] = np.float32(0.0) if lo_ else (np.float32(1.0) if hi_ else w[o, p, g] * np.float32(0.5))
+    return w, low.sum() / len(low)
+
+
+def update_method_4(weight_map, cells, values, epoch_idx, n_epochs, lower=0.1, upper=10.0, dist_lower=8.0, dist_upper=16.0):
+    """artiboost_loader.py:572-598: update_method_1 for the first 75 % of the epochs (ratio -1), update_method_3 after."""
+    if float(epoch_idx) / n_epochs < 0.75:
+        return update_method_1(weight_map, cells, values, lower, upper), -1.0
+    return update_method_3(weight_map, cells, values, dist_lower, dist_upper)
 
 
 def blacklist_map(root_aa, u_bins, theta_bins, rand2=None, threshold=-0.8, return_th=False):

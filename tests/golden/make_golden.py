@@ -10,6 +10,7 @@ The fixtures pin oracle/ (tests/test_oracle_golden.py); the GPU parity tests the
                      (third-party MANO / pytorch3d underneath are oracle shims: pins the composition)
   ortho6d.npz        anakin/utils/transform.py              compute_rotation_matrix_from_ortho6d, batch_uvd2xyz
   update_method.npz  anakin/artiboost/artiboost_loader.py   update_method_1 arithmetic (:503-523)
+  update_method234.npz  same file, update_method_2 / _3 / _4 (:526-598)
   losses.npz         anakin/criterions/{criterion,jointloss,ordinal}.py  Criterion.compute_losses with pinned random draws
 """
 import os
@@ -187,6 +188,16 @@ def gen_update_method():
     res = {tuple(int(x) for x in c): float(v) for c, v in zip(cells, vals)}
     w1 = al.ArtiBoostLoader.update_method_1(w, res, 0.1, 10.0)["sample_weight_map"]
     save("update_method.npz", w0=w0.numpy(), cells=cells, vals=vals, w1=w1.numpy())
+    # update_method_2..4 (:526-598); method_4 before and after 75 % of the epochs
+    L = al.ArtiBoostLoader
+    kw = dict(dist_lower_threshold=8.0, dist_upper_threshold=16.0, n_epochs=100)
+    w2 = L.update_method_2(w0.clone(), res, 0.1, 10.0)["sample_weight_map"]
+    r3 = L.update_method_3(w0.clone(), res, 0.1, 10.0, **kw)
+    r4a = L.update_method_4(w0.clone(), res, 0.1, 10.0, epoch_idx=10, **kw)
+    r4b = L.update_method_4(w0.clone(), res, 0.1, 10.0, epoch_idx=80, **kw)
+    save("update_method234.npz", w0=w0.numpy(), cells=cells, vals=vals, w2=w2.numpy(), w3=r3["sample_weight_map"].numpy(),
+         ratio3=np.float64(r3["dist_lower_ratio"]), w4a=r4a["sample_weight_map"].numpy(), ratio4a=np.float64(r4a["dist_lower_ratio"]),
+         w4b=r4b["sample_weight_map"].numpy(), ratio4b=np.float64(r4b["dist_lower_ratio"]))
 
 
 def gen_losses():

@@ -35,6 +35,32 @@ def test_criterion_matches_reference_losses(monkeypatch):
     assert torch.isfinite(total) and all(torch.isfinite(v.grad).all() for v in p.values())
 
 
+@pytest.mark.parametrize("method,epoch,key,ratio_key", [("method_2", 0, "w2", None), ("method_3", 0, "w3", "ratio3"),
+                                                         ("method_4", 10, "w4a", "ratio4a"), ("method_4", 80, "w4b", "ratio4b")])
+def test_ccv_feedback_update_methods_2_to_4_match_reference(method, epoch, key, ratio_key):
+    """CCVFeedback's mining strategies vs the outputs of the reference's own update_method_2/3/4
+    (artiboost_loader.py:526-598; tests/golden/make_golden.py gen_update_method) and vs the oracle restatement."""
+    from artiboost_b200.train import CCVFeedback
+    from oracle import ccv
+    g = golden("update_method234.npz")
+    fb = CCVFeedback(g["w0"].shape, "cpu", method=method, dist_lower=8.0, dist_upper=16.0, n_epochs=100)
+    cells, vals = torch.from_numpy(g["cells"]), torch.from_numpy(g["vals"]).float()
+    for delta in (-1.0, 1.0):
+        pred = torch.zeros((len(vals), 8, 3))
+        pred[:, :, 0] = ((vals + delta) / 1000.0)[:, None]
+        fb.feed(pred, torch.zeros_like(pred), cells[:, 0], cells[:, 1], cells[:, 2])
+    w = fb.step_eval(torch.from_numpy(g["w0"]), epoch_idx=epoch).numpy()
+    np.testing.assert_allclose(w, g[key], rtol=2e-5, atol=1e-7)
+    if ratio_key:
+        assert abs(fb.dist_lower_ratio - float(g[ratio_key])) < 1e-6
+    ref = {"method_2": lambda: (ccv.update_method_2(g["w0"], g["cells"], g["vals"]), None),
+           "method_3": lambda: ccv.update_method_3(g["w0"], g["cells"], g["vals"]),
+           "method_4": lambda: ccv.update_method_4(g["w0"], g["cells"], g["vals"], epoch, 100)}[method]()
+    np.testing.assert_allclose(w, ref[0], rtol=2e-5, atol=1e-7)
+    with pytest.raises(KeyError):
+        CCVFeedback(g["w0"].shape, "cpu", method="method_5")
+
+
 def test_ccv_feedback_matches_oracle_update_method_1():
     from artiboost_b200.train import CCVFeedback
     from oracle import ccv

@@ -106,6 +106,22 @@ def test_update_method_1_matches_reference():
     np.testing.assert_array_equal(w1[0, 0, :5], np.float32(0.1))  # blacklisted zeros lifted by the clamp (reference quirk)
 
 
+def test_update_methods_2_to_4_match_reference():
+    """oracle.ccv.update_method_2/3/4 vs the reference's own functions (artiboost_loader.py:526-598)."""
+    g = golden("update_method234.npz")
+    np.testing.assert_allclose(ccv.update_method_2(g["w0"], g["cells"], g["vals"]), g["w2"], rtol=1e-6, atol=0)
+    w3, r3 = ccv.update_method_3(g["w0"], g["cells"], g["vals"])
+    np.testing.assert_array_equal(w3, g["w3"])
+    assert r3 == float(g["ratio3"]) and 0.0 < r3 < 1.0
+    assert (w3 == 0).sum() > 5  # deactivated cells are NOT lifted back by a clamp (reference behaviour)
+    w4a, r4a = ccv.update_method_4(g["w0"], g["cells"], g["vals"], 10, 100)
+    np.testing.assert_allclose(w4a, g["w4a"], rtol=1e-6, atol=0)
+    assert r4a == float(g["ratio4a"]) == -1.0
+    w4b, r4b = ccv.update_method_4(g["w0"], g["cells"], g["vals"], 80, 100)
+    np.testing.assert_array_equal(w4b, g["w4b"])
+    assert r4b == float(g["ratio4b"])
+
+
 def test_blacklist_oracle_matches_reference_function():
     """oracle.ccv.blacklist_map vs tests/golden/blacklist.npz, recorded by running the reference's own
     ArtiBoostLoader._construct_blacklist_map (artiboost_loader.py:415-500; make_golden_blacklist.py)."""
