@@ -53,6 +53,14 @@ class AugmentCfgStruct(C.Structure):
                [("bbox_expand_ratio", C.c_float), ("center_jit", C.c_float), ("scale_jit", C.c_float), ("K", C.c_float * 9)]
 
 
+class TailCfgStruct(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("center_idx", C.c_int32)] + \
+               [(n, C.c_float) for n in ("inp_w", "inp_h", "img_w", "img_h", "depth_range", "w_joints", "w_corners", "w_joint_ord",
+                                         "w_part_ord", "w_scene_ord", "w_sym")] + \
+               [(n, C.c_int32) for n in ("n_views_hand", "n_pairs_joint", "n_pairs_part", "n_views_scene", "n_pairs_scene", "n_sym",
+                                         "sym_ho3d")]
+
+
 class WgradMapStruct(C.Structure):
     _fields_ = [("row_div", C.c_int32), ("col_div", C.c_int32), ("col_lo_valid", C.c_int32), ("s_row_hi", C.c_int64),
                 ("s_row_lo", C.c_int64), ("s_col_hi", C.c_int64), ("s_col_lo", C.c_int64)]
@@ -72,6 +80,8 @@ EXPORTS = {
     "ab_launch_count": (C.c_uint64, []),
     "ab_profile_enable": (C.c_int, [C.c_int]),
     "ab_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
+    "ab_tail_losses_workspace_bytes": (C.c_uint64, [C.c_int]),
+    "ab_tail_losses": (C.c_int, [C.POINTER(TailCfgStruct)] + [C.c_void_p] * 30),
     "ab_mano_forward": (C.c_int, [C.POINTER(ManoModelStruct), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_ccv_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
@@ -199,7 +209,7 @@ STAGES = {0: "raster_bin_kernel", 1: "raster_tile_kernel", 2: "synth_draw_kernel
           4: "posegen_prelude_kernel", 5: "ccv_cdf+draw_kernels", 6: "view_kernel", 7: "gemm_bf16_tn_kernel",
           8: "im2col_kernel", 9: "elementwise_kernels", 10: "head_decode_kernel", 11: "gemm_bf16_tn_kernel<im2col TMA>", 12: "wgrad_bf16_kernel", 13: "train_elementwise_kernels", 14: "optimizer_kernels", 15: "bn_apply_kernel", 16: "bn_bwd_reduce_kernel",
           17: "bn_bwd_apply_kernel", 18: "bn_finalize_kernel", 19: "augment_kernels",
-          20: "chamfer_nn_kernel", 21: "linear_f32_kernel", 22: "refine_misc_kernels"}
+          20: "chamfer_nn_kernel", 21: "linear_f32_kernel", 22: "refine_misc_kernels", 23: "tail_loss_kernel"}
 
 
 def profile_enable(on: bool) -> None:

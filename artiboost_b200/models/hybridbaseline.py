@@ -23,12 +23,18 @@ class HybridBaseline(nn.Module):
         self.hybrid_head = build_head(cfg["HYBRID_HEAD"], default_args=cfg["DATA_PRESET"])
         self.box_head = build_model(cfg["BOX_HEAD"], default_args=cfg["DATA_PRESET"])
         self.init_weights(pretrained=cfg["PRETRAINED"])
+        # training-step fusion (models/fused_tail.py, installed by train.TrainStep): tail + criterion + their gradient in one launch
+        self.fused_tail = None
 
     def forward(self, inputs: Dict):
         batch_size, n_channel, height, width = inputs["image"].shape
         feats = self.backbone.forward_acts(inputs["image"])
         pose_results = self.hybrid_head.forward_act(feats["res_layer4"])
         box_rot_6d = self.box_head(feats["res_layer4_mean_bf16"])
+        if self.fused_tail is not None and torch.is_grad_enabled() and self.fused_tail.usable(inputs):
+            preds, loss, parts = self.fused_tail(pose_results["kp3d"], box_rot_6d, inputs)
+            preds["_fused_loss"], preds["_fused_parts"] = loss, parts
+            return preds
         pose_3d_abs = batch_uvd2xyz(uvd=pose_results["kp3d"], root_joint=inputs["root_joint"], intr=inputs["cam_intr"],
                                     inp_res=self.inp_res)
         joints_3d_abs = pose_3d_abs[:, 0:21, :]

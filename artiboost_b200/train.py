@@ -203,13 +203,30 @@ class TrainStep:
         self.use_graph, self.graph_warmup = use_graph, graph_warmup
         self.async_wgrad = os.environ.get("AB_ASYNC_WGRAD", "1") != "0"
         self._graph, self._static, self._out, self._eager_steps = None, None, None, 0
+        self.fused_tail = self._install_fused_tail() if os.environ.get("AB_FUSED_TAIL", "1") != "0" else None
+
+    def _install_fused_tail(self):
+        """A single HybridBaseline with a criterion made of the clasbased losses gets its tail, the criterion and their
+        backward as ONE kernel (models/fused_tail.py); anything else keeps the torch composition."""
+        from .models.fused_tail import FusedTailCriterion
+        from .models.hybridbaseline import HybridBaseline
+        heads = [m for m in self.arch.modules() if isinstance(m, HybridBaseline)]
+        if len(heads) != 1:
+            return None
+        plan = FusedTailCriterion.plan(self.criterion, heads[0].center_idx, heads[0].inp_res)
+        heads[0].fused_tail = plan
+        return plan
 
     def _eager(self, batch: Dict[str, torch.Tensor]):
         self.arch.train()
         self.flat.grad.zero_()
         preds = self.arch(batch)
         preds = preds[next(iter(preds))] if "joints_3d_abs" not in preds else preds
-        loss, parts = self.criterion.compute_losses(preds, batch)
+        if "_fused_loss" in preds:
+            preds = dict(preds)
+            loss, parts = preds.pop("_fused_loss"), preds.pop("_fused_parts")
+        else:
+            loss, parts = self.criterion.compute_losses(preds, batch)
         if self.async_wgrad:
             with train_ops.async_wgrad():   # weight gradients on a side stream, joined before the all-reduce
                 loss.backward()

@@ -69,6 +69,7 @@ AB_API uint64_t ab_launch_count(void);
 #define AB_STAGE_CHAMFER 20
 #define AB_STAGE_LINEAR_F32 21
 #define AB_STAGE_REFINE_MISC 22
+#define AB_STAGE_TAIL_LOSS 23
 #define AB_STAGE_COUNT 24
 AB_API int ab_profile_enable(int on);
 AB_API int ab_profile_collect(double* ms_per_stage, int64_t* launches_per_stage, int n_stages);
@@ -416,6 +417,39 @@ AB_API int ab_head_decode_bwd(const float* logits, const float* dkp3d, int B, in
 AB_API int ab_sumsq(const float* g, int64_t n, float* out, void* stream);
 AB_API int ab_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                         float weight_decay, float* state, const float* grad_sumsq, float max_norm, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------ clasbased tail + criterion (training)
+ * ab_tail_losses: the HybridBaseline tail (anakin/models/hybridbaseline.py:41-96: uvd -> xyz utils/transform.py:512-546,
+ *   6D -> rotation :578-598, box corners, corner projection) and the Criterion of the clasbased configs
+ *   (anakin/criterions/criterion.py:57-67 over jointloss.py:14-67, ordinal.py:75-306, symcornerloss.py:18-108), forward and
+ *   gradient in one launch.  Inputs f32: kp3d [B,22,3] (21 joints + box root, the head's soft-argmax), rot6d [B,6],
+ *   root_joint [B,3], cam_intr [B,3,3], corners_can [B,8,3], targets joints_3d [B,21,3] / corners_3d [B,8,3] (root relative),
+ *   joints_vis [B,21], corners_vis [B,8].  Random draws of the ordinal losses are inputs (drawn by the caller in the
+ *   criterion's order): vv_hand [n_views_hand,3], jp [n_pairs_joint,2] joint pairs, pp [n_pairs_part,2] part pairs (parts are
+ *   numbered joint - 1), vv_scene [n_views_scene,3], hp [n_pairs_scene,2] (joint, corner).  SymCornerLoss: sym_R
+ *   [n_obj,n_sym,3,3], sym_t [n_obj,n_sym,3] (metres), obj_idx [B] (1-based), obj_transf [B,4,4].  A weight of 0 disables a
+ *   term (its inputs may be NULL); weights are criterion lambda x the loss's own lambda.
+ *   Outputs f32: the seven tensors of the reference's forward (joints_abs [B,21,3], corners_abs [B,8,3], joints_rel,
+ *   corners_rel (minus joint center_idx), uvd2d [B,30,3], boxroot [B,1,3], rotmat [B,3,3]); parts [8] = {joints_3d_loss,
+ *   corners_3d_loss, joint_ord_loss, part_ord_loss, scene_ord_loss, sym_corners_3d_loss, 0, weighted total};
+ *   d_kp3d [B,22,3], d_rot6d [B,6] = d total / d input.  Fixed-order reductions, no atomics (bit-reproducible).
+ *   ws: ab_tail_losses_workspace_bytes(B).                                                                        */
+typedef struct {
+    int32_t batch, center_idx;
+    float inp_w, inp_h;          /* DATA_PRESET.IMAGE_SIZE: scales kp3d's u, v                            */
+    float img_w, img_h;          /* network input width / height: normalises the projected corners       */
+    float depth_range;           /* 0.4 (utils/transform.py:516)                                          */
+    float w_joints, w_corners, w_joint_ord, w_part_ord, w_scene_ord, w_sym;
+    int32_t n_views_hand, n_pairs_joint, n_pairs_part, n_views_scene, n_pairs_scene, n_sym, sym_ho3d;
+} ab_tail_cfg;
+AB_API uint64_t ab_tail_losses_workspace_bytes(int batch);
+AB_API int ab_tail_losses(const ab_tail_cfg* cfg, const float* kp3d, const float* rot6d, const float* root_joint,
+                          const float* cam_intr, const float* corners_can, const float* joints_3d, const float* corners_3d,
+                          const float* joints_vis, const float* corners_vis, const float* vv_hand, const int32_t* jp,
+                          const int32_t* pp, const float* vv_scene, const int32_t* hp, const float* sym_R, const float* sym_t,
+                          const int32_t* obj_idx, const float* obj_transf, float* joints_abs, float* corners_abs,
+                          float* joints_rel, float* corners_rel, float* uvd2d, float* boxroot, float* rotmat, float* parts,
+                          float* d_kp3d, float* d_rot6d, void* ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------- crop / augment
  * RenderedDataset.__getitem__ for a batch of rendered views (anakin/artiboost/rendered_dataset.py:127-133,155-274;

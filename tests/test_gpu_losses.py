@@ -139,3 +139,115 @@ def test_rendered_dataset_emits_sample_idx(lib_built):
     assert out["sample_idx"].tolist() == list(range(100, 106))
     out = aug(dict(views, sample_idx=torch.tensor([5, 4, 3, 2, 1, 0])))
     assert out["sample_idx"].tolist() == [5, 4, 3, 2, 1, 0]
+
+
+# ---------------------------------------------------------------------------------------- fused tail + criterion
+def _tail_inputs(B, seed, with_sym=False, n_obj=5):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    r = lambda *s: torch.rand(s, device=DEV, generator=g)  # noqa: E731
+    n = lambda *s: torch.randn(s, device=DEV, generator=g)  # noqa: E731
+    kp = r(B, 22, 3) * 0.8 + 0.1
+    r6 = n(B, 6)
+    intr = torch.tensor([[610.0, 0.3, 131.0], [0.0, 605.0, 125.0], [0.0, 0.0, 1.0]], device=DEV).repeat(B, 1, 1)
+    intr[:, 0, 0] += r(B) * 20
+    jv, cv = torch.ones((B, 21), device=DEV), torch.ones((B, 8), device=DEV)
+    jv[1, 3:7] = 0
+    cv[2, :] = 0
+    cv[3, 1] = 0
+    inputs = {"image": torch.zeros((B, 3, 256, 256), device=DEV), "root_joint": n(B, 3) * 0.05 + torch.tensor([0.0, 0.0, 0.55], device=DEV),
+              "cam_intr": intr, "corners_can": n(B, 8, 3) * 0.06, "joints_3d": n(B, 21, 3) * 0.05, "corners_3d": n(B, 8, 3) * 0.07,
+              "joints_vis": jv, "corners_vis": cv}
+    if with_sym:
+        inputs["obj_idx"] = torch.randint(1, n_obj + 1, (B,), device=DEV, generator=g)
+        T = torch.eye(4, device=DEV).repeat(B, 1, 1)
+        from oracle import rotations
+        T[:, :3, :3] = torch.from_numpy(rotations.aa_to_rotmat(np.random.RandomState(seed).normal(size=(B, 3))).astype(np.float32)).to(DEV)
+        T[:, :3, 3] = n(B, 3) * 0.05 + torch.tensor([0.0, 0.0, 0.55], device=DEV)
+        inputs["obj_transf"] = T
+    return kp, r6, inputs
+
+
+def _unfused(kp, r6, inputs, crit, center_idx):
+    """The torch composition of hybridbaseline.py:41-96 + Criterion.compute_losses (the definition the fused kernel follows)."""
+    from artiboost_b200.models.transform import batch_uvd2xyz, compute_rotation_matrix_from_ortho6d
+    p = batch_uvd2xyz(kp, inputs["root_joint"], inputs["cam_intr"], [256, 256])
+    j, br = p[:, :21], p[:, 21:22]
+    R = compute_rotation_matrix_from_ortho6d(r6)
+    c = torch.matmul(R, inputs["corners_can"].permute(0, 2, 1)).permute(0, 2, 1) + br
+    root = j[:, center_idx]
+    c2 = torch.matmul(inputs["cam_intr"], c.permute(0, 2, 1)).permute(0, 2, 1)
+    c2 = c2[:, :, :2] / c2[:, :, 2:3]
+    c2 = torch.stack((c2[:, :, 0] / 256.0, c2[:, :, 1] / 256.0, torch.zeros_like(c2[:, :, 0])), dim=2)
+    preds = {"joints_3d_abs": j, "corners_3d_abs": c, "joints_3d": j - root.unsqueeze(1), "corners_3d": c - root.unsqueeze(1),
+             "2d_uvd": torch.cat((kp[:, :21], c2, kp[:, 21:22]), dim=1), "boxroot_3d_abs": br, "box_rot_rotmat": R}
+    total, parts = crit.compute_losses(preds, inputs)
+    return preds, total, parts
+
+
+def _sym_info(n_obj):
+    return {str(i + 1): ({"symmetries_continuous": [{"axis": [0, 0, 1], "offset": [0, 0, 0]}]} if i % 3 == 0 else
+                         {"symmetries_discrete": [[-1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]]} if i % 3 == 1 else {}) for i in range(n_obj)}
+
+
+@pytest.mark.parametrize("cfg_name,B,center", [("default", 7, 0), ("default", 128, 9), ("dexycb_sym", 16, 9), ("ho3d_sym", 5, 0)])
+def test_fused_tail_criterion_matches_torch_composition(cfg_name, B, center):
+    """ab_tail_losses (tail + criterion + gradient in one launch) vs the torch composition it replaces in TrainStep: the seven
+    outputs, every loss part, the total and d total / d (kp3d, rot6d).  Both paths draw from generators with the same seed."""
+    from artiboost_b200 import criterions as C
+    from artiboost_b200.models.fused_tail import FusedTailCriterion
+    if cfg_name == "default":
+        cfg = C.DEFAULT_CRITERION_CFG
+    else:
+        cfg = {"LAMBDAS": [1.0, 0.1, 1.0],
+               "CRITERION": [{"TYPE": "JointsLoss", "LAMBDA_JOINTS_3D": 1.0, "LAMBDA_CORNERS_3D": 0.0}, {"TYPE": "HandOrdLoss"},
+                             {"TYPE": "SymCornerLoss", "LAMBDA_SYM_CORNERS_3D": 1.0, "MODEL_INFO": _sym_info(5), "MAX_SYM_DISC_STEP": 0.05,
+                              "USE_HO3D_YCB": cfg_name == "ho3d_sym"}]}
+    kp, r6, inputs = _tail_inputs(B, 3 + B, with_sym=cfg_name != "default")
+    crit_a = C.Criterion(cfg, generator=torch.Generator(device=DEV).manual_seed(11))
+    crit_b = C.Criterion(cfg, generator=torch.Generator(device=DEV).manual_seed(11))
+    kp_a, r6_a = kp.clone().requires_grad_(True), r6.clone().requires_grad_(True)
+    preds_a, total_a, parts_a = _unfused(kp_a, r6_a, inputs, crit_a, center)
+    total_a.backward()
+    plan = FusedTailCriterion.plan(crit_b, center, [256, 256])
+    assert plan is not None and plan.usable(inputs)
+    kp_b, r6_b = kp.clone().requires_grad_(True), r6.clone().requires_grad_(True)
+    preds_b, total_b, parts_b = plan(kp_b, r6_b, inputs)
+    (total_b * 1.0).backward()
+    for k, v in preds_a.items():
+        torch.testing.assert_close(preds_b[k], v.detach(), rtol=1e-5, atol=1e-6, msg=lambda m, k=k: f"{k}: {m}")
+    assert set(parts_a) == set(parts_b)
+    for k, v in parts_a.items():
+        if v is None:
+            assert parts_b[k] is None
+            continue
+        torch.testing.assert_close(parts_b[k], v.detach(), rtol=2e-5, atol=1e-8, msg=lambda m, k=k: f"{k}: {m}")
+    torch.testing.assert_close(total_b.detach(), total_a.detach(), rtol=2e-5, atol=1e-8)
+    # gradients: relative to the largest entry (single terms flip sign on |x| ~ 1e-7 ordinal margins)
+    for name, ga, gb in (("kp3d", kp_a.grad, kp_b.grad), ("rot6d", r6_a.grad, r6_b.grad)):
+        scale = float(ga.abs().max())
+        assert scale > 0
+        err = float((ga - gb).abs().max()) / scale
+        assert err < 2e-4, (name, err)
+    # both generators advanced identically: the fused path consumed the same draws
+    assert torch.equal(crit_a.loss_list[1].generator.get_state(), crit_b.loss_list[1].generator.get_state())
+
+
+def test_fused_tail_is_bit_reproducible_and_refuses_unknown_losses():
+    from artiboost_b200 import criterions as C
+    from artiboost_b200.models.fused_tail import FusedTailCriterion
+    kp, r6, inputs = _tail_inputs(32, 5)
+    outs = []
+    for _ in range(2):
+        crit = C.Criterion(C.DEFAULT_CRITERION_CFG, generator=torch.Generator(device=DEV).manual_seed(3))
+        plan = FusedTailCriterion.plan(crit, 0, [256, 256])
+        a, b = kp.clone().requires_grad_(True), r6.clone().requires_grad_(True)
+        _, total, _ = plan(a, b, inputs)
+        total.backward()
+        outs.append((total.detach().clone(), a.grad.clone(), b.grad.clone()))
+    assert all(torch.equal(x, y) for x, y in zip(*outs))  # fixed-order reductions, no atomics
+
+    class Other:
+        def __call__(self, preds, targs, **kw):
+            return torch.zeros((), device=DEV), {}
+    crit = C.Criterion({"LAMBDAS": [1.0]}, loss_list=[Other()])
+    assert FusedTailCriterion.plan(crit, 0, [256, 256]) is None

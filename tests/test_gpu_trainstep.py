@@ -117,6 +117,38 @@ def test_cuda_graph_step_matches_eager_step(lib_built):
     assert float((after - before).abs().max()) > 1e-4
 
 
+def test_fused_tail_step_matches_unfused_step(lib_built, monkeypatch):
+    """TrainStep with the tail + criterion fused into ab_tail_losses (default) vs the torch composition (AB_FUSED_TAIL=0):
+    same weights, same batch, same generator seed -> same loss and the same flat gradient (to fp32 rounding)."""
+    import copy
+
+    import artiboost_b200.models as M
+    from artiboost_b200.train import TrainStep, real_shaped_batch
+    arch, preset = netcfg.arch_cfg("ResNet34")
+    torch.manual_seed(2)
+    model_a = M.Arch({"ARCH": arch}, M.build_arch_model_list(arch, preset_cfg=preset)).to(DEV)
+    model_b = copy.deepcopy(model_a)
+    fused = TrainStep(model_a, lr=0.0, grad_clip=1.0, generator=torch.Generator(device=DEV).manual_seed(7))
+    monkeypatch.setenv("AB_FUSED_TAIL", "0")
+    plain = TrainStep(model_b, lr=0.0, grad_clip=1.0, generator=torch.Generator(device=DEV).manual_seed(7))
+    assert fused.fused_tail is not None and plain.fused_tail is None
+    batch = real_shaped_batch(16, DEV, torch.Generator(device=DEV).manual_seed(3))
+    for _ in range(2):
+        la, pa = fused(batch)
+        lb, pb = plain(batch)
+        torch.testing.assert_close(la, lb, rtol=1e-4, atol=1e-7)
+        assert set(pa) == set(pb)
+        for k in pa:
+            torch.testing.assert_close(pa[k].float(), pb[k].float(), rtol=1e-4, atol=1e-5, msg=lambda m, k=k: f"{k}: {m}")
+        ga, gb = fused.flat.grad, plain.flat.grad
+        # the two paths hand head_decode_bwd / the MLP the same fp32 gradient to ~1e-4 (test_gpu_losses.py); below them every
+        # layer stores its data gradient in bf16, so that difference re-rolls the roundings of all 36 layers: the flat
+        # gradients agree to the bf16 noise floor (~0.2 % per layer, uncorrelated), not to fp32 accuracy
+        rel = float((ga - gb).norm() / gb.norm())
+        cos = float((ga * gb).sum() / (ga.norm() * gb.norm()))
+        assert rel < 3e-2 and cos > 0.9995, (rel, cos)
+
+
 def test_artiboost_loop_synthesises_augments_trains_and_reweights(lib_built):
     """CCV draw -> pose -> rasterise -> crop / augment -> mix -> train step -> per-cell errors -> new sampling weights."""
     import artiboost_b200.models as M
