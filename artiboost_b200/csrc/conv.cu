@@ -276,6 +276,84 @@ head_decode_kernel(const float* __restrict__ logits, int ncls, int D, int H, int
     }
 }
 
+// The same decode in ONE sweep for D % 4 == 0 (the shipped head: D = 28): 16-byte loads of four consecutive depth bins,
+// running maximum with rescaling (online softmax), four loads in flight per thread.  Also leaves lse = max + log(sum exp)
+// per (b, cls), with which the backward pass needs a single sweep as well (ab_head_decode_bwd).
+struct DecodeAcc { float m, s, su, sv, sd; };
+__device__ __forceinline__ void acc_rescale(DecodeAcc& a, float m_new) {
+    if (m_new > a.m) {
+        const float sc = __expf(a.m - m_new);  // exp(-inf) = 0 on the first element
+        a.s *= sc; a.su *= sc; a.sv *= sc; a.sd *= sc;
+        a.m = m_new;
+    }
+}
+__device__ __forceinline__ void acc_merge(DecodeAcc& a, const DecodeAcc& b) {
+    const float m = fmaxf(a.m, b.m);
+    const float fa = a.m == -INFINITY ? 0.0f : __expf(a.m - m), fb = b.m == -INFINITY ? 0.0f : __expf(b.m - m);
+    a.s = a.s * fa + b.s * fb; a.su = a.su * fa + b.su * fb; a.sv = a.sv * fa + b.sv * fb; a.sd = a.sd * fa + b.sd * fb;
+    a.m = m;
+}
+
+__global__ void __launch_bounds__(kDecodeThreads)
+head_decode_online_kernel(const float* __restrict__ logits, int ncls, int D, int H, int W, float* __restrict__ kp3d,
+                          float* __restrict__ confd, float* __restrict__ lse) {
+    __shared__ DecodeAcc red[kDecodeThreads / 32];
+    const int b = blockIdx.x / ncls, cls = blockIdx.x % ncls;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int HW = H * W, D4 = D / 4, n4 = HW * D4, ldc = ncls * D;
+    const float* base = logits + (long long)b * HW * ldc + cls * D;
+    DecodeAcc a = {-INFINITY, 0.f, 0.f, 0.f, 0.f};
+    constexpr int U = 4;
+    const int dq = kDecodeThreads % D4, dp = kDecodeThreads / D4;
+    int p = tid / D4, q = tid - p * D4;
+    for (int i0 = tid; i0 < n4; i0 += U * kDecodeThreads) {
+        float4 v[U];
+        int pp[U], qq[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            pp[u] = p; qq[u] = q;
+            v[u] = i0 + u * kDecodeThreads < n4 ? __ldg(reinterpret_cast<const float4*>(base + (long long)p * ldc + 4 * q))
+                                                : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            q += dq; p += dp;
+            if (q >= D4) { q -= D4; ++p; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * kDecodeThreads >= n4) break;
+            const int h = pp[u] / W, w = pp[u] - h * W;
+            const float d0 = (float)(4 * qq[u]);
+            acc_rescale(a, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+            const float e0 = __expf(v[u].x - a.m), e1 = __expf(v[u].y - a.m), e2 = __expf(v[u].z - a.m), e3 = __expf(v[u].w - a.m);
+            const float es = (e0 + e1) + (e2 + e3);
+            a.s += es; a.su += es * (float)w; a.sv += es * (float)h;
+            a.sd += es * d0 + (e1 + 2.0f * e2 + 3.0f * e3);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        DecodeAcc bb;
+        bb.m = __shfl_xor_sync(0xffffffffu, a.m, o); bb.s = __shfl_xor_sync(0xffffffffu, a.s, o);
+        bb.su = __shfl_xor_sync(0xffffffffu, a.su, o); bb.sv = __shfl_xor_sync(0xffffffffu, a.sv, o);
+        bb.sd = __shfl_xor_sync(0xffffffffu, a.sd, o);
+        // merge in lane order so both partners compute the same bits
+        if (lane & o) { DecodeAcc t = bb; acc_merge(t, a); a = t; } else acc_merge(a, bb);
+    }
+    if (lane == 0) red[wid] = a;
+    __syncthreads();
+    if (tid == 0) {
+        DecodeAcc t = red[0];
+        for (int w = 1; w < kDecodeThreads / 32; ++w) acc_merge(t, red[w]);
+        const float inv = 1.0f / t.s;
+        const float renorm = 1.0f / (1.0f + 1e-7f);
+        float* o = kp3d + ((long long)b * ncls + cls) * 3;
+        o[0] = t.su * inv * renorm / (float)W;
+        o[1] = t.sv * inv * renorm / (float)H;
+        o[2] = t.sd * inv * renorm / (float)D;
+        confd[(long long)b * ncls + cls] = inv;
+        if (lse) lse[(long long)b * ncls + cls] = t.m + logf(t.s);
+    }
+}
+
 static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace ab
@@ -375,13 +453,17 @@ extern "C" int ab_deconv4x4s2_col2im(const float* ycol, int B, int H, int W, int
 }
 
 extern "C" int ab_head_decode(const float* logits, int B, int ncls, int D, int H, int W, float* kp3d, float* confd,
-                              void* stream) {
+                              float* lse, void* stream) {
     AB_REQUIRE(B >= 0 && ncls > 0 && D > 0 && H > 0 && W > 0, "bad shape");
     if (B == 0) return AB_OK;
     AB_REQUIRE(logits && kp3d && confd, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_HEAD_DECODE, st);
-    head_decode_kernel<<<B * ncls, kDecodeThreads, 0, st>>>(logits, ncls, D, H, W, kp3d, confd);
+    AB_REQUIRE(!lse || D % 4 == 0, "lse is produced by the vector path: D must be a multiple of 4");
+    if (D % 4 == 0 && ((uintptr_t)logits & 15) == 0 && D / 4 <= kDecodeThreads)
+        head_decode_online_kernel<<<B * ncls, kDecodeThreads, 0, st>>>(logits, ncls, D, H, W, kp3d, confd, lse);
+    else
+        head_decode_kernel<<<B * ncls, kDecodeThreads, 0, st>>>(logits, ncls, D, H, W, kp3d, confd);
     count_launch();
     return check_launch("head_decode_kernel");
 }

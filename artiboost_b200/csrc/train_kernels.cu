@@ -457,6 +457,52 @@ head_decode_bwd_kernel(const float* __restrict__ logits, const float* __restrict
     }
 }
 
+// The same gradient in ONE sweep, given what the forward pass left behind: lse = max + log(sum exp) so that
+// p_i = exp(l_i - lse), and kp3d itself, because sum_j p_j g_j = du * u + dv * v + dd * d (g is linear in the bin
+// coordinates and kp3d holds their expectations with the same 1 / W, 1 / H, 1 / D and re-normalisation factors).
+// D % 4 == 0: 16-byte loads, 8-byte stores.
+__global__ void __launch_bounds__(kDecodeThreads)
+head_decode_bwd_lse_kernel(const float* __restrict__ logits, const float* __restrict__ dkp3d, const float* __restrict__ kp3d,
+                           const float* __restrict__ lse, int ncls, int D, int H, int W, __nv_bfloat16* __restrict__ dlogits) {
+    const int b = blockIdx.x / ncls, cls = blockIdx.x % ncls;
+    const int tid = threadIdx.x;
+    const int HW = H * W, D4 = D / 4, n4 = HW * D4, ldc = ncls * D;
+    const float* base = logits + (long long)b * HW * ldc + cls * D;
+    __nv_bfloat16* obase = dlogits + (long long)b * HW * ldc + cls * D;
+    const float renorm = 1.0f / (1.0f + 1e-7f);
+    const float* dk = dkp3d + ((long long)b * ncls + cls) * 3;
+    const float* kp = kp3d + ((long long)b * ncls + cls) * 3;
+    const float gu = dk[0] * renorm / (float)W, gv = dk[1] * renorm / (float)H, gd = dk[2] * renorm / (float)D;
+    const float gbar = dk[0] * kp[0] + dk[1] * kp[1] + dk[2] * kp[2];
+    const float L = lse[(long long)b * ncls + cls];
+    constexpr int U = 4;
+    const int dq = kDecodeThreads % D4, dp = kDecodeThreads / D4;
+    int p = tid / D4, q = tid - p * D4;
+    for (int i0 = tid; i0 < n4; i0 += U * kDecodeThreads) {
+        float4 v[U];
+        int pp[U], qq[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            pp[u] = p; qq[u] = q;
+            if (i0 + u * kDecodeThreads < n4) v[u] = __ldg(reinterpret_cast<const float4*>(base + (long long)p * ldc + 4 * q));
+            q += dq; p += dp;
+            if (q >= D4) { q -= D4; ++p; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * kDecodeThreads >= n4) break;
+            const int h = pp[u] / W, w = pp[u] - h * W;
+            const float g0 = gu * (float)w + gv * (float)h + gd * (float)(4 * qq[u]) - gbar;
+            const float r0 = __expf(v[u].x - L) * g0, r1 = __expf(v[u].y - L) * (g0 + gd), r2 = __expf(v[u].z - L) * (g0 + 2.0f * gd),
+                        r3 = __expf(v[u].w - L) * (g0 + 3.0f * gd);
+            __nv_bfloat162 o01 = __floats2bfloat162_rn(r0, r1), o23 = __floats2bfloat162_rn(r2, r3);
+            uint2 pk;
+            pk.x = *reinterpret_cast<unsigned*>(&o01); pk.y = *reinterpret_cast<unsigned*>(&o23);
+            *reinterpret_cast<uint2*>(obase + (long long)pp[u] * ldc + 4 * qq[u]) = pk;
+        }
+    }
+}
+
 // ---- optimiser: sum of squares of the flat gradient (for clip_grad_norm_) and the fused Adam update
 // Two passes in a fixed order (no atomics: the clip coefficient, and with it the whole step, is bit-reproducible):
 // CTA b leaves its partial in out[1 + b], sumsq_finish_kernel adds the partials up into out[0].
@@ -672,14 +718,18 @@ extern "C" int ab_deconv4x4s2_gather(const void* dy, int B, int H, int W, int C,
     AB_LAUNCH_END("deconv_gather_kernel");
 }
 
-extern "C" int ab_head_decode_bwd(const float* logits, const float* dkp3d, int B, int ncls, int D, int H, int W, void* dlogits,
-                                  void* stream) {
+extern "C" int ab_head_decode_bwd(const float* logits, const float* dkp3d, const float* kp3d, const float* lse, int B, int ncls,
+                                  int D, int H, int W, void* dlogits, void* stream) {
     AB_REQUIRE(B >= 0 && ncls > 0 && D > 0 && H > 0 && W > 0, "bad shape");
     if (B == 0) return AB_OK;
     AB_REQUIRE(logits && dkp3d && dlogits, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_HEAD_DECODE, st);
-    head_decode_bwd_kernel<<<B * ncls, kDecodeThreads, 0, st>>>(logits, dkp3d, ncls, D, H, W, (__nv_bfloat16*)dlogits);
+    AB_REQUIRE((kp3d == nullptr) == (lse == nullptr), "kp3d and lse come together (both from ab_head_decode) or not at all");
+    if (lse && D % 4 == 0 && D / 4 <= kDecodeThreads && ((uintptr_t)logits & 15) == 0 && ((uintptr_t)dlogits & 7) == 0)
+        head_decode_bwd_lse_kernel<<<B * ncls, kDecodeThreads, 0, st>>>(logits, dkp3d, kp3d, lse, ncls, D, H, W, (__nv_bfloat16*)dlogits);
+    else
+        head_decode_bwd_kernel<<<B * ncls, kDecodeThreads, 0, st>>>(logits, dkp3d, ncls, D, H, W, (__nv_bfloat16*)dlogits);
     AB_LAUNCH_END("head_decode_bwd_kernel");
 }
 

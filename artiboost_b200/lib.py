@@ -131,7 +131,7 @@ EXPORTS = {
     "ab_avgpool_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 3 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_deconv4x4s2_col2im": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                                       C.c_void_p, C.c_void_p]),
-    "ab_head_decode": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_head_decode": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_col_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_bn_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_float]
                        + [C.c_void_p] * 7),
@@ -146,7 +146,7 @@ EXPORTS = {
     "ab_avgpool_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ab_dilate2x": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
     "ab_deconv4x4s2_gather": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
-    "ab_head_decode_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    "ab_head_decode_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "ab_augment_workspace_bytes": (C.c_uint64, [C.POINTER(AugmentCfgStruct), C.c_int]),
     "ab_crop_augment": (C.c_int, [C.POINTER(AugmentCfgStruct), C.c_int] + [C.c_void_p] * 21),
     "ab_sumsq": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

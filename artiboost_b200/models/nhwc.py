@@ -234,12 +234,15 @@ def linear(x_bf16: torch.Tensor, fc: nn.Linear, relu: bool = False, out_fp32: bo
     return out[:, :n]
 
 
-def head_decode(logits_f32: torch.Tensor, B: int, ncls: int, D: int, H: int, W: int):
+def head_decode(logits_f32: torch.Tensor, B: int, ncls: int, D: int, H: int, W: int, with_lse: bool = False):
+    """-> (kp3d, confd) or, with_lse, (kp3d, confd, lse): lse [B, ncls] (None when D % 4 != 0) lets the backward pass run in
+    one sweep (ab_head_decode_bwd)."""
     dev = logits_f32.device
     kp3d = torch.empty((B, ncls, 3), dtype=torch.float32, device=dev)
     confd = torch.empty((B, ncls), dtype=torch.float32, device=dev)
+    lse = torch.empty((B, ncls), dtype=torch.float32, device=dev) if with_lse and D % 4 == 0 else None
     with torch.cuda.device(dev):
         rc = lib.load().ab_head_decode(logits_f32.data_ptr(), B, ncls, D, H, W, kp3d.data_ptr(), confd.data_ptr(),
-                                       lib.stream_ptr(dev))
+                                       None if lse is None else lse.data_ptr(), lib.stream_ptr(dev))
     lib.check(rc, "ab_head_decode")
-    return kp3d, confd
+    return (kp3d, confd, lse) if with_lse else (kp3d, confd)

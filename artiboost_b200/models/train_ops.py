@@ -424,20 +424,21 @@ class HeadDecodeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, dims):
         B, ncls, D, H, W = dims
-        kp3d, confd = nhwc.head_decode(logits, B, ncls, D, H, W)
-        ctx.save_for_backward(logits)
+        kp3d, confd, lse = nhwc.head_decode(logits, B, ncls, D, H, W, with_lse=True)
+        ctx.save_for_backward(logits, kp3d, *(() if lse is None else (lse,)))
         ctx.dims = dims
         ctx.mark_non_differentiable(confd)
         return kp3d, confd
 
     @staticmethod
     def backward(ctx, dkp3d, _dconfd):
-        (logits,) = ctx.saved_tensors
+        logits, kp3d, *rest = ctx.saved_tensors
         B, ncls, D, H, W = ctx.dims
         dl = torch.empty(logits.shape, dtype=torch.bfloat16, device=logits.device)
         dk = dkp3d.float().contiguous()
-        with torch.cuda.device(logits.device):
-            _call("ab_head_decode_bwd", logits.data_ptr(), dk.data_ptr(), B, ncls, D, H, W, dl.data_ptr(), _stream(logits.device))
+        with torch.cuda.device(logits.device):  # one sweep with the forward's log-sum-exp, three without
+            _call("ab_head_decode_bwd", logits.data_ptr(), dk.data_ptr(), kp3d.data_ptr() if rest else None,
+                  rest[0].data_ptr() if rest else None, B, ncls, D, H, W, dl.data_ptr(), _stream(logits.device))
         return dl, None
 
 

@@ -352,7 +352,9 @@ AB_API int ab_conv_wgrad_bf16_nhwc(const void* x, int B, int H, int W, int C, co
  *   (simplebaseline.py:161-170) -> out[b, 2H, 2W, Cout] = sum of the 4 contributing taps, * scale + bias, ReLU, bf16;
  *   out_raw (optional) receives the un-normalised f32 sums for training-mode batch statistics.
  * ab_head_decode: logits f32 [B, H*W, ncls*D] (channel = cls*D + d) -> kp3d f32 [B,ncls,3] = (u,v,d) in [0,1),
- *   confd f32 [B,ncls]: IntegralDeconvHead.forward after the final conv (simplebaseline.py:182-190).            */
+ *   confd f32 [B,ncls]: IntegralDeconvHead.forward after the final conv (simplebaseline.py:182-190).  One sweep over the
+ *   logits when D % 4 == 0 (online softmax).  lse (optional, needs D % 4 == 0) f32 [B,ncls] = log-sum-exp per class, what
+ *   ab_head_decode_bwd needs to run in one sweep too.                                                            */
 /* ab_pack_conv_filters: bf16 operand copies of an nn.Conv2d weight f32 [Cout,Cin,kh,kw] in one launch: wp [Cout,Kp]
  *   (K order (ky,kx,ci), ci padded to cin_pad, zero tail: the forward / implicit-GEMM filter matrix) and, optionally,
  *   wd [Cin, kh*kw*Cout] (taps flipped, (ky,kx,co) order: the filter matrix of the data gradient).               */
@@ -365,7 +367,7 @@ AB_API int ab_maxpool3x3s2_nhwc(const void* in, int B, int H, int W, int C, void
 AB_API int ab_avgpool_nhwc(const void* in, int B, int HW, int C, float* out_f32, void* out_bf16, void* stream);
 AB_API int ab_deconv4x4s2_col2im(const float* ycol, int B, int H, int W, int Cout, const float* scale, const float* bias,
                                  int relu, void* out_bf16, float* out_raw, void* stream);
-AB_API int ab_head_decode(const float* logits, int B, int ncls, int D, int H, int W, float* kp3d, float* confd,
+AB_API int ab_head_decode(const float* logits, int B, int ncls, int D, int H, int W, float* kp3d, float* confd, float* lse,
                           void* stream);
 
 /* ------------------------------------------------------------------------------------------ training-side kernels
@@ -386,7 +388,8 @@ AB_API int ab_head_decode(const float* logits, int B, int ncls, int D, int H, in
  * ab_affine_relu_bwd: dx = dy*(y>0)*scale for frozen / eval-mode BatchNorm.
  * ab_dilate2x: zero insertion, turns the data gradient of a stride-2 conv into a stride-1 conv of the dilated dy.
  * ab_deconv4x4s2_gather: dycol[b,iy,ix,(ky,kx,co)] = dy[b,2iy-1+ky,2ix-1+kx,co], the transpose of ab_deconv4x4s2_col2im.
- * ab_head_decode_bwd: gradient of ab_head_decode's kp3d w.r.t. the logits (bf16 [B*H*W, ncls*D]).
+ * ab_head_decode_bwd: gradient of ab_head_decode's kp3d w.r.t. the logits (bf16 [B*H*W, ncls*D]).  With kp3d and lse
+ *   (both as written by ab_head_decode; D % 4 == 0) it is a single sweep over the logits; with both NULL, three sweeps.
  * ab_sumsq / ab_adam_step: clip_grad_norm_(max_norm) + torch.optim.Adam on one flat fp32 parameter buffer;
  *   grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).  state f32 [3] = {step count,
  *   1 - beta1^t, 1 - beta2^t} lives on the device (zero it once) and is advanced by the call itself, so a captured
@@ -412,7 +415,8 @@ AB_API int ab_maxpool3x3s2_bwd(const void* idx, const void* dy, int B, int H, in
 AB_API int ab_avgpool_bwd(const float* dmean, int B, int HW, int C, void* dx, void* stream);
 AB_API int ab_dilate2x(const void* in, int B, int Ho, int Wo, int H, int W, int C, void* out, void* stream);
 AB_API int ab_deconv4x4s2_gather(const void* dy, int B, int H, int W, int C, void* dycol, void* stream);
-AB_API int ab_head_decode_bwd(const float* logits, const float* dkp3d, int B, int ncls, int D, int H, int W, void* dlogits,
+AB_API int ab_head_decode_bwd(const float* logits, const float* dkp3d, const float* kp3d, const float* lse, int B, int ncls, int D,
+                              int H, int W, void* dlogits,
                               void* stream);
 AB_API int ab_sumsq(const float* g, int64_t n, float* out, void* stream);
 AB_API int ab_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

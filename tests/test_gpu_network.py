@@ -169,6 +169,39 @@ def test_head_decode_matches_reference_formula_and_one_hot():
     assert abs(float(cf[0, 5]) - 1.0) < 1e-6
 
 
+@pytest.mark.parametrize("D", [28, 6])
+def test_head_decode_backward_one_sweep_and_three_sweeps_match_autograd(D):
+    """ab_head_decode_bwd with the forward's log-sum-exp (one sweep, D % 4 == 0) and without (three sweeps) vs torch autograd
+    of the reference formula (fp64); D = 6 exercises the scalar kernels on both sides."""
+    from artiboost_b200 import lib
+    from artiboost_b200.models import nhwc
+    B, ncls, H, W = 2, 22, 16, 16
+    logits_nchw = (2.0 * torch.randn((B, ncls * D, H, W), device=DEV)).double().requires_grad_(True)
+    ref_uvd, _ = reference_head_decode(logits_nchw, ncls, D, H, W)
+    dk = torch.randn((B, ncls, 3), device=DEV)
+    ref_uvd.backward(dk.double())
+    ref_dl = logits_nchw.grad.permute(0, 2, 3, 1).reshape(B * H * W, ncls * D).float()
+    lg = logits_nchw.detach().float().permute(0, 2, 3, 1).reshape(B * H * W, ncls * D).contiguous()
+    kp3d, confd, lse = nhwc.head_decode(lg, B, ncls, D, H, W, with_lse=True)
+    assert (lse is not None) == (D % 4 == 0)
+    torch.testing.assert_close(kp3d.double(), ref_uvd.detach(), rtol=1e-4, atol=1e-5)
+    L = lib.load()
+    outs = []
+    for use_lse in ([True, False] if lse is not None else [False]):
+        dl = torch.empty(lg.shape, dtype=torch.bfloat16, device=DEV)
+        lib.check(L.ab_head_decode_bwd(lg.data_ptr(), dk.data_ptr(), kp3d.data_ptr() if use_lse else None,
+                                       lse.data_ptr() if use_lse else None, B, ncls, D, H, W, dl.data_ptr(), lib.stream_ptr(lg.device)),
+                  "ab_head_decode_bwd")
+        scale = float(ref_dl.abs().max())
+        assert float((dl.float() - ref_dl).abs().max()) < 6e-3 * scale   # bf16 output
+        outs.append(dl.float())
+    if len(outs) == 2:
+        assert float((outs[0] - outs[1]).abs().max()) < 6e-3 * float(ref_dl.abs().max())
+    if lse is not None:  # lse is what it says
+        ref_lse = torch.logsumexp(logits_nchw.detach().reshape(B, ncls, -1), dim=2)
+        torch.testing.assert_close(lse.double(), ref_lse, rtol=1e-5, atol=1e-5)
+
+
 # -------------------------------------------------------------------------------------------- whole network
 def build(backbone):
     import artiboost_b200.models as M
