@@ -225,16 +225,28 @@ bn_apply_kernel(const uint4* __restrict__ raw, long long M, int C8, const float*
                 });
 }
 
-// dy' = dy * (y > 0);  partial column sums of dy' and dy' * raw (the x-hat form follows in bn_bwd_finalize_kernel)
+// dy' = dy * (y > 0);  partial column sums of dy' and dy' * raw (the x-hat form follows in bn_bwd_finalize_kernel).
+// Without a residual the forward output is y = relu(raw * scale + shift), so the mask follows from raw and the forward's
+// (scale, shift) and y need not be read at all (y == nullptr): one activation pass less.
 __global__ void __launch_bounds__(kRedThreads)
 bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ raw, int M, int C8,
-                     int relu, float* psum_dy, float* psum_dy_x) {
+                     int relu, const float* __restrict__ fwd_scale, const float* __restrict__ fwd_shift, float* psum_dy,
+                     float* psum_dy_x) {
     float* outs[2] = {psum_dy, psum_dy_x};
+    const bool from_raw = relu && y == nullptr;
+    float sc[8], sh[8];
+    int cur_g = -1;
     column_partial<2>(M, C8, outs, [&](long long r, int g, float* acc) {
         float d[8], yy[8], x[8];
         bf16x8_to_float(__ldg(dy + r * C8 + g), d);
         bf16x8_to_float(__ldg(raw + r * C8 + g), x);
-        if (relu) bf16x8_to_float(__ldg(y + r * C8 + g), yy);
+        if (from_raw) {
+            if (g != cur_g) { load8(fwd_scale + 8 * g, sc); load8(fwd_shift + 8 * g, sh); cur_g = g; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) yy[j] = fmaf(x[j], sc[j], sh[j]);
+        } else if (relu) {
+            bf16x8_to_float(__ldg(y + r * C8 + g), yy);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float dd = (relu && !(yy[j] > 0.0f)) ? 0.0f : d[j];
@@ -283,15 +295,25 @@ bn_bwd_finalize_kernel(const float* __restrict__ part0, const float* __restrict_
 
 __global__ void __launch_bounds__(kRedThreads)
 bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ raw, long long M,
-                    int C8, const float* __restrict__ coef, int relu, uint4* __restrict__ dx, uint4* __restrict__ dres) {
-    float A[8], Bc[8], K[8];
+                    int C8, const float* __restrict__ coef, int relu, const float* __restrict__ fwd_scale,
+                    const float* __restrict__ fwd_shift, uint4* __restrict__ dx, uint4* __restrict__ dres) {
+    float A[8], Bc[8], K[8], sc[8], sh[8];
     const int C = 8 * C8;
-    stream_rows(M, C8, [&](int g) { load8(coef + 8 * g, A); load8(coef + C + 8 * g, Bc); load8(coef + 2 * C + 8 * g, K); },
+    const bool from_raw = relu && y == nullptr;  // mask from raw * scale + shift (see bn_bwd_reduce_kernel)
+    stream_rows(M, C8, [&](int g) {
+                    load8(coef + 8 * g, A); load8(coef + C + 8 * g, Bc); load8(coef + 2 * C + 8 * g, K);
+                    if (from_raw) { load8(fwd_scale + 8 * g, sc); load8(fwd_shift + 8 * g, sh); }
+                },
                 [&](long long i) {
                     float d[8], yy[8], x[8], o[8];
                     bf16x8_to_float(__ldg(dy + i), d);
                     bf16x8_to_float(__ldg(raw + i), x);
-                    if (relu) bf16x8_to_float(__ldg(y + i), yy);
+                    if (from_raw) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) yy[j] = fmaf(x[j], sc[j], sh[j]);
+                    } else if (relu) {
+                        bf16x8_to_float(__ldg(y + i), yy);
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float dd = (relu && !(yy[j] > 0.0f)) ? 0.0f : d[j];
@@ -636,15 +658,16 @@ extern "C" int ab_bn_apply(const void* raw, int64_t M, int C, const float* scale
 
 extern "C" int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, int M, int C, const float* gamma,
                                 const float* mean, const float* invstd, int relu, float* dgamma, float* dbeta, int accumulate,
-                                float* coef, float* ws, void* stream) {
+                                float* coef, float* ws, const float* fwd_scale, const float* fwd_shift, void* stream) {
     AB_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "bad shape");
-    AB_REQUIRE(dy && raw && mean && invstd && coef && ws && (!relu || y), "null pointer");
+    AB_REQUIRE(dy && raw && mean && invstd && coef && ws && (!relu || y || (fwd_scale && fwd_shift)), "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_BN_BWD_REDUCE, st);
     const int parts = stat_parts(M, C / 8);
     float* p0 = ws;
     float* p1 = ws + (size_t)AB_STAT_PARTS * C;
-    bn_bwd_reduce_kernel<<<parts, kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M, C / 8, relu, p0, p1);
+    bn_bwd_reduce_kernel<<<parts, kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M, C / 8, relu,
+                                                        fwd_scale, fwd_shift, p0, p1);
     bn_bwd_finalize_kernel<<<nblk(C, 8), 1024, 0, st>>>(p0, p1, parts, C, 1.0f / (float)M, gamma, mean, invstd, dgamma, dbeta,
                                                        accumulate, coef);
     count_launch(2);
@@ -652,14 +675,14 @@ extern "C" int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, 
 }
 
 extern "C" int ab_bn_bwd_apply(const void* dy, const void* y, const void* raw, int64_t M, int C, const float* coef, int relu,
-                               void* dx, void* dres, void* stream) {
+                               void* dx, void* dres, const float* fwd_scale, const float* fwd_shift, void* stream) {
     AB_REQUIRE(M >= 0 && C > 0 && C % 8 == 0, "bad shape");
     if (M == 0) return AB_OK;
-    AB_REQUIRE(dy && raw && coef && dx && (!relu || y), "null pointer");
+    AB_REQUIRE(dy && raw && coef && dx && (!relu || y || (fwd_scale && fwd_shift)), "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_BN_BWD_APPLY, st);
     bn_bwd_apply_kernel<<<stream_grid(M, C / 8), kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M,
-                                                                       C / 8, coef, relu, (uint4*)dx, (uint4*)dres);
+                                                                       C / 8, coef, relu, fwd_scale, fwd_shift, (uint4*)dx, (uint4*)dres);
     AB_LAUNCH_END("bn_bwd_apply_kernel");
 }
 

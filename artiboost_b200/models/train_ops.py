@@ -118,7 +118,7 @@ def _conv_raw(x: Act, wp, cout, kh, kw, stride, pad, col_stats=None, scale=None,
 
 class _BNState:
     """What the backward pass needs from a training-mode BatchNorm."""
-    __slots__ = ("mean", "invstd", "scale")
+    __slots__ = ("mean", "invstd", "scale", "shift")   # scale / shift: the forward's folded affine (ab_bn_finalize)
 
 
 def _stat_ws(C, dev):
@@ -148,6 +148,7 @@ def _bn_forward_train(raw, M, C, bn, sums, residual, relu):
               _stream(dev))
     if track and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
+    st.scale, st.shift = scale, shift
     return y, st
 
 
@@ -165,11 +166,13 @@ def _norm_backward(dy, y, raw, M, C, bn, st, relu, want_res):
             if not in_place:
                 gbuf, bbuf = torch.empty(C, device=dev), torch.empty(C, device=dev)
             coef = torch.empty(3 * C, device=dev)
+            # y is None for a ReLU layer without a residual input: the mask then comes from raw and the forward's affine
+            fs, fh = (st.scale.data_ptr(), st.shift.data_ptr()) if (relu and y is None) else (None, None)
             _call("ab_bn_bwd_reduce", dy.data_ptr(), P(y), raw.data_ptr(), M, C, P(bn.weight), st.mean.data_ptr(),
                   st.invstd.data_ptr(), int(relu), gbuf.data_ptr(), bbuf.data_ptr(), int(in_place), coef.data_ptr(),
-                  _stat_ws(C, dev).data_ptr(), _stream(dev))
+                  _stat_ws(C, dev).data_ptr(), fs, fh, _stream(dev))
             _call("ab_bn_bwd_apply", dy.data_ptr(), P(y), raw.data_ptr(), M, C, coef.data_ptr(), int(relu), dx.data_ptr(), P(dres),
-                  _stream(dev))
+                  fs, fh, _stream(dev))
             if not in_place:
                 dgamma, dbeta = gbuf, bbuf
         else:
@@ -186,13 +189,26 @@ def _col_sum(mat, is_f32=False):
     return out
 
 
-def _conv_dgrad(dy: Act, conv_w, kh, kw, stride, pad, H, W, key, in_c) -> torch.Tensor:
-    """Data gradient of a convolution whose input was [B, H, W, in_c]; dy is [B, Ho, Wo, Cout].  key: the conv module."""
+class GradSink:
+    """Carries the skip-path gradient of an identity residual block from the block's last convolution (whose backward runs
+    first: a true data dependency) to its first one, where it is added inside the data-gradient GEMM's epilogue -- instead of
+    autograd summing two [M, C] tensors with a separate elementwise launch (and a clone) per block."""
+    __slots__ = ("grad",)
+
+    def __init__(self):
+        self.grad = None
+
+
+def _conv_dgrad(dy: Act, conv_w, kh, kw, stride, pad, H, W, key, in_c, add=None) -> torch.Tensor:
+    """Data gradient of a convolution whose input was [B, H, W, in_c]; dy is [B, Ho, Wo, Cout].  key: the conv module.
+    add: bf16 [B*H*W, in_c] summed into the result in the GEMM epilogue (stride 1 only)."""
     cout, cin = conv_w.shape[0], conv_w.shape[1]
     dev = dy.data.device
     _, wd = nhwc.packed_filters(key, in_c, with_dgrad=True)  # built together with the forward copy, one launch per step
+    if add is not None and stride != 1:
+        raise NotImplementedError("a skip gradient can only be folded into a stride-1 data gradient")
     if kh == 1 and kw == 1:
-        dx = ops.gemm_bf16(dy.data, wd)  # [M_out, Cin]
+        dx = ops.gemm_bf16(dy.data, wd, residual=add)  # [M_out, Cin]
         if stride == 1:
             return dx
         out = torch.empty((dy.B * H * W, cin), dtype=torch.bfloat16, device=dev)
@@ -207,7 +223,7 @@ def _conv_dgrad(dy: Act, conv_w, kh, kw, stride, pad, H, W, key, in_c) -> torch.
         g = Act(d, dy.B, H, W, cout)
     elif stride != 1:
         raise NotImplementedError("stride must be 1 or 2")
-    dx, Ho, Wo, _ = _conv_raw(g, wd, cin, kh, kw, 1, kh - 1 - pad)
+    dx, Ho, Wo, _ = _conv_raw(g, wd, cin, kh, kw, 1, kh - 1 - pad, residual=add)
     assert (Ho, Wo) == (H, W)
     return dx
 
@@ -236,14 +252,22 @@ class ConvBNActFn(torch.autograd.Function):
     """y = relu?(BN(conv(x)) (+ residual)); BN uses batch statistics when `bn_train`, running statistics otherwise."""
 
     @staticmethod
-    def forward(ctx, x_data, weight, bias, gamma, beta, residual, geom, conv, bn, relu, bn_train, out_fp32):
+    def forward(ctx, x_data, weight, bias, gamma, beta, residual, geom, conv, bn, relu, bn_train, out_fp32, res_sink=None,
+                grad_sink=None, res_data=None):
+        """res_sink: the residual is `res_data` (not an autograd input) and its gradient is left in the sink; grad_sink: the
+        sink's gradient is added to this layer's data gradient (see GradSink)."""
         B, H, W, C = geom
+        ctx.res_sink, ctx.grad_sink = res_sink, grad_sink
+        if res_sink is not None:
+            residual = res_data
         x = Act(x_data, B, H, W, C)
         kh, kw = conv.kernel_size
         stride, pad, cout = conv.stride[0], conv.padding[0], conv.out_channels
         wp, _ = nhwc.packed_filters(conv, C, with_dgrad=True)
         ctx.meta = (geom, conv, bn, relu, kh, kw, stride, pad, cout, out_fp32)
         ctx.has_res = residual is not None
+        if grad_sink is not None and not (conv.stride[0] == 1 and C == conv.in_channels):
+            raise NotImplementedError("GradSink needs a stride-1 convolution on an unpadded activation")
         empty = x_data.new_empty(0)
         if bn is not None and bn_train:
             if bias is not None:
@@ -274,24 +298,37 @@ class ConvBNActFn(torch.autograd.Function):
         Ho, Wo = ctx.out_hw
         M = B * Ho * Wo
         dy = dy.to(torch.bfloat16).contiguous()
-        draw, dgamma, dbeta, dres = _norm_backward(dy, y if relu else None, raw if raw.numel() else y, M, cout, bn, ctx.st, relu,
+        # the ReLU mask needs y only when a residual went into it (or the statistics were frozen: no raw is kept then)
+        need_y = relu and (ctx.has_res or not isinstance(ctx.st, _BNState))
+        draw, dgamma, dbeta, dres = _norm_backward(dy, y if need_y else None, raw if raw.numel() else y, M, cout, bn, ctx.st, relu,
                                                    ctx.has_res)
         dbias = _col_sum(draw) if (conv.bias is not None and ctx.needs_input_grad[2]) else None
         x = Act(x_data, B, H, W, C)
         dw = _conv_wgrad(x, xcol if xcol.numel() else None, draw, conv.weight, kh, kw, stride, pad) if ctx.needs_input_grad[1] else None
+        if ctx.res_sink is not None:   # the skip gradient travels through the sink, not through autograd
+            ctx.res_sink.grad, dres = dres, None
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = _conv_dgrad(Act(draw, B, Ho, Wo, cout), weight, kh, kw, stride, pad, H, W, conv, C)
+            add = None
+            if ctx.grad_sink is not None:
+                add, ctx.grad_sink.grad = ctx.grad_sink.grad, None
+                if add is None:
+                    raise RuntimeError("GradSink is empty: the block's last convolution must run its backward first")
+            dx = _conv_dgrad(Act(draw, B, Ho, Wo, cout), weight, kh, kw, stride, pad, H, W, conv, C, add=add)
         if not isinstance(ctx.st, _BNState):
             dgamma = dbeta = None  # frozen / eval-mode statistics carry no parameter gradient here
-        return dx, dw, dbias, dgamma, dbeta, dres, None, None, None, None, None, None
+        return dx, dw, dbias, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None
 
 
-def conv_bn_act(x: Act, conv: nn.Conv2d, bn=None, relu=False, residual: Act = None, training=False, out_fp32=False):
+def conv_bn_act(x: Act, conv: nn.Conv2d, bn=None, relu=False, residual: Act = None, training=False, out_fp32=False,
+                res_sink: GradSink = None, grad_sink: GradSink = None):
+    """res_sink / grad_sink: see GradSink (identity residual blocks: the last conv gets res_sink, the first grad_sink)."""
     bn_train = training and isinstance(bn, nn.BatchNorm2d)
+    res = None if residual is None else residual.data
     y = ConvBNActFn.apply(x.data, conv.weight, conv.bias, getattr(bn, "weight", None) if bn_train else None,
-                          getattr(bn, "bias", None) if bn_train else None, None if residual is None else residual.data,
-                          (x.B, x.H, x.W, x.C), conv, bn, relu, bn_train, out_fp32)
+                          getattr(bn, "bias", None) if bn_train else None, None if res_sink is not None else res,
+                          (x.B, x.H, x.W, x.C), conv, bn, relu, bn_train, out_fp32, res_sink, grad_sink,
+                          res.detach() if (res is not None and res_sink is not None) else None)
     kh, kw = conv.kernel_size
     Ho = (x.H + 2 * conv.padding[0] - kh) // conv.stride[0] + 1
     Wo = (x.W + 2 * conv.padding[0] - kw) // conv.stride[0] + 1
@@ -363,13 +400,14 @@ class DeconvBNReluFn(torch.autograd.Function):
         M = B * 4 * H * W
         ctx.meta = (geom, deconv, bn, cout)
         if bn_train:
-            raw32 = torch.empty((M, cout), device=dev)
+            # the un-normalised sums go out as bf16 (what ab_bn_apply normalises) and the batch statistics are taken from
+            # those values: no fp32 copy of the [M, Cout] activation is written, re-read and converted
+            raw = torch.empty((M, cout), dtype=torch.bfloat16, device=dev)
             with torch.cuda.device(dev):
-                _call("ab_deconv4x4s2_col2im", ycol.data_ptr(), B, H, W, cout, None, None, 0, None, raw32.data_ptr(), _stream(dev))
+                _call("ab_deconv4x4s2_col2im", ycol.data_ptr(), B, H, W, cout, None, None, 0, raw.data_ptr(), None, _stream(dev))
                 sums = torch.empty((2, 1, cout), device=dev)
-                _call("ab_col_stats", raw32.data_ptr(), 1, M, cout, cout, sums[0].data_ptr(), sums[1].data_ptr(),
+                _call("ab_col_stats", raw.data_ptr(), 0, M, cout, cout, sums[0].data_ptr(), sums[1].data_ptr(),
                       _stat_ws(cout, dev).data_ptr(), _stream(dev))
-            raw = raw32.to(torch.bfloat16)
             y, st = _bn_forward_train(raw, M, cout, bn, sums, None, True)
             ctx.st = st
             ctx.save_for_backward(x_data, weight, raw, y)
@@ -389,7 +427,8 @@ class DeconvBNReluFn(torch.autograd.Function):
         dev = dy.device
         M = B * 4 * H * W
         dy = dy.to(torch.bfloat16).contiguous()
-        draw, dgamma, dbeta, _ = _norm_backward(dy, y, raw if raw.numel() else y, M, cout, bn, ctx.st, True, False)
+        draw, dgamma, dbeta, _ = _norm_backward(dy, None if isinstance(ctx.st, _BNState) else y, raw if raw.numel() else y, M, cout,
+                                                bn, ctx.st, True, False)
         dycol = torch.empty((B * H * W, 16 * cout), dtype=torch.bfloat16, device=dev)
         with torch.cuda.device(dev):
             _call("ab_deconv4x4s2_gather", draw.data_ptr(), B, H, W, cout, dycol.data_ptr(), _stream(dev))

@@ -384,7 +384,9 @@ AB_API int ab_head_decode(const float* logits, int B, int ncls, int D, int H, in
  * ab_bn_bwd_reduce: dy' = dy*(y>0) when relu; dbeta = sum dy', dgamma = sum dy'*xhat, stored (accumulate = 0) or added
  *   (accumulate = 1) into dgamma / dbeta (either may be NULL), plus coef f32 [3, C] = the per-channel coefficients of
  * ab_bn_bwd_apply: dx = gamma*invstd*(dy' - dbeta/M - xhat*dgamma/M) = coef0*dy' + coef1*raw + coef2; dres (optional)
- *   receives dy' for the residual branch.
+ *   receives dy' for the residual branch.  Both backward passes: with y == NULL and the forward's folded (fwd_scale,
+ *   fwd_shift) from ab_bn_finalize the ReLU mask is raw*scale + shift > 0 (layers without a residual input), which
+ *   saves reading y.
  * ab_affine_relu_bwd: dx = dy*(y>0)*scale for frozen / eval-mode BatchNorm.
  * ab_dilate2x: zero insertion, turns the data gradient of a stride-2 conv into a stride-1 conv of the dilated dy.
  * ab_deconv4x4s2_gather: dycol[b,iy,ix,(ky,kx,co)] = dy[b,2iy-1+ky,2ix-1+kx,co], the transpose of ab_deconv4x4s2_col2im.
@@ -406,9 +408,9 @@ AB_API int ab_bn_apply(const void* raw, int64_t M, int C, const float* scale, co
                        int relu, void* y, void* stream);
 AB_API int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, int M, int C, const float* gamma,
                             const float* mean, const float* invstd, int relu, float* dgamma, float* dbeta, int accumulate,
-                            float* coef, float* ws, void* stream);
+                            float* coef, float* ws, const float* fwd_scale, const float* fwd_shift, void* stream);
 AB_API int ab_bn_bwd_apply(const void* dy, const void* y, const void* raw, int64_t M, int C, const float* coef, int relu,
-                           void* dx, void* dres, void* stream);
+                           void* dx, void* dres, const float* fwd_scale, const float* fwd_shift, void* stream);
 AB_API int ab_affine_relu_bwd(const void* dy, const void* y, int64_t M, int C, const float* scale, int relu, void* dx,
                               void* dres, void* stream);
 AB_API int ab_maxpool3x3s2_bwd(const void* idx, const void* dy, int B, int H, int W, int C, void* dx, void* stream);
