@@ -51,11 +51,6 @@ class BasicBlock(nn.Module):
 
     def forward_act(self, x: nhwc.Act) -> nhwc.Act:
         tr, ops_ = self.training, _prims()
-        if self.downsample is None and ops_ is train_ops and x.data.requires_grad:
-            # identity block under autograd: the skip gradient is folded into conv1's data-gradient GEMM (train_ops.GradSink)
-            sink = train_ops.GradSink()
-            out = ops_.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=tr, grad_sink=sink)
-            return ops_.conv_bn_act(out, self.conv2, self.bn2, relu=True, residual=x, training=tr, res_sink=sink)
         residual = x if self.downsample is None else ops_.conv_bn_act(x, self.downsample[0], self.downsample[1], training=tr)
         out = ops_.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=tr)
         return ops_.conv_bn_act(out, self.conv2, self.bn2, relu=True, residual=residual, training=tr)
@@ -78,11 +73,6 @@ class Bottleneck(nn.Module):
 
     def forward_act(self, x: nhwc.Act) -> nhwc.Act:
         tr, ops_ = self.training, _prims()
-        if self.downsample is None and ops_ is train_ops and x.data.requires_grad:
-            sink = train_ops.GradSink()
-            out = ops_.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=tr, grad_sink=sink)
-            out = ops_.conv_bn_act(out, self.conv2, self.bn2, relu=True, training=tr)
-            return ops_.conv_bn_act(out, self.conv3, self.bn3, relu=True, residual=x, training=tr, res_sink=sink)
         residual = x if self.downsample is None else ops_.conv_bn_act(x, self.downsample[0], self.downsample[1], training=tr)
         out = ops_.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=tr)
         out = ops_.conv_bn_act(out, self.conv2, self.bn2, relu=True, training=tr)
