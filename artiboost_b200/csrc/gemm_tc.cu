@@ -19,6 +19,9 @@
 //   warps 4-7 epilogue: tcgen05.ld 32x32b (one accumulator row per thread), fused math, 16-byte global stores.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include <atomic>
 
 #include "common.cuh"
 
@@ -291,6 +294,192 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 2) tmem_dealloc(tmem, BN);
 }
 
+
+// --------------------------------------------------------------------------- halo-resident 3x3 stride-1 convolution
+// The implicit GEMM above fetches the activation once per filter tap (TMA im2col): nine times through L2.  For the
+// 3x3 / stride 1 / pad 1 convolutions (every block convolution of ResNet-18/34 and their data gradients) the nine A
+// operands of a tile are ONE shared-memory window read at nine row offsets:
+//   * outputs are enumerated in the width-padded raster of an image, Wp = W + 2 columns per row (the last two of a row
+//     are dummies that are computed and dropped: 3 % at W = 64, 20 % at W = 8); a tile is 128 consecutive padded pixels;
+//   * the input rows the tile touches are loaded ONCE per 64-channel block by a tiled 4-D TMA box [64 ch, Wp, R, 1]
+//     starting at x = -1, y = y0 - 1: the zero padding of the convolution is the TMA unit's out-of-bounds fill, and the
+//     box lands as R * Wp pixel rows of 128 B (SWIZZLE_128B);
+//   * padded output pixel q of the tile needs, for tap (ky, kx), box row q + ky * Wp + kx: the A operand of a tap is the
+//     same 128-row window shifted by ky * Wp + kx rows, i.e. the same UMMA descriptor with its start address advanced by
+//     that many 128-byte rows.  tcgen05 applies the 128-byte swizzle to the absolute shared-memory address, so a start
+//     address that is not 1024-byte aligned reads the TMA-written tile correctly with the base-offset field left at zero
+//     (probed on B200 for shifts 0..79 with tools/umma_shift_test.py; setting the field breaks it).
+// L2 -> SM traffic per tile: one activation window (42 KB at W = 64) + the filters, instead of nine 16 KB tiles + the
+// filters.  Epilogue as above (scale / bias / residual / ReLU, bf16 or fp32 store, per-tile BatchNorm partial sums over
+// the real pixels); partial-sum rows are per (image, tile): ab_conv_stat_rows().
+struct HaloGeom {
+    int H, W, Wp, R, tiles_per_img, cblocks, a_stages;
+    unsigned a_bytes;   // bytes of one activation window, rounded up to 1024
+};
+
+__device__ __forceinline__ void tma_load_tile_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+constexpr int kHaloBStages = 3;
+template <int BN>
+struct HaloSmemTail {   // behind the activation windows
+    __nv_bfloat16 b[kHaloBStages][BN * kBK];
+    uint64_t a_full[2], a_empty[2], b_full[kHaloBStages], b_empty[kHaloBStages], tmem_full;
+    uint32_t tmem_base;
+    float stat[2][4][BN];
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB, int N, int C,
+                    const GemmEpilogue ep, const HaloGeom hg) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    auto& sm = *reinterpret_cast<HaloSmemTail<BN>*>(base + (size_t)hg.a_stages * hg.a_bytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int img = blockIdx.x / hg.tiles_per_img, t = blockIdx.x - img * hg.tiles_per_img, tile_n = blockIdx.y;
+    const int q_start = t * kBM, y0 = q_start / hg.Wp, q0 = q_start - y0 * hg.Wp;
+    const int CB = hg.cblocks;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.a_full[s], 1); mbar_init(&sm.a_empty[s], 1); }
+        for (int s = 0; s < kHaloBStages; ++s) { mbar_init(&sm.b_full[s], 1); mbar_init(&sm.b_empty[s], 1); }
+        mbar_init(&sm.tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(&sm.tmem_base, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int cb = 0; cb < CB; ++cb) {
+                const int as = cb % hg.a_stages;
+                mbar_wait(&sm.a_empty[as], ((cb / hg.a_stages) & 1) ^ 1);
+                mbar_expect_tx(&sm.a_full[as], (uint32_t)(hg.R * hg.Wp) * 128u);
+                tma_load_tile_4d(base + (size_t)as * hg.a_bytes, &tmX, &sm.a_full[as], cb * kBK, -1, y0 - 1, img);
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int kb = cb * 9 + tap, s = kb % kHaloBStages;
+                    mbar_wait(&sm.b_empty[s], ((kb / kHaloBStages) & 1) ^ 1);
+                    mbar_expect_tx(&sm.b_full[s], BN * kBK * 2);
+                    tma_load_2d(sm.b[s], &tmB, &sm.b_full[s], tap * C + cb * kBK, tile_n * BN);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            for (int cb = 0; cb < CB; ++cb) {
+                const int as = cb % hg.a_stages;
+                mbar_wait(&sm.a_full[as], (cb / hg.a_stages) & 1);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(base + (size_t)as * hg.a_bytes) + (uint32_t)q0 * 128u;
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int kb = cb * 9 + tap, s = kb % kHaloBStages;
+                    const int ky = tap / 3, kx = tap - 3 * ky;
+                    mbar_wait(&sm.b_full[s], (kb / kHaloBStages) & 1);
+                    tc_fence_after();
+                    const uint32_t start = a0 + (uint32_t)(ky * hg.Wp + kx) * 128u;   // the window, shifted by whole 128-byte rows
+                    const uint64_t ad = (uint64_t)((start >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+                    const uint64_t bd = umma_desc_k_sw128(sm.b[s]);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) umma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&sm.b_empty[s]);
+                }
+                umma_commit(&sm.a_empty[as]);
+            }
+            umma_commit(&sm.tmem_full);
+        }
+    } else if (warp >= 4) {
+        mbar_wait(&sm.tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int qq = q0 + q * 32 + lane, yl = qq / hg.Wp, xp = qq - yl * hg.Wp, y = y0 + yl;
+        const bool row_ok = xp < hg.W && y < hg.H;
+        const long long row = ((long long)img * hg.H + y) * hg.W + xp;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            const int col = tile_n * BN + c0;
+            if (col >= N) break;  // warp-uniform
+            uint32_t r[16];
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            if (ep.col_sum) {
+                float s1[16], s2[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { s1[j] = row_ok ? v[j] : 0.0f; s2[j] = s1[j] * s1[j]; }
+                const float t1 = warp_colsum16(s1, lane), t2 = warp_colsum16(s2, lane);
+                if (!(lane & 1)) {
+                    const int cj = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    sm.stat[0][q][cj] = t1;
+                    sm.stat[1][q][cj] = t2;
+                }
+            }
+            if (!row_ok) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int cc = col + 8 * h;
+                if (cc >= N) break;
+                float yv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float sc = ep.scale ? __ldg(ep.scale + cc + j) : 1.0f;
+                    const float bi = ep.bias ? __ldg(ep.bias + cc + j) : 0.0f;
+                    yv[j] = fmaf(v[8 * h + j], sc, bi);
+                }
+                if (ep.residual) {
+                    const uint4 rr = *reinterpret_cast<const uint4*>(ep.residual + (size_t)row * ep.ldr + cc);
+                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __bfloat1622float2(rp[j]);
+                        yv[2 * j] += f.x; yv[2 * j + 1] += f.y;
+                    }
+                }
+                if (ep.relu) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) yv[j] = fmaxf(yv[j], 0.0f);
+                }
+                if (ep.out_fp32) {
+                    float4* o = reinterpret_cast<float4*>((float*)ep.D + (size_t)row * ep.ldd + cc);
+                    o[0] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                    o[1] = make_float4(yv[4], yv[5], yv[6], yv[7]);
+                } else {
+                    uint4 pk;
+                    __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) pp[j] = __floats2bfloat162_rn(yv[2 * j], yv[2 * j + 1]);
+                    *reinterpret_cast<uint4*>((__nv_bfloat16*)ep.D + (size_t)row * ep.ldd + cc) = pk;
+                }
+            }
+        }
+        if (ep.col_sum) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int c = threadIdx.x - 128; c < BN; c += 128) {
+                const int col = tile_n * BN + c;
+                if (col < N) {
+                    ep.col_sum[(size_t)blockIdx.x * N + col] = (sm.stat[0][0][c] + sm.stat[0][1][c]) + (sm.stat[0][2][c] + sm.stat[0][3][c]);
+                    ep.col_sumsq[(size_t)blockIdx.x * N + col] = (sm.stat[1][0][c] + sm.stat[1][1][c]) + (sm.stat[1][2][c] + sm.stat[1][3][c]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, BN);
+}
+
 // --------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -400,6 +589,71 @@ int conv_bf16_implicit(const void* x, int B, int H, int W, int C, const void* w,
     return bn == 64 ? launch_gemm<64, 4, true>(ta, tb, M, Cout, K, ep, cg, st) : launch_gemm<128, 3, true>(ta, tb, M, Cout, K, ep, cg, st);
 }
 
+
+// ---- halo-resident 3x3: geometry, tensor map (tiled mode, box [64 ch, W + 2, R, 1]) and launch
+// Used where it measured faster than the im2col pipeline on B200 (tools/time_conv.py, batch 128): output tiles of 64
+// channels, i.e. the layer1 convolutions and their data gradients (C = Cout = 64 at 64 x 64: 95.6 -> 75.3 us).  With 128-wide
+// output tiles the im2col ring is already at 0.7-1.0 PFLOP/s and the window's start-up latency and dummy columns lose
+// (C = Cout = 128 at 32 x 32: 52.6 -> 74.9 us).  AB_CONV_HALO=0 turns it off, =2 forces it for every eligible geometry.
+static bool halo_eligible(int H, int W, int C, int Cout, int kh, int kw, int stride, int pad) {
+    static const int mode = getenv("AB_CONV_HALO") ? atoi(getenv("AB_CONV_HALO")) : 1;
+    if (!(mode && kh == 3 && kw == 3 && stride == 1 && pad == 1 && C % 64 == 0 && W + 2 <= 256 && W >= 2 && H >= 1)) return false;
+    return mode == 2 || Cout <= 64;
+}
+
+static HaloGeom halo_geom(int H, int W, int C) {
+    HaloGeom g;
+    g.H = H; g.W = W; g.Wp = W + 2;
+    g.tiles_per_img = cdiv(H * g.Wp, kBM);
+    g.R = cdiv(3 * g.Wp + kBM + 1, g.Wp);           // rows y0 - 1 .. : window start q0 <= Wp - 1, + 2 Wp + 2 of taps, + 128 pixels
+    g.cblocks = C / kBK;
+    g.a_stages = g.cblocks > 1 ? 2 : 1;
+    g.a_bytes = (unsigned)(((size_t)g.R * g.Wp * 128 + 1023) / 1024 * 1024);
+    return g;
+}
+
+static int make_halo_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, const HaloGeom& g) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return AB_ERR_UNSUPPORTED; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)g.Wp, (cuuint32_t)g.R, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (halo box) failed (%d)", (int)r); return AB_ERR_ARG; }
+    return AB_OK;
+}
+
+template <int BN>
+static int launch_halo(const CUtensorMap& tx, const CUtensorMap& tb, int B, int Cout, int C, const GemmEpilogue& ep,
+                       const HaloGeom& g, cudaStream_t st) {
+    const size_t smem = (size_t)g.a_stages * g.a_bytes + sizeof(HaloSmemTail<BN>) + 1024;
+    static std::atomic<size_t> smem_set[64] = {};  // per device, raised when a geometry needs more
+    int dev = 0;
+    AB_CUDA(cudaGetDevice(&dev));
+    if (smem_set[dev & 63].load(std::memory_order_relaxed) < smem) {
+        AB_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[dev & 63].store(smem, std::memory_order_relaxed);
+    }
+    dim3 grid(B * g.tiles_per_img, cdiv(Cout, BN));
+    StageTimer tm(AB_STAGE_CONV_IMPLICIT, st);
+    conv3x3_halo_kernel<BN><<<grid, kGemmThreads, smem, st>>>(tx, tb, Cout, C, ep, g);
+    count_launch();
+    return check_launch("conv3x3_halo_kernel");
+}
+
+int conv3x3_halo(const void* x, int B, int H, int W, int C, const void* w, int Cout, const GemmEpilogue& ep, cudaStream_t st) {
+    const HaloGeom g = halo_geom(H, W, C);
+    const int bn = (Cout <= 64) ? 64 : 128;
+    CUtensorMap tx, tb;
+    int rc = make_halo_map(&tx, x, B, H, W, C, g);
+    if (rc) return rc;
+    rc = make_map(&tb, w, Cout, 9 * C, 9 * C, bn);
+    if (rc) return rc;
+    return bn == 64 ? launch_halo<64>(tx, tb, B, Cout, C, ep, g, st) : launch_halo<128>(tx, tb, B, Cout, C, ep, g, st);
+}
 
 // ------------------------------------------------------------------------------------------------- weight gradient
 // D[Mo, No] += sum_p G[p, mo] * X[p, no]      (fp32 atomic accumulation, split over the pixel axis)
@@ -649,7 +903,73 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, int P, int
     return check_launch("wgrad_bf16_kernel");
 }
 
+#ifdef AB_UMMA_SHIFT_TEST
+// Debug build only (tools/umma_shift_test.py): does a K-major SWIZZLE_128B operand whose start address is `shift` rows
+// (128 B each) into a TMA-written tile read the right data, and does it need the descriptor's base-offset field?
+__global__ void __launch_bounds__(256)
+umma_shift_test_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* out, int shift,
+                       int use_base_offset, int a_rows) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(base);                       // a_rows x 64
+    __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(base + 256 * 128);           // 64 x 64
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + 256 * 128 + 64 * 128);
+    uint64_t* done = full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 1 && lane == 0) { mbar_init(full, 1); mbar_init(done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 2) tmem_alloc(tmem_slot, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (warp == 0 && lane == 0) {
+        mbar_expect_tx(full, (a_rows + 64) * 128);
+        tma_load_2d(a, &tmA, full, 0, 0);
+        tma_load_2d(b, &tmB, full, 0, 0);
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        mbar_wait(full, 0);
+        tc_fence_after();
+        const uint32_t start = smem_u32(a) + (uint32_t)shift * 128u;
+        uint64_t ad = (uint64_t)((start >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+        if (use_base_offset) ad |= (uint64_t)((start >> 7) & 7) << 49;
+        const uint64_t bd = umma_desc_k_sw128(b);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc, k != 0);
+        umma_commit(done);
+    } else if (warp >= 4) {
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const int q = warp & 3, row = q * 32 + lane;
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            for (int j = 0; j < 16; ++j) out[row * 64 + c0 + j] = __uint_as_float(r[j]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, 64);
+}
+#endif
+
 }  // namespace ab
+
+#ifdef AB_UMMA_SHIFT_TEST
+extern "C" __attribute__((visibility("default"))) int ab_debug_umma_shift(const void* A, int a_rows, const void* B, float* out,
+                                                                          int shift, int use_base_offset, void* stream) {
+    using namespace ab;
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, A, a_rows, 64, 64, a_rows);
+    if (rc) return rc;
+    rc = make_map(&tb, B, 64, 64, 64, 64);
+    if (rc) return rc;
+    const size_t smem = 256 * 128 + 64 * 128 + 64 + 1024;
+    AB_CUDA(cudaFuncSetAttribute(umma_shift_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_shift_test_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(ta, tb, out, shift, use_base_offset, a_rows);
+    return check_launch("umma_shift_test_kernel");
+}
+#endif
 
 extern "C" int ab_gemm_bf16(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
                             int out_fp32, const float* scale, const float* bias, const void* residual, int64_t ldr,
@@ -686,7 +1006,16 @@ extern "C" int ab_conv_bf16_nhwc(const void* x, int B, int H, int W, int C, cons
     ab::GemmEpilogue ep;
     ep.D = D; ep.ldd = ldd; ep.out_fp32 = out_fp32; ep.scale = scale; ep.bias = bias;
     ep.residual = (const __nv_bfloat16*)residual; ep.ldr = ldr; ep.relu = relu; ep.col_sum = col_sum; ep.col_sumsq = col_sumsq;
+    if (ab::halo_eligible(H, W, C, Cout, kh, kw, stride, pad))
+        return ab::conv3x3_halo(x, B, H, W, C, w_packed, Cout, ep, (cudaStream_t)stream);
     return ab::conv_bf16_implicit(x, B, H, W, C, w_packed, Cout, kh, kw, stride, pad, ep, (cudaStream_t)stream);
+}
+
+extern "C" int ab_conv_stat_rows(int B, int H, int W, int C, int Cout, int kh, int kw, int stride, int pad) {
+    if (B <= 0 || H <= 0 || W <= 0 || kh <= 0 || kw <= 0 || stride <= 0) return 0;
+    if (ab::halo_eligible(H, W, C, Cout, kh, kw, stride, pad)) return B * ab::halo_geom(H, W, C).tiles_per_img;
+    const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+    return ab::cdiv(B * Ho * Wo, ab::kBM);
 }
 
 extern "C" uint64_t ab_wgrad_workspace_bytes(int P, int Mo, int No) { return (uint64_t)ab::wgrad_workspace_bytes(P, Mo, No); }

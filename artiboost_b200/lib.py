@@ -116,6 +116,7 @@ EXPORTS = {
     "ab_gemm_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                C.c_void_p, C.c_void_p]),
+    "ab_conv_stat_rows": (C.c_int, [C.c_int] * 9),
     "ab_conv_bf16_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int64,
                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),

@@ -129,9 +129,10 @@ def _stat_ws(C, dev):
     return torch.empty(2 * lib.STAT_PARTS * C, device=dev)
 
 
-def _stat_partials(M, C, dev):
-    """Per-row-tile partial sums / sums of squares written by the convolution epilogue: [2, ceil(M/128), C]."""
-    return torch.empty((2, (M + 127) // 128, C), device=dev)
+def _stat_partials(M, C, dev, rows=None):
+    """Per-tile partial sums / sums of squares written by the convolution epilogue: [2, rows, C]; rows = ceil(M/128) for the
+    GEMM / im2col paths, ab_conv_stat_rows() for ab_conv_bf16_nhwc (the halo-resident 3x3 kernel tiles per image)."""
+    return torch.empty((2, (M + 127) // 128 if rows is None else rows, C), device=dev)
 
 
 def _bn_forward_train(raw, M, C, bn, sums, residual, relu):
@@ -255,7 +256,10 @@ class ConvBNActFn(torch.autograd.Function):
             if bias is not None:
                 raise NotImplementedError("conv bias followed by training-mode BatchNorm does not occur in the clasbased network")
             Ho_, Wo_ = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
-            sums = _stat_partials(B * Ho_ * Wo_, cout, x_data.device)
+            rows = None
+            if C % 64 == 0 and not (kh == 1 and kw == 1 and stride == 1):   # the ab_conv_bf16_nhwc branch of _conv_raw
+                rows = int(lib.load().ab_conv_stat_rows(B, H, W, C, cout, kh, kw, stride, pad))
+            sums = _stat_partials(B * Ho_ * Wo_, cout, x_data.device, rows)
             raw, Ho, Wo, xcol = _conv_raw(x, wp, cout, kh, kw, stride, pad, col_stats=(sums[0], sums[1]))
             y, st = _bn_forward_train(raw, raw.shape[0], cout, bn, sums, residual, relu)
             ctx.save_for_backward(x_data, weight, raw, y, xcol if xcol is not None else empty)

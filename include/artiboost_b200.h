@@ -318,6 +318,10 @@ AB_API int ab_gemm_bf16(int M, int N, int K, const void* A, int64_t lda, const v
 AB_API int ab_conv_bf16_nhwc(const void* x, int B, int H, int W, int C, const void* w_packed, int Cout, int kh, int kw,
                              int stride, int pad, void* D, int64_t ldd, int out_fp32, const float* scale, const float* bias,
                              const void* residual, int64_t ldr, int relu, float* col_sum, float* col_sumsq, void* stream);
+/* Rows of the col_sum / col_sumsq partial matrices ab_conv_bf16_nhwc writes for this geometry (one row per output tile):
+ * ceil(B*Ho*Wo / 128) for the im2col path, B * ceil(H * (W + 2) / 128) for the halo-resident 3x3 / stride 1 / pad 1
+ * path (Cout <= 64; tiles run over the width-padded raster of each image).  ab_bn_finalize takes the count as n_part.            */
+AB_API int ab_conv_stat_rows(int B, int H, int W, int C, int Cout, int kh, int kw, int stride, int pad);
 
 /* Weight gradients (the wgrad half of loss.backward() at train/train_artiboost.py:91-93, cuDNN wgrad in the
  * reference).  D(row, col) += sum_p G[p,row] * X[p,col], added into the caller's gradient buffer (which already holds

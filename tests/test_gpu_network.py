@@ -94,7 +94,11 @@ def to_act(x_nchw):
 
 
 @pytest.mark.parametrize("cin,cout,k,s,p,hw", [(3, 64, 7, 2, 3, 64), (3, 64, 7, 2, 3, 37), (40, 64, 3, 1, 1, 16), (64, 64, 3, 1, 1, 32), (64, 128, 3, 2, 1, 32),
-                                               (64, 128, 1, 2, 0, 32), (256, 64, 1, 1, 0, 16), (128, 128, 3, 1, 1, 15)])
+                                               (64, 128, 1, 2, 0, 32), (256, 64, 1, 1, 0, 16), (128, 128, 3, 1, 1, 15),
+                                               # the halo-resident 3x3 kernel (Cout <= 64): several tiles per image, ragged last
+                                               # tile, windows of 5 ... 34 input rows, two channel blocks
+                                               (64, 64, 3, 1, 1, 64), (64, 64, 3, 1, 1, 37), (128, 64, 3, 1, 1, 9), (256, 56, 3, 1, 1, 5),
+                                               (64, 64, 3, 1, 1, 2)])
 def test_conv_bn_relu_residual_matches_torch(cin, cout, k, s, p, hw):
     from artiboost_b200.models import nhwc
     torch.manual_seed(cin + cout + k)
