@@ -480,6 +480,185 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (warp == 2) tmem_dealloc(tmem, BN);
 }
 
+// Persistent form for one 64-channel block and one 64-wide output tile (C = 64, Cout <= 64: the layer1 convolutions and
+// their data gradients).  One CTA per SM walks the tiles of the whole batch: the nine filter tiles (72 KB) are loaded
+// ONCE and stay in shared memory, activation windows are double buffered (the TMA unit fetches tile i + 1 while tile i is
+// multiplied), and so are the accumulators (2 x 64 TMEM columns, one epilogue group of four warps each: the epilogue of tile
+// i runs beside the MMAs of tile i + 1).  L2 -> SM traffic per tile: the 42 KB window alone.  Measured at C = Cout = 64, 64 x 64, batch 128 (tools/time_conv.py):
+// im2col ring 95.6 us, one halo tile per CTA 75.3 us, this kernel 58.6 us (659 TFLOP/s).  Probed and neutral: three windows in
+// flight (60.6), four accumulators with four epilogue groups (57.9), one TMA box per input row (58.8), L2 prefetch of later
+// windows (59), 1024-byte aligned operand starts (59.1), shared-memory staged coalesced stores (67.5), four interleaved
+// accumulator chains per tile summed by the epilogue (61.6); without the window loads 56.9 us, without the MMAs 37.7 us.  What
+// remains is ~110 cycles per 128 x 64 x 16 tcgen05.mma against 32 nominal -- this pool's cuBLAS sustains 62 % of the nominal
+// bf16 rate (MEASURED_PEAKS.json), i.e. ~52 cycles for this shape, so the kernel stands at 47 % of the measured peak.
+constexpr int kHaloPA = 2;   // activation windows in flight (2 x 42 KB + 72 KB of filters at W = 64)
+constexpr int kHaloAcc = 2;  // accumulators (64 TMEM columns each), each drained by its own epilogue group
+struct HaloPersistSmemTail {
+    __nv_bfloat16 b[9][64 * kBK];
+    uint64_t b_full, a_full[kHaloPA], a_empty[kHaloPA], acc_full[kHaloAcc], acc_empty[kHaloAcc];
+    uint32_t tmem_base;
+    float stat[kHaloAcc][2][4][64];   // [epilogue group][sum, sum of squares][warp][column]
+};
+constexpr int kHaloPThreads = 128 + 128 * kHaloAcc;   // warps 0-3: TMA / MMA / TMEM roles; then one epilogue group of 4 warps per accumulator
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kHaloPThreads)
+conv3x3_halo_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB, int N,
+                               int n_tiles, const GemmEpilogue ep, const HaloGeom hg) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    auto& sm = *reinterpret_cast<HaloPersistSmemTail*>(base + kHaloPA * (size_t)hg.a_bytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(&sm.b_full, 1);
+        for (int s = 0; s < kHaloPA; ++s) { mbar_init(&sm.a_full[s], 1); mbar_init(&sm.a_empty[s], 1); }
+        for (int s = 0; s < kHaloAcc; ++s) { mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.acc_empty[s], 4); }   // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(&sm.tmem_base, 64 * kHaloAcc);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(&sm.b_full, 9 * 64 * kBK * 2);
+            for (int tap = 0; tap < 9; ++tap) tma_load_2d(sm.b[tap], &tmB, &sm.b_full, tap * kBK, 0);   // C = 64: K offset tap * 64
+            for (int it = 0; it < my_tiles; ++it) {
+                const int g = (int)blockIdx.x + it * (int)gridDim.x;
+                const int img = g / hg.tiles_per_img, t = g - img * hg.tiles_per_img;
+                const int y0 = (t * kBM) / hg.Wp, s = it % kHaloPA;
+                mbar_wait(&sm.a_empty[s], ((it / kHaloPA) & 1) ^ 1);
+                mbar_expect_tx(&sm.a_full[s], (uint32_t)(hg.R * hg.Wp) * 128u);
+                tma_load_tile_4d(base + (size_t)s * hg.a_bytes, &tmX, &sm.a_full[s], 0, -1, y0 - 1, img);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            mbar_wait(&sm.b_full, 0);
+            for (int it = 0; it < my_tiles; ++it) {
+                const int g = (int)blockIdx.x + it * (int)gridDim.x;
+                const int t = g % hg.tiles_per_img;
+                const int q_start = t * kBM, y0 = q_start / hg.Wp, q0 = q_start - y0 * hg.Wp, s = it % kHaloPA, ac = it % kHaloAcc;
+                mbar_wait(&sm.a_full[s], (it / kHaloPA) & 1);
+                mbar_wait(&sm.acc_empty[ac], ((it / kHaloAcc) & 1) ^ 1);   // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(base + (size_t)s * hg.a_bytes) + (uint32_t)q0 * 128u;
+                const uint32_t acc = tmem + (uint32_t)(ac * 64);
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap - 3 * ky;
+                    const uint32_t start = a0 + (uint32_t)(ky * hg.Wp + kx) * 128u;
+                    const uint64_t ad = (uint64_t)((start >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+                    const uint64_t bd = umma_desc_k_sw128(sm.b[tap]);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) umma_bf16(acc, ad + 2 * k, bd + 2 * k, idesc, (tap | k) != 0);
+                }
+                umma_commit(&sm.a_empty[s]);
+                umma_commit(&sm.acc_full[ac]);
+            }
+        }
+    } else if (warp >= 4) {
+        // epilogue group g drains accumulator g (tiles g, g + kHaloAcc, ...): a tile's TMEM loads and row-strided stores take
+        // several times its MMA time, so several tiles must be in their epilogue at once to keep the tensor pipe fed
+        const int q = warp & 3, grp = (warp - 4) >> 2;
+        for (int it = grp; it < my_tiles; it += kHaloAcc) {
+            const int g = (int)blockIdx.x + it * (int)gridDim.x;
+            const int img = g / hg.tiles_per_img, t = g - img * hg.tiles_per_img;
+            const int q_start = t * kBM, y0 = q_start / hg.Wp, q0 = q_start - y0 * hg.Wp, s = grp;
+            const int qq = q0 + q * 32 + lane, yl = qq / hg.Wp, xp = qq - yl * hg.Wp, y = y0 + yl;
+            const bool row_ok = xp < hg.W && y < hg.H;
+            const long long row = ((long long)img * hg.H + y) * hg.W + xp;
+            mbar_wait(&sm.acc_full[s], (it / kHaloAcc) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                if (c0 >= N) break;  // warp-uniform
+                uint32_t r[16];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 64 + c0), r);
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                if (ep.col_sum) {
+                    float s1[16], s2[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { s1[j] = row_ok ? v[j] : 0.0f; s2[j] = s1[j] * s1[j]; }
+                    const float t1 = warp_colsum16(s1, lane), t2 = warp_colsum16(s2, lane);
+                    if (!(lane & 1)) {
+                        const int cj = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                        sm.stat[grp][0][q][cj] = t1;
+                        sm.stat[grp][1][q][cj] = t2;
+                    }
+                }
+                if (!row_ok) continue;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int cc = c0 + 8 * h;
+                    if (cc >= N) break;
+                    float yv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float sc = ep.scale ? __ldg(ep.scale + cc + j) : 1.0f;
+                        const float bi = ep.bias ? __ldg(ep.bias + cc + j) : 0.0f;
+                        yv[j] = fmaf(v[8 * h + j], sc, bi);
+                    }
+                    if (ep.residual) {
+                        const uint4 rr = *reinterpret_cast<const uint4*>(ep.residual + (size_t)row * ep.ldr + cc);
+                        const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = __bfloat1622float2(rp[j]);
+                            yv[2 * j] += f.x; yv[2 * j + 1] += f.y;
+                        }
+                    }
+                    if (ep.relu) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) yv[j] = fmaxf(yv[j], 0.0f);
+                    }
+                    if (ep.out_fp32) {
+                        float4* o = reinterpret_cast<float4*>((float*)ep.D + (size_t)row * ep.ldd + cc);
+                        o[0] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                        o[1] = make_float4(yv[4], yv[5], yv[6], yv[7]);
+                    } else {
+                        uint4 pk;
+                        __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) pp[j] = __floats2bfloat162_rn(yv[2 * j], yv[2 * j + 1]);
+                        *reinterpret_cast<uint4*>((__nv_bfloat16*)ep.D + (size_t)row * ep.ldd + cc) = pk;
+                    }
+                }
+            }
+            // the accumulator has been read (tcgen05.wait::ld inside tmem_ld16): hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.acc_empty[s]);
+            if (ep.col_sum) {
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                for (int c = (threadIdx.x & 127); c < 64; c += 128) {
+                    if (c < N) {
+                        ep.col_sum[(size_t)g * N + c] = (sm.stat[grp][0][0][c] + sm.stat[grp][0][1][c]) + (sm.stat[grp][0][2][c] + sm.stat[grp][0][3][c]);
+                        ep.col_sumsq[(size_t)g * N + c] = (sm.stat[grp][1][0][c] + sm.stat[grp][1][1][c]) + (sm.stat[grp][1][2][c] + sm.stat[grp][1][3][c]);
+                    }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // the group's next tile rewrites the slots
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, 64 * kHaloAcc);
+}
+
 // --------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -644,14 +823,42 @@ static int launch_halo(const CUtensorMap& tx, const CUtensorMap& tb, int B, int 
     return check_launch("conv3x3_halo_kernel");
 }
 
+static int launch_halo_persistent(const CUtensorMap& tx, const CUtensorMap& tb, int B, int Cout, const GemmEpilogue& ep,
+                                  const HaloGeom& g, cudaStream_t st) {
+    const size_t smem = kHaloPA * (size_t)g.a_bytes + sizeof(HaloPersistSmemTail) + 1024;
+    static std::atomic<size_t> smem_set[64] = {};
+    static std::atomic<int> sm_count[64] = {};
+    int dev = 0;
+    AB_CUDA(cudaGetDevice(&dev));
+    if (smem_set[dev & 63].load(std::memory_order_relaxed) < smem) {
+        AB_CUDA(cudaFuncSetAttribute(conv3x3_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[dev & 63].store(smem, std::memory_order_relaxed);
+    }
+    int sms = sm_count[dev & 63].load(std::memory_order_relaxed);
+    if (sms == 0) {
+        AB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        sm_count[dev & 63].store(sms, std::memory_order_relaxed);
+    }
+    const int n_tiles = B * g.tiles_per_img;
+    StageTimer tm(AB_STAGE_CONV_IMPLICIT, st);
+    conv3x3_halo_persistent_kernel<<<min(n_tiles, sms), kHaloPThreads, smem, st>>>(tx, tb, Cout, n_tiles, ep, g);
+    count_launch();
+    return check_launch("conv3x3_halo_persistent_kernel");
+}
+
 int conv3x3_halo(const void* x, int B, int H, int W, int C, const void* w, int Cout, const GemmEpilogue& ep, cudaStream_t st) {
     const HaloGeom g = halo_geom(H, W, C);
+    static const int persist = getenv("AB_CONV_HALO_PERSISTENT") ? atoi(getenv("AB_CONV_HALO_PERSISTENT")) : 1;
+    const bool use_persistent = persist && C == kBK && Cout <= 64 &&
+                                kHaloPA * (size_t)g.a_bytes + sizeof(HaloPersistSmemTail) + 1024 <= 227 * 1024;
     const int bn = (Cout <= 64) ? 64 : 128;
     CUtensorMap tx, tb;
     int rc = make_halo_map(&tx, x, B, H, W, C, g);
     if (rc) return rc;
     rc = make_map(&tb, w, Cout, 9 * C, 9 * C, bn);
     if (rc) return rc;
+    // one channel block, one output tile, and the windows in flight + the nine filter tiles within the 227 KB of an SM
+    if (use_persistent) return launch_halo_persistent(tx, tb, B, Cout, ep, g, st);
     return bn == 64 ? launch_halo<64>(tx, tb, B, Cout, C, ep, g, st) : launch_halo<128>(tx, tb, B, Cout, C, ep, g, st);
 }
 
