@@ -179,3 +179,24 @@ def test_sym_corner_loss_matches_reference():
     crit = C.Criterion({"LAMBDAS": [1.0, 1.0], "CRITERION": [{"TYPE": "JointsLoss", "LAMBDA_JOINTS_3D": 1.0, "LAMBDA_CORNERS_3D": 0.0},
                                                             {"TYPE": "SymCornerLoss", "LAMBDA_SYM_CORNERS_3D": 1.0, "MODEL_INFO": info}]})
     assert [type(l).__name__ for l in crit.loss_list] == ["JointsLoss", "SymCornerLoss"]
+
+
+def test_fused_tail_plan_weights_and_refusals():
+    """FusedTailCriterion.plan (host logic of the fused tail + criterion kernel): effective weights = criterion lambda x the
+    loss's own lambda, draw order = criterion order, and None for criteria the kernel cannot express."""
+    from artiboost_b200 import criterions as C
+    from artiboost_b200.models.fused_tail import FusedTailCriterion
+    plan = FusedTailCriterion.plan(C.Criterion(C.DEFAULT_CRITERION_CFG), 9, [256, 256])
+    assert plan is not None and plan.order == ["JointsLoss", "HandOrdLoss", "SceneOrdLoss"] and plan.center_idx == 9
+    w = plan.weights
+    assert (w["joints"], w["corners"], w["sym"]) == (0.5 * 1.0, 0.5 * 0.2, 0.0)
+    assert w["joint_ord"] == w["part_ord"] == 0.2 and abs(w["scene_ord"] - 0.1) < 1e-12
+    assert not plan.usable({"root_joint": 0}) and plan.usable({k: 0 for k in plan.TARGET_KEYS})
+    info = {"1": {"symmetries_discrete": [[-1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]]}, "2": {}}
+    cfg = {"LAMBDAS": [1.0, 2.0], "CRITERION": [{"TYPE": "JointsLoss", "LAMBDA_JOINTS_3D": 1.0},
+                                                 {"TYPE": "SymCornerLoss", "LAMBDA_SYM_CORNERS_3D": 0.5, "MODEL_INFO": info}]}
+    plan = FusedTailCriterion.plan(C.Criterion(cfg), 0, [256, 256])
+    assert plan.weights["sym"] == 1.0 and plan.weights["corners"] == 0.0 and plan.sym_t3.shape == (2, 2, 3)
+    assert not plan.usable({k: 0 for k in plan.TARGET_KEYS})       # SymCornerLoss also needs obj_idx / obj_transf
+    twice = C.Criterion({"LAMBDAS": [1.0, 1.0]}, loss_list=[C.JointsLoss(LAMBDA_JOINTS_3D=1.0), C.JointsLoss(LAMBDA_CORNERS_3D=1.0)])
+    assert FusedTailCriterion.plan(twice, 0, [256, 256]) is None   # loss_lambdas is keyed by type: one of each at most
