@@ -77,7 +77,12 @@ class IntegralDeconvHead(nn.Module):
         if (x.H, x.W) != (self.height_res, self.width_res):
             # the reference's view_to_bcdhw would raise on this mismatch too (simplebaseline.py:120-135)
             raise RuntimeError(f"heatmap is {x.H}x{x.W} but HEATMAP_SIZE is {self.height_res}x{self.width_res}")
-        logits = ops_.conv_bn_act(x, self.final_layer, None, relu=False, out_fp32=True)  # [B*H*W, ncls*D], conv bias fused
+        fl = self.final_layer
+        if ops_ is train_ops and fl.kernel_size == (1, 1) and fl.stride == (1, 1) and fl.padding == (0, 0):
+            # one autograd node: the bf16 logit gradient goes from the decode's backward straight into the conv's
+            kp3d, confd = train_ops.conv_head_decode(x, fl, self.nclasses, self.depth_res)
+            return {"kp3d": kp3d, "kp3d_confd": confd}
+        logits = ops_.conv_bn_act(x, fl, None, relu=False, out_fp32=True)  # [B*H*W, ncls*D], conv bias fused
         kp3d, confd = ops_.head_decode(logits, x.B, self.nclasses, self.depth_res, x.H, x.W)
         return {"kp3d": kp3d, "kp3d_confd": confd}
 
