@@ -344,37 +344,64 @@ __global__ void affine_relu_bwd_kernel(const uint4* __restrict__ dy, const uint4
     if (dres) dres[i] = float_to_bf16x8(d);
 }
 
-// MaxPool2d(3, 2, 1) backward, gather form: input pixel (iy, ix) receives dy of every window (at most 4) whose recorded
+// MaxPool2d(3, 2, 1) backward, gather form: an input pixel receives dy of every window (at most 4) whose recorded
 // argmax tap (ky*3 + kx of the FIRST maximum in scan order -- torch's tie-break, written by the forward kernel) it is.
+// One thread per 2 x 2 block of input pixels (rows 2j, 2j+1; columns 2i, 2i+1) and 8 channels: the block lies inside
+// the four windows (j, i), (j, i+1), (j+1, i), (j+1, i+1) and no others, so idx / dy of each window are loaded once per
+// block (8 loads instead of 18 per four pixels) and each (window, channel) tap is compared with the 4 / 2 / 2 / 1 block
+// pixels the window covers.
 __global__ void maxpool_bwd_kernel(const uint2* __restrict__ idx, const uint4* __restrict__ dy, int B, int H, int W, int C8,
                                    int Ho, int Wo, uint4* __restrict__ dx) {
+    const int Hb = (H + 1) / 2, Wb = (W + 1) / 2;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)B * H * W * C8;
+    const long long total = (long long)B * Hb * Wb * C8;
     if (i >= total) return;
     const int g = (int)(i % C8);
     long long t = i / C8;
-    const int ix = (int)(t % W);
-    t /= W;
-    const int iy = (int)(t % H);
-    const int b = (int)(t / H);
-    float acc[8];
+    const int bi = (int)(t % Wb);
+    t /= Wb;
+    const int bj = (int)(t % Hb);
+    const int b = (int)(t / Hb);
+    float acc[4][8];   // block pixels (0,0), (0,1), (1,0), (1,1)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-    // windows oy with 2*oy - 1 <= iy <= 2*oy + 1
-    for (int oy = iy / 2; oy <= min((iy + 1) / 2, Ho - 1); ++oy)
-        for (int ox = ix / 2; ox <= min((ix + 1) / 2, Wo - 1); ++ox) {
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[p][j] = 0.0f;
+#pragma unroll
+    for (int wy = 0; wy < 2; ++wy)
+#pragma unroll
+        for (int wx = 0; wx < 2; ++wx) {
+            const int oy = bj + wy, ox = bi + wx;
+            if (oy >= Ho || ox >= Wo) continue;
             const long long o = (((long long)b * Ho + oy) * Wo + ox) * C8 + g;
             const uint2 id = __ldg(idx + o);
-            const uint32_t me = (uint32_t)((iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1)));
             float dv[8];
             bf16x8_to_float(__ldg(dy + o), dv);
+            // window (oy, ox) covers input rows 2 oy - 1 .. 2 oy + 1: block row r is its tap row ky = 2 bj + r - (2 oy - 1) = r + 1 - 2 wy
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t tap = ((j < 4 ? id.x : id.y) >> (8 * (j & 3))) & 0xffu;
-                if (tap == me) acc[j] += dv[j];
+            for (int r = 0; r < 2; ++r) {
+                const int ky = r + 1 - 2 * wy;
+                if (ky < 0) continue;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int kx = c + 1 - 2 * wx;
+                    if (kx < 0) continue;
+                    const uint32_t me = (uint32_t)(ky * 3 + kx);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t tap = ((j < 4 ? id.x : id.y) >> (8 * (j & 3))) & 0xffu;
+                        if (tap == me) acc[2 * r + c][j] += dv[j];
+                    }
+                }
             }
         }
-    dx[i] = float_to_bf16x8(acc);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int iy = 2 * bj + r, ix = 2 * bi + c;
+            if (iy < H && ix < W) dx[(((long long)b * H + iy) * W + ix) * C8 + g] = float_to_bf16x8(acc[2 * r + c]);
+        }
 }
 
 __global__ void avgpool_bwd_kernel(const float* __restrict__ dmean, int B, int HW, int C8, uint4* __restrict__ dx) {
@@ -706,7 +733,7 @@ extern "C" int ab_maxpool3x3s2_bwd(const void* idx, const void* dy, int B, int H
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_TRAIN_ELEMENTWISE, st);
-    maxpool_bwd_kernel<<<nblk((long long)B * H * W * (C / 8), 256), 256, 0, st>>>((const uint2*)idx, (const uint4*)dy, B, H, W, C / 8,
+    maxpool_bwd_kernel<<<nblk((long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8), 256), 256, 0, st>>>((const uint2*)idx, (const uint4*)dy, B, H, W, C / 8,
                                                                                   Ho, Wo, (uint4*)dx);
     AB_LAUNCH_END("maxpool_bwd_kernel");
 }
