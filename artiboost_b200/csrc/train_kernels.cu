@@ -12,6 +12,8 @@
 //   ab_adam_step + ab_sumsq (fused multi-tensor Adam with gradient-norm clipping, train_artiboost.py:94-96)
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ab {
@@ -57,16 +59,14 @@ __device__ __forceinline__ void column_partial(int M, int C8, float* const* part
 #pragma unroll
         for (int j = 0; j < 8 * NACC; ++j) red[t][j] = acc[j];
         __syncthreads();
-        if (rl == 0) {
-            for (int k = 1; k < rows_par; ++k)
-#pragma unroll
-                for (int j = 0; j < 8 * NACC; ++j) acc[j] += red[t + k * tpr][j];
-#pragma unroll
-            for (int a = 0; a < NACC; ++a) {
-                float4* o = reinterpret_cast<float4*>(part[a] + (size_t)blockIdx.x * C + 8 * g);
-                o[0] = make_float4(acc[8 * a], acc[8 * a + 1], acc[8 * a + 2], acc[8 * a + 3]);
-                o[1] = make_float4(acc[8 * a + 4], acc[8 * a + 5], acc[8 * a + 6], acc[8 * a + 7]);
-            }
+        // the rows_par row-lanes of a column are added by tpr * 8 * NACC threads in parallel (a fixed order: k ascending),
+        // consecutive threads on consecutive columns of the partial row
+        for (int i = t; i < tpr * 8 * NACC; i += kRedThreads) {
+            const int a = i / (tpr * 8), c = i - a * (tpr * 8);   // accumulator set, column within this pass
+            const int gg = c >> 3, j = a * 8 + (c & 7);
+            float sum = red[gg][j];
+            for (int k = 1; k < rows_par; ++k) sum += red[gg + k * tpr][j];
+            part[a][(size_t)blockIdx.x * C + 8 * (g - g0) + c] = sum;
         }
         __syncthreads();
     }
@@ -228,7 +228,8 @@ bn_apply_kernel(const uint4* __restrict__ raw, long long M, int C8, const float*
 // dy' = dy * (y > 0);  partial column sums of dy' and dy' * raw (the x-hat form follows in bn_bwd_finalize_kernel).
 // Without a residual the forward output is y = relu(raw * scale + shift), so the mask follows from raw and the forward's
 // (scale, shift) and y need not be read at all (y == nullptr): one activation pass less.
-__global__ void __launch_bounds__(kRedThreads)
+template <int MINB>
+__global__ void __launch_bounds__(kRedThreads, MINB)
 bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ raw, int M, int C8,
                      int relu, const float* __restrict__ fwd_scale, const float* __restrict__ fwd_shift, float* psum_dy,
                      float* psum_dy_x) {
@@ -293,7 +294,8 @@ bn_bwd_finalize_kernel(const float* __restrict__ part0, const float* __restrict_
     coef[2 * C + c] = A * (mu * is * dg - sdy) * inv_count;
 }
 
-__global__ void __launch_bounds__(kRedThreads)
+template <int MINB>
+__global__ void __launch_bounds__(kRedThreads, MINB)
 bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ raw, long long M,
                     int C8, const float* __restrict__ coef, int relu, const float* __restrict__ fwd_scale,
                     const float* __restrict__ fwd_shift, uint4* __restrict__ dx, uint4* __restrict__ dres) {
@@ -629,6 +631,19 @@ using namespace ab;
     count_launch();              \
     return check_launch(name)
 
+static inline bool bn_tuned() {
+    static const bool v = !(getenv("AB_BN_TUNE") && atoi(getenv("AB_BN_TUNE")) == 0);
+    return v;
+}
+static inline int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
 static inline int stat_parts(int M, int C8) {
     const int rows_par = kRedThreads / min(C8, kRedThreads);
     return max(1, min(AB_STAT_PARTS, (M + 4 * rows_par - 1) / (4 * rows_par)));
@@ -690,11 +705,18 @@ extern "C" int ab_bn_bwd_reduce(const void* dy, const void* y, const void* raw, 
     AB_REQUIRE(dy && raw && mean && invstd && coef && ws && (!relu || y || (fwd_scale && fwd_shift)), "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_BN_BWD_REDUCE, st);
-    const int parts = stat_parts(M, C / 8);
+    // 3 CTAs per SM (80 registers) in ONE wave of persistent CTAs: with the compiler's free choice (98 registers, 2 CTAs per
+    // SM) the 8-per-SM grid ran as four waves, each ending in its own shared-memory reduction (AB_BN_TUNE=0: that form)
+    const bool tuned = bn_tuned();
+    const int parts = tuned ? min(stat_parts(M, C / 8), 3 * sm_count()) : stat_parts(M, C / 8);
     float* p0 = ws;
     float* p1 = ws + (size_t)AB_STAT_PARTS * C;
-    bn_bwd_reduce_kernel<<<parts, kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M, C / 8, relu,
-                                                        fwd_scale, fwd_shift, p0, p1);
+    if (tuned)
+        bn_bwd_reduce_kernel<3><<<parts, kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M, C / 8, relu,
+                                                               fwd_scale, fwd_shift, p0, p1);
+    else
+        bn_bwd_reduce_kernel<1><<<parts, kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M, C / 8, relu,
+                                                               fwd_scale, fwd_shift, p0, p1);
     bn_bwd_finalize_kernel<<<nblk(C, 8), 1024, 0, st>>>(p0, p1, parts, C, 1.0f / (float)M, gamma, mean, invstd, dgamma, dbeta,
                                                        accumulate, coef);
     count_launch(2);
@@ -708,8 +730,12 @@ extern "C" int ab_bn_bwd_apply(const void* dy, const void* y, const void* raw, i
     AB_REQUIRE(dy && raw && coef && dx && (!relu || y || (fwd_scale && fwd_shift)), "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_BN_BWD_APPLY, st);
-    bn_bwd_apply_kernel<<<stream_grid(M, C / 8), kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M,
-                                                                       C / 8, coef, relu, fwd_scale, fwd_shift, (uint4*)dx, (uint4*)dres);
+    if (bn_tuned())
+        bn_bwd_apply_kernel<3><<<min(stream_grid(M, C / 8), 3u * (unsigned)sm_count()), kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M,
+                                                                              C / 8, coef, relu, fwd_scale, fwd_shift, (uint4*)dx, (uint4*)dres);
+    else
+        bn_bwd_apply_kernel<1><<<stream_grid(M, C / 8), kRedThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (const uint4*)raw, M,
+                                                                              C / 8, coef, relu, fwd_scale, fwd_shift, (uint4*)dx, (uint4*)dres);
     AB_LAUNCH_END("bn_bwd_apply_kernel");
 }
 

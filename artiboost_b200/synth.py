@@ -9,6 +9,7 @@ from __future__ import annotations
 from typing import Dict, List, Optional
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -233,10 +234,45 @@ class SynthPipeline:
         return rand
 
     @torch.no_grad()
-    def synthesise(self, n: int, out: Optional[dict] = None) -> dict:
-        poses = self.sample_poses(n)
-        views = self.render(poses, out=out)
+    def synthesise(self, n: int, out: Optional[dict] = None, prefetch: bool = False) -> dict:
+        """One batch of n views: sample_poses -> render.
+
+        prefetch: software-pipeline consecutive calls.  The draw + pose generator of the NEXT call (same n) are issued on a
+        high-priority side stream BEFORE this call's rasteriser is launched, so the three small latency-bound launches
+        (fused draw, prelude, LBS: ~80 us per 512 samples) run beside the ~0.3 ms rasteriser instead of in front of it.
+        The Philox offsets advance in call order either way, so a prefetching sequence produces the same views as a plain
+        one (tests/test_gpu_synthesis.py).  Poses drawn ahead use the weight map of the moment they were drawn:
+        `drop_prefetch()` (called by whoever changes `sample_weight_map`) discards them."""
+        main = torch.cuda.current_stream(self.device)
+        ahead, self._ahead = getattr(self, "_ahead", None), None
+        if ahead is not None and ahead[0] == n:
+            _, poses, rand, done = ahead
+            main.wait_event(done)
+        else:
+            poses = self.sample_poses(n)
+            rand, self._render_rand = (self._render_rand[1] if self._render_rand is not None else None), None
+        if prefetch:
+            if getattr(self, "_pose_stream", None) is None:
+                self._pose_stream = torch.cuda.Stream(self.device, priority=int(os.environ.get("AB_SYNTH_PRIO", "-1")))
+            fence = torch.cuda.Event()
+            fence.record(main)   # everything enqueued so far (a weight-map update included); NOT this call's rasteriser
+            with torch.cuda.stream(self._pose_stream):
+                self._pose_stream.wait_event(fence)
+                nxt = self.sample_poses(n)
+                nrand, self._render_rand = (self._render_rand[1] if self._render_rand is not None else None), None
+                for d in (nxt, nrand or {}):
+                    for t in d.values():
+                        if torch.is_tensor(t):
+                            t.record_stream(main)   # allocated on the side stream, consumed on the main one
+                done = torch.cuda.Event()
+                done.record(self._pose_stream)
+            self._ahead = (n, nxt, nrand, done)
+        views = self.render(poses, rand=rand, out=out)
         views.update(obj_id=poses["obj_id"], persp_id=poses["persp_id"], grasp_id=poses["grasp_id"],
                      obj_pose=poses["final_obj_pose"], hand_verts=poses["final_hand_verts"],
                      joints=poses["final_joints"])
         return views
+
+    def drop_prefetch(self):
+        """Discards poses drawn ahead by `synthesise(prefetch=True)` (their Philox offsets stay consumed)."""
+        self._ahead = None

@@ -421,6 +421,8 @@ class ArtiBoostLoop:
 
     def end_epoch(self):
         self._prefetched = None  # it was drawn with the old weights
+        if hasattr(self.pipe, "drop_prefetch"):
+            self.pipe.drop_prefetch()
         if self._side is not None:
             torch.cuda.current_stream(self.pipe.device).wait_stream(self._side)
         self.pipe.sample_weight_map = self.feedback.step_eval(self.pipe.sample_weight_map, epoch_idx=self.epoch_idx)

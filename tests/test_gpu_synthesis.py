@@ -231,6 +231,32 @@ def test_fused_draw_stream_is_reproducible_and_well_distributed(lib_built):
         torch.testing.assert_close(fused[k], staged[k], rtol=1e-4, atol=2e-6)
 
 
+def test_prefetching_synthesis_equals_the_plain_sequence(lib_built):
+    """synthesise(prefetch=True) issues the next batch's draw + pose generator on a side stream ahead of this batch's
+    rasteriser; the sequence of views must be the plain sequence's, bit for bit (same Philox offsets in call order), and a
+    change of batch size or drop_prefetch() must fall back to a fresh draw."""
+    a, b = _small_pipe(chunk=64), _small_pipe(chunk=64)
+    keys = ("rgba", "depth", "seg", "obj_id", "persp_id", "grasp_id", "obj_pose", "hand_verts", "joints")
+    for i in range(4):
+        va = a.synthesise(48)
+        vb = b.synthesise(48, prefetch=True)
+        torch.cuda.synchronize()
+        for k in keys:
+            assert torch.equal(va[k], vb[k]), (i, k)
+    assert b._ahead is not None and b._ahead[0] == 48
+    # a is one draw behind b now (b drew batch 4 ahead); let it catch up, then both continue with another size
+    a.sample_poses(48)
+    a._render_rand = None
+    va, vb = a.synthesise(16), b.synthesise(16, prefetch=True)   # b discards nothing it needs: size mismatch -> fresh draw
+    for k in keys:
+        assert torch.equal(va[k], vb[k]), k
+    b.drop_prefetch()
+    assert b._ahead is None
+    a.sample_poses(16)   # the batch b drew ahead and dropped
+    torch.cuda.synchronize()
+    assert torch.equal(a.occurence_map, b.occurence_map)
+
+
 def test_blacklist_kernel_matches_oracle_and_reference_fixture(lib_built):
     """ab_ccv_blacklist vs oracle.ccv.blacklist_map on the pipeline's CCV space, and vs the map the reference's own
     _construct_blacklist_map produced (tests/golden/blacklist.npz); blacklisted cells are never drawn."""
