@@ -1010,23 +1010,30 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
 }
 
 // The same for the convolution parameter layout [Cout, C, taps] (columns arrive as (tap, c)): one CTA per (row, 32 channels),
-// thread (tap, cc) reads 32 consecutive columns per tap (coalesced), the tile is transposed through shared memory and
-// written as 32 * taps consecutive floats of the destination.
-__global__ void wgrad_reduce_conv_kernel(const float* __restrict__ ws, int splits, int C, int taps, int Mp, int Np,
+// thread (zg, tap, cc) adds every ZG-th split of 32 consecutive columns per tap (coalesced; ZG groups of threads so that a
+// layer with few rows still has enough loads in flight: the kernel is pure latency), the groups are added in a fixed order,
+// the tile is transposed through shared memory and written as 32 * taps consecutive floats of the destination.
+__global__ void wgrad_reduce_conv_kernel(const float* __restrict__ ws, int splits, int C, int taps, int Mp, int Np, int zgroups,
                                          float* __restrict__ D) {
-    extern __shared__ float tile[];  // [32 * taps]
+    extern __shared__ float tile[];  // [zgroups][32 * taps]
     const int row = blockIdx.x, c0 = blockIdx.y * 32, t = threadIdx.x;
-    const int tap = t >> 5, cc = t & 31;
+    const int per = 32 * taps;
+    const int zg = t / per, tt = t - zg * per;
+    const int tap = tt >> 5, cc = tt & 31;
     const float* p = ws + (size_t)row * Np + (size_t)tap * C + c0 + cc;
     float acc = 0.0f;
     if (c0 + cc < C) {
 #pragma unroll 4
-        for (int z = 0; z < splits; ++z) acc += __ldg(p + (size_t)z * Mp * Np);
+        for (int z = zg; z < splits; z += zgroups) acc += __ldg(p + (size_t)z * Mp * Np);
     }
-    tile[cc * taps + tap] = acc;
+    tile[zg * per + cc * taps + tap] = acc;
     __syncthreads();
     const int n = min(32, C - c0) * taps;
-    if (t < n) D[((size_t)row * C + c0) * taps + t] += tile[t];
+    if (t < n) {
+        float sum = tile[t];
+        for (int g = 1; g < zgroups; ++g) sum += tile[g * per + t];
+        D[((size_t)row * C + c0) * taps + t] += sum;
+    }
 }
 
 // Pixel-axis split: CTAs are 2 per SM, so cost ~ waves(tiles * s) * (k-blocks per split + epilogue), minimised over s.
@@ -1100,8 +1107,9 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, int P, int
     StageTimer tm(AB_STAGE_WGRAD, st);
     wgrad_bf16_kernel<IM2COL><<<dim3(mt, nt, splits), kGemmThreads, smem, st>>>(tg, tx, P, Mo, No, ws, per, cg, taps);
     if (conv_param_C > 0 && taps <= 32) {
-        wgrad_reduce_conv_kernel<<<dim3(Mo, cdiv(conv_param_C, 32)), 32 * taps, 32 * taps * sizeof(float), st>>>(
-            ws, splits, conv_param_C, taps, mt * 128, nt * 128, D);
+        const int zg = max(1, min(min(3, splits), 1024 / (32 * taps)));
+        wgrad_reduce_conv_kernel<<<dim3(Mo, cdiv(conv_param_C, 32)), 32 * taps * zg, 32 * taps * zg * sizeof(float), st>>>(
+            ws, splits, conv_param_C, taps, mt * 128, nt * 128, zg, D);
     } else {
         const long long n = (long long)Mo * No;
         wgrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, splits, Mo, No, mt * 128, nt * 128, D, om);

@@ -22,12 +22,19 @@
 namespace ab {
 
 constexpr int kV = AB_MANO_VERTS;
+#ifndef AB_LBS_VPER
+#define AB_LBS_VPER 42
+#endif
+#ifndef AB_LBS_THREADS
+#define AB_LBS_THREADS 128
+#endif
 constexpr int kS = 16;         // samples per CTA
-constexpr int kVPer = 42;      // vertices per range: 126 columns = one round of the 128 threads
-constexpr int kSplit = (kV + kVPer - 1) / kVPer;   // 19
+constexpr int kVPer = AB_LBS_VPER;   // vertices per range: its columns (+ the extra vertices') fit one round of the threads
+constexpr int kSplit = (kV + kVPer - 1) / kVPer;
 constexpr int kMaxExtra = 6;   // 5 tips + centre tip
 constexpr int kMaxV = kVPer + kMaxExtra;
-constexpr int kThreads = 128;
+constexpr int kThreads = AB_LBS_THREADS;
+static_assert(kMaxV <= kThreads - 64 && kS * 5 <= kThreads && 48 <= 64, "phase thread ranges");
 constexpr int kNCoef = 10 + AB_MANO_POSE_FEAT;
 constexpr int kAhead = 27;     // blend-shape rows in flight per thread (135 = 5 x 27)
 
@@ -222,7 +229,7 @@ mano_lbs_kernel(ab_mano_model m, int batch, const float* __restrict__ pose, cons
 #pragma unroll
                 for (int k = 0; k < 10; ++k) fma_row(w[k], &sm.coef[k][0]);
             }
-            static_assert(sizeof(float) * 16 * 9 == sizeof(float) * kMaxV * 3, "R and vp alias exactly");
+            static_assert(kMaxV * 3 >= 16 * 9, "vp covers R in the union (R is dead when vp is written)");
             static_assert(AB_MANO_POSE_FEAT % kAhead == 0, "the pose rows are fetched kAhead at a time");
 #pragma unroll 1
             for (int k0 = 0; k0 < AB_MANO_POSE_FEAT; k0 += kAhead) {

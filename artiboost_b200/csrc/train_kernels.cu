@@ -48,11 +48,12 @@ __device__ __forceinline__ void column_partial(int M, int C8, float* const* part
     const int rows_par = kRedThreads / tpr;     // rows visited in parallel
     const int g0 = t % tpr, rl = t / tpr;
     const int C = 8 * C8;
-    for (int g = g0; g < C8; g += tpr) {
+    for (int gbase = 0; gbase < C8; gbase += tpr) {   // every thread takes every pass (barriers inside)
+        const int g = gbase + g0;
         float acc[8 * NACC];
 #pragma unroll
         for (int j = 0; j < 8 * NACC; ++j) acc[j] = 0.0f;
-        if (rl < rows_par) {
+        if (rl < rows_par && g < C8) {
 #pragma unroll 4
             for (long long r = (long long)blockIdx.x * rows_par + rl; r < M; r += (long long)gridDim.x * rows_par) fn(r, g, acc);
         }
@@ -64,9 +65,10 @@ __device__ __forceinline__ void column_partial(int M, int C8, float* const* part
         for (int i = t; i < tpr * 8 * NACC; i += kRedThreads) {
             const int a = i / (tpr * 8), c = i - a * (tpr * 8);   // accumulator set, column within this pass
             const int gg = c >> 3, j = a * 8 + (c & 7);
+            if (8 * gbase + c >= C) continue;
             float sum = red[gg][j];
             for (int k = 1; k < rows_par; ++k) sum += red[gg + k * tpr][j];
-            part[a][(size_t)blockIdx.x * C + 8 * (g - g0) + c] = sum;
+            part[a][(size_t)blockIdx.x * C + 8 * gbase + c] = sum;
         }
         __syncthreads();
     }

@@ -401,7 +401,8 @@ class ArtiBoostLoop:
                            batch["is_synth"])
         if own and self.prefetch:
             if self._side is None:
-                self._side = torch.cuda.Stream(dev)
+                # high priority: the synthesis kernels are small and must not queue behind the training graph's
+                self._side = torch.cuda.Stream(dev, priority=int(os.environ.get("AB_LOOP_PRIO", "-1")))
             with torch.cuda.stream(self._side):
                 self._side.wait_event(fence)
                 nxt = self.make_batch()

@@ -352,7 +352,7 @@ def run_ours(args):
             dex = {"error": repr(e)}
         wall["dexycb_sym"] = time.perf_counter()
     equiv = None
-    if world == 1 and not args.no_train:
+    if world == 1 and not args.no_train and args.equiv_steps > 0:
         try:
             equiv = train_equivalence(dev, steps=args.equiv_steps)
         except Exception as e:
