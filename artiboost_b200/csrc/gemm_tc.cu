@@ -147,6 +147,105 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
     return d + __shfl_xor_sync(0xffffffffu, d, 1);
 }
 
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&w)[8]) {   // 256-bit store (PTX ISA 8.8, sm_100)
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&w)[8]) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+}
+
+// 32-byte row stores need 32-byte aligned rows: base and pitch of D (and of the residual)
+__device__ __forceinline__ bool epilogue_wide_ok(const GemmEpilogue& ep) {
+    const int esz = ep.out_fp32 ? 4 : 2;
+    return (((uintptr_t)ep.D | (uintptr_t)(ep.ldd * esz)) & 31) == 0 &&
+           (!ep.residual || (((uintptr_t)ep.residual | (uintptr_t)(ep.ldr * 2)) & 31) == 0);
+}
+
+// Fused epilogue of one accumulator fragment (one output row, 16 consecutive columns from `col`) held by a lane:
+// scale / bias / residual / ReLU, bf16 or fp32 store.  When the whole fragment is inside N and the rows are 32-byte
+// aligned the lane writes its 16 columns with ONE 32-byte store (st.global.v8.b32): a lane's two 16-byte stores went to
+// the same sector of 32 different lines, i.e. two passes of the store path per line (1x1 convolution 64 -> 256 at
+// 64 x 64, batch 128: 147 -> 97 us).  Otherwise two groups of 8 columns (N is a multiple of 8).
+__device__ __forceinline__ void epilogue_frag16(const GemmEpilogue& ep, bool wide, long long row, int col, int N, const float (&v)[16]) {
+    if (wide && col + 16 <= N) {
+        float y[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float sc = ep.scale ? __ldg(ep.scale + col + j) : 1.0f;
+            const float bi = ep.bias ? __ldg(ep.bias + col + j) : 0.0f;
+            y[j] = fmaf(v[j], sc, bi);
+        }
+        if (ep.residual) {
+            uint32_t rr[8];
+            ld_global_v8(ep.residual + (size_t)row * ep.ldr + col, rr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[j]));
+                y[2 * j] += f.x; y[2 * j + 1] += f.y;
+            }
+        }
+        if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.0f);
+        }
+        if (ep.out_fp32) {
+            float* o = (float*)ep.D + (size_t)row * ep.ldd + col;
+            uint32_t w0[8], w1[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { w0[j] = __float_as_uint(y[j]); w1[j] = __float_as_uint(y[8 + j]); }
+            st_global_v8(o, w0);
+            st_global_v8(o + 8, w1);
+        } else {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+                pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            st_global_v8((__nv_bfloat16*)ep.D + (size_t)row * ep.ldd + col, pk);
+        }
+        return;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int cc = col + 8 * h;
+        if (cc >= N) break;
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float sc = ep.scale ? __ldg(ep.scale + cc + j) : 1.0f;
+            const float bi = ep.bias ? __ldg(ep.bias + cc + j) : 0.0f;
+            y[j] = fmaf(v[8 * h + j], sc, bi);
+        }
+        if (ep.residual) {
+            const uint4 rr = *reinterpret_cast<const uint4*>(ep.residual + (size_t)row * ep.ldr + cc);
+            const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(rp[j]);
+                y[2 * j] += f.x; y[2 * j + 1] += f.y;
+            }
+        }
+        if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.0f);
+        }
+        if (ep.out_fp32) {
+            float4* o = reinterpret_cast<float4*>((float*)ep.D + (size_t)row * ep.ldd + cc);
+            o[0] = make_float4(y[0], y[1], y[2], y[3]);
+            o[1] = make_float4(y[4], y[5], y[6], y[7]);
+        } else {
+            uint4 pk;
+            __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pp[j] = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+            *reinterpret_cast<uint4*>((__nv_bfloat16*)ep.D + (size_t)row * ep.ldd + cc) = pk;
+        }
+    }
+}
+
 template <int BN, int STAGES, bool IM2COL>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
@@ -218,6 +317,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&sm.tmem_full, 0);
         tc_fence_after();
         const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const bool wide = epilogue_wide_ok(ep);
         const int row = tile_m * kBM + q * 32 + lane;
         const bool row_ok = row < M;
 #pragma unroll 1
@@ -241,42 +341,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             }
             if (!row_ok) continue;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {  // two groups of 8 columns (N is a multiple of 8)
-                const int cc = col + 8 * h;
-                if (cc >= N) break;
-                float y[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float sc = ep.scale ? __ldg(ep.scale + cc + j) : 1.0f;
-                    const float bi = ep.bias ? __ldg(ep.bias + cc + j) : 0.0f;
-                    y[j] = fmaf(v[8 * h + j], sc, bi);
-                }
-                if (ep.residual) {
-                    const uint4 rr = *reinterpret_cast<const uint4*>(ep.residual + (size_t)row * ep.ldr + cc);
-                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rr);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = __bfloat1622float2(rp[j]);
-                        y[2 * j] += f.x; y[2 * j + 1] += f.y;
-                    }
-                }
-                if (ep.relu) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.0f);
-                }
-                if (ep.out_fp32) {
-                    float4* o = reinterpret_cast<float4*>((float*)ep.D + (size_t)row * ep.ldd + cc);
-                    o[0] = make_float4(y[0], y[1], y[2], y[3]);
-                    o[1] = make_float4(y[4], y[5], y[6], y[7]);
-                } else {
-                    uint4 pk;
-                    __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) pp[j] = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
-                    *reinterpret_cast<uint4*>((__nv_bfloat16*)ep.D + (size_t)row * ep.ldd + cc) = pk;
-                }
-            }
+            epilogue_frag16(ep, wide, row, col, N, v);
         }
         if (ep.col_sum) {  // combine the four epilogue warps, one plain store per (row tile, column)
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -294,6 +359,160 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 2) tmem_dealloc(tmem, BN);
 }
 
+
+// ------------------------------------------------------------------------------------------ persistent form
+// The same contraction with a static tile scheduler: gridDim.x CTAs (two per SM) walk the output tiles t = blockIdx.x,
+// blockIdx.x + gridDim.x, ... (tile_n fastest, so the CTAs that share an A tile run at the same time).  The TMA producer and
+// the MMA issuer run ahead across tile boundaries through the same shared-memory ring; the accumulator is double buffered
+// in TMEM (2 x BN columns) and each buffer has its own epilogue group of four warps, so the TMEM loads / row-strided
+// stores of tile i overlap the loads and MMAs of tile i + 1.  What this buys: the one-tile-per-CTA kernel pays barrier
+// set-up, TMEM allocation, the first load's latency and the whole epilogue once per tile with nothing of its own to
+// overlap them -- for the short-K contractions (1x1 convolutions of ResNet-50: K = 64 ... 512, one to eight k-blocks)
+// that is most of a CTA's life.
+constexpr int kGemmPThreads = 128 + 2 * 128;   // warps 0-3: TMA / MMA / TMEM roles; warps 4-7 and 8-11: the two epilogue groups
+
+template <int BN, int STAGES>
+struct GemmPSmem {
+    __nv_bfloat16 a[STAGES][kBM * kBK];
+    __nv_bfloat16 b[STAGES][BN * kBK];
+    uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    float stat[2][2][4][BN];   // [epilogue group][sum, sum of squares][warp][column]
+};
+
+__device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int STAGES, bool IM2COL>
+__global__ void __launch_bounds__(kGemmPThreads)
+gemm_bf16_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                               int K, const GemmEpilogue ep, const ConvGeom cg, int tiles_n, int n_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    auto& sm = *reinterpret_cast<GemmPSmem<BN, STAGES>*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_k = (K + kBK - 1) / kBK;
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.acc_empty[s], 4); }   // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(&sm.tmem_base, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int kbg = 0;   // k-blocks issued so far, over all tiles: ring position
+            for (int it = 0; it < my_tiles; ++it) {
+                const int t = (int)blockIdx.x + it * (int)gridDim.x;
+                const int tile_m = t / tiles_n, tile_n = t - tile_m * tiles_n;
+                int base_w = 0, base_h = 0, img = 0;
+                if (IM2COL) {
+                    const int m0 = tile_m * kBM, per = cg.Ho * cg.Wo;
+                    img = m0 / per;
+                    const int r = m0 - img * per, oy = r / cg.Wo, ox = r - oy * cg.Wo;
+                    base_w = ox * cg.stride - cg.pad;
+                    base_h = oy * cg.stride - cg.pad;
+                }
+                for (int kb = 0; kb < num_k; ++kb, ++kbg) {
+                    const int s = kbg % STAGES;
+                    mbar_wait(&sm.empty[s], ((kbg / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&sm.full[s], (kBM + BN) * kBK * 2);
+                    if (IM2COL) {
+                        const int tap = kb / cg.cblocks, cb = kb - tap * cg.cblocks;
+                        const int ky = tap / cg.kw, kx = tap - ky * cg.kw;
+                        tma_load_im2col_4d(sm.a[s], &tmA, &sm.full[s], cb * kBK, base_w, base_h, img, (uint16_t)kx, (uint16_t)ky);
+                    } else {
+                        tma_load_2d(sm.a[s], &tmA, &sm.full[s], kb * kBK, tile_m * kBM);
+                    }
+                    tma_load_2d(sm.b[s], &tmB, &sm.full[s], kb * kBK, tile_n * BN);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            int kbg = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int ac = it & 1;
+                mbar_wait(&sm.acc_empty[ac], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t acc = tmem + (uint32_t)(ac * BN);
+                for (int kb = 0; kb < num_k; ++kb, ++kbg) {
+                    const int s = kbg % STAGES;
+                    mbar_wait(&sm.full[s], (kbg / STAGES) & 1);
+                    tc_fence_after();
+                    const uint64_t ad = umma_desc_k_sw128(sm.a[s]), bd = umma_desc_k_sw128(sm.b[s]);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) umma_bf16(acc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&sm.empty[s]);
+                }
+                umma_commit(&sm.acc_full[ac]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3, grp = (warp - 4) >> 2;
+        const bool wide = epilogue_wide_ok(ep);
+        for (int it = grp; it < my_tiles; it += 2) {
+            const int t = (int)blockIdx.x + it * (int)gridDim.x;
+            const int tile_m = t / tiles_n, tile_n = t - tile_m * tiles_n;
+            const int row = tile_m * kBM + q * 32 + lane;
+            const bool row_ok = row < M;
+            mbar_wait(&sm.acc_full[grp], (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                const int col = tile_n * BN + c0;
+                if (col >= N) break;  // warp-uniform
+                uint32_t r[16];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * BN + c0), r);
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                if (ep.col_sum) {
+                    float s1[16], s2[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { s1[j] = row_ok ? v[j] : 0.0f; s2[j] = s1[j] * s1[j]; }
+                    const float t1 = warp_colsum16(s1, lane), t2 = warp_colsum16(s2, lane);
+                    if (!(lane & 1)) {
+                        const int cj = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                        sm.stat[grp][0][q][cj] = t1;
+                        sm.stat[grp][1][q][cj] = t2;
+                    }
+                }
+                if (!row_ok) continue;
+                epilogue_frag16(ep, wide, row, col, N, v);
+            }
+            // the accumulator has been read (tcgen05.wait::ld inside tmem_ld16): hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(&sm.acc_empty[grp]);
+            if (ep.col_sum) {
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                for (int c = (threadIdx.x & 127); c < BN; c += 128) {
+                    const int col = tile_n * BN + c;
+                    if (col < N) {
+                        ep.col_sum[(size_t)tile_m * N + col] = (sm.stat[grp][0][0][c] + sm.stat[grp][0][1][c]) + (sm.stat[grp][0][2][c] + sm.stat[grp][0][3][c]);
+                        ep.col_sumsq[(size_t)tile_m * N + col] = (sm.stat[grp][1][0][c] + sm.stat[grp][1][1][c]) + (sm.stat[grp][1][2][c] + sm.stat[grp][1][3][c]);
+                    }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // the group's next tile rewrites the slots
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, 2 * BN);
+}
 
 // --------------------------------------------------------------------------- halo-resident 3x3 stride-1 convolution
 // The implicit GEMM above fetches the activation once per filter tap (TMA im2col): nine times through L2.  For the
@@ -403,6 +622,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         mbar_wait(&sm.tmem_full, 0);
         tc_fence_after();
         const int q = warp & 3;
+        const bool wide = epilogue_wide_ok(ep);
         const int qq = q0 + q * 32 + lane, yl = qq / hg.Wp, xp = qq - yl * hg.Wp, y = y0 + yl;
         const bool row_ok = xp < hg.W && y < hg.H;
         const long long row = ((long long)img * hg.H + y) * hg.W + xp;
@@ -427,42 +647,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 }
             }
             if (!row_ok) continue;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int cc = col + 8 * h;
-                if (cc >= N) break;
-                float yv[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float sc = ep.scale ? __ldg(ep.scale + cc + j) : 1.0f;
-                    const float bi = ep.bias ? __ldg(ep.bias + cc + j) : 0.0f;
-                    yv[j] = fmaf(v[8 * h + j], sc, bi);
-                }
-                if (ep.residual) {
-                    const uint4 rr = *reinterpret_cast<const uint4*>(ep.residual + (size_t)row * ep.ldr + cc);
-                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rr);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = __bfloat1622float2(rp[j]);
-                        yv[2 * j] += f.x; yv[2 * j + 1] += f.y;
-                    }
-                }
-                if (ep.relu) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) yv[j] = fmaxf(yv[j], 0.0f);
-                }
-                if (ep.out_fp32) {
-                    float4* o = reinterpret_cast<float4*>((float*)ep.D + (size_t)row * ep.ldd + cc);
-                    o[0] = make_float4(yv[0], yv[1], yv[2], yv[3]);
-                    o[1] = make_float4(yv[4], yv[5], yv[6], yv[7]);
-                } else {
-                    uint4 pk;
-                    __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) pp[j] = __floats2bfloat162_rn(yv[2 * j], yv[2 * j + 1]);
-                    *reinterpret_cast<uint4*>((__nv_bfloat16*)ep.D + (size_t)row * ep.ldd + cc) = pk;
-                }
-            }
+            epilogue_frag16(ep, wide, row, col, N, v);
         }
         if (ep.col_sum) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -572,6 +757,7 @@ conv3x3_halo_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __
         // epilogue group g drains accumulator g (tiles g, g + kHaloAcc, ...): a tile's TMEM loads and row-strided stores take
         // several times its MMA time, so several tiles must be in their epilogue at once to keep the tensor pipe fed
         const int q = warp & 3, grp = (warp - 4) >> 2;
+        const bool wide = epilogue_wide_ok(ep);
         for (int it = grp; it < my_tiles; it += kHaloAcc) {
             const int g = (int)blockIdx.x + it * (int)gridDim.x;
             const int img = g / hg.tiles_per_img, t = g - img * hg.tiles_per_img;
@@ -601,42 +787,7 @@ conv3x3_halo_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __
                     }
                 }
                 if (!row_ok) continue;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int cc = c0 + 8 * h;
-                    if (cc >= N) break;
-                    float yv[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float sc = ep.scale ? __ldg(ep.scale + cc + j) : 1.0f;
-                        const float bi = ep.bias ? __ldg(ep.bias + cc + j) : 0.0f;
-                        yv[j] = fmaf(v[8 * h + j], sc, bi);
-                    }
-                    if (ep.residual) {
-                        const uint4 rr = *reinterpret_cast<const uint4*>(ep.residual + (size_t)row * ep.ldr + cc);
-                        const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rr);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 f = __bfloat1622float2(rp[j]);
-                            yv[2 * j] += f.x; yv[2 * j + 1] += f.y;
-                        }
-                    }
-                    if (ep.relu) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) yv[j] = fmaxf(yv[j], 0.0f);
-                    }
-                    if (ep.out_fp32) {
-                        float4* o = reinterpret_cast<float4*>((float*)ep.D + (size_t)row * ep.ldd + cc);
-                        o[0] = make_float4(yv[0], yv[1], yv[2], yv[3]);
-                        o[1] = make_float4(yv[4], yv[5], yv[6], yv[7]);
-                    } else {
-                        uint4 pk;
-                        __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) pp[j] = __floats2bfloat162_rn(yv[2 * j], yv[2 * j + 1]);
-                        *reinterpret_cast<uint4*>((__nv_bfloat16*)ep.D + (size_t)row * ep.ldd + cc) = pk;
-                    }
-                }
+                epilogue_frag16(ep, wide, row, c0, N, v);
             }
             // the accumulator has been read (tcgen05.wait::ld inside tmem_ld16): hand it back to the MMA warp
             tc_fence_before();
@@ -724,17 +875,41 @@ static int make_im2col_map(CUtensorMap* m, const void* ptr, int B, int H, int W,
     return AB_OK;
 }
 
+// One tile per CTA when the grid is at most about two waves of co-resident CTAs; the persistent form above beyond that
+// (AB_GEMM_PERSISTENT=0: never).
 template <int BN, int STAGES, bool IM2COL>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpilogue& ep,
                        const ConvGeom& cg, cudaStream_t st) {
+    static const int persist = getenv("AB_GEMM_PERSISTENT") ? atoi(getenv("AB_GEMM_PERSISTENT")) : 1;
+    static std::atomic<int> sm_count[64] = {};
+    int dev = 0;
+    AB_CUDA(cudaGetDevice(&dev));
+    int sms = sm_count[dev & 63].load(std::memory_order_relaxed);
+    if (sms == 0) {
+        AB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        sm_count[dev & 63].store(sms, std::memory_order_relaxed);
+    }
+    const int tiles_m = cdiv(M, kBM), tiles_n = cdiv(N, BN);
+    const long long n_tiles = (long long)tiles_m * tiles_n;
+    StageTimer tm(IM2COL ? AB_STAGE_CONV_IMPLICIT : AB_STAGE_GEMM, st);
+    if (persist && n_tiles > 4ll * sms && n_tiles < (1ll << 31)) {
+        const size_t smem = sizeof(GemmPSmem<BN, STAGES>) + 1024;
+        static std::atomic<bool> configured[64] = {};
+        if (!configured[dev & 63].load(std::memory_order_relaxed)) {
+            AB_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_persistent_kernel<BN, STAGES, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[dev & 63].store(true, std::memory_order_relaxed);
+        }
+        gemm_bf16_tn_persistent_kernel<BN, STAGES, IM2COL><<<2 * sms, kGemmPThreads, smem, st>>>(ta, tb, M, N, K, ep, cg, tiles_n, (int)n_tiles);
+        count_launch();
+        return check_launch("gemm_bf16_tn_persistent_kernel");
+    }
     const size_t smem = sizeof(GemmSmem<BN, STAGES>) + 1024;
     static bool configured = false;
     if (!configured) {
         AB_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, STAGES, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid(cdiv(M, kBM), cdiv(N, BN));
-    StageTimer tm(IM2COL ? AB_STAGE_CONV_IMPLICIT : AB_STAGE_GEMM, st);
+    dim3 grid(tiles_m, tiles_n);
     gemm_bf16_tn_kernel<BN, STAGES, IM2COL><<<grid, kGemmThreads, smem, st>>>(ta, tb, M, N, K, ep, cg);
     count_launch();
     return check_launch("gemm_bf16_tn_kernel");
@@ -979,11 +1154,19 @@ wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             // this split's partial tile goes to the workspace [split][mt*128][nt*128] with plain 16-byte stores (whole
             // tile, padding included: nothing to zero, no atomics); wgrad_reduce_kernel adds the splits up
-            float4* o = reinterpret_cast<float4*>(ws + ((size_t)blockIdx.z * gridDim.x * 128 + row) * ((size_t)gridDim.y * 128) + col);
+            float* o = ws + ((size_t)blockIdx.z * gridDim.x * 128 + row) * ((size_t)gridDim.y * 128) + col;
+            if (((uintptr_t)ws & 31) == 0) {   // two 32-byte stores per lane (rows are 512-byte multiples apart)
+                uint32_t w0[8], w1[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                   __uint_as_float(r[4 * j + 3]));
+                for (int j = 0; j < 8; ++j) { w0[j] = r[j]; w1[j] = r[8 + j]; }
+                st_global_v8(o, w0);
+                st_global_v8(o + 8, w1);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    reinterpret_cast<float4*>(o)[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            }
         }
     }
     tc_fence_before();
