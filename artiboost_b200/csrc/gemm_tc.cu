@@ -1290,7 +1290,9 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, int P, int
     StageTimer tm(AB_STAGE_WGRAD, st);
     wgrad_bf16_kernel<IM2COL><<<dim3(mt, nt, splits), kGemmThreads, smem, st>>>(tg, tx, P, Mo, No, ws, per, cg, taps);
     if (conv_param_C > 0 && taps <= 32) {
-        const int zg = max(1, min(min(3, splits), 1024 / (32 * taps)));
+        // split groups only where the grid alone is too small to keep the loads in flight (layer1: 128 CTAs)
+        const int ctas = Mo * cdiv(conv_param_C, 32);
+        const int zg = ctas >= 296 ? 1 : max(1, min(min(3, splits), 1024 / (32 * taps)));
         wgrad_reduce_conv_kernel<<<dim3(Mo, cdiv(conv_param_C, 32)), 32 * taps * zg, 32 * taps * zg * sizeof(float), st>>>(
             ws, splits, conv_param_C, taps, mt * 128, nt * 128, zg, D);
     } else {

@@ -62,15 +62,21 @@ def _pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+def _pad16(n: int) -> int:
+    """K of a filter matrix / materialised im2col matrix: rows of a multiple of 32 bytes start on DRAM-sector boundaries
+    (the stem's K = 196 -> 208: a 400-byte pitch made every 128-byte TMA box row straddle five sectors)."""
+    return (n + 15) // 16 * 16
+
+
 def pack_conv_weight(w: torch.Tensor, cin_pad: int = 0) -> torch.Tensor:
-    """[Cout, Cin, kh, kw] fp32 -> bf16 [Cout, Kp], K order (ky, kx, ci), zero padded to a multiple of 8.
+    """[Cout, Cin, kh, kw] fp32 -> bf16 [Cout, Kp], K order (ky, kx, ci), zero padded to a multiple of 16.
     cin_pad > Cin pads the input-channel axis with zeros first (the 3-channel image travels as 4 channels)."""
     cout = w.shape[0]
     m = w.detach().permute(0, 2, 3, 1)
     if cin_pad > m.shape[3]:
         m = torch.nn.functional.pad(m, (0, cin_pad - m.shape[3]))
     m = m.reshape(cout, -1)
-    kp = _pad8(m.shape[1])
+    kp = _pad16(m.shape[1])
     out = torch.zeros((cout, kp), dtype=torch.bfloat16, device=w.device)
     out[:, :m.shape[1]] = m.to(torch.bfloat16)
     return out
@@ -85,7 +91,7 @@ def packed_filters(conv: nn.Conv2d, cin_pad: int, with_dgrad: bool = False):
 
     def build():
         lib.require_cuda(w, "conv.weight")
-        kp = _pad8(kh * kw * cin_pad)
+        kp = _pad16(kh * kw * cin_pad)
         wp = torch.empty((cout, kp), dtype=torch.bfloat16, device=w.device)
         wd = torch.empty((cin, kh * kw * cout), dtype=torch.bfloat16, device=w.device) if with_dgrad else None
         src = w.detach().float().contiguous()

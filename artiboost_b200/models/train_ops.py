@@ -135,6 +135,23 @@ def _stat_partials(M, C, dev, rows=None):
     return torch.empty((2, (M + 127) // 128 if rows is None else rows, C), device=dev)
 
 
+class _BatchCounters:
+    """`num_batches_tracked += 1` of every training-mode BatchNorm of a forward pass as ONE multi-tensor launch: inside
+    `batch_counters()` the counters are collected and bumped together on exit (38 one-element launches per ResNet34 step)."""
+    pending = None
+
+
+@contextlib.contextmanager
+def batch_counters():
+    outer, _BatchCounters.pending = _BatchCounters.pending, []
+    try:
+        yield
+    finally:
+        todo, _BatchCounters.pending = _BatchCounters.pending, outer
+        if todo:
+            torch._foreach_add_(todo, 1)
+
+
 def _bn_forward_train(raw, M, C, bn, sums, residual, relu):
     """sums: [2, n_part, C] partial column sums / sums of squares of `raw`."""
     dev = raw.device
@@ -151,7 +168,10 @@ def _bn_forward_train(raw, M, C, bn, sums, residual, relu):
         _call("ab_bn_apply", raw.data_ptr(), M, C, scale.data_ptr(), shift.data_ptr(), P(residual), int(relu), y.data_ptr(),
               _stream(dev))
     if track and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+        if _BatchCounters.pending is not None:
+            _BatchCounters.pending.append(bn.num_batches_tracked)
+        else:
+            bn.num_batches_tracked += 1
     st.scale, st.shift = scale, shift
     return y, st
 

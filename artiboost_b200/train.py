@@ -220,7 +220,8 @@ class TrainStep:
     def _eager(self, batch: Dict[str, torch.Tensor]):
         self.arch.train()
         self.flat.grad.zero_()
-        preds = self.arch(batch)
+        with train_ops.batch_counters():   # the BatchNorm layers' num_batches_tracked in one launch
+            preds = self.arch(batch)
         preds = preds[next(iter(preds))] if "joints_3d_abs" not in preds else preds
         if "_fused_loss" in preds:
             preds = dict(preds)
