@@ -25,6 +25,16 @@ __global__ void image_to_nhwc_kernel(const float* __restrict__ img, int B, int C
     const int b = (int)(i / ((long long)H * W));
     const long long hw = i - (long long)b * H * W;
     __nv_bfloat16* o = out + i * Cp;
+    if (Cp == 4) {   // the RGB image padded to 4 channels: one 8-byte store per pixel
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = c < C ? __ldg(img + ((long long)b * C + c) * H * W + hw) : 0.0f;
+        uint2 pk;
+        *reinterpret_cast<__nv_bfloat162*>(&pk.x) = __floats2bfloat162_rn(v[0], v[1]);
+        *reinterpret_cast<__nv_bfloat162*>(&pk.y) = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(o) = pk;
+        return;
+    }
     for (int c = 0; c < Cp; ++c)
         o[c] = __float2bfloat16(c < C ? img[((long long)b * C + c) * H * W + hw] : 0.0f);
 }

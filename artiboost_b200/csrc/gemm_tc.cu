@@ -281,15 +281,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 base_w = ox * cg.stride - cg.pad;
                 base_h = oy * cg.stride - cg.pad;
             }
+            int cb = 0, kx = 0, ky = 0;   // (channel block, tap) of the k-block, advanced without divisions
             for (int kb = 0; kb < num_k; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&sm.empty[s], ph ^ 1);
                 mbar_expect_tx(&sm.full[s], (kBM + BN) * kBK * 2);
                 if (IM2COL) {
-                    const int tap = kb / cg.cblocks, cb = kb - tap * cg.cblocks;
-                    const int ky = tap / cg.kw, kx = tap - ky * cg.kw;
                     tma_load_im2col_4d(sm.a[s], &tmA, &sm.full[s], cb * kBK, base_w, base_h, img, (uint16_t)kx, (uint16_t)ky);
+                    if (++cb == cg.cblocks) { cb = 0; if (++kx == cg.kw) { kx = 0; ++ky; } }
                 } else {
                     tma_load_2d(sm.a[s], &tmA, &sm.full[s], kb * kBK, tile_m * kBM);
                 }
@@ -423,14 +423,14 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
                     base_w = ox * cg.stride - cg.pad;
                     base_h = oy * cg.stride - cg.pad;
                 }
+                int cb = 0, kx = 0, ky = 0;   // (channel block, tap) of the k-block, advanced without divisions
                 for (int kb = 0; kb < num_k; ++kb, ++kbg) {
                     const int s = kbg % STAGES;
                     mbar_wait(&sm.empty[s], ((kbg / STAGES) & 1) ^ 1);
                     mbar_expect_tx(&sm.full[s], (kBM + BN) * kBK * 2);
                     if (IM2COL) {
-                        const int tap = kb / cg.cblocks, cb = kb - tap * cg.cblocks;
-                        const int ky = tap / cg.kw, kx = tap - ky * cg.kw;
                         tma_load_im2col_4d(sm.a[s], &tmA, &sm.full[s], cb * kBK, base_w, base_h, img, (uint16_t)kx, (uint16_t)ky);
+                        if (++cb == cg.cblocks) { cb = 0; if (++kx == cg.kw) { kx = 0; ++ky; } }
                     } else {
                         tma_load_2d(sm.a[s], &tmA, &sm.full[s], kb * kBK, tile_m * kBM);
                     }
@@ -1101,6 +1101,24 @@ wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             // second halves of the tiles may fall outside Mo / No: plain TMA zero-fills them, im2col boxes are skipped
             int nb_valid = 2;
             if (IM2COL) nb_valid = min(2, taps * cg.cblocks - tile_n * 2);
+            // everything that does not change along the pixel axis is worked out once: the (tap, channel block) of the two
+            // column halves, and the first pixel block's (image, row, column), advanced by 64 pixels per k-block without a
+            // division (the producer is ONE thread: five integer divisions per k-block were on the critical path of the ring)
+            int h_cb[2] = {0, 0}, h_kx[2] = {0, 0}, h_ky[2] = {0, 0};
+            int img = 0, oy = 0, ox = 0;
+            if (IM2COL) {
+                for (int h = 0; h < nb_valid; ++h) {
+                    const int nblk = tile_n * 2 + h, tap = nblk / cg.cblocks;
+                    h_cb[h] = nblk - tap * cg.cblocks;
+                    h_ky[h] = tap / cg.kw;
+                    h_kx[h] = tap - h_ky[h] * cg.kw;
+                }
+                const int per = cg.Ho * cg.Wo, p0 = kb0 * 64;
+                img = p0 / per;
+                const int r = p0 - img * per;
+                oy = r / cg.Wo;
+                ox = r - oy * cg.Wo;
+            }
             for (int kb = 0; kb < num_k; ++kb) {
                 const int s = kb % kWgStages;
                 const uint32_t ph = (kb / kWgStages) & 1;
@@ -1110,14 +1128,11 @@ wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 tma_load_2d(sm.a[s][0], &tmG, &sm.full[s], tile_m * 128, p0);
                 tma_load_2d(sm.a[s][1], &tmG, &sm.full[s], tile_m * 128 + 64, p0);
                 if (IM2COL) {
-                    const int per = cg.Ho * cg.Wo;
-                    const int img = p0 / per, r = p0 - img * per, oy = r / cg.Wo, ox = r - oy * cg.Wo;
                     const int base_w = ox * cg.stride - cg.pad, base_h = oy * cg.stride - cg.pad;
-                    for (int h = 0; h < nb_valid; ++h) {
-                        const int nblk = tile_n * 2 + h, tap = nblk / cg.cblocks, cb = nblk - tap * cg.cblocks;
-                        const int ky = tap / cg.kw, kx = tap - ky * cg.kw;
-                        tma_load_im2col_4d(sm.b[s][h], &tmX, &sm.full[s], cb * 64, base_w, base_h, img, (uint16_t)kx, (uint16_t)ky);
-                    }
+                    for (int h = 0; h < nb_valid; ++h)
+                        tma_load_im2col_4d(sm.b[s][h], &tmX, &sm.full[s], h_cb[h] * 64, base_w, base_h, img, (uint16_t)h_kx[h], (uint16_t)h_ky[h]);
+                    ox += 64;
+                    while (ox >= cg.Wo) { ox -= cg.Wo; if (++oy == cg.Ho) { oy = 0; ++img; } }
                 } else {
                     tma_load_2d(sm.b[s][0], &tmX, &sm.full[s], tile_n * 128, p0);
                     tma_load_2d(sm.b[s][1], &tmX, &sm.full[s], tile_n * 128 + 64, p0);
