@@ -534,7 +534,13 @@ gemm_bf16_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __
 struct HaloGeom {
     int H, W, Wp, R, tiles_per_img, cblocks, a_stages;
     unsigned a_bytes;   // bytes of one activation window, rounded up to 1024
+    unsigned mul_wp, mul_tpi;   // exact multiply-shift division by Wp / tiles_per_img over the ranges the kernels use (halo_geom)
 };
+
+// floor(n / d) as (n * ceil(2^20 / d)) >> 20: the role threads of the persistent kernel divide once or twice per tile, and a
+// runtime integer division is ~100 cycles on the one thread that issues a tile's 36 MMAs
+__device__ __forceinline__ int div_wp(const HaloGeom& hg, int n) { return (int)(((unsigned long long)(unsigned)n * hg.mul_wp) >> 20); }
+__device__ __forceinline__ int div_tpi(const HaloGeom& hg, int n) { return (int)(((unsigned long long)(unsigned)n * hg.mul_tpi) >> 20); }
 
 __device__ __forceinline__ void tma_load_tile_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -721,8 +727,8 @@ conv3x3_halo_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __
             for (int tap = 0; tap < 9; ++tap) tma_load_2d(sm.b[tap], &tmB, &sm.b_full, tap * kBK, 0);   // C = 64: K offset tap * 64
             for (int it = 0; it < my_tiles; ++it) {
                 const int g = (int)blockIdx.x + it * (int)gridDim.x;
-                const int img = g / hg.tiles_per_img, t = g - img * hg.tiles_per_img;
-                const int y0 = (t * kBM) / hg.Wp, s = it % kHaloPA;
+                const int img = div_tpi(hg, g), t = g - img * hg.tiles_per_img;
+                const int y0 = div_wp(hg, t * kBM), s = it % kHaloPA;
                 mbar_wait(&sm.a_empty[s], ((it / kHaloPA) & 1) ^ 1);
                 mbar_expect_tx(&sm.a_full[s], (uint32_t)(hg.R * hg.Wp) * 128u);
                 tma_load_tile_4d(base + (size_t)s * hg.a_bytes, &tmX, &sm.a_full[s], 0, -1, y0 - 1, img);
@@ -734,8 +740,8 @@ conv3x3_halo_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __
             mbar_wait(&sm.b_full, 0);
             for (int it = 0; it < my_tiles; ++it) {
                 const int g = (int)blockIdx.x + it * (int)gridDim.x;
-                const int t = g % hg.tiles_per_img;
-                const int q_start = t * kBM, y0 = q_start / hg.Wp, q0 = q_start - y0 * hg.Wp, s = it % kHaloPA, ac = it % kHaloAcc;
+                const int t = g - div_tpi(hg, g) * hg.tiles_per_img;
+                const int q_start = t * kBM, y0 = div_wp(hg, q_start), q0 = q_start - y0 * hg.Wp, s = it % kHaloPA, ac = it % kHaloAcc;
                 mbar_wait(&sm.a_full[s], (it / kHaloPA) & 1);
                 mbar_wait(&sm.acc_empty[ac], ((it / kHaloAcc) & 1) ^ 1);   // the epilogue has drained this accumulator
                 tc_fence_after();
@@ -760,9 +766,9 @@ conv3x3_halo_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __
         const bool wide = epilogue_wide_ok(ep);
         for (int it = grp; it < my_tiles; it += kHaloAcc) {
             const int g = (int)blockIdx.x + it * (int)gridDim.x;
-            const int img = g / hg.tiles_per_img, t = g - img * hg.tiles_per_img;
-            const int q_start = t * kBM, y0 = q_start / hg.Wp, q0 = q_start - y0 * hg.Wp, s = grp;
-            const int qq = q0 + q * 32 + lane, yl = qq / hg.Wp, xp = qq - yl * hg.Wp, y = y0 + yl;
+            const int img = div_tpi(hg, g), t = g - img * hg.tiles_per_img;
+            const int q_start = t * kBM, y0 = div_wp(hg, q_start), q0 = q_start - y0 * hg.Wp, s = grp;
+            const int qq = q0 + q * 32 + lane, yl = div_wp(hg, qq), xp = qq - yl * hg.Wp, y = y0 + yl;
             const bool row_ok = xp < hg.W && y < hg.H;
             const long long row = ((long long)img * hg.H + y) * hg.W + xp;
             mbar_wait(&sm.acc_full[s], (it / kHaloAcc) & 1);
@@ -963,6 +969,8 @@ static HaloGeom halo_geom(int H, int W, int C) {
     g.cblocks = C / kBK;
     g.a_stages = g.cblocks > 1 ? 2 : 1;
     g.a_bytes = (unsigned)(((size_t)g.R * g.Wp * 128 + 1023) / 1024 * 1024);
+    g.mul_wp = (unsigned)(((1ull << 20) + g.Wp - 1) / g.Wp);
+    g.mul_tpi = (unsigned)(((1ull << 20) + g.tiles_per_img - 1) / g.tiles_per_img);
     return g;
 }
 
@@ -1024,7 +1032,20 @@ static int launch_halo_persistent(const CUtensorMap& tx, const CUtensorMap& tb, 
 int conv3x3_halo(const void* x, int B, int H, int W, int C, const void* w, int Cout, const GemmEpilogue& ep, cudaStream_t st) {
     const HaloGeom g = halo_geom(H, W, C);
     static const int persist = getenv("AB_CONV_HALO_PERSISTENT") ? atoi(getenv("AB_CONV_HALO_PERSISTENT")) : 1;
-    const bool use_persistent = persist && C == kBK && Cout <= 64 &&
+    // the persistent kernel's multiply-shift divisions must be exact: n / Wp for n < tiles_per_img * 128 + 128, and
+    // g / tiles_per_img for g < B * tiles_per_img
+    auto magic_exact = [](unsigned d, unsigned mul, unsigned long long n_max) {
+        if (n_max >= (1ull << 24)) return false;
+        for (unsigned long long n = 0; n <= n_max; ++n) if (((n * mul) >> 20) != n / d) return false;
+        return true;
+    };
+    static int cached_key[4] = {0, 0, 0, 0}, cached_ok = 0;   // (Wp, tiles_per_img, B) -> exactness, checked once per geometry
+    if (cached_key[0] != g.Wp || cached_key[1] != g.tiles_per_img || cached_key[2] != B) {
+        cached_ok = magic_exact((unsigned)g.Wp, g.mul_wp, (unsigned long long)g.tiles_per_img * kBM + kBM) &&
+                    magic_exact((unsigned)g.tiles_per_img, g.mul_tpi, (unsigned long long)B * g.tiles_per_img);
+        cached_key[0] = g.Wp; cached_key[1] = g.tiles_per_img; cached_key[2] = B;
+    }
+    const bool use_persistent = persist && cached_ok && C == kBK && Cout <= 64 &&
                                 kHaloPA * (size_t)g.a_bytes + sizeof(HaloPersistSmemTail) + 1024 <= 227 * 1024;
     const int bn = (Cout <= 64) ? 64 : 128;
     CUtensorMap tx, tb;

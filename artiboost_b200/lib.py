@@ -2,6 +2,7 @@
 library is missing or a call fails, this raises."""
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 
@@ -193,7 +194,27 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+_stream_override = None
+
+
+@contextlib.contextmanager
+def use_stream(stream):
+    """Inside the block every library launch goes to `stream` while torch's current stream -- and with it the caching
+    allocator's bookkeeping -- stays where it is.  For callers that order the two streams themselves with events: buffers
+    allocated here belong to the current stream, so no Tensor.record_stream() (slow, and it defers the blocks' reuse) is
+    needed as long as the consumer on the current stream waits for the launches and the launches wait for the current
+    stream's earlier work."""
+    global _stream_override
+    prev, _stream_override = _stream_override, stream
+    try:
+        yield
+    finally:
+        _stream_override = prev
+
+
 def stream_ptr(device=None):
+    if _stream_override is not None:
+        return C.c_void_p(_stream_override.cuda_stream)
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

@@ -132,6 +132,8 @@ class SynthPipeline:
     def occurence_map(self) -> torch.Tensor:
         """bool [n_obj, n_persp, n_grasp]: cells drawn so far (ovg_set.py:172-178).  The fused draw counts on the device;
         the counts are folded into the map when it is read."""
+        if getattr(self, "_pose_stream", None) is not None:   # draws issued ahead by synthesise(prefetch=True) count too
+            torch.cuda.current_stream(self.device).wait_stream(self._pose_stream)
         self._occ_map |= self._occ_count > 0
         self._occ_count.zero_()
         return self._occ_map
@@ -256,16 +258,24 @@ class SynthPipeline:
                 self._pose_stream = torch.cuda.Stream(self.device, priority=int(os.environ.get("AB_SYNTH_PRIO", "-1")))
             fence = torch.cuda.Event()
             fence.record(main)   # everything enqueued so far (a weight-map update included); NOT this call's rasteriser
-            with torch.cuda.stream(self._pose_stream):
-                self._pose_stream.wait_event(fence)
-                nxt = self.sample_poses(n)
+            self._pose_stream.wait_event(fence)
+            if self.fused_draw:
+                # three library launches and no torch op: only the launches move to the side stream (lib.use_stream); the
+                # buffers stay with the current stream's allocator pool -- their writers wait for `fence`, their reader
+                # (the next call's rasteriser, on the current stream) waits for `done`
+                with lib.use_stream(self._pose_stream):
+                    nxt = self.sample_poses(n)
                 nrand, self._render_rand = (self._render_rand[1] if self._render_rand is not None else None), None
-                for d in (nxt, nrand or {}):
-                    for t in d.values():
-                        if torch.is_tensor(t):
-                            t.record_stream(main)   # allocated on the side stream, consumed on the main one
-                done = torch.cuda.Event()
-                done.record(self._pose_stream)
+            else:
+                with torch.cuda.stream(self._pose_stream):
+                    nxt = self.sample_poses(n)
+                    nrand, self._render_rand = (self._render_rand[1] if self._render_rand is not None else None), None
+                    for d in (nxt, nrand or {}):
+                        for t in d.values():
+                            if torch.is_tensor(t):
+                                t.record_stream(main)   # allocated on the side stream, consumed on the main one
+            done = torch.cuda.Event()
+            done.record(self._pose_stream)
             self._ahead = (n, nxt, nrand, done)
         views = self.render(poses, rand=rand, out=out)
         views.update(obj_id=poses["obj_id"], persp_id=poses["persp_id"], grasp_id=poses["grasp_id"],
