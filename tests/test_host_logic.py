@@ -200,3 +200,23 @@ def test_fused_tail_plan_weights_and_refusals():
     assert not plan.usable({k: 0 for k in plan.TARGET_KEYS})       # SymCornerLoss also needs obj_idx / obj_transf
     twice = C.Criterion({"LAMBDAS": [1.0, 1.0]}, loss_list=[C.JointsLoss(LAMBDA_JOINTS_3D=1.0), C.JointsLoss(LAMBDA_CORNERS_3D=1.0)])
     assert FusedTailCriterion.plan(twice, 0, [256, 256]) is None   # loss_lambdas is keyed by type: one of each at most
+
+
+def test_filter_k_padding_and_batch_counter_context():
+    """K of the filter / im2col matrices is padded to 16 elements (32-byte rows); BatchNorm batch counters collected inside
+    train_ops.batch_counters() are bumped once, together, on exit -- also when the contexts nest."""
+    import torch
+    from artiboost_b200.models import nhwc, train_ops
+    assert [nhwc._pad16(n) for n in (1, 16, 17, 196, 576)] == [16, 16, 32, 208, 576]
+    w = torch.arange(2 * 3 * 7 * 7, dtype=torch.float32).reshape(2, 3, 7, 7)
+    wp = nhwc.pack_conv_weight(w, cin_pad=4)
+    assert wp.shape == (2, 208) and float(wp[:, 196:].abs().sum()) == 0.0
+    assert float(wp[1, (2 * 7 + 5) * 4 + 1]) == float(w[1, 1, 2, 5].to(torch.bfloat16))   # K order (ky, kx, ci)
+    a, b = torch.zeros((), dtype=torch.long), torch.zeros((), dtype=torch.long)
+    assert train_ops._BatchCounters.pending is None
+    with train_ops.batch_counters():
+        train_ops._BatchCounters.pending.append(a)
+        with train_ops.batch_counters():
+            train_ops._BatchCounters.pending.append(b)
+        assert int(b) == 1 and int(a) == 0
+    assert int(a) == 1 and train_ops._BatchCounters.pending is None
