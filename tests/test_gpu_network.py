@@ -261,3 +261,20 @@ def test_registry_and_checkpoint_names_follow_the_reference():
     inp = {k: v.to(DEV) for k, v in netcfg.make_inputs(1).items()}
     with torch.no_grad(), pytest.raises(NotImplementedError):
         model(inp)  # train mode without a graph is refused loudly rather than silently using running statistics
+
+
+@pytest.mark.parametrize("cout,cin,k,cin_pad", [(64, 64, 3, 64), (128, 64, 1, 64), (256, 128, 3, 128), (96, 32, 3, 32), (64, 3, 7, 4),
+                                               (40, 24, 3, 24)])
+def test_packed_filters_match_the_torch_packing(cout, cin, k, cin_pad):
+    """ab_pack_conv_filters (tiled shared-memory transpose for channel counts that are multiples of 32 and 1 / 9 taps, the
+    per-element kernel otherwise) vs the torch packing: forward matrix [Cout, Kp] in (ky, kx, ci) order and the
+    data-gradient matrix [Cin, kh*kw*Cout] with reversed taps, bit for bit."""
+    from artiboost_b200.models import nhwc
+    torch.manual_seed(cout + cin + k)
+    conv = torch.nn.Conv2d(cin, cout, k, 1, k // 2, bias=False).to(DEV)
+    wp, wd = nhwc.packed_filters(conv, cin_pad, with_dgrad=True)
+    ref = nhwc.pack_conv_weight(conv.weight.detach(), cin_pad=cin_pad)
+    assert wp.shape == ref.shape and torch.equal(wp, ref)
+    w = conv.weight.detach()
+    ref_d = w.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k * cout).to(torch.bfloat16)   # [ci][(ky', kx', co)]
+    assert wd.shape == ref_d.shape and torch.equal(wd, ref_d)
