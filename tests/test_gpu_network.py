@@ -278,3 +278,61 @@ def test_packed_filters_match_the_torch_packing(cout, cin, k, cin_pad):
     w = conv.weight.detach()
     ref_d = w.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k * cout).to(torch.bfloat16)   # [ci][(ky', kx', co)]
     assert wd.shape == ref_d.shape and torch.equal(wd, ref_d)
+
+
+# ------------------------------------------------------------------------- persistent form (more than 4 tiles per SM)
+def test_persistent_gemm_matches_fp32_matmul_ragged_and_fused():
+    """Grids beyond four tiles per SM take gemm_bf16_tn_persistent_kernel (static tile scheduler, double-buffered TMEM
+    accumulators, two epilogue groups, 32-byte row stores when the rows are 32-byte aligned).  Ragged M / N / K, every
+    epilogue option, per-tile column statistics, aligned and unaligned output pitches."""
+    from artiboost_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(11)
+    M, N, K = 80003, 136, 72          # 626 x 2 tiles of 128 x 128, 2 k-blocks (the second 8 columns wide)
+    a, b = bf(torch.randn((M, K), device=DEV, generator=g) * 0.5), bf(torch.randn((N, K), device=DEV, generator=g) * 0.5)
+    raw = a.float() @ b.float().T
+    out = ops.gemm_bf16(a, b, out_fp32=True)
+    torch.testing.assert_close(out, raw, rtol=1e-5, atol=1e-5 * raw.abs().max().item())
+    scale, bias = torch.rand(N, device=DEV, generator=g) + 0.5, torch.randn(N, device=DEV, generator=g)
+    res = bf(torch.randn((M, N), device=DEV, generator=g))
+    ref = torch.relu(raw * scale + bias + res.float())
+    tiles = (M + 127) // 128
+    cs, cq = torch.full((tiles, N), float("nan"), device=DEV), torch.full((tiles, N), float("nan"), device=DEV)
+    out16 = ops.gemm_bf16(a, b, scale=scale, bias=bias, residual=res, relu=True, col_stats=(cs, cq))
+    torch.testing.assert_close(out16.float(), ref, rtol=1e-2, atol=1e-2 * ref.abs().max().item())
+    pad = torch.zeros((tiles * 128, N), device=DEV)
+    pad[:M] = raw
+    torch.testing.assert_close(cs, pad.view(tiles, 128, N).sum(1), rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(cq, (pad * pad).view(tiles, 128, N).sum(1), rtol=1e-4, atol=1e-3)
+    cs2, cq2 = torch.empty_like(cs), torch.empty_like(cq)
+    ops.gemm_bf16(a, b, col_stats=(cs2, cq2))
+    assert torch.equal(cs, cs2) and torch.equal(cq, cq2)
+    # N = 64 tiles (BN = 64, four stages), 16-column fragments all inside N: the 32-byte store path in bf16 and fp32 ...
+    b64 = bf(torch.randn((64, K), device=DEV, generator=g) * 0.5)
+    ref64 = a.float() @ b64.float().T
+    torch.testing.assert_close(ops.gemm_bf16(a, b64, out_fp32=True), ref64, rtol=1e-5, atol=1e-5 * ref64.abs().max().item())
+    torch.testing.assert_close(ops.gemm_bf16(a, b64).float(), ref64, rtol=1e-2, atol=1e-2 * ref64.abs().max().item())
+    # ... and an output whose pitch is NOT a multiple of 32 bytes (16-byte stores), framed by guard columns
+    big = torch.zeros((M, 64 + 24), dtype=torch.bfloat16, device=DEV)
+    ops.gemm_bf16(a, b64, out=big[:, 8:72])
+    torch.testing.assert_close(big[:, 8:72].float(), ref64, rtol=1e-2, atol=1e-2 * ref64.abs().max().item())
+    assert float(big[:, :8].abs().sum()) == 0 and float(big[:, 72:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("cin,cout,k,s,hw,B", [(128, 128, 3, 1, 32, 80), (64, 128, 3, 2, 64, 80), (64, 256, 1, 1, 32, 40)])
+def test_persistent_implicit_gemm_convolution_matches_torch(cin, cout, k, s, hw, B):
+    """The same kernel in im2col mode (and the 1x1 plain-GEMM route) at tile counts above 4 x 148, against F.conv2d on the
+    bf16-rounded operands: fp32 output (accumulation order only) and the fused BatchNorm + residual + ReLU bf16 output."""
+    from artiboost_b200.models import nhwc
+    torch.manual_seed(cin + cout + k + s)
+    conv = torch.nn.Conv2d(cin, cout, k, s, k // 2, bias=False).to(DEV)
+    bn = torch.nn.BatchNorm2d(cout).to(DEV).eval()
+    netcfg.randomise_bn(bn)
+    x = torch.randn((B, cin, hw, hw), device=DEV)
+    raw = F.conv2d(bf(x).float(), bf(conv.weight).float(), None, s, k // 2)
+    assert (raw.shape[0] * raw.shape[2] * raw.shape[3] + 127) // 128 * ((cout + 127) // 128) > 4 * 148
+    out32 = nhwc.conv_bn_act(to_act(x), conv, None, out_fp32=True).view(B, raw.shape[2], raw.shape[3], cout).permute(0, 3, 1, 2)
+    torch.testing.assert_close(out32, raw, rtol=1e-5, atol=2e-4)
+    res = torch.randn_like(raw)
+    ref = torch.relu(F.batch_norm(raw, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps) + bf(res).float())
+    out = nhwc.conv_bn_act(to_act(x), conv, bn, relu=True, residual=to_act(res))
+    torch.testing.assert_close(out.nchw(), ref, rtol=1e-2, atol=2e-2)
