@@ -39,7 +39,7 @@ class SynthPipeline:
     def __init__(self, obj_names: Optional[List[str]] = None, device="cuda", seed: int = 0, cfg: Optional[dict] = None,
                  n_hand_tex: int = 51, n_bg: int = 8, chunk: int = 512, mano_model: Optional[Dict] = None,
                  objects: Optional[Dict[str, dict]] = None, grasps: Optional[Dict[str, list]] = None,
-                 filter_back: bool = True, fused_draw: bool = True):
+                 filter_back: bool = True, fused_draw: bool = True, sample_seed: Optional[int] = None):
         self.cfg = cfg = dict(DEFAULT_CFG if cfg is None else cfg)
         self.device = dev = torch.device(device)
         if dev.type != "cuda":
@@ -52,9 +52,12 @@ class SynthPipeline:
         self.grasp_engine = GraspEngine(self.grasps, self.obj_names, n_grasp=cfg["GRASP_NUM"], device=dev)
         self.view_engine = ViewEngine(cfg["VIEW"])
         self.generator = torch.Generator(device=dev)
-        self.generator.manual_seed(seed)
+        # `seed` makes the (synthetic) assets; `sample_seed` (default: the same) seeds everything that is DRAWN -- CCV cells,
+        # jitter, scrambler noise, the renderer's per-view choices.  Ranks of one job share the assets and differ in the draws.
+        draw_seed = int(seed if sample_seed is None else sample_seed)
+        self.generator.manual_seed(draw_seed)
         shape = (len(self.obj_names), self.view_engine.n_persp_center, self.grasp_engine.n_grasp)
-        self._seed, self._offset = int(seed), 0       # the Philox stream of the fused draw: (seed, per-call offset)
+        self._seed, self._offset = draw_seed, 0       # the Philox stream of the fused draw: (seed, per-call offset)
         self._space = None                            # ab_synth_space; completed once the renderer exists (texture / bg counts)
         self._cdf, self._cdf_key = None, None
         self._occ_map = torch.zeros(shape, dtype=torch.bool, device=dev)
@@ -88,7 +91,7 @@ class SynthPipeline:
         self.hand_meshes = [make_mesh(self.mano_model["v_template"], hand_faces, tex[i]) for i in range(n_hand_tex)]
         self.backgrounds = list(assets.make_backgrounds(n_bg, int(1.5 * H), int(1.5 * W), seed)) if n_bg else None
         self.renderer = Renderer(W, H, gpu_id=dev.index or 0, chunk=chunk)
-        self.renderer.rng = np.random.RandomState(seed + 1)
+        self.renderer.rng = np.random.RandomState(draw_seed + 1)
         self.renderer.setup(self.cam_intr, PYRENDER_EXTRINSIC, self.obj_engine.obj_trimeshes_mapping, self.hand_meshes,
                             self.backgrounds, [PointLight(np.array([0.9, 0.9, 0.9]), 5.0, np.eye(4))])
 
