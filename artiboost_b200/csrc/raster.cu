@@ -45,6 +45,7 @@ constexpr unsigned kHandBit = 0x8000u;    // list entries: patch index (relative
 constexpr unsigned kMultiBit = 0x4000u;   //               | kMultiBit when the binning box spans several tiles (the tile kernel then
 constexpr unsigned kIndexMask = 0x3fffu;  //               tests the exact box of the projected vertices before the face phase)
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kBigCap = 512;              // queue of triangles of >= 64 px per tile (more than that: the tile is redone slowly, see below)
 constexpr float kSnapEps = 0.0032f;       // bound on the displacement (pixels) of a projected vertex by fp32 evaluation + 24.8 snapping
 
 // floor(n / d) for n < 2^30 as (n * m) >> s with m = ceil(2^s / d), s = 31 + ceil(log2 d): m < 2^32, and with
@@ -413,6 +414,120 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 #endif
 
+// ---- triangles of 64 px and more in either axis (close-ups; the cap fans of a mesh seen face-on) --------------------------
+// int64 edge functions E_i(px, py) = A_i px + B_i py + C_i over the pixel centres of the triangle's box clipped to the tile.
+// Such a triangle's box is up to the whole tile while the triangle itself is often a sliver, so the box is cut into 8 x 8
+// pixel blocks first: a lane per block evaluates each edge at the block corner where it is largest (exact integers) and
+// drops the block when one edge is negative there; the warp then walks the surviving blocks, two pixels per lane.  The
+// integers that reach the z-test are the ones a per-pixel evaluation produces.  Kept out of line: it is rare, and inlined
+// its registers cost the common path of the kernel (a tile crossed by 53 such triangles took 362 us when every pixel of
+// every box was tested with three int64 products inside the patch loop: the whole launch waited for it).
+__device__ __noinline__ void raster_big_triangle(unsigned long long* zbuf, int4 ca, int4 cb, int4 cd, int cx0, int cy0, int cw, int ch,
+                                                 int tx0, int ty0, unsigned cprim, int lane) {
+    const int vx[3] = {ca.x, cb.x, cd.x}, vy[3] = {ca.y, cb.y, cd.y};
+    const float jz0 = __int_as_float(ca.z), jz1 = __int_as_float(cb.z), jz2 = __int_as_float(cd.z);
+    const long long carea2 = area2_of(ca, cb, cd, false);
+    const int s = carea2 > 0 ? 1 : -1;
+    const float jarea = __ll2float_rn(carea2 > 0 ? carea2 : -carea2);
+    long long A[3], B[3], C[3];   // E_i = A_i px + B_i py + C_i with px, py in 24.8 units; the bias of the fill rule folded into C
+    int bias[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+        const int dx = s * (vx[i2] - vx[i1]), dy = s * (vy[i2] - vy[i1]);  // |.| <= 2^23: no overflow
+        bias[i] = ((dy < 0) || (dy == 0 && dx > 0)) ? 0 : 1;
+        A[i] = -(long long)dy;
+        B[i] = (long long)dx;
+        C[i] = (long long)dy * vx[i1] - (long long)dx * vy[i1];
+    }
+    const int nbx = (cw + 7) >> 3, nby = (ch + 7) >> 3, nblk = nbx * nby;   // <= 64 blocks
+    for (int b0 = 0; b0 < nblk; b0 += 32) {
+        const int bi = b0 + lane;
+        bool keep = false;
+        int bx = 0, by = 0;
+        if (bi < nblk) {
+            by = bi / nbx; bx = bi - by * nbx;
+            const int px0 = cx0 + 8 * bx, py0 = cy0 + 8 * by;
+            const int px1 = min(px0 + 7, cx0 + cw - 1), py1 = min(py0 + 7, cy0 + ch - 1);
+            keep = true;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {   // the largest value of edge i over the block's pixel centres
+                const long long qx = 256ll * (A[i] > 0 ? px1 : px0) + 128, qy = 256ll * (B[i] > 0 ? py1 : py0) + 128;
+                if (A[i] * qx + B[i] * qy + C[i] - bias[i] < 0) keep = false;
+            }
+        }
+        unsigned live = __ballot_sync(kFull, keep);
+        while (live) {
+            const int l = __ffs(live) - 1;
+            live &= live - 1;
+            const int kbx = __shfl_sync(kFull, bx, l), kby = __shfl_sync(kFull, by, l);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int px = cx0 + 8 * kbx + (lane & 7), py = cy0 + 8 * kby + (lane >> 3) + 4 * j;
+                if (px >= cx0 + cw || py >= cy0 + ch) continue;
+                const long long qx = 256ll * px + 128, qy = 256ll * py + 128;
+                const long long e0 = A[0] * qx + B[0] * qy + C[0], e1 = A[1] * qx + B[1] * qy + C[1], e2 = A[2] * qx + B[2] * qy + C[2];
+                if (((e0 - bias[0]) | (e1 - bias[1]) | (e2 - bias[2])) >= 0)
+                    emit(zbuf, (py - ty0) * kTile + (px - tx0), __ll2float_rn(e0), __ll2float_rn(e1), __ll2float_rn(e2), jz0, jz1, jz2,
+                         jarea, cprim);
+            }
+        }
+    }
+}
+
+// The triangles the patch loop queued (their projected vertices are gone with the warp's slab): a warp per triangle re-projects
+// its three vertices the way the vertex phase did -- the same operations on the same inputs, hence the same integers -- and
+// hands it to raster_big_triangle.  If the queue overflowed (more than kBigCap such triangles in one tile), every patch of the
+// tile's list is searched again for them instead: slow, correct, and never seen on ArtiBoost views.
+__device__ __noinline__ void raster_big_queue(const RasterParams& P, unsigned long long* zbuf, const unsigned* big_q, int n_q, bool overflow,
+                                              int view, int bin, int count, int tx0, int ty0, int tx1, int ty1, const float* Msh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int oid = P.obj_id[view];
+    const int n_of = oid >= 0 ? P.face_off[oid + 1] - P.face_off[oid] : 0;
+    const int poff = oid >= 0 ? P.patch_off[oid] : 0;
+    const float* hverts = P.hand_verts + 3 * (size_t)view * P.n_hv;
+    const unsigned short* list = P.bin_list + (size_t)bin * P.list_cap;
+    const int total = overflow ? count * 32 : n_q;   // overflow: every (list entry, face lane) pair is a candidate
+    for (int i = wid; i < total; i += kWarps) {
+        const unsigned q = overflow ? ((unsigned)list[i >> 5] | ((unsigned)(i & 31) << 16)) : big_q[i];
+        const unsigned entry = q & 0xffffu, fl = q >> 16;
+        const bool hand = (entry & kHandBit) != 0;
+        const size_t poffs = (size_t)(entry & kIndexMask) * 32u;
+        const unsigned fw = hand ? __ldg(P.hp_face + poffs + fl) : __ldg(P.op_face + (size_t)poff * 32 + poffs + fl);
+        if (fw == 0xFFFFFFFFu) continue;   // warp-uniform
+        const int prim_local = hand ? __ldg(P.hp_prim + poffs + fl) : __ldg(P.op_prim + (size_t)poff * 32 + poffs + fl);
+        int4 pv[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const unsigned vs = (fw >> (8 * j)) & 31u;
+            float c[3] = {0.0f, 0.0f, 0.0f};
+            bool on;
+            if (!hand) {
+                const float4 v4 = __ldg(P.op_pos + (size_t)poff * 32 + poffs + vs);
+                on = v4.w != 0.0f;
+                xform(Msh, v4.x, v4.y, v4.z, c);
+            } else {
+                const int v = __ldg(P.hp_vid + poffs + vs);
+                on = v >= 0;
+                if (on) { c[0] = hverts[3 * v]; c[1] = hverts[3 * v + 1]; c[2] = hverts[3 * v + 2]; }
+            }
+            pv[j] = project(P, c[0], c[1], c[2]);
+            if (!on) pv[j].w = 0;
+        }
+        if (!(pv[0].w & pv[1].w & pv[2].w)) continue;
+        const int minx = min(pv[0].x, min(pv[1].x, pv[2].x)), maxx = max(pv[0].x, max(pv[1].x, pv[2].x));
+        const int miny = min(pv[0].y, min(pv[1].y, pv[2].y)), maxy = max(pv[0].y, max(pv[1].y, pv[2].y));
+        if ((maxx - minx < kSmallExtent) && (maxy - miny < kSmallExtent)) continue;   // (overflow search) drawn by the patch loop
+        const int x0 = max(floordiv256(minx + 127), tx0), y0 = max(floordiv256(miny + 127), ty0);
+        const int x1 = min(floordiv256(maxx - 128), tx1), y1 = min(floordiv256(maxy - 128), ty1);
+        if (x0 > x1 || y0 > y1) continue;
+        const long long a2 = area2_of(pv[0], pv[1], pv[2], false);
+        if (a2 == 0 || (a2 > 0 && P.cull)) continue;
+        raster_big_triangle(zbuf, pv[0], pv[1], pv[2], x0, y0, x1 - x0 + 1, y1 - y0 + 1, tx0, ty0,
+                            (unsigned)(prim_local + (hand ? n_of : 0)), lane);
+    }
+}
+
 // ---- the tile kernel -----------------------------------------------------------------------------------------
 // PX = pixels per thread in the output stream: 4 when W % 4 == 0 and the output rows are 16-byte aligned, else 1.
 // BG4: backgrounds are RGBX (one aligned 32-bit load per pixel) instead of packed RGB.
@@ -425,7 +540,8 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
     __shared__ __align__(16) float Msh[12];
     __shared__ unsigned char rank_lane[kWarps][32];             // per warp: lane of the k-th box that has rows
     __shared__ __align__(16) int colmap[kTile];                 // background source column of every tile column
-    __shared__ int n_hit, next_entry;
+    __shared__ int n_hit, next_entry, n_bigq;
+    __shared__ unsigned big_q[kBigCap];                        // (list entry | face lane << 16) of the triangles of >= 64 px
 
     // CTAs are handed out in launch order, so the order of the work decides how the grid ends.  Groups too large for the
     // work-ordered launch fall back to a static order: the tiles of a view ranked by their distance from the principal point
@@ -486,7 +602,7 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
     if (count > 0) {
         const int oid = P.obj_id[view];
         const int n_of = oid >= 0 ? P.face_off[oid + 1] - P.face_off[oid] : 0;
-        if (t == 0) { n_hit = 0; next_entry = kWarps; }
+        if (t == 0) { n_hit = 0; next_entry = kWarps; n_bigq = 0; }
         if (t < 12) Msh[t] = oid >= 0 ? P.obj_pose[16 * (size_t)view + t] : 0.0f;
         ulonglong2* z2 = reinterpret_cast<ulonglong2*>(zbuf);
         for (int i = t; i < kTilePx / 2; i += kThreads) z2[i] = make_ulonglong2(kEmptyKey, kEmptyKey);
@@ -510,6 +626,7 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
         int li = wid;
         unsigned entry = li < count ? list[li] : 0u;
         while (li < count) {
+            const unsigned cur_entry = entry;
             const bool hand = (entry & kHandBit) != 0;
             const unsigned poffs = (entry & kIndexMask) * 32u;
             const bool multi = (entry & kMultiBit) != 0;
@@ -660,39 +777,10 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
                         }
                     }
                 }
-                // ---- extents of 64 px and more (close-ups): int64 edge functions, the warp walks the box pixel by pixel
-                unsigned big = __ballot_sync(kFull, n > 0 && !small);
-                while (big) {
-                    const int src = __ffs(big) - 1;
-                    big &= big - 1;
-                    const unsigned cfw = __shfl_sync(kFull, fw, src);
-                    const int cx0 = __shfl_sync(kFull, x0, src), cy0 = __shfl_sync(kFull, y0, src);
-                    const int cw = __shfl_sync(kFull, w, src), cn = __shfl_sync(kFull, n, src);
-                    const unsigned cprim = __shfl_sync(kFull, prim, src);
-                    const int4 ca = my_slab[cfw & 31], cb = my_slab[(cfw >> 8) & 31], cd = my_slab[(cfw >> 16) & 31];
-                    const int vx[3] = {ca.x, cb.x, cd.x}, vy[3] = {ca.y, cb.y, cd.y};
-                    const float jz0 = __int_as_float(ca.z), jz1 = __int_as_float(cb.z), jz2 = __int_as_float(cd.z);
-                    const long long carea2 = area2_of(ca, cb, cd, false);
-                    const int s = carea2 > 0 ? 1 : -1;
-                    const float jarea = __ll2float_rn(carea2 > 0 ? carea2 : -carea2);
-                    int bias[3];
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-                        const int dx = s * (vx[i2] - vx[i1]), dy = s * (vy[i2] - vy[i1]);  // |.| <= 2^23: no overflow
-                        bias[i] = ((dy < 0) || (dy == 0 && dx > 0)) ? 0 : 1;
-                    }
-                    const float inv_w = 1.0f / (float)cw;
-                    for (int k = lane; k < cn; k += 32) {
-                        const int ry = (int)(((float)k + 0.5f) * inv_w), rx = k - ry * cw;  // exact: k < 4096, cw <= 64
-                        const int px = cx0 + rx, py = cy0 + ry;
-                        const long long ccx = 256ll * px + 128, ccy = 256ll * py + 128;
-                        const long long e0 = edge64(vx, vy, s, 0, ccx, ccy), e1 = edge64(vx, vy, s, 1, ccx, ccy),
-                                        e2 = edge64(vx, vy, s, 2, ccx, ccy);
-                        if (((e0 - bias[0]) | (e1 - bias[1]) | (e2 - bias[2])) >= 0)
-                            emit(zbuf, (py - ty0) * kTile + (px - tx0), __ll2float_rn(e0), __ll2float_rn(e1), __ll2float_rn(e2), jz0,
-                                 jz1, jz2, jarea, cprim);
-                    }
+                // ---- extents of 64 px and more (close-ups, cap fans seen face-on): queued for the pass after the patch loop
+                if (n > 0 && !small) {
+                    const int slot = atomicAdd(&n_bigq, 1);
+                    if (slot < kBigCap) big_q[slot] = (cur_entry & 0xffffu) | ((unsigned)lane << 16);
                 }
             }
             __syncwarp();  // the slab and the rank table are rewritten by the next patch
@@ -762,6 +850,10 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
 #endif
     if (count == 0) return;
     __syncthreads();  // every warp's fragments are in the z-buffer, every placeholder store has been issued
+    if (n_bigq > 0) {     // CTA-uniform
+        raster_big_queue(P, zbuf, big_q, min(n_bigq, kBigCap), n_bigq > kBigCap, view, bin, count, tx0, ty0, tx1, ty1, Msh);
+        __syncthreads();
+    }
 #ifdef AB_RASTER_TRACE
     t_patch = gtime();
 #endif
@@ -799,7 +891,7 @@ raster_tile_kernel(const __grid_constant__ RasterParams P) {
     __syncthreads();
     if (threadIdx.x == 0 && blockIdx.x < 32768) {
         unsigned long long* q = g_trace + 6 * blockIdx.x;
-        q[0] = t_start; q[1] = gtime(); q[2] = smid(); q[3] = count; q[4] = total; q[5] = t_patch;
+        q[0] = t_start; q[1] = gtime(); q[2] = smid() | ((unsigned long long)n_bigq << 32); q[3] = count; q[4] = total; q[5] = t_patch;
     }
 #endif
 }

@@ -62,6 +62,7 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._halt = threading.Event()
+        self._paused = threading.Event()
 
     def run(self):
         try:
@@ -72,6 +73,9 @@ class ClockSampler(threading.Thread):
             names = {getattr(nv, n): n[len("nvmlClocksThrottleReason"):] for n in dir(nv)
                      if n.startswith("nvmlClocksThrottleReason") and isinstance(getattr(nv, n), int)}
             while not self._halt.is_set():
+                if self._paused.is_set():   # no NVML traffic to this GPU inside the timed window
+                    time.sleep(0.001)
+                    continue
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, name in names.items():
@@ -80,6 +84,9 @@ class ClockSampler(threading.Thread):
                 time.sleep(self.period)
         except Exception as e:  # NVML missing: report it instead of failing the bench
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def pause(self, on=True):
+        (self._paused.set if on else self._paused.clear)()
 
     def stop(self):
         self._halt.set()
@@ -197,7 +204,8 @@ def run_ours(args):
     lib.load()
     wall = {"start": time.perf_counter()}
 
-    pipe = SynthPipeline(device=dev, seed=1, sample_seed=1 + rank, chunk=BATCH)   # same assets on every rank, different draws
+    pipe = SynthPipeline(device=dev, seed=1, sample_seed=1 + rank + int(os.environ.get("AB_BENCH_SEED_OFFSET", "0")),
+                         chunk=BATCH)   # same assets on every rank, different draws
     # N_RES different batches of 512 views stay resident and the steps cycle through them: the triangle work of ONE random batch
     # varies by +-10 % with its views (per-rank times of a single batch: 0.255 ... 0.318 ms at N = 4), and the job's time is the
     # slowest rank's, so a single batch per rank would make the 1 -> 8 curve a statement about seeds
@@ -263,12 +271,21 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     counter[1] = 0   # the timed steps start at resident batch 0 on every rank
+    sampler.pause(True)   # the clock record is taken under this same load right before and right after the timed window
+    time.sleep(0.003)
+    barrier()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
     ms_total_local = e0.elapsed_time(e1)
+    sampler.pause(False)
+    t_end = time.perf_counter() + 0.2
+    while time.perf_counter() < t_end:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize(dev)
     clocks = sampler.stop()
     per_rank = torch.zeros(world, dtype=torch.float64, device=dev)
     per_rank[rank] = ms_total_local / args.steps

@@ -13,7 +13,7 @@ from artiboost_b200.synth import SynthPipeline  # noqa: E402
 
 B = int(os.environ.get("B", 512))
 dev = torch.device("cuda", 0)
-pipe = SynthPipeline(device=dev, seed=1, chunk=B)
+pipe = SynthPipeline(device=dev, seed=1, sample_seed=int(os.environ.get("SAMPLE_SEED", "1")), chunk=B)
 poses = pipe.sample_poses(B)
 rand = pipe.draw_render_randoms(B)
 out = {"rgba": torch.empty((B, 256, 256, 4), dtype=torch.uint8, device=dev),
@@ -32,7 +32,8 @@ t0 = buf[:, 0].min()
 start = (buf[:, 0] - t0).astype(np.float64) / 1e3
 end = (buf[:, 1] - t0).astype(np.float64) / 1e3
 patch_end = (buf[:, 5] - t0).astype(np.float64) / 1e3
-sm = buf[:, 2].astype(int)
+sm = (buf[:, 2] & np.uint64(0xffffffff)).astype(int)
+nbig = (buf[:, 2] >> np.uint64(32)).astype(int)   # triangles that took the >= 64 px (int64) path in this tile
 cnt = buf[:, 3].astype(int)
 hit = buf[:, 4].astype(int)
 dur = end - start
@@ -62,5 +63,6 @@ for t in ts[::4]:
 # the stragglers
 order = np.argsort(-end)[:12]
 for i in order:
-    print("late CTA blk %5d sm %3d start %.1f end %.1f dur %.1f count %d hits %d" % (i, sm[i], start[i], end[i], dur[i], cnt[i], hit[i]))
+    print("late CTA blk %5d sm %3d start %.1f end %.1f dur %.1f count %d hits %d big-path triangles %d" % (i, sm[i], start[i], end[i], dur[i], cnt[i], hit[i], nbig[i]))
+print("tiles with big-path triangles:", int((nbig > 0).sum()), "triangles", int(nbig.sum()), "max per tile", int(nbig.max()))
 np.save(os.path.join("gpurun_out", os.environ.get("TAG", "trace") + ".npy"), buf)
