@@ -234,3 +234,41 @@ def test_render_provider_queue_protocol(pipe):
         assert all(g.shape == (256, 256, 3) and g.dtype == np.uint8 for g in got)
     finally:
         prov.end()
+
+
+def test_many_large_triangles_in_one_tile_match_oracle(lib_built):
+    """Triangles of 64 px and more are queued by the patch loop and drawn after it over 8 x 8 blocks.  A disc fan of slivers
+    (each ~80 px long, all meeting in one tile) in front of the object: 300 of them fit the tile's queue (512 entries), 700
+    overflow it and the tile searches its patch list again.  Both must equal the oracle bit for bit, with and without
+    back-face culling."""
+    from artiboost_b200 import assets
+    names = list(assets.HO3D_TRAIN_OBJS)[:2]
+    objs = assets.make_synthetic_objects(names, 4)
+    for name, n_fan in zip(names, (300, 700)):
+        o = objs[name]
+        v, f, c = np.asarray(o["vertices"]), np.asarray(o["faces"]), np.asarray(o["colors"])
+        ang = np.linspace(0.0, 2 * np.pi, n_fan, endpoint=False)
+        zf = v[:, 2].min() - 0.02
+        rim = np.stack([0.16 * np.cos(ang), 0.16 * np.sin(ang), np.full(n_fan, zf)], 1)
+        fan_v = np.concatenate([[[0.0, 0.0, zf]], rim])
+        base = len(v)
+        i = np.arange(n_fan)
+        fan_f = np.stack([np.full(n_fan, base), base + 1 + i, base + 1 + (i + 1) % n_fan], 1)
+        rng = np.random.RandomState(n_fan)
+        objs[name] = dict(o, vertices=np.concatenate([v, fan_v]), faces=np.concatenate([f, fan_f]),
+                          colors=np.concatenate([c, rng.randint(40, 255, size=(n_fan + 1, 3)).astype(np.uint8)]))
+    p = _pipe_with_camera((256, 256), (217.5, 217.5), (128.0, 128.0), obj_names=names, objects=objs)
+    B = 4
+    poses = p.sample_poses(B)
+    rand = p.draw_render_randoms(B)
+    poses["obj_id"] = torch.tensor([0, 1, 0, 1], dtype=torch.int32, device=DEV)
+    pose = torch.eye(4, device=DEV).repeat(B, 1, 1)
+    pose[:, 0, 3] = torch.tensor([0.0, 0.01, -0.05, 0.06], device=DEV)   # fan centre inside a tile, on a tile corner, off-centre
+    pose[:, 1, 3] = torch.tensor([0.0, -0.01, 0.04, 0.0], device=DEV)
+    pose[:, 2, 3] = torch.tensor([0.42, 0.40, 0.36, 0.45], device=DEV)
+    poses["final_obj_pose"] = pose
+    for cull in (0, 1):
+        p.renderer.camera.cull_backface = cull
+        views = p.render(poses, rand)
+        check(views, oracle_views(p, poses, rand, range(B), cull=cull), range(B))
+    assert int((views["seg"] == 2).sum()) > 20000
