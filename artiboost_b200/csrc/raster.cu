@@ -531,8 +531,11 @@ __device__ __noinline__ void raster_big_queue(const RasterParams& P, unsigned lo
 // ---- the tile kernel -----------------------------------------------------------------------------------------
 // PX = pixels per thread in the output stream: 4 when W % 4 == 0 and the output rows are 16-byte aligned, else 1.
 // BG4: backgrounds are RGBX (one aligned 32-bit load per pixel) instead of packed RGB.
+#ifndef AB_TILE_CTAS
+#define AB_TILE_CTAS 4   // CTAs per SM the register budget is cut for (64 registers); 3 and 5 measured slower
+#endif
 template <int PX, bool BG4>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, AB_TILE_CTAS)
 raster_tile_kernel(const __grid_constant__ RasterParams P) {
     __shared__ __align__(16) unsigned long long zbuf[kTilePx];  // 32 KB
     __shared__ __align__(16) int4 slab[kWarps][32];             // projected vertices of the patch a warp is on
