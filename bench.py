@@ -107,13 +107,14 @@ def cpu_reference(steps, warmup, sample_views, threads=None):
     from oracle.synth_cpu import CpuSynth
     threads = threads or os.cpu_count() or 1
     synth = CpuSynth(assets, seed=0)
-    inp = synth.sample(sample_views)
+    n_res = max(1, int(os.environ.get("AB_BENCH_BATCHES", "10")))   # the same cycle of resident batches as the GPU arm
+    inps = [synth.sample(sample_views) for _ in range(n_res)]
     out = None
-    for _ in range(warmup):
-        out = synth.render(inp, n_threads=threads, out=out)
+    for i in range(warmup):
+        out = synth.render(inps[i % n_res], n_threads=threads, out=out)
     t0 = time.perf_counter()
-    for _ in range(steps):
-        out = synth.render(inp, n_threads=threads, out=out)
+    for i in range(steps):
+        out = synth.render(inps[i % n_res], n_threads=threads, out=out)
     dt = time.perf_counter() - t0
     return sample_views * steps / dt, dt / steps * 1e3, threads
 
@@ -128,7 +129,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": vps,
         "unit": "views/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(args.gpus, views_per_launch=BATCH, submission="host loop over oracle/raster.c (OpenMP over views)",
+                                  resident_batches=f"{max(1, int(os.environ.get('AB_BENCH_BATCHES', '10')))} different batches of {BATCH} views, visited in turn by the steps"),
         "cpu_baseline": {"value": vps, "unit": "views/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} views/step x {args.steps} steps of the batch-512 workload, oracle/raster.c "
                                    f"with OpenMP over views on {threads} host threads (pyrender/EGL cannot run here)"},
