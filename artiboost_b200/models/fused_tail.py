@@ -76,6 +76,40 @@ class _TailLossFn(torch.autograd.Function):
         return (d_kp * g_loss).to(ctx.in_dtypes[0]), (d_r6 * g_loss).to(ctx.in_dtypes[1]), None, None
 
 
+@torch.no_grad()
+def tail_forward(kp3d: torch.Tensor, rot6d: torch.Tensor, inputs: Dict[str, torch.Tensor], center_idx: int, inp_res) -> Dict[str, torch.Tensor]:
+    """The clasbased tail alone (hybridbaseline.py:41-96: uvd -> xyz, 6D -> R, corners, projection, the seven outputs) for the
+    inference path: the same `ab_tail_losses` launch with every loss weight zero (no targets, no draws) instead of ~40 torch
+    launches.  The torch composition in HybridBaseline.forward stays the definition; tests hold this call to it."""
+    dev = kp3d.device
+    B = kp3d.shape[0]
+    f = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+    kp, r6 = f(kp3d), f(rot6d)
+    root, intr, can = f(inputs["root_joint"]), f(inputs["cam_intr"]), f(inputs["corners_can"])
+    cfg = lib.TailCfgStruct()
+    cfg.batch, cfg.center_idx = B, int(center_idx)
+    cfg.inp_w, cfg.inp_h = float(inp_res[0]), float(inp_res[1])
+    cfg.img_w, cfg.img_h = float(inputs["image"].shape[3]), float(inputs["image"].shape[2])
+    cfg.depth_range = 0.4
+    cfg.w_joints = cfg.w_corners = cfg.w_joint_ord = cfg.w_part_ord = cfg.w_scene_ord = cfg.w_sym = 0.0
+    cfg.n_views_hand = cfg.n_pairs_joint = cfg.n_pairs_part = cfg.n_views_scene = cfg.n_pairs_scene = cfg.n_sym = cfg.sym_ho3d = 0
+    new = lambda *s_: torch.empty(s_, dtype=torch.float32, device=dev)  # noqa: E731
+    out = {"joints_3d_abs": new(B, 21, 3), "corners_3d_abs": new(B, 8, 3), "joints_3d": new(B, 21, 3), "corners_3d": new(B, 8, 3),
+           "2d_uvd": new(B, 30, 3), "boxroot_3d_abs": new(B, 1, 3), "box_rot_rotmat": new(B, 3, 3)}
+    parts, d_kp, d_r6 = new(8), new(B, 22, 3), new(B, 6)
+    zero = torch.zeros(B * (63 + 24 + 21 + 8), dtype=torch.float32, device=dev)   # the (unweighted) targets the entry point insists on
+    tj, tc, vj, vc = zero[:63 * B], zero[63 * B:87 * B], zero[87 * B:108 * B], zero[108 * B:]
+    L = lib.load()
+    ws = torch.empty(max(int(L.ab_tail_losses_workspace_bytes(B)), 4), dtype=torch.uint8, device=dev)
+    P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    with torch.cuda.device(dev):
+        lib.check(L.ab_tail_losses(C.byref(cfg), P(kp), P(r6), P(root), P(intr), P(can), P(tj), P(tc), P(vj), P(vc), None, None, None, None,
+                                   None, None, None, None, None, P(out["joints_3d_abs"]), P(out["corners_3d_abs"]), P(out["joints_3d"]),
+                                   P(out["corners_3d"]), P(out["2d_uvd"]), P(out["boxroot_3d_abs"]), P(out["box_rot_rotmat"]), P(parts),
+                                   P(d_kp), P(d_r6), P(ws), lib.stream_ptr(dev)), "ab_tail_losses")
+    return out
+
+
 class FusedTailCriterion:
     OUT_KEYS = ("joints_3d_abs", "corners_3d_abs", "joints_3d", "corners_3d", "2d_uvd", "boxroot_3d_abs", "box_rot_rotmat")
     TARGET_KEYS = ("root_joint", "cam_intr", "corners_can", "joints_3d", "corners_3d", "joints_vis", "corners_vis", "image")

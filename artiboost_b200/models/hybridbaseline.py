@@ -35,6 +35,9 @@ class HybridBaseline(nn.Module):
             preds, loss, parts = self.fused_tail(pose_results["kp3d"], box_rot_6d, inputs)
             preds["_fused_loss"], preds["_fused_parts"] = loss, parts
             return preds
+        if (not torch.is_grad_enabled() and pose_results["kp3d"].is_cuda and os.environ.get("AB_FUSED_TAIL", "1") != "0"):
+            from .fused_tail import tail_forward   # inference: the tail as ONE launch (the composition below defines it)
+            return tail_forward(pose_results["kp3d"], box_rot_6d, inputs, self.center_idx, self.inp_res)
         pose_3d_abs = batch_uvd2xyz(uvd=pose_results["kp3d"], root_joint=inputs["root_joint"], intr=inputs["cam_intr"],
                                     inp_res=self.inp_res)
         joints_3d_abs = pose_3d_abs[:, 0:21, :]

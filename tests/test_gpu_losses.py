@@ -251,3 +251,31 @@ def test_fused_tail_is_bit_reproducible_and_refuses_unknown_losses():
             return torch.zeros((), device=DEV), {}
     crit = C.Criterion({"LAMBDAS": [1.0]}, loss_list=[Other()])
     assert FusedTailCriterion.plan(crit, 0, [256, 256]) is None
+
+
+def test_inference_tail_launch_matches_the_torch_composition(lib_built):
+    """HybridBaseline's no-grad forward runs the tail as one ab_tail_losses launch with zero weights; AB_FUSED_TAIL=0 keeps the
+    torch composition (hybridbaseline.py:41-96), which defines it: the seven outputs agree to fp32 round-off."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import netcfg
+    import artiboost_b200.models as M
+    from artiboost_b200.train import real_shaped_batch
+    dev = torch.device("cuda", 0)
+    arch, preset = netcfg.arch_cfg("ResNet34")
+    torch.manual_seed(2)
+    model = M.Arch({"ARCH": arch}, M.build_arch_model_list(arch, preset_cfg=preset)).to(dev).eval()
+    batch = real_shaped_batch(5, dev, torch.Generator(device=dev).manual_seed(9))
+    with torch.no_grad():
+        fused = model(batch)
+        os.environ["AB_FUSED_TAIL"] = "0"
+        try:
+            plain = model(batch)
+        finally:
+            os.environ.pop("AB_FUSED_TAIL")
+    fused = fused[next(iter(fused))] if "joints_3d_abs" not in fused else fused
+    plain = plain[next(iter(plain))] if "joints_3d_abs" not in plain else plain
+    assert set(fused) == set(plain)
+    for k in plain:
+        torch.testing.assert_close(fused[k].float(), plain[k].float(), rtol=1e-4, atol=2e-5, msg=k)
