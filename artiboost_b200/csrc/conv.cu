@@ -160,8 +160,13 @@ __global__ void pack_conv_filters_kernel(const float* __restrict__ w, int Cout, 
 
 // idx (optional, training): uint8 per output element = ky*3 + kx of the FIRST maximum in scan order (torch's tie-break),
 // consumed by ab_maxpool3x3s2_bwd.
+// AFFINE: the input is a RAW convolution output and every tap goes through y = bf16(relu(raw * scale[c] + shift[c])) first
+// (the training-mode BatchNorm + ReLU of the stem, the same fp32 operations and bf16 rounding as ab_bn_apply): the
+// normalised activation -- 268 MB at batch 128 -- is never written or read.
+template <bool AFFINE>
 __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int B, int H, int W, int C8, int Ho, int Wo,
-                                    uint4* __restrict__ out, uint2* __restrict__ idx) {
+                                    uint4* __restrict__ out, uint2* __restrict__ idx, const float* __restrict__ scale,
+                                    const float* __restrict__ shift) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * Ho * Wo * C8;
     if (i >= total) return;
@@ -173,6 +178,11 @@ __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int B, int H, 
     const int b = (int)(t / Ho);
     float best[8];
     uint32_t tap[8];
+    float sc[8], sh[8];
+    if (AFFINE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + 8 * c8 + j); sh[j] = __ldg(shift + 8 * c8 + j); }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; tap[j] = 4; }
 #pragma unroll
@@ -185,7 +195,11 @@ __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int B, int H, 
             const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float2 f = __bfloat1622float2(pv[j]);
+                float2 f = __bfloat1622float2(pv[j]);
+                if (AFFINE) {   // relu(fma) rounded to bf16, as the separate BatchNorm pass stores it
+                    f = __bfloat1622float2(__floats2bfloat162_rn(fmaxf(fmaf(f.x, sc[2 * j], sh[2 * j]), 0.0f),
+                                                                 fmaxf(fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]), 0.0f)));
+                }
                 if (f.x > best[2 * j]) { best[2 * j] = f.x; tap[2 * j] = ky * 3 + kx; }
                 if (f.y > best[2 * j + 1]) { best[2 * j + 1] = f.y; tap[2 * j + 1] = ky * 3 + kx; }
             }
@@ -476,8 +490,22 @@ extern "C" int ab_maxpool3x3s2_nhwc(const void* in, int B, int H, int W, int C, 
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     cudaStream_t st = (cudaStream_t)stream;
     StageTimer tm(AB_STAGE_ELEMENTWISE, st);
-    maxpool3x3s2_kernel<<<blocks_for((long long)B * Ho * Wo * (C / 8), 256), 256, 0, st>>>((const uint4*)in, B, H, W, C / 8,
-                                                                                           Ho, Wo, (uint4*)out, (uint2*)idx);
+    maxpool3x3s2_kernel<false><<<blocks_for((long long)B * Ho * Wo * (C / 8), 256), 256, 0, st>>>((const uint4*)in, B, H, W, C / 8,
+                                                                                                  Ho, Wo, (uint4*)out, (uint2*)idx, nullptr, nullptr);
+    count_launch();
+    return check_launch("maxpool3x3s2_kernel");
+}
+
+extern "C" int ab_maxpool3x3s2_affine_nhwc(const void* raw, int B, int H, int W, int C, const float* scale, const float* shift,
+                                           void* out, void* idx, void* stream) {
+    AB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad shape (C must be a multiple of 8)");
+    if (B == 0) return AB_OK;
+    AB_REQUIRE(raw && out && scale && shift, "null pointer");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    StageTimer tm(AB_STAGE_ELEMENTWISE, st);
+    maxpool3x3s2_kernel<true><<<blocks_for((long long)B * Ho * Wo * (C / 8), 256), 256, 0, st>>>((const uint4*)raw, B, H, W, C / 8,
+                                                                                                 Ho, Wo, (uint4*)out, (uint2*)idx, scale, shift);
     count_launch();
     return check_launch("maxpool3x3s2_kernel");
 }

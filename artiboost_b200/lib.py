@@ -130,6 +130,7 @@ EXPORTS = {
     "ab_image_to_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "ab_im2col_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p]),
     "ab_maxpool3x3s2_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ab_maxpool3x3s2_affine_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 5),
     "ab_avgpool_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 3 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ab_deconv4x4s2_col2im": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                                       C.c_void_p, C.c_void_p]),

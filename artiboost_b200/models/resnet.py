@@ -150,8 +150,11 @@ class ResNet(nn.Module):
         """NHWC bf16 feature maps (what the head consumes without a layout round trip)."""
         ops_ = _prims()
         x = nhwc.image_to_act(image)
-        x = ops_.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=self.training)
-        x = ops_.maxpool3x3s2(x)
+        if self.training and ops_ is not nhwc and ops_.stem_fusable(self.conv1, self.bn1):
+            x = ops_.stem_conv_bn_relu_maxpool(x, self.conv1, self.bn1)   # bn1 + ReLU evaluated inside the pooling kernel
+        else:
+            x = ops_.conv_bn_act(x, self.conv1, self.bn1, relu=True, training=self.training)
+            x = ops_.maxpool3x3s2(x)
         feats = OrderedDict()
         for name in ("layer1", "layer2", "layer3", "layer4"):
             for blk in getattr(self, name):

@@ -152,9 +152,9 @@ def batch_counters():
             torch._foreach_add_(todo, 1)
 
 
-def _bn_forward_train(raw, M, C, bn, sums, residual, relu):
-    """sums: [2, n_part, C] partial column sums / sums of squares of `raw`."""
-    dev = raw.device
+def _bn_finalize_train(M, C, bn, sums, dev):
+    """Batch statistics -> (scale, shift, _BNState); running statistics and the batch counter advance.
+    sums: [2, n_part, C] partial column sums / sums of squares of the raw convolution output."""
     scale, shift = torch.empty(C, device=dev), torch.empty(C, device=dev)
     st = _BNState()
     st.mean, st.invstd = torch.empty(C, device=dev), torch.empty(C, device=dev)
@@ -164,15 +164,23 @@ def _bn_forward_train(raw, M, C, bn, sums, residual, relu):
         _call("ab_bn_finalize", sums[0].data_ptr(), sums[1].data_ptr(), sums.shape[1], C, float(M), P(bn.weight), P(bn.bias), float(bn.eps),
               float(momentum), scale.data_ptr(), shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
               P(bn.running_mean) if track else None, P(bn.running_var) if track else None, _stream(dev))
-        y = torch.empty_like(raw)
-        _call("ab_bn_apply", raw.data_ptr(), M, C, scale.data_ptr(), shift.data_ptr(), P(residual), int(relu), y.data_ptr(),
-              _stream(dev))
     if track and bn.num_batches_tracked is not None:
         if _BatchCounters.pending is not None:
             _BatchCounters.pending.append(bn.num_batches_tracked)
         else:
             bn.num_batches_tracked += 1
     st.scale, st.shift = scale, shift
+    return scale, shift, st
+
+
+def _bn_forward_train(raw, M, C, bn, sums, residual, relu):
+    """sums: [2, n_part, C] partial column sums / sums of squares of `raw`."""
+    dev = raw.device
+    scale, shift, st = _bn_finalize_train(M, C, bn, sums, dev)
+    with torch.cuda.device(dev):
+        y = torch.empty_like(raw)
+        _call("ab_bn_apply", raw.data_ptr(), M, C, scale.data_ptr(), shift.data_ptr(), P(residual), int(relu), y.data_ptr(),
+              _stream(dev))
     return y, st
 
 
@@ -353,6 +361,72 @@ class MaxPoolFn(torch.autograd.Function):
         with torch.cuda.device(dy.device):
             _call("ab_maxpool3x3s2_bwd", idx.data_ptr(), dy.data_ptr(), B, H, W, C, dx.data_ptr(), _stream(dy.device))
         return dx, None
+
+
+class StemFn(torch.autograd.Function):
+    """conv1 -> bn1 (batch statistics) -> ReLU -> MaxPool2d(3, 2, 1) of the ResNet stem (resnet.py:154-157) as one node: the
+    pooling kernel normalises the raw convolution output on the fly (ab_maxpool3x3s2_affine_nhwc), so the normalised
+    activation -- [B, 128, 128, 64] at a 256 x 256 input, 268 MB at batch 128 -- is neither written by a BatchNorm pass nor
+    read by the pooling.  Same values and argmax taps as ConvBNActFn + MaxPoolFn; the backward is theirs (the ReLU mask
+    comes from raw * scale + shift)."""
+
+    @staticmethod
+    def forward(ctx, x_data, weight, gamma, beta, geom, conv, bn):
+        B, H, W, C = geom
+        x = Act(x_data, B, H, W, C)
+        kh, kw = conv.kernel_size
+        stride, pad, cout = conv.stride[0], conv.padding[0], conv.out_channels
+        wp, _ = nhwc.packed_filters(conv, C, with_dgrad=True)
+        Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+        rows = None
+        if C % 64 == 0 and not (kh == 1 and kw == 1 and stride == 1):
+            rows = int(lib.load().ab_conv_stat_rows(B, H, W, C, cout, kh, kw, stride, pad))
+        sums = _stat_partials(B * Ho * Wo, cout, x_data.device, rows)
+        raw, Ho, Wo, xcol = _conv_raw(x, wp, cout, kh, kw, stride, pad, col_stats=(sums[0], sums[1]))
+        scale, shift, st = _bn_finalize_train(raw.shape[0], cout, bn, sums, raw.device)
+        Hp, Wp = (Ho + 2 - 3) // 2 + 1, (Wo + 2 - 3) // 2 + 1
+        out = torch.empty((B * Hp * Wp, cout), dtype=torch.bfloat16, device=raw.device)
+        idx = torch.empty((B * Hp * Wp, cout), dtype=torch.uint8, device=raw.device)
+        with torch.cuda.device(raw.device):
+            _call("ab_maxpool3x3s2_affine_nhwc", raw.data_ptr(), B, Ho, Wo, cout, scale.data_ptr(), shift.data_ptr(), out.data_ptr(),
+                  idx.data_ptr(), _stream(raw.device))
+        ctx.save_for_backward(x_data, raw, idx, xcol if xcol is not None else x_data.new_empty(0))
+        ctx.meta = (geom, conv, bn, kh, kw, stride, pad, cout, Ho, Wo)
+        ctx.st = st
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_data, raw, idx, xcol = ctx.saved_tensors
+        geom, conv, bn, kh, kw, stride, pad, cout, Ho, Wo = ctx.meta
+        B, H, W, C = geom
+        M = B * Ho * Wo
+        dev = dy.device
+        dy = dy.to(torch.bfloat16).contiguous()
+        dact = torch.empty((M, cout), dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            _call("ab_maxpool3x3s2_bwd", idx.data_ptr(), dy.data_ptr(), B, Ho, Wo, cout, dact.data_ptr(), _stream(dev))
+        draw, dgamma, dbeta, _ = _norm_backward(dact, None, raw, M, cout, bn, ctx.st, True, False)
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = _conv_wgrad(Act(x_data, B, H, W, C), xcol if xcol.numel() else None, draw, conv.weight, kh, kw, stride, pad)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _conv_dgrad(Act(draw, B, Ho, Wo, cout), conv.weight, kh, kw, stride, pad, H, W, conv, C)
+        return dx, dw, dgamma, dbeta, None, None, None
+
+
+def stem_fusable(conv: nn.Conv2d, bn) -> bool:
+    """The fused stem needs training-mode batch statistics, no conv bias and the ReLU mask taken from the raw output."""
+    return (MASK_FROM_RAW and isinstance(bn, nn.BatchNorm2d) and conv.bias is None and os.environ.get("AB_FUSED_STEM", "1") != "0")
+
+
+def stem_conv_bn_relu_maxpool(x: Act, conv: nn.Conv2d, bn) -> Act:
+    y = StemFn.apply(x.data, conv.weight, bn.weight, bn.bias, (x.B, x.H, x.W, x.C), conv, bn)
+    kh = conv.kernel_size[0]
+    Ho = (x.H + 2 * conv.padding[0] - kh) // conv.stride[0] + 1
+    Wo = (x.W + 2 * conv.padding[0] - kh) // conv.stride[0] + 1
+    return Act(y, x.B, (Ho + 2 - 3) // 2 + 1, (Wo + 2 - 3) // 2 + 1, conv.out_channels)
 
 
 def maxpool3x3s2(x: Act) -> Act:

@@ -368,6 +368,11 @@ AB_API int ab_image_to_nhwc(const float* image, int B, int C, int H, int W, int 
 AB_API int ab_im2col_nhwc(const void* in, int B, int H, int W, int C, int kh, int kw, int stride, int pad, int Kp,
                           void* out, void* stream);
 AB_API int ab_maxpool3x3s2_nhwc(const void* in, int B, int H, int W, int C, void* out, void* idx, void* stream);
+/* The same pooling over y = relu(raw * scale[c] + shift[c]) evaluated on the fly from the RAW convolution output (training-mode
+ * BatchNorm + ReLU of the stem, resnet.py:154-157: bn1, relu, maxpool): fp32 fma, ReLU, bf16 rounding per tap as ab_bn_apply
+ * stores it, so outputs and argmax taps equal ab_bn_apply followed by ab_maxpool3x3s2_nhwc; the activation is never stored. */
+AB_API int ab_maxpool3x3s2_affine_nhwc(const void* raw, int B, int H, int W, int C, const float* scale, const float* shift,
+                                       void* out, void* idx, void* stream);
 AB_API int ab_avgpool_nhwc(const void* in, int B, int HW, int C, float* out_f32, void* out_bf16, void* stream);
 AB_API int ab_deconv4x4s2_col2im(const float* ycol, int B, int H, int W, int Cout, const float* scale, const float* bias,
                                  int relu, void* out_bf16, float* out_raw, void* stream);

@@ -282,3 +282,38 @@ def test_maxpool_argmax_index_and_backward_match_torch():
     y.data.backward(dy.permute(0, 2, 3, 1).reshape(-1, 16).contiguous())
     yr.backward(dy.float())
     close(nchw(a.data.grad, 3, 37, 41), xr.grad, tol=4e-3, name="maxpool dx")
+
+
+def test_fused_stem_equals_conv_bn_relu_then_maxpool():
+    """StemFn (bn1 + ReLU evaluated inside the pooling kernel, the normalised activation never stored) against ConvBNActFn +
+    MaxPoolFn on the same input: pooled output, weight / gamma / beta gradients and the running statistics, bit for bit."""
+    import copy
+    from artiboost_b200.models import nhwc, train_ops
+    torch.manual_seed(5)
+    conv = torch.nn.Conv2d(3, 64, 7, 2, 3, bias=False).to(DEV)
+    bn_a = torch.nn.BatchNorm2d(64).to(DEV).train()
+    with torch.no_grad():
+        bn_a.weight.uniform_(0.5, 1.5)
+        bn_a.bias.normal_(0, 0.3)
+    bn_b = copy.deepcopy(bn_a)
+    image = torch.randn((6, 3, 70, 66), device=DEV)
+    g = bf(torch.randn((6 * 18 * 17, 64), device=DEV))
+    assert train_ops.stem_fusable(conv, bn_a)
+
+    def run(bn, fused):
+        conv.weight.grad = None
+        x = nhwc.image_to_act(image)
+        if fused:
+            y = train_ops.stem_conv_bn_relu_maxpool(x, conv, bn)
+        else:
+            y = train_ops.maxpool3x3s2(train_ops.conv_bn_act(x, conv, bn, relu=True, training=True))
+        assert (y.H, y.W, y.C) == (18, 17, 64)
+        y.data.backward(g)
+        return y.data.detach().clone(), conv.weight.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone()
+
+    ya, dwa, dga, dba = run(bn_a, False)
+    yb, dwb, dgb, dbb = run(bn_b, True)
+    assert torch.equal(ya, yb)
+    assert torch.equal(dwa, dwb) and torch.equal(dga, dgb) and torch.equal(dba, dbb)
+    assert torch.equal(bn_a.running_mean, bn_b.running_mean) and torch.equal(bn_a.running_var, bn_b.running_var)
+    assert int(bn_a.num_batches_tracked) == int(bn_b.num_batches_tracked) == 1
