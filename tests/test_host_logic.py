@@ -220,3 +220,28 @@ def test_filter_k_padding_and_batch_counter_context():
             train_ops._BatchCounters.pending.append(b)
         assert int(b) == 1 and int(a) == 0
     assert int(a) == 1 and train_ops._BatchCounters.pending is None
+
+
+def test_stream_override_redirects_library_launches_and_restores():
+    """lib.use_stream(s): inside the block every stream handle the library is given is s's (torch's current stream is not
+    consulted), nested blocks restore the outer one, and an exception leaves no override behind."""
+    from artiboost_b200 import lib
+
+    class FakeStream:
+        def __init__(self, handle):
+            self.cuda_stream = handle
+
+    a, b = FakeStream(0x1000), FakeStream(0x2000)
+    assert lib._stream_override is None
+    with lib.use_stream(a):
+        assert lib.stream_ptr().value == 0x1000
+        with lib.use_stream(b):
+            assert lib.stream_ptr("cuda:3").value == 0x2000
+        assert lib.stream_ptr().value == 0x1000
+    assert lib._stream_override is None
+    try:
+        with lib.use_stream(b):
+            raise RuntimeError("boom")
+    except RuntimeError:
+        pass
+    assert lib._stream_override is None
