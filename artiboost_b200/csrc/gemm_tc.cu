@@ -881,7 +881,7 @@ static int make_im2col_map(CUtensorMap* m, const void* ptr, int B, int H, int W,
     return AB_OK;
 }
 
-// One tile per CTA when the grid is at most about two waves of co-resident CTAs; the persistent form above beyond that
+// One tile per CTA when the grid is at most one wave of co-resident CTAs (two tiles per SM); the persistent form above beyond that
 // (AB_GEMM_PERSISTENT=0: never).
 template <int BN, int STAGES, bool IM2COL>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpilogue& ep,
@@ -898,7 +898,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
     const int tiles_m = cdiv(M, kBM), tiles_n = cdiv(N, BN);
     const long long n_tiles = (long long)tiles_m * tiles_n;
     StageTimer tm(IM2COL ? AB_STAGE_CONV_IMPLICIT : AB_STAGE_GEMM, st);
-    if (persist && n_tiles > 4ll * sms && n_tiles < (1ll << 31)) {
+    static const int min_per_sm = getenv("AB_GEMM_PERSIST_MIN") ? atoi(getenv("AB_GEMM_PERSIST_MIN")) : 2;   // tiles per SM beyond which the persistent form runs (4: 10.34, 2: 10.22, 1: 10.21 ms per step)
+    if (persist && n_tiles > (long long)min_per_sm * sms && n_tiles < (1ll << 31)) {
         const size_t smem = sizeof(GemmPSmem<BN, STAGES>) + 1024;
         static std::atomic<bool> configured[64] = {};
         if (!configured[dev & 63].load(std::memory_order_relaxed)) {

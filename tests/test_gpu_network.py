@@ -280,7 +280,7 @@ def test_packed_filters_match_the_torch_packing(cout, cin, k, cin_pad):
     assert wd.shape == ref_d.shape and torch.equal(wd, ref_d)
 
 
-# ------------------------------------------------------------------------- persistent form (more than 4 tiles per SM)
+# ------------------------------------------------------------------------- persistent form (more than 2 tiles per SM)
 def test_persistent_gemm_matches_fp32_matmul_ragged_and_fused():
     """Grids beyond four tiles per SM take gemm_bf16_tn_persistent_kernel (static tile scheduler, double-buffered TMEM
     accumulators, two epilogue groups, 32-byte row stores when the rows are 32-byte aligned).  Ragged M / N / K, every
